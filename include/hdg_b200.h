@@ -1,0 +1,135 @@
+/*
+ * hdg_b200.h -- C-ABI of the B200-native HDG solve engine.
+ *
+ * Drop-in boundary for the hybridisation / static-condensation path of
+ * eikehmueller/IncompressibleEulerHDG (citations are into the reference tree):
+ *
+ *   - the statically condensed mixed-Poisson solver objects built in
+ *     src/timesteppers/hdg_imex.py:123-221 ("pc_python_type": "firedrake.SCPC",
+ *     "pc_sc_eliminate_fields": "0, 1", condensed_field gmres rtol 1e-12) and called through
+ *     pressure_solve() at hdg_imex.py:257-272, and the same operator solved directly at
+ *     src/timesteppers/hdg_implicit.py:133-146;
+ *   - project_bdm() at src/timesteppers/common.py:91-108;
+ *   - the tentative-velocity solves at hdg_imex.py:223-255,274-281 and hdg_implicit.py:103-129.
+ *
+ * Conventions
+ *   * FP64 everywhere, int32 indices, all arrays C-contiguous.
+ *   * Every function returns 0 on success and a non-zero HDG_E* code otherwise; the message is
+ *     available from hdg_last_error().  No exceptions and no callbacks cross this boundary.
+ *   * Host ("AoS") layout, used by the *_host entry points -- cell/facet major like a
+ *     Firedrake Function.dat.data array in the engine's modal basis:
+ *         Q[nc][2][NQ1]   p[nc][NP]   lam[nf][K+1]
+ *     with NQ1 = (K+2)(K+3)/2, NP = (K+1)(K+2)/2.
+ *   * Device ("SoA") layout, used by the *_dev entry points -- dof major, entity minor, so that a
+ *     thread-per-entity kernel is perfectly coalesced:
+ *         Q[(c*NQ1+i)*nc + cell]   p[a*nc + cell]   lam[m*nf + facet]
+ *   * One handle drives one GPU (one process per GPU); multi-GPU runs create one handle per rank
+ *     on that rank's partition and join them with hdg_comm_init().
+ *   * Calls are asynchronous on the engine stream unless stated; *_host entry points and
+ *     functions returning scalars synchronise before returning.
+ */
+#ifndef HDG_B200_H
+#define HDG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hdg_engine* hdg_handle;
+
+enum {
+  HDG_OK = 0,
+  HDG_EINVAL = 1,   /* bad argument */
+  HDG_ECUDA = 2,    /* CUDA runtime error */
+  HDG_ENOGPU = 3,   /* no CUDA device: the engine has no CPU fallback */
+  HDG_ESTATE = 4,   /* call order violated (e.g. apply before setup) */
+  HDG_ENCCL = 5,    /* NCCL error */
+  HDG_ENOCONV = 6   /* Krylov solver hit maxit (results are still written) */
+};
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+
+/* Library version string and the pressure degrees compiled in (bit k set => degree k available). */
+const char* hdg_version(void);
+int hdg_supported_degrees(void);
+/* Number of CUDA devices visible (0 => every other call fails with HDG_ENOGPU). */
+int hdg_device_count(void);
+
+/* Create an engine on CUDA device `device` for pressure degree k (spaces [DG_{k+1}]^2 x DG_k x
+ * DGT_k, hdg_imex.py:65-69) and stabilisation tau (hdg_imex.py:58).
+ *   cell_xy[nc][3][2]   vertex coordinates per cell, counter-clockwise
+ *   cell_facet[nc][3]   global facet of local facet e (opposite local vertex e, running e+1 -> e+2)
+ *   cell_flip[nc][3]    1 if the cell traverses the facet against its global direction
+ *   facet_cell[nf][2]   adjacent cells (-1 in slot 1 on the domain boundary)
+ *   facet_local[nf][2]  local facet index within each adjacent cell (-1 if absent)
+ * The host arrays are copied; the engine keeps no host pointer. */
+int hdg_create(int k, double tau, int nc, int nf, const double* cell_xy, const int32_t* cell_facet,
+               const int32_t* cell_flip, const int32_t* facet_cell, const int32_t* facet_local,
+               int device, hdg_handle* out);
+int hdg_destroy(hdg_handle h);
+/* Message of the last error on this handle (or of the last failed hdg_create if h == NULL). */
+const char* hdg_last_error(hdg_handle h);
+/* Run all engine work on an externally owned cudaStream_t (e.g. torch's current stream). */
+int hdg_set_stream(hdg_handle h, void* cuda_stream);
+int hdg_synchronize(hdg_handle h);
+
+/* ---- condensed mixed-Poisson path (SCPC replacement) ----------------------------------------- */
+
+/* K1-K3: per-cell local operators + Schur complements S_K = D - C A^-1 B (hdg_imex.py:123-133),
+ * deterministic gather into the global trace matrix (mat_type aij, hdg_imex.py:135) stored as
+ * blocked ELL, and the facet-block-Jacobi inverse (the ASMStarPC patches of hdg_imex.py:143-152).
+ * Repeatable (re-assembles).  keep_local != 0 keeps the S_K array for hdg_get_local_schur(). */
+int hdg_setup_poisson(hdg_handle h, int keep_local);
+
+/* Copy S_K (SoA: SK[(r*NL+c)*nc + cell], NL = 3(K+1)) to a host buffer of nc*NL*NL doubles. */
+int hdg_get_local_schur(hdg_handle h, double* SK_host);
+/* Copy the assembled trace matrix as dense facet blocks: val[nf][5][b][b], col[nf][5] (b = K+1;
+ * slot 0 is the diagonal block, slots 1-2 the other facets of cell 0, slots 3-4 of cell 1). */
+int hdg_get_trace_matrix(hdg_handle h, double* val_host, int32_t* col_host);
+
+/* a3+a4+a6: forward elimination, trace Krylov solve (CG on -S, facet-block-Jacobi, relative
+ * tolerance rtol on the preconditioned residual norm, at most maxit iterations) and local
+ * back-substitution for the residual (rhs_Q, rhs_p, rhs_l) in the dual space; any rhs pointer may
+ * be NULL (= zero).  Writes the solution (Q, p, l); *iters receives the Krylov iteration count
+ * that the reference reads at hdg_imex.py:265-271.  shift != 0 additionally applies
+ * _shift_pressure (hdg_imex.py:471-478).  Host buffers, AoS layout; synchronous. */
+int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
+                           double* Q, double* p, double* l, double rtol, int maxit, int shift,
+                           int* iters);
+/* Same with device pointers in SoA layout; asynchronous except for the iteration-count read. */
+int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
+                          double* Q, double* p, double* l, double rtol, int maxit, int shift,
+                          int* iters);
+
+/* y = P x with P = -S (the symmetric positive semi-definite matrix the CG iterates on), device
+ * SoA pointers -- the SpMV of the Krylov loop, exposed for tests and the roofline microbenchmark. */
+int hdg_trace_spmv_dev(hdg_handle h, const double* x, double* y);
+/* Per-cell pieces exposed for tests / microbenchmarks (device SoA pointers):
+ *   forward elimination  r_l = rhs_l - sum_K C_K A_K^-1 (rhs_Q, rhs_p)
+ *   back-substitution    (Q,p) = A_K^-1 ((rhs_Q, rhs_p) - B_K l)                               */
+int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p,
+                              const double* rhs_l, double* r_l);
+int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* l,
+                            double* Q, double* p);
+
+/* ---- layout conversion / buffer helpers -------------------------------------------------------- */
+
+/* kind: 0 = velocity (2*NQ1 per cell), 1 = pressure (NP per cell), 2 = trace (K+1 per facet). */
+int hdg_field_size(hdg_handle h, int kind, int64_t* n);
+int hdg_upload(hdg_handle h, int kind, const double* host_aos, double* dev_soa);
+int hdg_download(hdg_handle h, int kind, const double* dev_soa, double* host_aos);
+
+/* ---- timers (CUDA-event time accumulated per reference PerformanceLog label) ------------------ */
+/* labels: 0 setup_poisson, 1 forward_elimination, 2 trace_solve, 3 back_substitution,
+ *         4 bdm_projection, 5 tentative_velocity_solve, 6 h2d, 7 d2h */
+int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n);
+int hdg_reset_timers(hdg_handle h);
+/* Number of engine kernels launched since creation (bench.py "gpu_launches"). */
+int64_t hdg_launch_count(hdg_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDG_B200_H */

@@ -1,0 +1,1123 @@
+// B200-native HDG solve engine: condensed mixed-Poisson path (K1-K5) and the C-ABI of
+// include/hdg_b200.h.  sm_100a only; there is no CPU fallback.
+//
+// Data layout in HBM (everything FP64, SoA = dof major / entity minor so that thread-per-entity
+// kernels are perfectly coalesced):
+//   cell_xy   [6][nc]            vertex coordinates
+//   cell_facet/cell_flip [3][nc] facet ids / orientation bits
+//   facet_cell/facet_local [2][nf]
+//   SK        [NL*NL][nc]        local Schur complements (setup only, optional keep)
+//   ell_val   [5*b*b][nf]        blocked-ELL trace matrix P = -S (slot 0 = diagonal), b = K+1
+//   ell_col   [5][nf]
+//   dinv      [b*b][nf]          facet-block-Jacobi inverse blocks
+//   trace vectors [b][nf], velocity [2*NQ1][nc], pressure [NP][nc]
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hdg_b200.h"
+#include "hdg_local.cuh"
+
+#define HDG_VERSION "hdg_b200 0.1 (sm_100a)"
+
+// ------------------------------------------------------------------------------------------------
+// engine state
+// ------------------------------------------------------------------------------------------------
+enum { T_SETUP = 0, T_FWD, T_SOLVE, T_BACK, T_BDM, T_TENT, T_H2D, T_D2H, T_COUNT };
+
+struct CgScalars {
+  double rz0;      // initial <r,z>
+  double rz;       // current <r,z>
+  double tol2;     // rtol^2
+  int iters;
+  int done;        // 0 running, 1 converged, 2 maxit
+  int maxit;
+  int pad;
+};
+
+struct hdg_engine {
+  int k = 0, nc = 0, nf = 0, device = 0;
+  double tau = 1.0;
+  double volume = 0.0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  int grid = 0;  // persistent grid for reductions
+  // mesh
+  double* cell_xy = nullptr;
+  int *cell_facet = nullptr, *cell_flip = nullptr, *facet_cell = nullptr, *facet_local = nullptr;
+  // poisson
+  bool poisson_ready = false;
+  double* SK = nullptr;
+  double *ell_val = nullptr, *dinv = nullptr;
+  int* ell_col = nullptr;
+  // work vectors
+  double *gK = nullptr;                                      // [NL][nc]
+  double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
+  double *partial = nullptr;                                 // [8][grid]
+  CgScalars* scal = nullptr;                                 // device
+  CgScalars* scal_host = nullptr;                            // pinned
+  double *wQ = nullptr, *wP = nullptr, *wL = nullptr;        // staging for host API (SoA)
+  double *wQ2 = nullptr, *wP2 = nullptr, *wL2 = nullptr;
+  double *stage = nullptr;                                   // AoS staging on device
+  size_t stage_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // bookkeeping
+  int64_t launches = 0;
+  std::string err;
+  struct Timer {
+    double ms = 0;
+    int64_t n = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  } timers[T_COUNT];
+  std::vector<cudaEvent_t> event_pool;
+};
+
+static std::string g_create_err;
+
+#define CUDA_TRY(h, expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +     \
+                 std::to_string(__LINE__) + ")";                                              \
+      return HDG_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+#define FAIL(h, code, msg) \
+  do {                     \
+    (h)->err = (msg);      \
+    return (code);         \
+  } while (0)
+
+#define LAUNCH(h, kernel, grid, block, ...)                      \
+  do {                                                           \
+    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);    \
+    (h)->launches++;                                             \
+  } while (0)
+
+static inline int cdiv(int64_t a, int b) { return (int)((a + b - 1) / b); }
+
+// ---- timers -------------------------------------------------------------------------------------
+static cudaEvent_t get_event(hdg_engine* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+static void flush_timer(hdg_engine* h, int label) {
+  auto& t = h->timers[label];
+  for (auto& pr : t.pending) {
+    cudaEventSynchronize(pr.second);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pr.first, pr.second);
+    t.ms += ms;
+    h->event_pool.push_back(pr.first);
+    h->event_pool.push_back(pr.second);
+  }
+  t.pending.clear();
+}
+struct ScopedTimer {
+  hdg_engine* h;
+  int label;
+  cudaEvent_t a, b;
+  ScopedTimer(hdg_engine* h_, int label_) : h(h_), label(label_) {
+    a = get_event(h);
+    b = get_event(h);
+    cudaEventRecord(a, h->stream);
+  }
+  ~ScopedTimer() {
+    cudaEventRecord(b, h->stream);
+    auto& t = h->timers[label];
+    t.n++;
+    t.pending.emplace_back(a, b);
+    if (t.pending.size() > 512) flush_timer(h, label);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+constexpr int BLOCK = 256;
+
+// deterministic block reduction (fixed tree); result valid in thread 0
+__device__ __forceinline__ double block_reduce(double v) {
+  __shared__ double sm[BLOCK / 32];
+  HDG_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < BLOCK / 32) ? sm[lane] : 0.0;
+    HDG_UNROLL
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+// every block sums the same `n` partials in the same order => identical result in all blocks
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ part, int n) {
+  __shared__ double res;
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += BLOCK) v += part[i];
+  v = block_reduce(v);
+  if (threadIdx.x == 0) res = v;
+  __syncthreads();
+  return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2: local operator build + static condensation, one thread per cell
+//   S_K = -tau G - E E^T / detJ + W H^-1 W^T,   W = E B^T / detJ + tau F,  H = T + B B^T / detJ
+// (equal to D - C A^-1 B of hdg_imex.py:128-133 for the blocks of hdg_imex.py:123-127)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ double W_entry(const Geo& g, const double (&nu)[3][2], double tau, int e, int m, int a) {
+  using T = RefTables<K>;
+  double v = 0.0;
+  if (T::LL(e, 0, m, a) != 0.0) v = fma(nu[e][0], T::LL(e, 0, m, a), v);
+  if (T::LL(e, 1, m, a) != 0.0) v = fma(nu[e][1], T::LL(e, 1, m, a), v);
+  if (T::F(e, m, a) != 0.0) v = fma(tau, T::F(e, m, a), v);
+  return v * g.le[e];
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_condense(const double* __restrict__ xy, const int* __restrict__ flip, int nc,
+                                                  double tau, double* __restrict__ SK) {
+  using T = RefTables<K>;
+  using D = Dims<K>;
+  constexpr int NP = D::NP, NL1 = D::NL1, NL = D::NL;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double L[D::NH];
+    build_H<K>(g, tau, L);
+    cholesky<NP>(L);
+    double nu[3][2];
+    int fl[3];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      fl[e] = flip[(size_t)e * nc + cell];
+      nu[e][0] = g.Ji[0][0] * g.n[e][0] + g.Ji[0][1] * g.n[e][1];
+      nu[e][1] = g.Ji[1][0] * g.n[e][0] + g.Ji[1][1] * g.n[e][1];
+    }
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) {
+        double v[NP];
+        HDG_UNROLL
+        for (int a = 0; a < NP; ++a) v[a] = W_entry<K>(g, nu, tau, e, m, a);
+        chol_solve<NP>(L, v);
+        double sg = flip_sign(fl[e], m);
+        HDG_UNROLL
+        for (int e2 = 0; e2 < 3; ++e2) {
+          double nn = (g.n[e][0] * g.n[e2][0] + g.n[e][1] * g.n[e2][1]) * g.le[e] * g.le[e2] * g.idetJ;
+          HDG_UNROLL
+          for (int m2 = 0; m2 < NL1; ++m2) {
+            double s = 0.0;
+            HDG_UNROLL
+            for (int a = 0; a < NP; ++a) s = fma(v[a], W_entry<K>(g, nu, tau, e2, m2, a), s);
+            if (T::NN(e, e2, m, m2) != 0.0) s = fma(-nn, T::NN(e, e2, m, m2), s);
+            if (e == e2 && m == m2) s -= tau * g.le[e];
+            s *= sg * flip_sign(fl[e2], m2);
+            SK[(size_t)((e * NL1 + m) * NL + e2 * NL1 + m2) * nc + cell] = s;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: deterministic gather of S_K into the blocked-ELL trace matrix P = -S, one thread per facet.
+// Row block f: slot 0 = (f,f) summed cell 0 then cell 1; slots 1,2 = the other facets of cell 0 in
+// local order (e0+1)%3,(e0+2)%3; slots 3,4 = those of cell 1 (zero blocks pointing at f on the
+// boundary).  No atomics: every entry has exactly one writer and a fixed summation order.
+// Also inverts the diagonal block (facet-block-Jacobi, the ASMStarPC patches hdg_imex.py:143-152).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) k_assemble(const double* __restrict__ SK, const int* __restrict__ cell_facet,
+                                                  const int* __restrict__ facet_cell,
+                                                  const int* __restrict__ facet_local, int nc, int nf,
+                                                  double* __restrict__ val, int* __restrict__ col,
+                                                  double* __restrict__ dinv) {
+  using D = Dims<K>;
+  constexpr int b = D::NL1, NL = D::NL;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    double diag[b][b];
+    HDG_UNROLL
+    for (int r = 0; r < b; ++r)
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) diag[r][c] = 0.0;
+    col[f] = f;
+    HDG_UNROLL
+    for (int side = 0; side < 2; ++side) {
+      int cell = facet_cell[(size_t)side * nf + f];
+      int e0 = facet_local[(size_t)side * nf + f];
+      if (cell < 0) {
+        HDG_UNROLL
+        for (int j = 1; j <= 2; ++j) {
+          int slot = 2 * side + j;
+          col[(size_t)slot * nf + f] = f;
+          HDG_UNROLL
+          for (int r = 0; r < b; ++r)
+            HDG_UNROLL
+            for (int c = 0; c < b; ++c) val[(size_t)((slot * b + r) * b + c) * nf + f] = 0.0;
+        }
+        continue;
+      }
+      HDG_UNROLL
+      for (int j = 0; j < 3; ++j) {
+        int e2 = (e0 + j) % 3;
+        HDG_UNROLL
+        for (int r = 0; r < b; ++r) {
+          HDG_UNROLL
+          for (int c = 0; c < b; ++c) {
+            double s = -SK[(size_t)((e0 * b + r) * NL + e2 * b + c) * nc + cell];
+            if (j == 0)
+              diag[r][c] += s;
+            else
+              val[(size_t)(((2 * side + j) * b + r) * b + c) * nf + f] = s;
+          }
+        }
+        if (j > 0) col[(size_t)(2 * side + j) * nf + f] = cell_facet[(size_t)e2 * nc + cell];
+      }
+    }
+    HDG_UNROLL
+    for (int r = 0; r < b; ++r)
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) val[(size_t)(r * b + c) * nf + f] = diag[r][c];
+    // inverse of the SPD diagonal block by Gauss-Jordan (no pivoting needed)
+    double inv[b][b];
+    HDG_UNROLL
+    for (int r = 0; r < b; ++r)
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) inv[r][c] = (r == c) ? 1.0 : 0.0;
+    HDG_UNROLL
+    for (int p = 0; p < b; ++p) {
+      double ip = 1.0 / diag[p][p];
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) {
+        diag[p][c] *= ip;
+        inv[p][c] *= ip;
+      }
+      HDG_UNROLL
+      for (int r = 0; r < b; ++r) {
+        if (r == p) continue;
+        double fct = diag[r][p];
+        HDG_UNROLL
+        for (int c = 0; c < b; ++c) {
+          diag[r][c] = fma(-fct, diag[p][c], diag[r][c]);
+          inv[r][c] = fma(-fct, inv[p][c], inv[r][c]);
+        }
+      }
+    }
+    HDG_UNROLL
+    for (int r = 0; r < b; ++r)
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) dinv[(size_t)(r * b + c) * nf + f] = inv[r][c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3: forward elimination, per cell:  gK = C_K A_K^-1 (Ru, Rp)   (SCPC.apply, first half)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) k_forward(const double* __restrict__ xy, const int* __restrict__ flip, int nc,
+                                                 double tau, const double* __restrict__ Ru,
+                                                 const double* __restrict__ Rp, double* __restrict__ gK) {
+  using D = Dims<K>;
+  constexpr int NQ1 = D::NQ1, NP = D::NP, NL1 = D::NL1;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double L[D::NH];
+    build_H<K>(g, tau, L);
+    cholesky<NP>(L);
+    double u[2][NQ1], phi[NP], lam[3][NL1];
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) u[c][i] = Ru ? Ru[(size_t)(c * NQ1 + i) * nc + cell] : 0.0;
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) phi[a] = Rp ? Rp[(size_t)a * nc + cell] : 0.0;
+    local_solve<K, false>(g, tau, L, lam, u, phi);
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e)
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) lam[e][m] = 0.0;
+    apply_E<K>(g, u, 1.0, lam);
+    apply_F<K>(g, phi, tau, lam);
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int fl = flip[(size_t)e * nc + cell];
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) gK[(size_t)(e * NL1 + m) * nc + cell] = flip_sign(fl, m) * lam[e][m];
+    }
+  }
+}
+
+// trace right-hand side of  P lam = b,  b = -(R_l - sum_K gK)  (P = -S); partial sums of the
+// constant-mode component for the range projection
+template <int K>
+__global__ void __launch_bounds__(BLOCK) k_trace_rhs(const double* __restrict__ gK, const double* __restrict__ Rl,
+                                                     const int* __restrict__ facet_cell,
+                                                     const int* __restrict__ facet_local, int nc, int nf,
+                                                     double* __restrict__ b, double* __restrict__ partial) {
+  constexpr int NL1 = Dims<K>::NL1;
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    int c0 = facet_cell[f], c1 = facet_cell[(size_t)nf + f];
+    int e0 = facet_local[f], e1 = facet_local[(size_t)nf + f];
+    HDG_UNROLL
+    for (int m = 0; m < NL1; ++m) {
+      double v = gK[(size_t)(e0 * NL1 + m) * nc + c0];
+      if (c1 >= 0) v += gK[(size_t)(e1 * NL1 + m) * nc + c1];
+      if (Rl) v -= Rl[(size_t)m * nf + f];
+      b[(size_t)m * nf + f] = v;
+      if (m == 0) acc += v;
+    }
+  }
+  acc = block_reduce(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: preconditioned CG on P = -S with facet-block-Jacobi.  Three kernels per iteration, all
+// reductions two-stage and deterministic (per-block partials re-reduced by every consumer block).
+// ------------------------------------------------------------------------------------------------
+// init: r = b - mean0(b) on mode 0 (projection onto range(S)), x = 0, z = Dinv r, p = z, <r,z>
+template <int b>
+__global__ void __launch_bounds__(BLOCK) k_cg_init(int nf, const double* __restrict__ dinv,
+                                                   const double* __restrict__ part_mean, double* __restrict__ r,
+                                                   double* __restrict__ x, double* __restrict__ z,
+                                                   double* __restrict__ p, double* __restrict__ part_rz) {
+  double mean = reduce_partials(part_mean, gridDim.x) / (double)nf;
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    double rv[b], zv[b];
+    HDG_UNROLL
+    for (int m = 0; m < b; ++m) rv[m] = r[(size_t)m * nf + f];
+    rv[0] -= mean;
+    r[f] = rv[0];
+    HDG_UNROLL
+    for (int i = 0; i < b; ++i) {
+      double s = 0.0;
+      HDG_UNROLL
+      for (int j = 0; j < b; ++j) s = fma(dinv[(size_t)(i * b + j) * nf + f], rv[j], s);
+      zv[i] = s;
+      acc = fma(s, rv[i], acc);
+    }
+    HDG_UNROLL
+    for (int m = 0; m < b; ++m) {
+      x[(size_t)m * nf + f] = 0.0;
+      z[(size_t)m * nf + f] = zv[m];
+      p[(size_t)m * nf + f] = zv[m];
+    }
+  }
+  acc = block_reduce(acc);
+  if (threadIdx.x == 0) part_rz[blockIdx.x] = acc;
+}
+
+__global__ void k_cg_start(CgScalars* s, const double* __restrict__ part_rz, int n, double rtol, int maxit) {
+  double rz = reduce_partials(part_rz, n);
+  if (threadIdx.x == 0) {
+    s->rz0 = rz;
+    s->rz = rz;
+    s->tol2 = rtol * rtol;
+    s->iters = 0;
+    s->maxit = maxit;
+    s->done = (rz <= 0.0 || maxit <= 0) ? 1 : 0;
+  }
+}
+
+// A: q = P p, partial <p,q>
+template <int b>
+__global__ void __launch_bounds__(BLOCK) k_cg_spmv(int nf, const double* __restrict__ val, const int* __restrict__ col,
+                                                   const double* __restrict__ p, double* __restrict__ q,
+                                                   double* __restrict__ part_pq, const CgScalars* __restrict__ s) {
+  if (s && s->done) return;
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    double y[b];
+    HDG_UNROLL
+    for (int i = 0; i < b; ++i) y[i] = 0.0;
+    HDG_UNROLL
+    for (int j = 0; j < 5; ++j) {
+      int cj = col[(size_t)j * nf + f];
+      double xv[b];
+      HDG_UNROLL
+      for (int c = 0; c < b; ++c) xv[c] = p[(size_t)c * nf + cj];
+      HDG_UNROLL
+      for (int r = 0; r < b; ++r)
+        HDG_UNROLL
+        for (int c = 0; c < b; ++c) y[r] = fma(val[(size_t)((j * b + r) * b + c) * nf + f], xv[c], y[r]);
+    }
+    HDG_UNROLL
+    for (int i = 0; i < b; ++i) {
+      q[(size_t)i * nf + f] = y[i];
+      if (part_pq) acc = fma(y[i], p[(size_t)i * nf + f], acc);
+    }
+  }
+  if (part_pq) {
+    acc = block_reduce(acc);
+    if (threadIdx.x == 0) part_pq[blockIdx.x] = acc;
+  }
+}
+
+// B: alpha = <r,z>/<p,q>; x += alpha p; r -= alpha q; z = Dinv r; partial <r,z>
+template <int b>
+__global__ void __launch_bounds__(BLOCK) k_cg_update(int nf, const double* __restrict__ dinv,
+                                                     const double* __restrict__ p, const double* __restrict__ q,
+                                                     double* __restrict__ x, double* __restrict__ r,
+                                                     double* __restrict__ z, const double* __restrict__ part_pq,
+                                                     double* __restrict__ part_rz, const CgScalars* __restrict__ s) {
+  if (s->done) return;
+  double pq = reduce_partials(part_pq, gridDim.x);
+  double alpha = s->rz / pq;
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    double rv[b];
+    HDG_UNROLL
+    for (int m = 0; m < b; ++m) {
+      size_t idx = (size_t)m * nf + f;
+      x[idx] = fma(alpha, p[idx], x[idx]);
+      rv[m] = fma(-alpha, q[idx], r[idx]);
+      r[idx] = rv[m];
+    }
+    HDG_UNROLL
+    for (int i = 0; i < b; ++i) {
+      double v = 0.0;
+      HDG_UNROLL
+      for (int j = 0; j < b; ++j) v = fma(dinv[(size_t)(i * b + j) * nf + f], rv[j], v);
+      z[(size_t)i * nf + f] = v;
+      acc = fma(v, rv[i], acc);
+    }
+  }
+  acc = block_reduce(acc);
+  if (threadIdx.x == 0) part_rz[blockIdx.x] = acc;
+}
+
+// C: beta = <r,z>_new / <r,z>_old; p = z + beta p; convergence bookkeeping.
+// Every block derives the same decision from the same partials; block 0 publishes it.
+template <int b>
+__global__ void __launch_bounds__(BLOCK) k_cg_pupdate(int nf, const double* __restrict__ z, double* __restrict__ p,
+                                                      const double* __restrict__ part_rz, CgScalars* s) {
+  __shared__ int done_in;
+  __shared__ double rz_old, rz0, tol2;
+  __shared__ int it, maxit;
+  if (threadIdx.x == 0) {
+    done_in = s->done;
+    rz_old = s->rz;
+    rz0 = s->rz0;
+    tol2 = s->tol2;
+    it = s->iters;
+    maxit = s->maxit;
+  }
+  __syncthreads();
+  if (done_in) return;
+  double rz_new = reduce_partials(part_rz, gridDim.x);
+  bool conv = rz_new <= tol2 * rz0;
+  bool stop = conv || (it + 1 >= maxit);
+  if (!stop) {
+    double beta = rz_new / rz_old;
+    size_t n = (size_t)b * nf;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      p[i] = fma(beta, p[i], z[i]);
+  }
+  // publish after all blocks have read the old scalars: a grid-wide ordering is not available, so
+  // the *last* block to arrive writes (ticket counter in s->pad)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int ticket = atomicAdd(&s->pad, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      s->pad = 0;
+      s->rz = rz_new;
+      s->iters = it + 1;
+      s->done = conv ? 1 : (stop ? 2 : 0);
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 / a6: back-substitution per cell  (u,phi) = A_K^-1 ((Ru,Rp) - B_K lam_K)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) k_back(const double* __restrict__ xy, const int* __restrict__ flip,
+                                              const int* __restrict__ cell_facet, int nc, int nf, double tau,
+                                              const double* __restrict__ Ru, const double* __restrict__ Rp,
+                                              const double* __restrict__ lamg, double* __restrict__ uo,
+                                              double* __restrict__ po) {
+  using D = Dims<K>;
+  constexpr int NQ1 = D::NQ1, NP = D::NP, NL1 = D::NL1;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double L[D::NH];
+    build_H<K>(g, tau, L);
+    cholesky<NP>(L);
+    double u[2][NQ1], phi[NP], lam[3][NL1];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int f = cell_facet[(size_t)e * nc + cell];
+      int fl = flip[(size_t)e * nc + cell];
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) lam[e][m] = flip_sign(fl, m) * lamg[(size_t)m * nf + f];
+    }
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) u[c][i] = Ru ? Ru[(size_t)(c * NQ1 + i) * nc + cell] : 0.0;
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) phi[a] = Rp ? Rp[(size_t)a * nc + cell] : 0.0;
+    local_solve<K, true>(g, tau, L, lam, u, phi);
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) uo[(size_t)(c * NQ1 + i) * nc + cell] = u[c][i];
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) po[(size_t)a * nc + cell] = phi[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a7/a8: _shift_pressure  (hdg_imex.py:471-478):  p -= mean(p), lam -= mean(p)
+// int_K p dx = detJ * p_0 / sqrt(2)  (Dubiner mode 0 is the constant sqrt(2))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_pmean_partial(const double* __restrict__ xy, int nc,
+                                                         const double* __restrict__ p, double* __restrict__ partial) {
+  double acc = 0.0;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    double x0 = xy[cell], y0 = xy[(size_t)nc + cell];
+    double x1 = xy[2 * (size_t)nc + cell], y1 = xy[3 * (size_t)nc + cell];
+    double x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];
+    double detJ = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+    acc = fma(detJ, p[cell], acc);
+  }
+  acc = block_reduce(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(BLOCK) k_shift(int nc, int nf, double inv_volume, const double* __restrict__ partial,
+                                                 double* __restrict__ p, double* __restrict__ lam) {
+  double integral = reduce_partials(partial, gridDim.x) * 0.70710678118654752440;
+  double shift = integral * inv_volume;
+  double ps = shift * 0.70710678118654752440;  // coefficient of the constant in mode 0
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) p[i] -= ps;
+  if (lam)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) lam[i] -= shift;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion AoS (entity major) <-> SoA (dof major); ndof is small
+// ------------------------------------------------------------------------------------------------
+__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int n, int ndof) {
+  size_t total = (size_t)n * ndof;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t ent = i / ndof;
+    int d = (int)(i - ent * ndof);
+    soa[(size_t)d * n + ent] = aos[i];
+  }
+}
+__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int n, int ndof) {
+  size_t total = (size_t)n * ndof;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t ent = i / ndof;
+    int d = (int)(i - ent * ndof);
+    aos[i] = soa[(size_t)d * n + ent];
+  }
+}
+__global__ void k_int_transpose(const int* __restrict__ aos, int* __restrict__ soa, int n, int ndof) {
+  size_t total = (size_t)n * ndof;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t ent = i / ndof;
+    int d = (int)(i - ent * ndof);
+    soa[(size_t)d * n + ent] = aos[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch over the compiled-in degrees
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH_K(h, ...)                                         \
+  switch ((h)->k) {                                                \
+    case 1: { constexpr int K = 1; __VA_ARGS__; } break;           \
+    case 2: { constexpr int K = 2; __VA_ARGS__; } break;           \
+    case 3: { constexpr int K = 3; __VA_ARGS__; } break;           \
+    case 4: { constexpr int K = 4; __VA_ARGS__; } break;           \
+    default: FAIL(h, HDG_EINVAL, "unsupported degree");            \
+  }
+
+static void dims_of(int k, int& nq1, int& np, int& nl1) {
+  nq1 = (k + 2) * (k + 3) / 2;
+  np = (k + 1) * (k + 2) / 2;
+  nl1 = k + 1;
+}
+
+static int field_len(const hdg_engine* h, int kind, int64_t& n, int& ent, int& ndof) {
+  int nq1, np, nl1;
+  dims_of(h->k, nq1, np, nl1);
+  switch (kind) {
+    case 0: ent = h->nc; ndof = 2 * nq1; break;
+    case 1: ent = h->nc; ndof = np; break;
+    case 2: ent = h->nf; ndof = nl1; break;
+    default: return HDG_EINVAL;
+  }
+  n = (int64_t)ent * ndof;
+  return HDG_OK;
+}
+
+template <class Tp>
+static cudaError_t dmalloc(Tp** p, size_t count) {
+  return cudaMalloc((void**)p, count * sizeof(Tp));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hdg_version(void) { return HDG_VERSION; }
+int hdg_supported_degrees(void) { return (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4); }
+int hdg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* hdg_last_error(hdg_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int hdg_destroy(hdg_handle h) {
+  if (!h) return HDG_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  void* ptrs[] = {h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local, h->SK, h->ell_val,
+                  h->dinv, h->ell_col, h->gK, h->cg_x, h->cg_r, h->cg_z, h->cg_p, h->cg_q, h->partial, h->scal,
+                  h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->scal_host) cudaFreeHost(h->scal_host);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  for (int i = 0; i < T_COUNT; ++i) flush_timer(h, i);
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return HDG_OK;
+}
+
+int hdg_create(int k, double tau, int nc, int nf, const double* cell_xy, const int32_t* cell_facet,
+               const int32_t* cell_flip, const int32_t* facet_cell, const int32_t* facet_local, int device,
+               hdg_handle* out) {
+  if (!out) return HDG_EINVAL;
+  *out = nullptr;
+  if (k < 1 || k > 4) {
+    g_create_err = "hdg_create: degree k must be in 1..4";
+    return HDG_EINVAL;
+  }
+  if (nc <= 0 || nf <= 0 || !cell_xy || !cell_facet || !cell_flip || !facet_cell || !facet_local || !(tau > 0)) {
+    g_create_err = "hdg_create: invalid mesh arguments";
+    return HDG_EINVAL;
+  }
+  int ndev = hdg_device_count();
+  if (ndev == 0) {
+    g_create_err = "hdg_create: no CUDA device visible; this engine has no CPU fallback";
+    return HDG_ENOGPU;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "hdg_create: device index out of range";
+    return HDG_EINVAL;
+  }
+  hdg_engine* h = new hdg_engine();
+  h->k = k;
+  h->nc = nc;
+  h->nf = nf;
+  h->tau = tau;
+  h->device = device;
+#define CREATE_TRY(expr)                                                          \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      g_create_err = std::string(#expr) + ": " + cudaGetErrorString(_e);          \
+      hdg_destroy(h);                                                             \
+      return HDG_ECUDA;                                                           \
+    }                                                                             \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+  h->num_sms = prop.multiProcessorCount;
+  h->grid = h->num_sms * 8;
+  CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  int nq1, np, nl1;
+  dims_of(k, nq1, np, nl1);
+  // validate topology on the host (cheap, catches adapter bugs early)
+  double vol = 0.0;
+  for (int c = 0; c < nc; ++c) {
+    const double* x = cell_xy + 6 * (size_t)c;
+    double det = (x[2] - x[0]) * (x[5] - x[1]) - (x[4] - x[0]) * (x[3] - x[1]);
+    if (!(det > 0)) {
+      g_create_err = "hdg_create: cell " + std::to_string(c) + " is degenerate or not counter-clockwise";
+      hdg_destroy(h);
+      return HDG_EINVAL;
+    }
+    vol += 0.5 * det;
+    for (int e = 0; e < 3; ++e) {
+      int f = cell_facet[3 * (size_t)c + e];
+      if (f < 0 || f >= nf) {
+        g_create_err = "hdg_create: cell_facet out of range";
+        hdg_destroy(h);
+        return HDG_EINVAL;
+      }
+    }
+  }
+  for (int f = 0; f < nf; ++f) {
+    int c0 = facet_cell[2 * (size_t)f], c1 = facet_cell[2 * (size_t)f + 1];
+    int e0 = facet_local[2 * (size_t)f], e1 = facet_local[2 * (size_t)f + 1];
+    bool ok = c0 >= 0 && c0 < nc && e0 >= 0 && e0 < 3 && cell_facet[3 * (size_t)c0 + e0] == f;
+    if (c1 >= 0) ok = ok && c1 < nc && e1 >= 0 && e1 < 3 && cell_facet[3 * (size_t)c1 + e1] == f;
+    if (!ok) {
+      g_create_err = "hdg_create: facet_cell/facet_local inconsistent with cell_facet at facet " + std::to_string(f);
+      hdg_destroy(h);
+      return HDG_EINVAL;
+    }
+  }
+  h->volume = vol;
+  // device copies (transposed to SoA on the device)
+  CREATE_TRY(dmalloc(&h->cell_xy, 6 * (size_t)nc));
+  CREATE_TRY(dmalloc(&h->cell_facet, 3 * (size_t)nc));
+  CREATE_TRY(dmalloc(&h->cell_flip, 3 * (size_t)nc));
+  CREATE_TRY(dmalloc(&h->facet_cell, 2 * (size_t)nf));
+  CREATE_TRY(dmalloc(&h->facet_local, 2 * (size_t)nf));
+  {
+    size_t bytes = std::max<size_t>(6 * (size_t)nc * sizeof(double), 2 * (size_t)nf * sizeof(int));
+    void* tmp = nullptr;
+    CREATE_TRY(cudaMalloc(&tmp, bytes));
+    auto up_d = [&](const double* src, double* dst, int n, int nd) {
+      cudaMemcpyAsync(tmp, src, (size_t)n * nd * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+      k_aos_to_soa<<<h->grid, BLOCK, 0, h->stream>>>((const double*)tmp, dst, n, nd);
+      cudaStreamSynchronize(h->stream);
+    };
+    auto up_i = [&](const int32_t* src, int* dst, int n, int nd) {
+      cudaMemcpyAsync(tmp, src, (size_t)n * nd * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+      k_int_transpose<<<h->grid, BLOCK, 0, h->stream>>>((const int*)tmp, dst, n, nd);
+      cudaStreamSynchronize(h->stream);
+    };
+    up_d(cell_xy, h->cell_xy, nc, 6);
+    up_i(cell_facet, h->cell_facet, nc, 3);
+    up_i(cell_flip, h->cell_flip, nc, 3);
+    up_i(facet_cell, h->facet_cell, nf, 2);
+    up_i(facet_local, h->facet_local, nf, 2);
+    h->launches += 5;
+    cudaFree(tmp);
+    CREATE_TRY(cudaGetLastError());
+  }
+  CREATE_TRY(dmalloc(&h->partial, 8 * (size_t)h->grid));
+  CREATE_TRY(dmalloc(&h->scal, 1));
+  CREATE_TRY(cudaMemset(h->scal, 0, sizeof(CgScalars)));
+  CREATE_TRY(cudaMallocHost((void**)&h->scal_host, sizeof(CgScalars)));
+#undef CREATE_TRY
+  *out = h;
+  return HDG_OK;
+}
+
+int hdg_set_stream(hdg_handle h, void* cuda_stream) {
+  if (!h) return HDG_EINVAL;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->own_stream = false;
+  h->stream = (cudaStream_t)cuda_stream;
+  return HDG_OK;
+}
+
+int hdg_synchronize(hdg_handle h) {
+  if (!h) return HDG_EINVAL;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return HDG_OK;
+}
+
+int hdg_setup_poisson(hdg_handle h, int keep_local) {
+  if (!h) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int nq1, np, b;
+  dims_of(h->k, nq1, np, b);
+  const int NL = 3 * b;
+  const size_t nc = h->nc, nf = h->nf;
+  if (!h->SK) CUDA_TRY(h, dmalloc(&h->SK, (size_t)NL * NL * nc));
+  if (!h->ell_val) {
+    CUDA_TRY(h, dmalloc(&h->ell_val, 5 * (size_t)b * b * nf));
+    CUDA_TRY(h, dmalloc(&h->ell_col, 5 * nf));
+    CUDA_TRY(h, dmalloc(&h->dinv, (size_t)b * b * nf));
+    CUDA_TRY(h, dmalloc(&h->gK, (size_t)NL * nc));
+    CUDA_TRY(h, dmalloc(&h->cg_x, b * nf));
+    CUDA_TRY(h, dmalloc(&h->cg_r, b * nf));
+    CUDA_TRY(h, dmalloc(&h->cg_z, b * nf));
+    CUDA_TRY(h, dmalloc(&h->cg_p, b * nf));
+    CUDA_TRY(h, dmalloc(&h->cg_q, b * nf));
+  }
+  {
+    ScopedTimer t(h, T_SETUP);
+    DISPATCH_K(h, {
+      LAUNCH(h, k_condense<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
+      LAUNCH(h, k_assemble<K>, cdiv(h->nf, 128), 128, h->SK, h->cell_facet, h->facet_cell, h->facet_local, h->nc,
+             h->nf, h->ell_val, h->ell_col, h->dinv);
+    });
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  if (!keep_local) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->SK);
+    h->SK = nullptr;
+  }
+  h->poisson_ready = true;
+  return HDG_OK;
+}
+
+int hdg_get_local_schur(hdg_handle h, double* SK_host) {
+  if (!h || !SK_host) return HDG_EINVAL;
+  if (!h->SK) FAIL(h, HDG_ESTATE, "hdg_get_local_schur: call hdg_setup_poisson(h, keep_local=1) first");
+  int b = h->k + 1;
+  size_t n = (size_t)9 * b * b * h->nc;
+  CUDA_TRY(h, cudaMemcpyAsync(SK_host, h->SK, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return HDG_OK;
+}
+
+int hdg_get_trace_matrix(hdg_handle h, double* val_host, int32_t* col_host) {
+  if (!h || !val_host || !col_host) return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_get_trace_matrix: call hdg_setup_poisson first");
+  int b = h->k + 1;
+  size_t nf = h->nf;
+  double* tmp;
+  CUDA_TRY(h, dmalloc(&tmp, 5 * (size_t)b * b * nf));
+  LAUNCH(h, k_soa_to_aos, h->grid, BLOCK, h->ell_val, tmp, h->nf, 5 * b * b);
+  CUDA_TRY(h, cudaMemcpyAsync(val_host, tmp, 5 * (size_t)b * b * nf * sizeof(double), cudaMemcpyDeviceToHost,
+                              h->stream));
+  std::vector<int> cols(5 * nf);
+  CUDA_TRY(h, cudaMemcpyAsync(cols.data(), h->ell_col, 5 * nf * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(tmp);
+  for (size_t f = 0; f < nf; ++f)
+    for (int j = 0; j < 5; ++j) col_host[5 * f + j] = cols[(size_t)j * nf + f];
+  return HDG_OK;
+}
+
+int hdg_trace_spmv_dev(hdg_handle h, const double* x, double* y) {
+  if (!h || !x || !y) return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_trace_spmv_dev: call hdg_setup_poisson first");
+  // y = S x = -(P x)
+  switch (h->k) {
+    case 1: LAUNCH(h, k_cg_spmv<2>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
+    case 2: LAUNCH(h, k_cg_spmv<3>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
+    case 3: LAUNCH(h, k_cg_spmv<4>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
+    case 4: LAUNCH(h, k_cg_spmv<5>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
+                              double* r_l) {
+  if (!h || !r_l) return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_forward_eliminate_dev: call hdg_setup_poisson first");
+  ScopedTimer t(h, T_FWD);
+  DISPATCH_K(h, {
+    LAUNCH(h, k_forward<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, rhs_Q, rhs_p, h->gK);
+    LAUNCH(h, k_trace_rhs<K>, h->grid, BLOCK, h->gK, rhs_l, h->facet_cell, h->facet_local, h->nc, h->nf, r_l,
+           h->partial);
+  });
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* l, double* Q,
+                            double* p) {
+  if (!h || !l || !Q || !p) return HDG_EINVAL;
+  ScopedTimer t(h, T_BACK);
+  DISPATCH_K(h, {
+    LAUNCH(h, k_back<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
+           rhs_p, l, Q, p);
+  });
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+}  // extern "C"
+
+template <int b>
+static int run_cg(hdg_engine* h, double rtol, int maxit, int* iters) {
+  const int G = h->grid;
+  double* part_mean = h->partial;
+  double* part_pq = h->partial + G;
+  double* part_rz = h->partial + 2 * (size_t)G;
+  // b already sits in cg_r (written by k_trace_rhs), its mode-0 partial sums in part_mean
+  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z, h->cg_p, part_rz);
+  LAUNCH(h, k_cg_start, 1, BLOCK, h->scal, part_rz, G, rtol, maxit);
+  const int chunk = 20;
+  int launched = 0;
+  bool finished = false;
+  while (!finished) {
+    int n = std::min(chunk, maxit - launched);
+    if (n <= 0) n = 1;
+    for (int i = 0; i < n; ++i) {
+      LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+      LAUNCH(h, k_cg_update<b>, G, BLOCK, h->nf, h->dinv, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->cg_z, part_pq,
+             part_rz, h->scal);
+      LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);
+    }
+    launched += n;
+    CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->scal_host->done || launched >= maxit) finished = true;
+  }
+  if (iters) *iters = h->scal_host->iters;
+  return h->scal_host->done == 1 ? HDG_OK : HDG_ENOCONV;
+}
+
+extern "C" {
+
+int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
+                          double* p, double* l, double rtol, int maxit, int shift, int* iters) {
+  if (!h || !Q || !p || !l) return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_poisson_apply: call hdg_setup_poisson first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = hdg_forward_eliminate_dev(h, rhs_Q, rhs_p, rhs_l, h->cg_r);
+  if (rc) return rc;
+  int cg_rc;
+  {
+    ScopedTimer t(h, T_SOLVE);
+    switch (h->k) {
+      case 1: cg_rc = run_cg<2>(h, rtol, maxit, iters); break;
+      case 2: cg_rc = run_cg<3>(h, rtol, maxit, iters); break;
+      case 3: cg_rc = run_cg<4>(h, rtol, maxit, iters); break;
+      default: cg_rc = run_cg<5>(h, rtol, maxit, iters); break;
+    }
+  }
+  if (cg_rc == HDG_ECUDA) return cg_rc;
+  int b = h->k + 1;
+  CUDA_TRY(h, cudaMemcpyAsync(l, h->cg_x, (size_t)b * h->nf * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  rc = hdg_back_substitute_dev(h, rhs_Q, rhs_p, l, Q, p);
+  if (rc) return rc;
+  if (shift) {
+    LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, p, h->partial);
+    LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  if (cg_rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "trace CG did not converge within maxit");
+  return HDG_OK;
+}
+
+int hdg_field_size(hdg_handle h, int kind, int64_t* n) {
+  if (!h || !n) return HDG_EINVAL;
+  int ent, ndof;
+  return field_len(h, kind, *n, ent, ndof);
+}
+
+static int ensure_stage(hdg_engine* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return HDG_OK;
+  if (h->stage) cudaFree(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  CUDA_TRY(h, cudaMalloc((void**)&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return HDG_OK;
+}
+
+int hdg_upload(hdg_handle h, int kind, const double* host_aos, double* dev_soa) {
+  if (!h || !host_aos || !dev_soa) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  if (field_len(h, kind, n, ent, ndof)) FAIL(h, HDG_EINVAL, "hdg_upload: bad kind");
+  int rc = ensure_stage(h, n * sizeof(double));
+  if (rc) return rc;
+  ScopedTimer t(h, T_H2D);
+  CUDA_TRY(h, cudaMemcpyAsync(h->stage, host_aos, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_aos_to_soa, h->grid, BLOCK, h->stage, dev_soa, ent, ndof);
+  // the staging buffer is reused by the next call on the same stream: stream order keeps it safe
+  return HDG_OK;
+}
+
+int hdg_download(hdg_handle h, int kind, const double* dev_soa, double* host_aos) {
+  if (!h || !host_aos || !dev_soa) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  if (field_len(h, kind, n, ent, ndof)) FAIL(h, HDG_EINVAL, "hdg_download: bad kind");
+  int rc = ensure_stage(h, n * sizeof(double));
+  if (rc) return rc;
+  {
+    ScopedTimer t(h, T_D2H);
+    LAUNCH(h, k_soa_to_aos, h->grid, BLOCK, dev_soa, h->stage, ent, ndof);
+    CUDA_TRY(h, cudaMemcpyAsync(host_aos, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return HDG_OK;
+}
+
+int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
+                           double* p, double* l, double rtol, int maxit, int shift, int* iters) {
+  if (!h || !Q || !p || !l) return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_poisson_apply: call hdg_setup_poisson first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int nq1, np, b;
+  dims_of(h->k, nq1, np, b);
+  size_t nQ = 2 * (size_t)nq1 * h->nc, nP = (size_t)np * h->nc, nL = (size_t)b * h->nf;
+  if (!h->wQ) {
+    CUDA_TRY(h, dmalloc(&h->wQ, nQ));
+    CUDA_TRY(h, dmalloc(&h->wP, nP));
+    CUDA_TRY(h, dmalloc(&h->wL, nL));
+    CUDA_TRY(h, dmalloc(&h->wQ2, nQ));
+    CUDA_TRY(h, dmalloc(&h->wP2, nP));
+    CUDA_TRY(h, dmalloc(&h->wL2, nL));
+  }
+  int rc;
+  if (rhs_Q && (rc = hdg_upload(h, 0, rhs_Q, h->wQ))) return rc;
+  if (rhs_p && (rc = hdg_upload(h, 1, rhs_p, h->wP))) return rc;
+  if (rhs_l && (rc = hdg_upload(h, 2, rhs_l, h->wL))) return rc;
+  int arc = hdg_poisson_apply_dev(h, rhs_Q ? h->wQ : nullptr, rhs_p ? h->wP : nullptr, rhs_l ? h->wL : nullptr,
+                                  h->wQ2, h->wP2, h->wL2, rtol, maxit, shift, iters);
+  if (arc && arc != HDG_ENOCONV) return arc;
+  if ((rc = hdg_download(h, 0, h->wQ2, Q))) return rc;
+  if ((rc = hdg_download(h, 1, h->wP2, p))) return rc;
+  if ((rc = hdg_download(h, 2, h->wL2, l))) return rc;
+  return arc;
+}
+
+int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n) {
+  if (!h) return HDG_EINVAL;
+  for (int i = 0; i < n && i < T_COUNT; ++i) {
+    flush_timer(h, i);
+    if (ms) ms[i] = h->timers[i].ms;
+    if (ncalls) ncalls[i] = h->timers[i].n;
+  }
+  return HDG_OK;
+}
+
+int hdg_reset_timers(hdg_handle h) {
+  if (!h) return HDG_EINVAL;
+  for (int i = 0; i < T_COUNT; ++i) {
+    flush_timer(h, i);
+    h->timers[i].ms = 0;
+    h->timers[i].n = 0;
+  }
+  return HDG_OK;
+}
+
+int64_t hdg_launch_count(hdg_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""ctypes binding of ``libhdg_b200.so`` (the C-ABI declared in ``include/hdg_b200.h``).
+
+Host code stays Python (BASELINE.json north_star); PyTorch is used only to own device buffers and
+streams.  There is no CPU fallback: constructing an :class:`HDGEngine` without the CUDA library or
+without a GPU raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["HDGEngine", "HDGError", "load_library", "LIB_PATH", "TIMER_LABELS"]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdg_b200.so")
+
+TIMER_LABELS = ("setup_poisson", "forward_elimination", "trace_solve", "back_substitution", "bdm_projection",
+                "tentative_velocity_solve", "h2d", "d2h")
+
+HDG_OK, HDG_EINVAL, HDG_ECUDA, HDG_ENOGPU, HDG_ESTATE, HDG_ENCCL, HDG_ENOCONV = range(7)
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_vp = C.c_void_p
+
+#: every symbol of include/hdg_b200.h with (restype, argtypes); tests check the library exports all
+SIGNATURES = {
+    "hdg_version": (C.c_char_p, []),
+    "hdg_supported_degrees": (C.c_int, []),
+    "hdg_device_count": (C.c_int, []),
+    "hdg_create": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, _dp, _ip, _ip, _ip, _ip, C.c_int, C.POINTER(_vp)]),
+    "hdg_destroy": (C.c_int, [_vp]),
+    "hdg_last_error": (C.c_char_p, [_vp]),
+    "hdg_set_stream": (C.c_int, [_vp, _vp]),
+    "hdg_synchronize": (C.c_int, [_vp]),
+    "hdg_setup_poisson": (C.c_int, [_vp, C.c_int]),
+    "hdg_get_local_schur": (C.c_int, [_vp, _dp]),
+    "hdg_get_trace_matrix": (C.c_int, [_vp, _dp, _ip]),
+    "hdg_poisson_apply_host": (C.c_int, [_vp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int)]),
+    "hdg_poisson_apply_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int)]),
+    "hdg_trace_spmv_dev": (C.c_int, [_vp, _vp, _vp]),
+    "hdg_forward_eliminate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdg_field_size": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
+    "hdg_upload": (C.c_int, [_vp, C.c_int, _dp, _vp]),
+    "hdg_download": (C.c_int, [_vp, C.c_int, _vp, _dp]),
+    "hdg_get_timers": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int]),
+    "hdg_reset_timers": (C.c_int, [_vp]),
+    "hdg_launch_count": (C.c_int64, [_vp]),
+}
+
+
+class HDGError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hdg_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: str | None = None):
+    """dlopen the engine; raises if it has not been built (run ``python __graft_entry__.py`` or
+    ``python -m incompressibleeulerhdg_b200.build``)"""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise HDGError(HDG_ENOGPU, f"{path} not found: build the CUDA engine first "
+                                   "(python -m incompressibleeulerhdg_b200.build); there is no CPU fallback")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _dev(t):
+    """raw device pointer of a torch tensor (or None)"""
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 8 and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+class HDGEngine:
+    """One engine per GPU.  Mirrors the role of the SCPC python context of `hdg_imex.py:128-133`."""
+
+    def __init__(self, mesh, k: int, tau: float = 1.0, device: int = 0):
+        self.lib = load_library()
+        self.mesh = mesh
+        self.k = int(k)
+        self.tau = float(tau)
+        self.device = int(device)
+        self.nc, self.nf = mesh.nc, mesh.nf
+        self.nQ1 = (k + 2) * (k + 3) // 2
+        self.np_ = (k + 1) * (k + 2) // 2
+        self.nl1 = k + 1
+        self._h = _vp()
+        xy = np.ascontiguousarray(mesh.cell_xy, dtype=np.float64)
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in
+                (mesh.cell_facet, mesh.cell_flip, mesh.facet_cell, mesh.facet_local)]
+        rc = self.lib.hdg_create(self.k, self.tau, self.nc, self.nf, _ptr(xy), *[a.ctypes.data_as(_ip) for a in arrs],
+                                 self.device, C.byref(self._h))
+        if rc != HDG_OK:
+            raise HDGError(rc, self.lib.hdg_last_error(None).decode())
+        self.last_iterations = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc, allow=()):
+        if rc != HDG_OK and rc not in allow:
+            raise HDGError(rc, self.lib.hdg_last_error(self._h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.hdg_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        import torch
+
+        self._check(self.lib.hdg_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.hdg_synchronize(self._h))
+
+    def shapes(self):
+        return (self.nc, 2, self.nQ1), (self.nc, self.np_), (self.nf, self.nl1)
+
+    # -- device buffers (torch owns the memory; SoA layout) ------------------------------------
+    def empty(self, kind: int):
+        import torch
+
+        n = {0: 2 * self.nQ1 * self.nc, 1: self.np_ * self.nc, 2: self.nl1 * self.nf}[kind]
+        return torch.empty(n, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def zeros(self, kind: int):
+        return self.empty(kind).zero_()
+
+    def upload(self, kind: int, host_aos, out=None):
+        a = _f64(host_aos)
+        out = self.empty(kind) if out is None else out
+        assert a.size == out.numel()
+        self._check(self.lib.hdg_upload(self._h, kind, _ptr(a), _dev(out)))
+        self.synchronize()  # `a` may be a temporary
+        return out
+
+    def download(self, kind: int, dev):
+        shp = self.shapes()[kind]
+        out = np.empty(shp, dtype=np.float64)
+        self._check(self.lib.hdg_download(self._h, kind, _dev(dev), _ptr(out)))
+        return out
+
+    # -- condensed mixed-Poisson path ----------------------------------------------------------------
+    def setup_poisson(self, keep_local: bool = False):
+        self._check(self.lib.hdg_setup_poisson(self._h, int(keep_local)))
+
+    def get_local_schur(self):
+        """S_K as [nc, NL, NL]"""
+        NL = 3 * self.nl1
+        buf = np.empty((NL * NL, self.nc), dtype=np.float64)
+        self._check(self.lib.hdg_get_local_schur(self._h, _ptr(buf)))
+        return np.ascontiguousarray(buf.T).reshape(self.nc, NL, NL)
+
+    def get_trace_matrix(self):
+        """blocked ELL of P = -S: (val [nf,5,b,b], col [nf,5])"""
+        b = self.nl1
+        val = np.empty((self.nf, 5, b, b), dtype=np.float64)
+        col = np.empty((self.nf, 5), dtype=np.int32)
+        self._check(self.lib.hdg_get_trace_matrix(self._h, _ptr(val), col.ctypes.data_as(_ip)))
+        return val, col
+
+    def poisson_apply_host(self, rhs_Q=None, rhs_p=None, rhs_l=None, rtol=1e-12, maxit=10000, shift=True,
+                           check=True):
+        """solve the mixed-Poisson system for host residuals (AoS); returns (Q, p, l, iterations)"""
+        rq, rp, rl = _f64(rhs_Q), _f64(rhs_p), _f64(rhs_l)
+        sQ, sp_, sl = self.shapes()
+        Q, p, l = np.empty(sQ), np.empty(sp_), np.empty(sl)
+        its = C.c_int(0)
+        rc = self.lib.hdg_poisson_apply_host(self._h, _ptr(rq), _ptr(rp), _ptr(rl), _ptr(Q), _ptr(p), _ptr(l),
+                                             float(rtol), int(maxit), int(bool(shift)), C.byref(its))
+        self._check(rc, allow=() if check else (HDG_ENOCONV,))
+        self.last_iterations = its.value
+        return Q, p, l, its.value
+
+    def poisson_apply_dev(self, rhs_Q, rhs_p, rhs_l, Q, p, l, rtol=1e-12, maxit=10000, shift=True, check=True):
+        its = C.c_int(0)
+        rc = self.lib.hdg_poisson_apply_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(rhs_l), _dev(Q), _dev(p), _dev(l),
+                                            float(rtol), int(maxit), int(bool(shift)), C.byref(its))
+        self._check(rc, allow=() if check else (HDG_ENOCONV,))
+        self.last_iterations = its.value
+        return its.value
+
+    def trace_spmv_dev(self, x, y):
+        self._check(self.lib.hdg_trace_spmv_dev(self._h, _dev(x), _dev(y)))
+
+    def forward_eliminate_dev(self, rhs_Q, rhs_p, rhs_l, r_l):
+        self._check(self.lib.hdg_forward_eliminate_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(rhs_l), _dev(r_l)))
+
+    def back_substitute_dev(self, rhs_Q, rhs_p, l, Q, p):
+        self._check(self.lib.hdg_back_substitute_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(l), _dev(Q), _dev(p)))
+
+    # -- reporting -----------------------------------------------------------------------------------
+    def timers(self):
+        n = len(TIMER_LABELS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.hdg_get_timers(self._h, ms, cnt, n))
+        return {lab: (ms[i], cnt[i]) for i, lab in enumerate(TIMER_LABELS)}
+
+    def reset_timers(self):
+        self._check(self.lib.hdg_reset_timers(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hdg_launch_count(self._h))

@@ -114,6 +114,41 @@ int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* r
 int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* l,
                             double* Q, double* p);
 
+/* ---- velocity side of the timesteppers (device SoA pointers) -------------------------------- */
+
+/* penalty parameter alpha of f_impl (hdg_imex.py:56, default 1) */
+int hdg_set_penalty(hdg_handle h, double alpha);
+/* project_bdm (common.py:91-108): Qstar has averaged facet normal moments (zero on the boundary)
+ * and the interior moments of Q; kept in the cell-wise [P_{k+1}]^2 representation. */
+int hdg_project_bdm_dev(hdg_handle h, const double* Q, double* Qstar);
+/* Y = c0 X + c1 M^-1 f_impl(w, X; Qstar)  (hdg_imex.py:313-331), upwind != 0 for flux="upwind".
+ * Qstar must be H(div)-conforming (output of hdg_project_bdm_dev).  X and Y must not alias. */
+int hdg_fimpl_apply_dev(hdg_handle h, const double* Qstar, const double* X, double c0, double c1, int upwind,
+                        double* Y);
+/* tentative velocity (hdg_imex.py:233-255,274-281; hdg_implicit.py:103-129), in Riesz form:
+ *   (I - adt M^-1 f_impl(.;Qstar)) x = rhs     by BiCGStab, relative residual tolerance rtol.
+ * zero_guess != 0 starts from x = 0, otherwise from the incoming x. */
+int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int upwind, const double* rhs, double* x,
+                            double rtol, int maxit, int zero_guess, int* iters);
+/* dual vector on the pressure space: mode 0  scale * int psi div Q dx      (hdg_implicit.py:145)
+ *                                    mode 1  scale * _weak_divergence      (hdg_imex.py:353-365) */
+int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mode, double* Rp);
+/* Y = c0 Y + c1 M^-1 g(w, p, l)   (_pressure_gradient, hdg_imex.py:333-340) */
+int hdg_pressure_gradient_dev(hdg_handle h, const double* p, const double* l, double c0, double c1, double* Y);
+/* _reconstruct_trace (hdg_imex.py:450-469) and _shift_pressure (hdg_imex.py:471-478; l may be NULL) */
+int hdg_reconstruct_trace_dev(hdg_handle h, const double* Q, const double* p, double* l);
+int hdg_shift_pressure_dev(hdg_handle h, double* p, double* l);
+/* pressure-reconstruction right-hand side (hdg_imex.py:204-207):
+ *   Rp = _weak_divergence(psi, -b + (grad Q) Q),   Rl = - mu n.b ds  (zero on interior facets) */
+int hdg_reconstruction_rhs_dev(hdg_handle h, const double* Q, const double* b, double* Rp, double* Rl);
+/* *result = int_Omega x . y dx for two cell fields of the same kind (synchronous) */
+int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, double* result);
+/* out = sum_t coefs[t] * ptrs[t]  over n doubles (nterms <= 8; out may alias any input) */
+int hdg_lincomb_dev(hdg_handle h, int64_t n, double* out, int nterms, const double* coefs,
+                    const double* const* ptrs);
+/* y = M x (inverse == 0) or M^-1 x for a cell field (kind 0 velocity, 1 pressure); M = detJ I */
+int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y);
+
 /* ---- layout conversion / buffer helpers -------------------------------------------------------- */
 
 /* kind: 0 = velocity (2*NQ1 per cell), 1 = pressure (NP per cell), 2 = trace (K+1 per facet). */

@@ -38,6 +38,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, *(os.path.join(CSRC, s) for s in SOURCES), "-o", LIB]
+    # development shortcut: HDG_DEV_DEGREES="2" compiles only k=2 (the shipped build has k=1..4)
+    dev = os.environ.get("HDG_DEV_DEGREES")
+    if dev:
+        mask = sum(1 << int(k) for k in dev.split(","))
+        cmd.insert(1, f"-DHDG_DEGREES={mask}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

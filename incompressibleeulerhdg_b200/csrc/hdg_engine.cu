@@ -22,6 +22,7 @@
 
 #include "../../include/hdg_b200.h"
 #include "hdg_local.cuh"
+#include "hdg_flow.cuh"
 
 #define HDG_VERSION "hdg_b200 0.1 (sm_100a)"
 
@@ -40,6 +41,11 @@ struct CgScalars {
   int pad;
 };
 
+struct BiScalars {
+  double rho, rr0, rr, tol2;
+  int iters, done, maxit, ticket;
+};
+
 struct hdg_engine {
   int k = 0, nc = 0, nf = 0, device = 0;
   double tau = 1.0;
@@ -56,12 +62,19 @@ struct hdg_engine {
   double* SK = nullptr;
   double *ell_val = nullptr, *dinv = nullptr;
   int* ell_col = nullptr;
+  // velocity side
+  double alpha = 1.0;                                        // penalty parameter (hdg_imex.py:56)
+  int *cell_nbr = nullptr, *cell_nbr_e = nullptr;            // [3][nc]
+  double* bdm_fm = nullptr;                                  // [2*(K+2)][nf]
+  double* bi[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // BiCGStab work: r, rhat, p, v, s, t
   // work vectors
   double *gK = nullptr;                                      // [NL][nc]
   double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
   double *partial = nullptr;                                 // [8][grid]
   CgScalars* scal = nullptr;                                 // device
   CgScalars* scal_host = nullptr;                            // pinned
+  BiScalars* bscal = nullptr;
+  BiScalars* bscal_host = nullptr;
   double *wQ = nullptr, *wP = nullptr, *wL = nullptr;        // staging for host API (SoA)
   double *wQ2 = nullptr, *wP2 = nullptr, *wL2 = nullptr;
   double *stage = nullptr;                                   // AoS staging on device
@@ -651,13 +664,39 @@ __global__ void k_int_transpose(const int* __restrict__ aos, int* __restrict__ s
 // ------------------------------------------------------------------------------------------------
 // dispatch over the compiled-in degrees
 // ------------------------------------------------------------------------------------------------
-#define DISPATCH_K(h, ...)                                         \
-  switch ((h)->k) {                                                \
-    case 1: { constexpr int K = 1; __VA_ARGS__; } break;           \
-    case 2: { constexpr int K = 2; __VA_ARGS__; } break;           \
-    case 3: { constexpr int K = 3; __VA_ARGS__; } break;           \
-    case 4: { constexpr int K = 4; __VA_ARGS__; } break;           \
-    default: FAIL(h, HDG_EINVAL, "unsupported degree");            \
+// HDG_DEGREES is a bit mask of the pressure degrees to compile (default: 1..4).  Development builds
+// use e.g. -DHDG_DEGREES=4 (k=2 only) to keep nvcc turnaround short.
+#ifndef HDG_DEGREES
+#define HDG_DEGREES 30
+#endif
+#define HDG_HAS_K(k) ((HDG_DEGREES >> (k)) & 1)
+#if HDG_HAS_K(1)
+#define HDG_CASE1(...) case 1: { constexpr int K = 1; __VA_ARGS__; } break;
+#else
+#define HDG_CASE1(...)
+#endif
+#if HDG_HAS_K(2)
+#define HDG_CASE2(...) case 2: { constexpr int K = 2; __VA_ARGS__; } break;
+#else
+#define HDG_CASE2(...)
+#endif
+#if HDG_HAS_K(3)
+#define HDG_CASE3(...) case 3: { constexpr int K = 3; __VA_ARGS__; } break;
+#else
+#define HDG_CASE3(...)
+#endif
+#if HDG_HAS_K(4)
+#define HDG_CASE4(...) case 4: { constexpr int K = 4; __VA_ARGS__; } break;
+#else
+#define HDG_CASE4(...)
+#endif
+#define DISPATCH_K(h, ...)                                              \
+  switch ((h)->k) {                                                     \
+    HDG_CASE1(__VA_ARGS__)                                              \
+    HDG_CASE2(__VA_ARGS__)                                              \
+    HDG_CASE3(__VA_ARGS__)                                              \
+    HDG_CASE4(__VA_ARGS__)                                              \
+    default: FAIL(h, HDG_EINVAL, "degree not compiled into this build"); \
   }
 
 static void dims_of(int k, int& nq1, int& np, int& nl1) {
@@ -685,12 +724,194 @@ static cudaError_t dmalloc(Tp** p, size_t count) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// BiCGStab for the tentative-velocity system  (I - a dt M^-1 f_impl(.;Q*)) x = b   (Riesz form of
+// hdg_imex.py:233-247 / hdg_implicit.py:103-129; the reference uses GMRES+ILU resp. direct LU).
+// Five kernels per iteration, reductions deterministic as in the CG.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                const double* __restrict__ c, double* __restrict__ p_ab,
+                                                double* __restrict__ p_cc) {
+  // partial <a,b> and (optionally) <c,c>
+  double s0 = 0.0, s1 = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    s0 = fma(a[i], b[i], s0);
+    if (c) s1 = fma(c[i], c[i], s1);
+  }
+  s0 = block_reduce(s0);
+  if (threadIdx.x == 0) p_ab[blockIdx.x] = s0;
+  if (c) {
+    s1 = block_reduce(s1);
+    if (threadIdx.x == 0) p_cc[blockIdx.x] = s1;
+  }
+}
+
+// r = b - t (t = A x0, or r = b if t == nullptr); rhat = r; p = r; partial <r,r>
+__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* __restrict__ b, const double* __restrict__ t,
+                                                   double* __restrict__ r, double* __restrict__ rhat,
+                                                   double* __restrict__ p, double* __restrict__ part) {
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = t ? b[i] - t[i] : b[i];
+    r[i] = v;
+    rhat[i] = v;
+    p[i] = v;
+    s = fma(v, v, s);
+  }
+  s = block_reduce(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void k_bi_start(BiScalars* s, const double* __restrict__ part, int n, double rtol, int maxit) {
+  double rr = reduce_partials(part, n);
+  if (threadIdx.x == 0) {
+    s->rho = rr;
+    s->rr0 = rr;
+    s->rr = rr;
+    s->tol2 = rtol * rtol;
+    s->iters = 0;
+    s->maxit = maxit;
+    s->ticket = 0;
+    s->done = (rr <= 0.0 || maxit <= 0) ? 1 : 0;
+  }
+}
+// s = r - alpha v, alpha = rho / <rhat, v>
+__global__ void __launch_bounds__(BLOCK) k_bi_s(size_t n, const double* __restrict__ r, const double* __restrict__ v,
+                                                double* __restrict__ sv, const double* __restrict__ p_rv,
+                                                const BiScalars* __restrict__ s) {
+  if (s->done) return;
+  double alpha = s->rho / reduce_partials(p_rv, gridDim.x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    sv[i] = fma(-alpha, v[i], r[i]);
+}
+// omega = <t,s>/<t,t>; x += alpha p + omega s; r = s - omega t; partials <rhat,r>, <r,r>
+__global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, const double* __restrict__ p, const double* __restrict__ sv,
+                                                 const double* __restrict__ t, const double* __restrict__ rhat,
+                                                 double* __restrict__ x, double* __restrict__ r,
+                                                 const double* __restrict__ p_rv, const double* __restrict__ p_ts,
+                                                 const double* __restrict__ p_tt, double* __restrict__ p_rho,
+                                                 double* __restrict__ p_rr, const BiScalars* __restrict__ s) {
+  if (s->done) return;
+  double alpha = s->rho / reduce_partials(p_rv, gridDim.x);
+  double tt = reduce_partials(p_tt, gridDim.x);
+  double omega = tt > 0.0 ? reduce_partials(p_ts, gridDim.x) / tt : 0.0;
+  double a0 = 0.0, a1 = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double si = sv[i];
+    x[i] += alpha * p[i] + omega * si;
+    double ri = fma(-omega, t[i], si);
+    r[i] = ri;
+    a0 = fma(rhat[i], ri, a0);
+    a1 = fma(ri, ri, a1);
+  }
+  a0 = block_reduce(a0);
+  if (threadIdx.x == 0) p_rho[blockIdx.x] = a0;
+  a1 = block_reduce(a1);
+  if (threadIdx.x == 0) p_rr[blockIdx.x] = a1;
+}
+// beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v); bookkeeping (last block publishes)
+__global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restrict__ r, const double* __restrict__ v,
+                                                double* __restrict__ p, const double* __restrict__ p_rv,
+                                                const double* __restrict__ p_ts, const double* __restrict__ p_tt,
+                                                const double* __restrict__ p_rho, const double* __restrict__ p_rr,
+                                                BiScalars* s) {
+  __shared__ int done_in, it, maxit;
+  __shared__ double rho_old, rr0, tol2;
+  if (threadIdx.x == 0) {
+    done_in = s->done;
+    it = s->iters;
+    maxit = s->maxit;
+    rho_old = s->rho;
+    rr0 = s->rr0;
+    tol2 = s->tol2;
+  }
+  __syncthreads();
+  if (done_in) return;
+  double alpha = rho_old / reduce_partials(p_rv, gridDim.x);
+  double tt = reduce_partials(p_tt, gridDim.x);
+  double omega = tt > 0.0 ? reduce_partials(p_ts, gridDim.x) / tt : 0.0;
+  double rho_new = reduce_partials(p_rho, gridDim.x);
+  double rr = reduce_partials(p_rr, gridDim.x);
+  bool conv = rr <= tol2 * rr0;
+  bool stop = conv || (it + 1 >= maxit) || !(omega != 0.0) || !(rho_new != 0.0);
+  if (!stop) {
+    double beta = (rho_new / rho_old) * (alpha / omega);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int ticket = atomicAdd(&s->ticket, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      s->ticket = 0;
+      s->rho = rho_new;
+      s->rr = rr;
+      s->iters = it + 1;
+      s->done = conv ? 1 : (stop ? 2 : 0);
+      __threadfence();
+    }
+  }
+}
+
+template <int K>
+static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const double* X, double c0, double c1,
+                         double* Y) {
+  int grid = cdiv(h->nc, 128);
+  if (upwind)
+    LAUNCH(h, (k_fimpl<K, true>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, h->alpha, Qstar, X, c0, c1,
+           Y);
+  else
+    LAUNCH(h, (k_fimpl<K, false>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, h->alpha, Qstar, X, c0,
+           c1, Y);
+}
+
+template <int K>
+static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
+                        double rtol, int maxit, bool zero_guess, int* iters) {
+  const int G = h->grid;
+  const size_t n = 2 * (size_t)Dims<K>::NQ1 * h->nc;
+  for (int i = 0; i < 6; ++i)
+    if (!h->bi[i]) CUDA_TRY(h, dmalloc(&h->bi[i], n));
+  double *r = h->bi[0], *rhat = h->bi[1], *p = h->bi[2], *v = h->bi[3], *sv = h->bi[4], *t = h->bi[5];
+  double* P = h->partial;
+  double *p_rv = P, *p_ts = P + G, *p_tt = P + 2 * (size_t)G, *p_rho = P + 3 * (size_t)G, *p_rr = P + 4 * (size_t)G;
+  if (zero_guess) {
+    CUDA_TRY(h, cudaMemsetAsync(x, 0, n * sizeof(double), h->stream));
+    LAUNCH(h, k_bi_init, G, BLOCK, n, b, (const double*)nullptr, r, rhat, p, p_rr);
+  } else {
+    launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, t);
+    LAUNCH(h, k_bi_init, G, BLOCK, n, b, (const double*)t, r, rhat, p, p_rr);
+  }
+  LAUNCH(h, k_bi_start, 1, BLOCK, h->bscal, p_rr, G, rtol, maxit);
+  const int chunk = 4;
+  int launched = 0;
+  bool finished = false;
+  while (!finished) {
+    int m = std::min(chunk, std::max(1, maxit - launched));
+    for (int i = 0; i < m; ++i) {
+      launch_fimpl<K>(h, upwind, Qstar, p, 1.0, -adt, v);
+      LAUNCH(h, k_dot2, G, BLOCK, n, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
+      LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
+      launch_fimpl<K>(h, upwind, Qstar, sv, 1.0, -adt, t);
+      LAUNCH(h, k_dot2, G, BLOCK, n, t, sv, (const double*)t, p_ts, p_tt);
+      LAUNCH(h, k_bi_xr, G, BLOCK, n, p, sv, t, rhat, x, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+      LAUNCH(h, k_bi_p, G, BLOCK, n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+    }
+    launched += m;
+    CUDA_TRY(h, cudaMemcpyAsync(h->bscal_host, h->bscal, sizeof(BiScalars), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->bscal_host->done || launched >= maxit) finished = true;
+  }
+  if (iters) *iters = h->bscal_host->iters;
+  return h->bscal_host->done == 1 ? HDG_OK : HDG_ENOCONV;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
 const char* hdg_version(void) { return HDG_VERSION; }
-int hdg_supported_degrees(void) { return (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4); }
+int hdg_supported_degrees(void) { return HDG_DEGREES; }
 int hdg_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -708,10 +929,12 @@ int hdg_destroy(hdg_handle h) {
   cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local, h->SK, h->ell_val,
                   h->dinv, h->ell_col, h->gK, h->cg_x, h->cg_r, h->cg_z, h->cg_p, h->cg_q, h->partial, h->scal,
-                  h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage};
+                  h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
+                  h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->scal_host) cudaFreeHost(h->scal_host);
+  if (h->bscal_host) cudaFreeHost(h->bscal_host);
   if (h->pinned) cudaFreeHost(h->pinned);
   for (int i = 0; i < T_COUNT; ++i) flush_timer(h, i);
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -831,6 +1054,15 @@ int hdg_create(int k, double tau, int nc, int nf, const double* cell_xy, const i
   CREATE_TRY(dmalloc(&h->scal, 1));
   CREATE_TRY(cudaMemset(h->scal, 0, sizeof(CgScalars)));
   CREATE_TRY(cudaMallocHost((void**)&h->scal_host, sizeof(CgScalars)));
+  CREATE_TRY(dmalloc(&h->bscal, 1));
+  CREATE_TRY(cudaMemset(h->bscal, 0, sizeof(BiScalars)));
+  CREATE_TRY(cudaMallocHost((void**)&h->bscal_host, sizeof(BiScalars)));
+  CREATE_TRY(dmalloc(&h->cell_nbr, 3 * (size_t)nc));
+  CREATE_TRY(dmalloc(&h->cell_nbr_e, 3 * (size_t)nc));
+  k_build_nbr<<<h->grid, BLOCK, 0, h->stream>>>(h->cell_facet, h->facet_cell, h->facet_local, nc, nf, h->cell_nbr,
+                                                h->cell_nbr_e);
+  h->launches++;
+  CREATE_TRY(cudaStreamSynchronize(h->stream));
 #undef CREATE_TRY
   *out = h;
   return HDG_OK;
@@ -922,12 +1154,7 @@ int hdg_trace_spmv_dev(hdg_handle h, const double* x, double* y) {
   if (!h || !x || !y) return HDG_EINVAL;
   if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_trace_spmv_dev: call hdg_setup_poisson first");
   // y = S x = -(P x)
-  switch (h->k) {
-    case 1: LAUNCH(h, k_cg_spmv<2>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
-    case 2: LAUNCH(h, k_cg_spmv<3>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
-    case 3: LAUNCH(h, k_cg_spmv<4>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
-    case 4: LAUNCH(h, k_cg_spmv<5>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr); break;
-  }
+  DISPATCH_K(h, LAUNCH(h, k_cg_spmv<K + 1>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr));
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
 }
@@ -999,15 +1226,10 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc = hdg_forward_eliminate_dev(h, rhs_Q, rhs_p, rhs_l, h->cg_r);
   if (rc) return rc;
-  int cg_rc;
+  int cg_rc = HDG_EINVAL;
   {
     ScopedTimer t(h, T_SOLVE);
-    switch (h->k) {
-      case 1: cg_rc = run_cg<2>(h, rtol, maxit, iters); break;
-      case 2: cg_rc = run_cg<3>(h, rtol, maxit, iters); break;
-      case 3: cg_rc = run_cg<4>(h, rtol, maxit, iters); break;
-      default: cg_rc = run_cg<5>(h, rtol, maxit, iters); break;
-    }
+    DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, maxit, iters));
   }
   if (cg_rc == HDG_ECUDA) return cg_rc;
   int b = h->k + 1;
@@ -1119,5 +1341,141 @@ int hdg_reset_timers(hdg_handle h) {
 }
 
 int64_t hdg_launch_count(hdg_handle h) { return h ? h->launches : 0; }
+
+// ---- velocity side ------------------------------------------------------------------------------
+int hdg_set_penalty(hdg_handle h, double alpha) {
+  if (!h || !(alpha >= 0)) return HDG_EINVAL;
+  h->alpha = alpha;
+  return HDG_OK;
+}
+
+int hdg_project_bdm_dev(hdg_handle h, const double* Q, double* Qstar) {
+  if (!h || !Q || !Qstar) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->bdm_fm) CUDA_TRY(h, dmalloc(&h->bdm_fm, 2 * (size_t)(h->k + 2) * h->nf));
+  ScopedTimer t(h, T_BDM);
+  DISPATCH_K(h, {
+    LAUNCH(h, k_bdm_moments<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_facet, h->facet_cell, h->nc, h->nf, Q,
+           h->bdm_fm);
+    LAUNCH(h, k_bdm_lift<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_facet, h->facet_cell, h->nc, h->nf, Q,
+           h->bdm_fm, Qstar);
+  });
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_fimpl_apply_dev(hdg_handle h, const double* Qstar, const double* X, double c0, double c1, int upwind,
+                        double* Y) {
+  if (!h || !Qstar || !X || !Y) return HDG_EINVAL;
+  if (X == Y) FAIL(h, HDG_EINVAL, "hdg_fimpl_apply_dev: X and Y must not alias (neighbour gathers)");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  DISPATCH_K(h, launch_fimpl<K>(h, upwind != 0, Qstar, X, c0, c1, Y));
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int upwind, const double* rhs, double* x,
+                            double rtol, int maxit, int zero_guess, int* iters) {
+  if (!h || !Qstar || !rhs || !x) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc;
+  {
+    ScopedTimer t(h, T_TENT);
+    DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
+  }
+  if (rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "tentative-velocity BiCGStab did not converge within maxit");
+  return rc;
+}
+
+int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mode, double* Rp) {
+  if (!h || !Q || !Rp || mode < 0 || mode > 1) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  DISPATCH_K(h, LAUNCH(h, k_weak_div<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, Q,
+                       scale, mode, Rp));
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_pressure_gradient_dev(hdg_handle h, const double* p, const double* l, double c0, double c1, double* Y) {
+  if (!h || !p || !l || !Y) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  DISPATCH_K(h, LAUNCH(h, k_pgrad<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, p,
+                       l, c0, c1, Y));
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_reconstruct_trace_dev(hdg_handle h, const double* Q, const double* p, double* l) {
+  if (!h || !Q || !p || !l) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!h->gK) CUDA_TRY(h, dmalloc(&h->gK, (size_t)3 * (h->k + 1) * h->nc));
+  DISPATCH_K(h, {
+    LAUNCH(h, k_trace_moments<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, Q, p, h->gK);
+    LAUNCH(h, k_trace_avg<K>, h->grid, BLOCK, h->gK, h->facet_cell, h->facet_local, h->nc, h->nf, l);
+  });
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_shift_pressure_dev(hdg_handle h, double* p, double* l) {
+  if (!h || !p) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, p, h->partial);
+  LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_lincomb_dev(hdg_handle h, int64_t n, double* out, int nterms, const double* coefs,
+                    const double* const* ptrs) {
+  if (!h || !out || nterms < 1 || nterms > 8 || !coefs || !ptrs || n <= 0) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  LinComb lc;
+  lc.n = nterms;
+  for (int i = 0; i < nterms; ++i) {
+    lc.c[i] = coefs[i];
+    lc.x[i] = ptrs[i];
+  }
+  LAUNCH(h, k_lincomb, h->grid, BLOCK, (size_t)n, lc, out);
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y) {
+  if (!h || !x || !y || kind < 0 || kind > 1) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  field_len(h, kind, n, ent, ndof);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  LAUNCH(h, k_mass, h->grid, BLOCK, h->cell_xy, h->nc, ndof, inverse, x, y);
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_reconstruction_rhs_dev(hdg_handle h, const double* Q, const double* b, double* Rp, double* Rl) {
+  if (!h || !Q || !b || !Rp || !Rl) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemsetAsync(Rl, 0, (size_t)(h->k + 1) * h->nf * sizeof(double), h->stream));
+  DISPATCH_K(h, LAUNCH(h, k_recon_rhs<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e,
+                       h->cell_facet, h->cell_flip, h->nc, h->nf, Q, b, Rp, Rl));
+  CUDA_TRY(h, cudaGetLastError());
+  return HDG_OK;
+}
+
+int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, double* result) {
+  if (!h || !x || !y || !result || kind < 0 || kind > 1) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  field_len(h, kind, n, ent, ndof);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  LAUNCH(h, k_l2_inner, h->grid, 256, h->cell_xy, h->nc, ndof, x, y, h->partial);
+  std::vector<double> part(h->grid);
+  CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, h->grid * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  double s = 0.0;
+  for (double v : part) s += v;
+  *result = s;
+  return HDG_OK;
+}
 
 }  // extern "C"

@@ -47,6 +47,19 @@ SIGNATURES = {
     "hdg_trace_spmv_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_forward_eliminate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdg_set_penalty": (C.c_int, [_vp, C.c_double]),
+    "hdg_project_bdm_dev": (C.c_int, [_vp, _vp, _vp]),
+    "hdg_fimpl_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
+    "hdg_tentative_solve_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_int, _vp, _vp, C.c_double, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int)]),
+    "hdg_weak_divergence_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_int, _vp]),
+    "hdg_pressure_gradient_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, _vp]),
+    "hdg_reconstruct_trace_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "hdg_shift_pressure_dev": (C.c_int, [_vp, _vp, _vp]),
+    "hdg_reconstruction_rhs_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "hdg_l2_inner_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
+    "hdg_lincomb_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _dp, C.POINTER(_vp)]),
+    "hdg_mass_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "hdg_field_size": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "hdg_upload": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "hdg_download": (C.c_int, [_vp, C.c_int, _vp, _dp]),
@@ -100,8 +113,10 @@ def _dev(t):
 class HDGEngine:
     """One engine per GPU.  Mirrors the role of the SCPC python context of `hdg_imex.py:128-133`."""
 
-    def __init__(self, mesh, k: int, tau: float = 1.0, device: int = 0):
+    def __init__(self, mesh, k: int, tau: float = 1.0, device: int = 0, torch_stream: bool = True):
         self.lib = load_library()
+        if not (self.lib.hdg_supported_degrees() >> int(k)) & 1:
+            raise HDGError(HDG_EINVAL, f"degree k={k} is not compiled into {LIB_PATH}")
         self.mesh = mesh
         self.k = int(k)
         self.tau = float(tau)
@@ -119,6 +134,9 @@ class HDGEngine:
         if rc != HDG_OK:
             raise HDGError(rc, self.lib.hdg_last_error(None).decode())
         self.last_iterations = 0
+        if torch_stream:
+            # order engine work with torch's current stream so that torch-owned buffers are safe to share
+            self.use_torch_stream()
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _check(self, rc, allow=()):
@@ -220,6 +238,56 @@ class HDGEngine:
 
     def back_substitute_dev(self, rhs_Q, rhs_p, l, Q, p):
         self._check(self.lib.hdg_back_substitute_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(l), _dev(Q), _dev(p)))
+
+    # -- velocity side -----------------------------------------------------------------------------------
+    def set_penalty(self, alpha: float):
+        self._check(self.lib.hdg_set_penalty(self._h, float(alpha)))
+
+    def project_bdm_dev(self, Q, Qstar):
+        self._check(self.lib.hdg_project_bdm_dev(self._h, _dev(Q), _dev(Qstar)))
+
+    def fimpl_apply_dev(self, Qstar, X, Y, c0=0.0, c1=1.0, upwind=True):
+        self._check(self.lib.hdg_fimpl_apply_dev(self._h, _dev(Qstar), _dev(X), float(c0), float(c1), int(upwind), _dev(Y)))
+
+    def tentative_solve_dev(self, Qstar, adt, rhs, x, upwind=True, rtol=1e-10, maxit=1000, zero_guess=True,
+                            check=True):
+        its = C.c_int(0)
+        rc = self.lib.hdg_tentative_solve_dev(self._h, _dev(Qstar), float(adt), int(upwind), _dev(rhs), _dev(x),
+                                              float(rtol), int(maxit), int(zero_guess), C.byref(its))
+        self._check(rc, allow=() if check else (HDG_ENOCONV,))
+        return its.value
+
+    def weak_divergence_dev(self, Q, Rp, scale=1.0, mode=1):
+        self._check(self.lib.hdg_weak_divergence_dev(self._h, _dev(Q), float(scale), int(mode), _dev(Rp)))
+
+    def pressure_gradient_dev(self, p, l, Y, c0=0.0, c1=1.0):
+        self._check(self.lib.hdg_pressure_gradient_dev(self._h, _dev(p), _dev(l), float(c0), float(c1), _dev(Y)))
+
+    def reconstruct_trace_dev(self, Q, p, l):
+        self._check(self.lib.hdg_reconstruct_trace_dev(self._h, _dev(Q), _dev(p), _dev(l)))
+
+    def shift_pressure_dev(self, p, l=None):
+        self._check(self.lib.hdg_shift_pressure_dev(self._h, _dev(p), _dev(l)))
+
+    def reconstruction_rhs_dev(self, Q, b, Rp, Rl):
+        self._check(self.lib.hdg_reconstruction_rhs_dev(self._h, _dev(Q), _dev(b), _dev(Rp), _dev(Rl)))
+
+    def l2_inner_dev(self, kind, x, y):
+        out = C.c_double(0.0)
+        self._check(self.lib.hdg_l2_inner_dev(self._h, int(kind), _dev(x), _dev(y), C.byref(out)))
+        return out.value
+
+    def lincomb_dev(self, out, terms):
+        """out = sum c_t * x_t for terms = [(c, tensor), ...] (at most 8; out may alias an input)"""
+        n = len(terms)
+        coefs = (C.c_double * n)(*[float(c) for c, _ in terms])
+        ptrs = (_vp * n)(*[t.data_ptr() for _, t in terms])
+        for _, t in terms:
+            assert t.numel() == out.numel()
+        self._check(self.lib.hdg_lincomb_dev(self._h, out.numel(), _dev(out), n, coefs, ptrs))
+
+    def mass_dev(self, kind, x, y, inverse=False):
+        self._check(self.lib.hdg_mass_dev(self._h, int(kind), int(inverse), _dev(x), _dev(y)))
 
     # -- reporting -----------------------------------------------------------------------------------
     def timers(self):

@@ -32,6 +32,8 @@ __all__ = [
     "legendre01",
     "legendre01_deriv",
     "triangle_quadrature",
+    "triangle_quadrature_gj",
+    "gauss_jacobi10",
     "facet_points",
     "FACET_VERTS",
     "REF_VERTS",
@@ -258,6 +260,33 @@ def triangle_quadrature(degree: int, dtype=np.float64):
     pts = np.stack([(u * (1 - v)).ravel(), v.ravel()], axis=-1)
     w = (wu * wv * (1 - v)).ravel()
     return pts, w
+
+
+def gauss_jacobi10(n: int, dtype=np.float64):
+    """n-point Gauss-Jacobi rule for the weight (1-v) on [0,1] (nodes, weights), Newton-refined."""
+    from scipy.special import roots_jacobi
+
+    x0, _ = roots_jacobi(n, 1.0, 0.0)
+    x = np.asarray(x0, dtype=dtype)
+    for _ in range(4):
+        # orthonormal Jacobi P_n^{(1,0)} and its derivative
+        x = x - jacobi(x, 1, n) / grad_jacobi(x, 1, n)
+    # weights from the Christoffel function: w_i = 1 / sum_{j<n} p_j(x_i)^2  (orthonormal p_j)
+    den = sum(jacobi(x, 1, j) ** 2 for j in range(n))
+    w = 1 / den
+    # map [-1,1] with weight (1-x) to [0,1] with weight (1-v): x = 2v-1, (1-x) = 2(1-v), dx = 2 dv
+    return (x + 1) / 2, w / 4
+
+
+def triangle_quadrature_gj(degree: int, dtype=np.float64):
+    """collapsed Gauss-Legendre x Gauss-Jacobi rule, n^2 points with n = ceil((degree+1)/2)"""
+    n = degree // 2 + 1
+    xu, wu = gauss_legendre(n, dtype)
+    xv, wv = gauss_jacobi10(n, dtype)
+    u, v = np.meshgrid(xu, xv, indexing="ij")
+    a, b = np.meshgrid(wu, wv, indexing="ij")
+    pts = np.stack([(u * (1 - v)).ravel(), v.ravel()], axis=-1)
+    return pts, (a * b).ravel()
 
 
 def facet_points(e: int, s):

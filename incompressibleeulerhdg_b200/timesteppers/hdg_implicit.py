@@ -1,0 +1,101 @@
+"""First-order HDG timestepper (Chorin projection or fully implicit), mirroring
+`src/timesteppers/hdg_implicit.py:10-197` on the B200 engine.
+
+Per step (reference line numbers):
+  :98      Q* = project_bdm(Q)
+  :100     f  = interpolate(f_rhs(t_n))
+  :103-129 tentative velocity   (M + dt [adv(Q*) - flux + penalty]) Q~ = M Q + dt M f
+  :133-146 mixed Poisson        a_poisson(u, phi, lambda) = -(1/dt) psi div(Q~) dx
+  :150     Q <- Q~ + dt u
+  :189-190 p <- phi - mean(phi)
+
+The reference solves both systems with Firedrake's default direct LU; the engine uses BiCGStab
+on the matrix-free tentative operator and the statically condensed CG trace solve, converged to
+``krylov_rtol`` so that results agree with the direct solves to ~1e-10.  The Chorin right-hand side
+is not in the range of the singular mixed-Poisson operator in general; the engine removes the
+defect along the null vector (see oracle/hdg_oracle.py `_project_trace_rhs`).
+"""
+
+from __future__ import annotations
+
+import tqdm
+
+from ..auxilliary.logging import PerformanceLog
+from ..auxilliary.utils import Averager
+from ..functions import Function
+from .common import IncompressibleEuler
+
+__all__ = ["IncompressibleEulerHDGImplicit"]
+
+
+class IncompressibleEulerHDGImplicit(IncompressibleEuler):
+    def __init__(self, mesh, degree, dt, flux="upwind", use_projection_method=True, callbacks=None, device=0,
+                 krylov_rtol=1e-12, progress=False):
+        super().__init__(mesh, degree, dt, label="HDG Implicit", device=device)
+        self.flux = flux
+        assert self.flux in ["upwind", "centered"]
+        self.use_projection_method = use_projection_method
+        self.callbacks = [] if callbacks is None else callbacks
+        self.alpha = 1  # penalty parameter (:41)
+        self.engine.set_penalty(self.alpha)
+        self.krylov_rtol = krylov_rtol
+        self.progress = progress
+        self.niter_tentative = Averager()
+        self.niter_pressure = Averager()
+        if not use_projection_method:
+            from .monolithic import MonolithicStage
+
+            self._monolithic = MonolithicStage(self)
+
+    @PerformanceLog("tentative_velocity_solve")
+    def tentative_velocity_solve(self, Q_star, rhs, Q_tentative, zero_guess):
+        return self.engine.tentative_solve_dev(Q_star.data, self._dt, rhs.data, Q_tentative.data,
+                                               upwind=(self.flux == "upwind"), rtol=self.krylov_rtol,
+                                               zero_guess=zero_guess)
+
+    @PerformanceLog("pressure_solve")
+    def pressure_solve(self, Rp, u, phi, lmbda):
+        return self.engine.poisson_apply_dev(None, Rp.data, None, u.data, phi.data, lmbda.data, rtol=self.krylov_rtol,
+                                             maxit=100000, shift=True)
+
+    def solve(self, Q_initial, p_initial, q_initial, f_rhs, T_final, warmup=False):
+        if q_initial:
+            raise NotImplementedError("passive tracer advection is not on the engine's hot path yet")
+        eng = self.engine
+        nt = self.get_timesteps(T_final, warmup)
+        Q = self._V_Q.interpolate(Q_initial)
+        Q.rename("velocity")
+        p = self._V_p.interpolate(p_initial)
+        p.rename("pressure")
+        eng.shift_pressure_dev(p.data, None)  # :84
+        Q_star, f, rhs, Q_tentative, u = (Function(self._V_Q) for _ in range(5))
+        Rp, phi = Function(self._V_p), Function(self._V_p)
+        lmbda = Function(self._V_trace)
+        self.niter_tentative.reset()
+        self.niter_pressure.reset()
+        for callback in self.callbacks:
+            callback.reset()
+            callback(Q, p, 0, q_tracer=None)
+        steps = tqdm.tqdm(range(nt)) if self.progress else range(nt)
+        for k in steps:
+            with PerformanceLog("timestep"):
+                with PerformanceLog("bdm_projection"):
+                    self.project_bdm(Q, out=Q_star)  # :98
+                self._V_Q.interpolate(f_rhs(k * self._dt), out=f)  # :100
+                eng.lincomb_dev(rhs.data, [(1.0, Q.data), (self._dt, f.data)])  # :126 / :182 in Riesz form
+                if self.use_projection_method:
+                    Q_tentative.assign(Q)  # warm start
+                    its = self.tentative_velocity_solve(Q_star, rhs, Q_tentative, zero_guess=False)  # :129
+                    self.niter_tentative.update(its)
+                    eng.weak_divergence_dev(Q_tentative.data, Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
+                    its = self.pressure_solve(Rp, u, phi, lmbda)  # :146
+                    self.niter_pressure.update(its)
+                    eng.lincomb_dev(Q.data, [(1.0, Q_tentative.data), (self._dt, u.data)])  # :150
+                else:
+                    with PerformanceLog("unsplit_solve"):
+                        self._monolithic.solve(Q_star, self._dt, rhs, Q, phi, lmbda)  # :185
+                p.assign(phi)  # :189-190 (phi is already mean free)
+                eng.shift_pressure_dev(p.data, None)
+            for callback in self.callbacks:
+                callback(Q, p, (k + 1) * self._dt, q_tracer=None)
+        return Q, p

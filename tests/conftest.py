@@ -19,3 +19,11 @@ def engine_lib():
 
     build.build()
     return engine.load_library()
+
+
+def require_degree(k):
+    """skip when a development build (HDG_DEV_DEGREES) left this degree out"""
+    from incompressibleeulerhdg_b200 import engine
+
+    if not (engine.load_library().hdg_supported_degrees() >> k) & 1:
+        pytest.skip(f"degree {k} not compiled into this build")

@@ -1,0 +1,150 @@
+"""GPU parity of the velocity-side kernels (BDM projection, f_impl, weak divergence, pressure
+gradient, trace reconstruction, tentative-velocity solve) against the oracle, through the C-ABI."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from incompressibleeulerhdg_b200.engine import HDGEngine
+from incompressibleeulerhdg_b200.mesh import PeriodicSquareMesh, UnitDiskMesh, UnitSquareMesh
+from oracle.hdg_oracle import HDGOracle
+
+pytestmark = pytest.mark.gpu
+
+MESHES = [lambda: UnitSquareMesh(5, perturb=0.2), lambda: PeriodicSquareMesh(4, L=2 * np.pi), lambda: UnitDiskMesh(1)]
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(params=[1, 2, 3, 4])
+def k(request):
+    from incompressibleeulerhdg_b200.engine import load_library
+
+    if not (load_library().hdg_supported_degrees() >> request.param) & 1:
+        pytest.skip("degree not compiled in")
+    return request.param
+
+
+@pytest.mark.parametrize("mesh_fn", MESHES)
+def test_project_bdm(k, mesh_fn):
+    m = mesh_fn()
+    o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    Q = np.random.default_rng(1).standard_normal((m.nc, 2, o.nQ1))
+    dQ = eng.upload(0, Q)
+    dS = eng.empty(0)
+    eng.project_bdm_dev(dQ, dS)
+    assert rel(eng.download(0, dS), o.project_bdm(Q)) < 1e-11
+
+
+@pytest.mark.parametrize("flux", ["upwind", "centered"])
+@pytest.mark.parametrize("mesh_fn", MESHES)
+def test_fimpl_apply(k, mesh_fn, flux):
+    m = mesh_fn()
+    o, eng = HDGOracle(m, k, flux=flux), HDGEngine(m, k)
+    rng = np.random.default_rng(2)
+    Qs = o.project_bdm(rng.standard_normal((m.nc, 2, o.nQ1)))
+    X = rng.standard_normal((m.nc, 2, o.nQ1))
+    ref = o.f_impl_apply(X, Qs) / o.detJ[:, None, None]  # Riesz form
+    dY = eng.empty(0)
+    eng.fimpl_apply_dev(eng.upload(0, Qs), eng.upload(0, X), dY, c0=0.0, c1=1.0, upwind=(flux == "upwind"))
+    assert rel(eng.download(0, dY), ref) < 1e-11
+
+
+@pytest.mark.parametrize("mesh_fn", MESHES)
+def test_weak_divergence_and_pressure_gradient(k, mesh_fn):
+    m = mesh_fn()
+    o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    rng = np.random.default_rng(3)
+    Q = rng.standard_normal((m.nc, 2, o.nQ1))
+    dQ = eng.upload(0, Q)
+    dR = eng.empty(1)
+    eng.weak_divergence_dev(dQ, dR, scale=-2.5, mode=1)
+    assert rel(eng.download(1, dR), -2.5 * o.weak_divergence(Q)) < 1e-11
+    eng.weak_divergence_dev(dQ, dR, scale=0.5, mode=0)
+    assert rel(eng.download(1, dR), 0.5 * o.cell_divergence(Q)) < 1e-11
+    p = rng.standard_normal((m.nc, o.np_))
+    lam = rng.standard_normal((m.nf, k + 1))
+    dY = eng.zeros(0)
+    eng.pressure_gradient_dev(eng.upload(1, p), eng.upload(2, lam), dY)
+    assert rel(eng.download(0, dY), o.pressure_gradient(p, lam) / o.detJ[:, None, None]) < 1e-11
+
+
+@pytest.mark.parametrize("mesh_fn", MESHES)
+def test_reconstruct_trace_and_shift(k, mesh_fn):
+    m = mesh_fn()
+    o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    rng = np.random.default_rng(4)
+    Q = rng.standard_normal((m.nc, 2, o.nQ1))
+    p = rng.standard_normal((m.nc, o.np_))
+    dl = eng.empty(2)
+    dp = eng.upload(1, p)
+    eng.reconstruct_trace_dev(eng.upload(0, Q), dp, dl)
+    lam = o.reconstruct_trace(Q, p)
+    assert rel(eng.download(2, dl), lam) < 1e-11
+    eng.shift_pressure_dev(dp, dl)
+    ps, ls = o.shift_pressure(p, lam)
+    assert rel(eng.download(1, dp), ps) < 1e-11 and rel(eng.download(2, dl), ls) < 1e-11
+
+
+@pytest.mark.parametrize("mesh_fn", MESHES[:2])
+def test_tentative_solve(k, mesh_fn):
+    m = mesh_fn()
+    o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    rng = np.random.default_rng(5)
+    Qs = o.project_bdm(rng.standard_normal((m.nc, 2, o.nQ1)))
+    b = rng.standard_normal((m.nc, 2, o.nQ1))
+    adt = 0.02
+    # oracle: (M - adt F) x = M b  by sparse LU
+    Mdiag = sp.diags(np.repeat(o.detJ, o.nQ))
+    A = (Mdiag - adt * o.f_impl_matrix(Qs)).tocsc()
+    ref = spla.splu(A).solve((Mdiag @ b.ravel())).reshape(b.shape)
+    dx = eng.empty(0)
+    its = eng.tentative_solve_dev(eng.upload(0, Qs), adt, eng.upload(0, b), dx, rtol=1e-13, maxit=500)
+    assert its > 0
+    assert rel(eng.download(0, dx), ref) < 1e-10
+
+
+def test_lincomb_and_mass():
+    import torch
+
+    m = UnitSquareMesh(4, perturb=0.1)
+    k = 2
+    o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    a, b = eng.zeros(0), eng.zeros(0)
+    a += torch.arange(a.numel(), device="cuda", dtype=torch.float64)
+    b += 2.0
+    out = eng.empty(0)
+    eng.lincomb_dev(out, [(0.5, a), (-3.0, b)])
+    eng.synchronize()
+    assert torch.equal(out, 0.5 * a - 3.0 * b)
+    Q = np.random.default_rng(0).standard_normal((m.nc, 2, o.nQ1))
+    dQ = eng.upload(0, Q)
+    eng.mass_dev(0, dQ, out)
+    assert rel(eng.download(0, out), o.mass_Q(Q)) < 1e-13
+
+
+@pytest.mark.parametrize("mesh_fn", MESHES[:2])
+def test_reconstruction_rhs(k, mesh_fn):
+    """hdg_imex.py:204-207 against the oracle's quadrature restatement"""
+    from oracle.timesteppers import IMEXOracle
+
+    m = mesh_fn()
+    ts = IMEXOracle(m, k, 0.1)
+    o = ts.o
+    eng = HDGEngine(m, k)
+    rng = np.random.default_rng(6)
+    Q = rng.standard_normal((m.nc, 2, o.nQ1))
+    b = rng.standard_normal((m.nc, 2, o.nQ1))
+    Rp, Rl = ts.reconstruction_rhs(Q, b)
+    dRp, dRl = eng.empty(1), eng.empty(2)
+    eng.reconstruction_rhs_dev(eng.upload(0, Q), eng.upload(0, b), dRp, dRl)
+    assert rel(eng.download(1, dRp), Rp) < 1e-11
+    if np.abs(Rl).max() > 0:
+        assert rel(eng.download(2, dRl), Rl) < 1e-11
+    else:
+        assert np.abs(eng.download(2, dRl)).max() == 0.0
+    # mass-weighted inner product
+    ip = eng.l2_inner_dev(0, eng.upload(0, Q), eng.upload(0, b))
+    assert abs(ip - np.sum(o.detJ[:, None, None] * Q * b)) < 1e-10 * abs(ip)

@@ -8,6 +8,7 @@ import pytest
 from incompressibleeulerhdg_b200.engine import HDGEngine
 from incompressibleeulerhdg_b200.mesh import PeriodicSquareMesh, RandomAffineCells, UnitDiskMesh, UnitSquareMesh
 from oracle.hdg_oracle import HDGOracle
+from conftest import require_degree
 
 pytestmark = pytest.mark.gpu
 
@@ -29,6 +30,7 @@ def ell_to_dense(val, col, nf, b):
 
 @pytest.mark.parametrize("k", [1, 2, 3, 4])
 def test_local_schur_matches_oracle(k):
+    require_degree(k)
     m = RandomAffineCells(257)
     o = HDGOracle(m, k)
     eng = HDGEngine(m, k)
@@ -41,6 +43,7 @@ def test_local_schur_matches_oracle(k):
 @pytest.mark.parametrize("k", [1, 2, 3])
 @pytest.mark.parametrize("mesh_fn", [lambda: UnitSquareMesh(5, perturb=0.2), lambda: PeriodicSquareMesh(4, L=2 * np.pi)])
 def test_trace_matrix_matches_oracle(k, mesh_fn):
+    require_degree(k)
     m = mesh_fn()
     o = HDGOracle(m, k)
     eng = HDGEngine(m, k)
@@ -55,6 +58,7 @@ def test_trace_matrix_matches_oracle(k, mesh_fn):
 @pytest.mark.parametrize("mesh_fn", [lambda: UnitSquareMesh(8, perturb=0.15), lambda: PeriodicSquareMesh(5, L=2 * np.pi),
                                       lambda: UnitDiskMesh(2)])
 def test_poisson_apply_matches_oracle(k, mesh_fn):
+    require_degree(k)
     m = mesh_fn()
     o = HDGOracle(m, k)
     eng = HDGEngine(m, k)

@@ -104,7 +104,7 @@ def tables(k):
     out = dict(D=D, E=E, F=F, KK=KK, TT=TT, LL=LL, NN=NN)
     # ---- advection / BDM tabulations -------------------------------------------------------
     # cell rule exact for degree 3k+2 (w in P_{k+1}, Q* in P_{k+1}, grad Q in P_k)
-    xa, wa = R.triangle_quadrature(3 * k + 2, LD)
+    xa, wa = R.triangle_quadrature_gj(3 * k + 2, LD)
     out["WQ"] = wa
     out["PHI"] = R.dubiner(k + 1, xa).T  # [q][i]
     out["DPHI"] = np.moveaxis(R.dubiner_grad(k + 1, xa), [0, 1, 2], [2, 1, 0])  # [d][q][i]
@@ -116,6 +116,8 @@ def tables(k):
     out["PHIF"] = np.array([R.dubiner(k + 1, R.facet_points(e, sf).astype(LD)).T for e in range(3)])  # [e][q][i]
     out["PSIF"] = np.array([R.dubiner(k, R.facet_points(e, sf).astype(LD)).T for e in range(3)])  # [e][q][a]
     out["LEG"] = R.legendre01(k + 1, sf)  # [m][q], m <= k+1
+    out["DPHIF"] = np.array([np.moveaxis(R.dubiner_grad(k + 1, R.facet_points(e, sf).astype(LD)), [0, 1, 2], [2, 1, 0])
+                             for e in range(3)])  # [e][d][q][i]
     # BDM facet functionals in modal form: BF[e][j][i] = int_0^1 phi_i(x_e(s)) l_j(s) ds, j <= k+1
     s2, w2 = R.gauss_legendre(k + 4, LD)
     leg2 = R.legendre01(k + 1, s2)
@@ -125,6 +127,26 @@ def tables(k):
     xb, wb = R.triangle_quadrature(2 * k + 3, LD)
     ned = nedelec_ref(k, xb)
     out["BI"] = np.einsum("q,wdq,iq->wdi", wb, ned, R.dubiner(k + 1, xb)) if k > 0 else np.zeros((1, 2, nQ1))
+    # LIFT = columns of N^-1 that belong to the facet functionals, N = all BDM functionals on the
+    # Piola-pulled-back coefficients Qhat[c][i]:
+    #   facet (e,j):  |e^| n^_e[c] BF[e][j][i]      with |e^| n^_e = (1,1), (-1,0), (0,-1)
+    #   interior w :  BI[w][c][i]
+    nref = np.array([[1, 1], [-1, 0], [0, -1]], dtype=LD)
+    nfm = 3 * (k + 2)
+    N = np.zeros((2 * nQ1, 2, nQ1), dtype=LD)
+    for e in range(3):
+        for j in range(k + 2):
+            for c in range(2):
+                N[e * (k + 2) + j, c, :] = nref[e, c] * out["BF"][e][j]
+    if k > 0:
+        N[nfm:, :, :] = out["BI"]
+    Ninv = np.linalg.inv(N.reshape(2 * nQ1, 2 * nQ1).astype(np.float64))
+    # one step of iterative refinement in long double
+    Nl = N.reshape(2 * nQ1, 2 * nQ1)
+    Ninv = Ninv.astype(LD)
+    Ninv = Ninv + Ninv @ (np.eye(2 * nQ1, dtype=LD) - Nl @ Ninv)
+    Ninv = Ninv + Ninv @ (np.eye(2 * nQ1, dtype=LD) - Nl @ Ninv)
+    out["LIFT"] = Ninv[:, :nfm].reshape(2, nQ1, 3, k + 2)  # [c][i][e][j]
     return {n: snap(v) for n, v in out.items()}, dict(nQ1=nQ1, np_=np_, nl1=nl1, nq=len(wa), nqf=nqf,
                                                        nint=k * (k + 2))
 

@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Headline benchmark: HDG timesteps/s (BASELINE.json metric), Chorin projection k=2 on nx=1024.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nx NX] [--degree k]
+
+A "step" is one Chorin timestep (`hdg_implicit.py:92-190`): BDM projection, tentative-velocity
+solve, statically condensed mixed-Poisson solve (forward elimination, trace CG, back-substitution)
+and the velocity/pressure update, on synthetic Taylor-Green data.
+
+own arm (default)   device-resident timestepping through the Python timestepper mirror -> C-ABI;
+                    `value` = timesteps/s with all inputs in HBM; `e2e` = the same step driven with
+                    HOST buffers: per step the forcing comes from pinned host memory (H2D) and the
+                    new velocity/pressure go back to the host (D2H), all inside the timed region.
+reference arm       the CPU restatement of the reference path (oracle/, numpy+scipy sparse direct
+                    solvers; the reference itself needs Firedrake/PETSc which cannot be installed
+                    here) on a bounded sample, scaled to the same unit.
+
+Prints ONE JSON line (see the task contract for the keys).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hdg_chorin_timesteps_per_second"
+UNIT = "timesteps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's Chorin step on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_chorin_sample(nx_sample, degree, nsteps, target_cells):
+    from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+    from oracle.timesteppers import ChorinOracle, TaylorGreenOracle
+
+    mesh = UnitSquareMesh(nx_sample, perturb=0.1)
+    dt = 0.32 / nx_sample
+    ts = ChorinOracle(mesh, degree, dt)
+    prob = TaylorGreenOracle("exponential", 0.5)
+    Q, p = ts.initial_state(prob)
+    times = []
+    for k in range(nsteps):
+        t0 = time.perf_counter()
+        Q, p = ts.step(Q, p, prob.f_rhs(k * dt))
+        times.append(time.perf_counter() - t0)
+    sec_per_step = float(np.mean(times))
+    # scale linearly in the number of cells (generous to the CPU: sparse direct solvers grow faster)
+    scaled = sec_per_step * target_cells / mesh.nc
+    return {
+        "value": 1.0 / scaled, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{nsteps} Chorin step(s) of oracle/timesteppers.py (numpy + scipy splu, 1 thread) on nx={nx_sample} "
+                  f"k={degree} ({mesh.nc} cells, {sec_per_step:.2f} s/step), scaled linearly to {target_cells} cells",
+    }, sec_per_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    target_cells = 2 * args.nx * args.nx
+    t_all = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        b, sec = cpu_chorin_sample(args.cpu_nx, args.degree, 1, target_cells)
+        if s >= args.warmup:
+            t_all.append(1.0 / b["value"])
+            base = b
+    val = 1.0 / float(np.mean(t_all))
+    base["value"] = val
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": base,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Firedrake/PETSc (the reference's own code path) is not installable in this image; this arm times "
+                "the CPU restatement under oracle/",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        "workload": f"HDG Chorin projection (hdg_implicit.py, use_projection_method=True), k={args.degree}, "
+                    f"UnitSquareMesh({args.nx},{args.nx}) = {2 * args.nx * args.nx} triangles per GPU, upwind flux, "
+                    f"Taylor-Green kappa=0.5, dt=0.32/nx, Krylov rtol {args.rtol:g}",
+        "nx": args.nx, "degree": args.degree, "dt": 0.32 / args.nx, "mesh_perturbation": 0.1,
+        "cache": "inputs (>=1.1 GB trace matrix, 0.3 GB velocity fields) exceed the 126 MB L2",
+        "partition": "one mesh replica per GPU (weak scaling, no data-path collective yet)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+    from incompressibleeulerhdg_b200.timesteppers import IncompressibleEulerHDGImplicit
+
+    nx, k = args.nx, args.degree
+    dt = 0.32 / nx
+    mesh = UnitSquareMesh(nx, perturb=0.1)
+    ts = IncompressibleEulerHDGImplicit(mesh, k, dt, flux="upwind", use_projection_method=True, device=local,
+                                        krylov_rtol=args.rtol)
+    eng = ts.engine
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    f_rhs = prob.f_rhs()
+    ts.initialise(Q0, p0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_no = 0
+    # ---- device-resident arm -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        ts.step(step_no, f_rhs)
+        step_no += 1
+    eng.reset_timers()
+    l0 = eng.launch_count
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            ts.step(step_no, f_rhs)
+            step_no += 1
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count - l0
+    timers = eng.timers()
+    its_p, its_t = ts.niter_pressure.value, ts.niter_tentative.value
+    value = world * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: forcing from pinned host memory each step, (Q, p) back to the host ----
+    from incompressibleeulerhdg_b200.functions import Function
+
+    sQ, sp_, _ = eng.shapes()
+    f_dev = Function(ts._V_Q)
+    ts._V_Q.interpolate(f_rhs(0.0), out=f_dev)
+    f_host = torch.from_numpy(eng.download(0, f_dev.data)).pin_memory()
+    Q_host = torch.empty(sQ, dtype=torch.float64).pin_memory()
+    p_host = torch.empty(sp_, dtype=torch.float64).pin_memory()
+
+    def e2e_step(kstep):
+        scale = float(np.exp(-0.5 * dt))  # host-side update of the forcing values for the next step
+        eng.upload(0, f_host.numpy(), out=f_dev.data)
+        ts.step(kstep, f_rhs, f_field=f_dev)
+        eng.download(0, ts.Q.data, out=Q_host.numpy())
+        eng.download(1, ts.p.data, out=p_host.numpy())
+        return scale
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_step(step_no)
+    step_no += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step(step_no)
+        step_no += 1
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * e2e_steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        b = k + 1
+        nblocks = 5 * mesh.nf
+        spmv_bytes = nblocks * b * b * 8 + nblocks * 4 + 2 * b * mesh.nf * 8
+        spmv_ms, spmv_n = timers["spmv_sampled"]
+        ach = spmv_bytes / (spmv_ms / max(spmv_n, 1)) / 1e6 if spmv_ms > 0 else None
+        roofline = {
+            "kernel": "k_cg_spmv<3> (blocked-ELL trace SpMV inside the CG)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+            "launch_ms": spmv_ms / max(spmv_n, 1), "sampled_launches": int(spmv_n),
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_chorin_sample(args.cpu_nx, k, 1, mesh.nc)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.prod(sQ)) * 8,
+                    "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t},
+            "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
+                                      ("bdm_projection", "tentative_velocity_solve", "forward_elimination",
+                                       "trace_solve", "back_substitution")},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--degree", type=int, default=2)
+    ap.add_argument("--rtol", type=float, default=1e-12)
+    ap.add_argument("--cpu-nx", type=int, default=16, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -158,7 +158,9 @@ int hdg_download(hdg_handle h, int kind, const double* dev_soa, double* host_aos
 
 /* ---- timers (CUDA-event time accumulated per reference PerformanceLog label) ------------------ */
 /* labels: 0 setup_poisson, 1 forward_elimination, 2 trace_solve, 3 back_substitution,
- *         4 bdm_projection, 5 tentative_velocity_solve, 6 h2d, 7 d2h */
+ *         4 bdm_projection, 5 tentative_velocity_solve, 6 h2d, 7 d2h,
+ *         8 spmv_sampled (every 16th trace SpMV of the CG, per-launch events),
+ *         9 fimpl_sampled (first f_impl application of every BiCGStab iteration) */
 int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n);
 int hdg_reset_timers(hdg_handle h);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */

@@ -29,7 +29,7 @@
 // ------------------------------------------------------------------------------------------------
 // engine state
 // ------------------------------------------------------------------------------------------------
-enum { T_SETUP = 0, T_FWD, T_SOLVE, T_BACK, T_BDM, T_TENT, T_H2D, T_D2H, T_COUNT };
+enum { T_SETUP = 0, T_FWD, T_SOLVE, T_BACK, T_BDM, T_TENT, T_H2D, T_D2H, T_SPMV, T_FIMPL, T_COUNT };
 
 struct CgScalars {
   double rz0;      // initial <r,z>
@@ -888,7 +888,10 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
   while (!finished) {
     int m = std::min(chunk, std::max(1, maxit - launched));
     for (int i = 0; i < m; ++i) {
-      launch_fimpl<K>(h, upwind, Qstar, p, 1.0, -adt, v);
+      {
+        ScopedTimer tf(h, T_FIMPL);
+        launch_fimpl<K>(h, upwind, Qstar, p, 1.0, -adt, v);
+      }
       LAUNCH(h, k_dot2, G, BLOCK, n, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
       LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
       launch_fimpl<K>(h, upwind, Qstar, sv, 1.0, -adt, t);
@@ -1203,7 +1206,12 @@ static int run_cg(hdg_engine* h, double rtol, int maxit, int* iters) {
     int n = std::min(chunk, maxit - launched);
     if (n <= 0) n = 1;
     for (int i = 0; i < n; ++i) {
-      LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+      if (((launched + i) & 15) == 0) {
+        // sampled per-launch timing of the dominant kernel (every 16th SpMV) for bench.py's roofline
+        ScopedTimer ts(h, T_SPMV);
+        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+      } else
+        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
       LAUNCH(h, k_cg_update<b>, G, BLOCK, h->nf, h->dinv, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->cg_z, part_pq,
              part_rz, h->scal);
       LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);

@@ -17,7 +17,7 @@ __all__ = ["HDGEngine", "HDGError", "load_library", "LIB_PATH", "TIMER_LABELS"]
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdg_b200.so")
 
 TIMER_LABELS = ("setup_poisson", "forward_elimination", "trace_solve", "back_substitution", "bdm_projection",
-                "tentative_velocity_solve", "h2d", "d2h")
+                "tentative_velocity_solve", "h2d", "d2h", "spmv_sampled", "fimpl_sampled")
 
 HDG_OK, HDG_EINVAL, HDG_ECUDA, HDG_ENOGPU, HDG_ESTATE, HDG_ENCCL, HDG_ENOCONV = range(7)
 
@@ -184,9 +184,10 @@ class HDGEngine:
         self.synchronize()  # `a` may be a temporary
         return out
 
-    def download(self, kind: int, dev):
+    def download(self, kind: int, dev, out=None):
         shp = self.shapes()[kind]
-        out = np.empty(shp, dtype=np.float64)
+        out = np.empty(shp, dtype=np.float64) if out is None else out
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == int(np.prod(shp))
         self._check(self.lib.hdg_download(self._h, kind, _dev(dev), _ptr(out)))
         return out
 

@@ -58,44 +58,55 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         return self.engine.poisson_apply_dev(None, Rp.data, None, u.data, phi.data, lmbda.data, rtol=self.krylov_rtol,
                                              maxit=100000, shift=True)
 
+    def initialise(self, Q_initial, p_initial):
+        """interpolate the initial conditions and allocate the per-step work fields (:82-84)"""
+        self.Q = self._V_Q.interpolate(Q_initial)
+        self.Q.rename("velocity")
+        self.p = self._V_p.interpolate(p_initial)
+        self.p.rename("pressure")
+        self.engine.shift_pressure_dev(self.p.data, None)  # :84
+        self._Q_star, self._f, self._rhs, self._Q_tentative, self._u = (Function(self._V_Q) for _ in range(5))
+        self._Rp, self._phi = Function(self._V_p), Function(self._V_p)
+        self._lmbda = Function(self._V_trace)
+        self.niter_tentative.reset()
+        self.niter_pressure.reset()
+        return self.Q, self.p
+
+    def step(self, k, f_rhs, f_field=None):
+        """one timestep t_k -> t_{k+1} (:92-190).  f_field, if given, is an already interpolated
+        forcing Function (host-driven forcing); otherwise f_rhs(t_k) is interpolated."""
+        eng, Q, p = self.engine, self.Q, self.p
+        with PerformanceLog("timestep"):
+            with PerformanceLog("bdm_projection"):
+                self.project_bdm(Q, out=self._Q_star)  # :98
+            f = f_field if f_field is not None else self._V_Q.interpolate(f_rhs(k * self._dt), out=self._f)  # :100
+            eng.lincomb_dev(self._rhs.data, [(1.0, Q.data), (self._dt, f.data)])  # :126 / :182 in Riesz form
+            if self.use_projection_method:
+                self._Q_tentative.assign(Q)  # warm start
+                its = self.tentative_velocity_solve(self._Q_star, self._rhs, self._Q_tentative, zero_guess=False)  # :129
+                self.niter_tentative.update(its)
+                eng.weak_divergence_dev(self._Q_tentative.data, self._Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
+                its = self.pressure_solve(self._Rp, self._u, self._phi, self._lmbda)  # :146
+                self.niter_pressure.update(its)
+                eng.lincomb_dev(Q.data, [(1.0, self._Q_tentative.data), (self._dt, self._u.data)])  # :150
+            else:
+                with PerformanceLog("unsplit_solve"):
+                    self._monolithic.solve(self._Q_star, self._dt, self._rhs, Q, self._phi, self._lmbda)  # :185
+            p.assign(self._phi)  # :189-190
+            eng.shift_pressure_dev(p.data, None)
+        return Q, p
+
     def solve(self, Q_initial, p_initial, q_initial, f_rhs, T_final, warmup=False):
         if q_initial:
             raise NotImplementedError("passive tracer advection is not on the engine's hot path yet")
-        eng = self.engine
         nt = self.get_timesteps(T_final, warmup)
-        Q = self._V_Q.interpolate(Q_initial)
-        Q.rename("velocity")
-        p = self._V_p.interpolate(p_initial)
-        p.rename("pressure")
-        eng.shift_pressure_dev(p.data, None)  # :84
-        Q_star, f, rhs, Q_tentative, u = (Function(self._V_Q) for _ in range(5))
-        Rp, phi = Function(self._V_p), Function(self._V_p)
-        lmbda = Function(self._V_trace)
-        self.niter_tentative.reset()
-        self.niter_pressure.reset()
+        Q, p = self.initialise(Q_initial, p_initial)
         for callback in self.callbacks:
             callback.reset()
             callback(Q, p, 0, q_tracer=None)
         steps = tqdm.tqdm(range(nt)) if self.progress else range(nt)
         for k in steps:
-            with PerformanceLog("timestep"):
-                with PerformanceLog("bdm_projection"):
-                    self.project_bdm(Q, out=Q_star)  # :98
-                self._V_Q.interpolate(f_rhs(k * self._dt), out=f)  # :100
-                eng.lincomb_dev(rhs.data, [(1.0, Q.data), (self._dt, f.data)])  # :126 / :182 in Riesz form
-                if self.use_projection_method:
-                    Q_tentative.assign(Q)  # warm start
-                    its = self.tentative_velocity_solve(Q_star, rhs, Q_tentative, zero_guess=False)  # :129
-                    self.niter_tentative.update(its)
-                    eng.weak_divergence_dev(Q_tentative.data, Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
-                    its = self.pressure_solve(Rp, u, phi, lmbda)  # :146
-                    self.niter_pressure.update(its)
-                    eng.lincomb_dev(Q.data, [(1.0, Q_tentative.data), (self._dt, u.data)])  # :150
-                else:
-                    with PerformanceLog("unsplit_solve"):
-                        self._monolithic.solve(Q_star, self._dt, rhs, Q, phi, lmbda)  # :185
-                p.assign(phi)  # :189-190 (phi is already mean free)
-                eng.shift_pressure_dev(p.data, None)
+            self.step(k, f_rhs)
             for callback in self.callbacks:
                 callback(Q, p, (k + 1) * self._dt, q_tracer=None)
         return Q, p

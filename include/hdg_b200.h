@@ -103,6 +103,28 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
                           double* Q, double* p, double* l, double rtol, int maxit, int shift,
                           int* iters);
 
+/* ---- multigrid preconditioner for the trace solve (GTMGPC replacement, hdg_imex.py:138-169) ---- */
+typedef struct {
+  int32_t nrows, ncols;
+  const int32_t* rowptr; /* [nrows+1] */
+  const int32_t* col;    /* [nnz] */
+  const double* val;     /* [nnz] */
+} hdg_csr;
+/* Upload a hierarchy built on the host (multigrid.py) and switch the trace solve to
+ * multigrid-preconditioned CG.  A[0..nlevels): P1 operators (level 0 = P1 on the mesh, the
+ * reference's get_coarse_operator hdg_imex.py:101-106 with the sign of P = -S); P[l]/R[l]:
+ * prolongation level l+1 -> l and its transpose; T/Tt: P1 level 0 -> trace space (SoA numbering
+ * mode*nf+facet) and its transpose; lmax[l]: estimate of lambda_max(D^-1 A[l]); coarsest_pinv:
+ * dense pseudo-inverse of A[nlevels-1]; smooth_fine / smooth_coarse: Chebyshev sweeps per
+ * pre-/post-smoothing on the trace level (facet-block-Jacobi, hdg_imex.py:143-152) and on the P1
+ * levels (point Jacobi); cheb_ratio: the smoother targets [lmax/cheb_ratio, 1.1 lmax]. */
+int hdg_mg_setup(hdg_handle h, int nlevels, const hdg_csr* A, const hdg_csr* P, const hdg_csr* R,
+                 const hdg_csr* T, const hdg_csr* Tt, const double* lmax, const double* coarsest_pinv,
+                 int smooth_fine, int smooth_coarse, double cheb_ratio);
+/* on = 0 falls back to facet-block-Jacobi CG, on != 0 re-enables the hierarchy */
+int hdg_mg_enable(hdg_handle h, int on);
+int hdg_mg_info(hdg_handle h, int* nlevels, double* fine_lmax);
+
 /* y = P x with P = -S (the symmetric positive semi-definite matrix the CG iterates on), device
  * SoA pointers -- the SpMV of the Krylov loop, exposed for tests and the roofline microbenchmark. */
 int hdg_trace_spmv_dev(hdg_handle h, const double* x, double* y);

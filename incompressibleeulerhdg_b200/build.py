@@ -11,7 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdg_b200.so")
 SOURCES = ["hdg_engine.cu"]
-HEADERS = ["hdg_local.cuh", "hdg_tables.inc", os.path.join("..", "..", "include", "hdg_b200.h")]
+HEADERS = ["hdg_local.cuh", "hdg_flow.cuh", "hdg_mg.cuh", "hdg_tables.inc",
+           os.path.join("..", "..", "include", "hdg_b200.h")]
+STAMP = LIB + ".flags"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
@@ -25,8 +27,21 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the engine is CUDA-only and cannot be built without it")
 
 
+def _command() -> list:
+    cmd = [_nvcc(), *NVCC_FLAGS, *(os.path.join(CSRC, s) for s in SOURCES), "-o", LIB]
+    # development shortcut: HDG_DEV_DEGREES="2" compiles only k=2 (the shipped build has k=1..4)
+    dev = os.environ.get("HDG_DEV_DEGREES")
+    if dev:
+        mask = sum(1 << int(k) for k in dev.split(","))
+        cmd.insert(1, f"-DHDG_DEGREES={mask}")
+    return cmd
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
+        return True
+    # a library built with other flags (e.g. a development subset of the degrees) is stale
+    if not os.path.exists(STAMP) or open(STAMP).read() != " ".join(_command()):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
@@ -37,12 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """compile csrc/*.cu -> libhdg_b200.so; returns the library path"""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *(os.path.join(CSRC, s) for s in SOURCES), "-o", LIB]
-    # development shortcut: HDG_DEV_DEGREES="2" compiles only k=2 (the shipped build has k=1..4)
-    dev = os.environ.get("HDG_DEV_DEGREES")
-    if dev:
-        mask = sum(1 << int(k) for k in dev.split(","))
-        cmd.insert(1, f"-DHDG_DEGREES={mask}")
+    cmd = _command()
+    stamp = " ".join(cmd)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
@@ -51,6 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr, file=sys.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(stamp)
     return LIB
 
 

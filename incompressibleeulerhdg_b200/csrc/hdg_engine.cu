@@ -46,7 +46,10 @@ struct BiScalars {
   int iters, done, maxit, ticket;
 };
 
+struct MgState;
+
 struct hdg_engine {
+  MgState* mg = nullptr;
   int k = 0, nc = 0, nf = 0, device = 0;
   double tau = 1.0;
   double volume = 0.0;
@@ -191,6 +194,8 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
   __syncthreads();
   return res;
 }
+
+#include "hdg_mg.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K1+K2: local operator build + static condensation, one thread per cell
@@ -909,6 +914,173 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
 }
 
 // ------------------------------------------------------------------------------------------------
+// multigrid-preconditioned CG (host orchestration)
+// ------------------------------------------------------------------------------------------------
+static void free_csr(DevCsr& m) {
+  if (m.rowptr) cudaFree(m.rowptr);
+  if (m.col) cudaFree(m.col);
+  if (m.val) cudaFree(m.val);
+  m = DevCsr();
+}
+static void mg_free(hdg_engine* h) {
+  MgState* mg = h->mg;
+  if (!mg) return;
+  for (auto& l : mg->L) {
+    free_csr(l.A);
+    free_csr(l.P);
+    free_csr(l.R);
+    double* v[] = {l.dinv, l.x, l.x2, l.b, l.r, l.d};
+    for (double* p : v)
+      if (p) cudaFree(p);
+  }
+  free_csr(mg->T);
+  free_csr(mg->Tt);
+  double* v[] = {mg->pinv, mg->fx, mg->fx2, mg->fd, mg->fr};
+  for (double* p : v)
+    if (p) cudaFree(p);
+  delete mg;
+  h->mg = nullptr;
+}
+
+static int upload_csr(hdg_engine* h, const hdg_csr& src, DevCsr& dst) {
+  dst.nrows = src.nrows;
+  dst.ncols = src.ncols;
+  dst.nnz = src.rowptr[src.nrows];
+  CUDA_TRY(h, dmalloc(&dst.rowptr, (size_t)src.nrows + 1));
+  CUDA_TRY(h, dmalloc(&dst.col, (size_t)std::max(dst.nnz, 1)));
+  CUDA_TRY(h, dmalloc(&dst.val, (size_t)std::max(dst.nnz, 1)));
+  CUDA_TRY(h, cudaMemcpy(dst.rowptr, src.rowptr, ((size_t)src.nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(dst.col, src.col, (size_t)dst.nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(dst.val, src.val, (size_t)dst.nnz * sizeof(double), cudaMemcpyHostToDevice));
+  return HDG_OK;
+}
+
+static inline int small_grid(const hdg_engine* h, int n) { return std::max(1, std::min(h->grid, cdiv(n, 256))); }
+
+static void csr_spmv(hdg_engine* h, const DevCsr& A, const double* x, const double* b, double* y, int mode) {
+  LAUNCH(h, k_csr_spmv, small_grid(h, A.nrows), 256, A.nrows, A.rowptr, A.col, A.val, x, b, y, mode);
+}
+
+// smooth on CSR level l: result ends in L.x (x and x2 ping-pong)
+static void mg_smooth_csr(hdg_engine* h, MgLevel& L, int ns, double ratio, bool zero) {
+  std::vector<ChebCoef> cc;
+  cheb_coefs(L.lmax, ratio, ns, cc);
+  for (int j = 0; j < ns; ++j) {
+    LAUNCH(h, k_csr_cheb, small_grid(h, L.n), 256, L.n, L.A.rowptr, L.A.col, L.A.val, L.dinv, L.b, L.x, L.d, L.x2,
+           cc[j].cd, cc[j].cr, (zero && j == 0) ? 1 : 0);
+    std::swap(L.x, L.x2);
+  }
+}
+
+static void mg_vcycle(hdg_engine* h, int l) {
+  MgState* mg = h->mg;
+  MgLevel& L = mg->L[l];
+  if (l == mg->nlevels - 1) {
+    LAUNCH(h, k_dense_matvec, small_grid(h, L.n), 256, L.n, mg->pinv, L.b, L.x);
+    return;
+  }
+  MgLevel& C = mg->L[l + 1];
+  mg_smooth_csr(h, L, mg->ns_coarse, mg->ratio, true);
+  csr_spmv(h, L.A, L.x, L.b, L.r, 2);       // r = b - A x
+  csr_spmv(h, L.R, L.r, nullptr, C.b, 0);   // b_c = R r
+  mg_vcycle(h, l + 1);
+  csr_spmv(h, L.P, C.x, nullptr, L.x, 1);   // x += P x_c
+  mg_smooth_csr(h, L, mg->ns_coarse, mg->ratio, false);
+}
+
+// z = M^-1 r: symmetric V-cycle (Chebyshev/block-Jacobi, P1 coarse correction, Chebyshev/block-Jacobi)
+template <int b>
+static void mg_apply(hdg_engine* h, const double* r, double* z) {
+  MgState* mg = h->mg;
+  const int G = h->grid;
+  std::vector<ChebCoef> cc;
+  cheb_coefs(mg->fine_lmax, mg->ratio, mg->ns_fine, cc);
+  double *x = mg->fx, *x2 = mg->fx2;
+  for (int j = 0; j < mg->ns_fine; ++j) {
+    LAUNCH(h, k_ell_cheb<b>, G, 256, h->nf, h->ell_val, h->ell_col, h->dinv, r, x, mg->fd, x2, cc[j].cd, cc[j].cr,
+           j == 0 ? 1 : 0);
+    std::swap(x, x2);
+  }
+  LAUNCH(h, k_ell_residual<b>, G, 256, h->nf, h->ell_val, h->ell_col, r, x, mg->fr);
+  MgLevel& L0 = mg->L[0];
+  csr_spmv(h, mg->Tt, mg->fr, nullptr, L0.b, 0);
+  mg_vcycle(h, 0);
+  csr_spmv(h, mg->T, L0.x, nullptr, x, 1);
+  for (int j = 0; j < mg->ns_fine; ++j) {
+    double* out = (j == mg->ns_fine - 1) ? z : x2;
+    LAUNCH(h, k_ell_cheb<b>, G, 256, h->nf, h->ell_val, h->ell_col, h->dinv, r, x, mg->fd, out, cc[j].cd, cc[j].cr, 0);
+    if (j != mg->ns_fine - 1) std::swap(x, x2);
+  }
+  mg->fx = x;
+  mg->fx2 = x2;
+}
+
+template <int b>
+static int run_pcg_mg(hdg_engine* h, double rtol, int maxit, int* iters) {
+  const int G = h->grid;
+  const size_t n = (size_t)b * h->nf;
+  double* part_mean = h->partial;
+  double* part_pq = h->partial + G;
+  double* part_rz = h->partial + 2 * (size_t)G;
+  // r = b - mean (mode 0), x = 0; k_cg_init also writes a block-Jacobi z/p which we overwrite
+  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z, h->cg_p, part_rz);
+  mg_apply<b>(h, h->cg_r, h->cg_z);
+  CUDA_TRY(h, cudaMemcpyAsync(h->cg_p, h->cg_z, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  LAUNCH(h, k_dot2, G, BLOCK, n, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+  LAUNCH(h, k_cg_start, 1, BLOCK, h->scal, part_rz, G, rtol, maxit);
+  int it = 0;
+  while (true) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->scal_host->done || it >= maxit) break;
+    {
+      ScopedTimer ts(h, T_SPMV);
+      LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+    }
+    LAUNCH(h, k_cg_update_plain, G, 256, n, h->cg_p, h->cg_q, h->cg_x, h->cg_r, part_pq, h->scal);
+    mg_apply<b>(h, h->cg_r, h->cg_z);
+    LAUNCH(h, k_dot2, G, BLOCK, n, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+    LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);
+    ++it;
+  }
+  if (iters) *iters = h->scal_host->iters;
+  return h->scal_host->done == 1 ? HDG_OK : HDG_ENOCONV;
+}
+
+// lambda_max(Dinv P) by power iteration (setup only)
+template <int b>
+static int mg_fine_lmax(hdg_engine* h, double* lmax_out) {
+  MgState* mg = h->mg;
+  const int G = h->grid;
+  const size_t n = (size_t)b * h->nf;
+  std::vector<double> v0(n);
+  uint64_t st = 88172645463325252ull;
+  for (size_t i = 0; i < n; ++i) {  // xorshift: deterministic start vector
+    st ^= st << 13;
+    st ^= st >> 7;
+    st ^= st << 17;
+    v0[i] = (double)(st >> 11) / 9007199254740992.0 - 0.5;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(mg->fx, v0.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  std::vector<double> part(G);
+  double lam = 1.0;
+  for (int it = 0; it < 25; ++it) {
+    LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, mg->fx, mg->fr, (double*)nullptr,
+           (const CgScalars*)nullptr);
+    LAUNCH(h, k_blockjac<b>, G, 256, h->nf, h->dinv, mg->fr, mg->fx);
+    LAUNCH(h, k_dot2, G, BLOCK, n, mg->fx, mg->fx, (const double*)nullptr, h->partial, (double*)nullptr);
+    CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (double p : part) s += p;
+    lam = std::sqrt(s);
+    LAUNCH(h, k_scale, G, 256, n, 1.0 / lam, mg->fx);
+  }
+  *lmax_out = lam;
+  return HDG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -930,6 +1102,7 @@ int hdg_destroy(hdg_handle h) {
   if (!h) return HDG_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  mg_free(h);
   void* ptrs[] = {h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local, h->SK, h->ell_val,
                   h->dinv, h->ell_col, h->gK, h->cg_x, h->cg_r, h->cg_z, h->cg_p, h->cg_q, h->partial, h->scal,
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
@@ -1237,7 +1410,11 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   int cg_rc = HDG_EINVAL;
   {
     ScopedTimer t(h, T_SOLVE);
-    DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, maxit, iters));
+    if (h->mg && h->mg->enabled) {
+      DISPATCH_K(h, cg_rc = run_pcg_mg<K + 1>(h, rtol, maxit, iters));
+    } else {
+      DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, maxit, iters));
+    }
   }
   if (cg_rc == HDG_ECUDA) return cg_rc;
   int b = h->k + 1;
@@ -1483,6 +1660,83 @@ int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, d
   double s = 0.0;
   for (double v : part) s += v;
   *result = s;
+  return HDG_OK;
+}
+
+// ---- multigrid preconditioner ---------------------------------------------------------------------
+int hdg_mg_setup(hdg_handle h, int nlevels, const hdg_csr* A, const hdg_csr* P, const hdg_csr* R, const hdg_csr* T,
+                 const hdg_csr* Tt, const double* lmax, const double* coarsest_pinv, int smooth_fine,
+                 int smooth_coarse, double cheb_ratio) {
+  if (!h || nlevels < 1 || !A || !T || !Tt || !lmax || !coarsest_pinv || (nlevels > 1 && (!P || !R)))
+    return HDG_EINVAL;
+  if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_mg_setup: call hdg_setup_poisson first");
+  if (smooth_fine < 1 || smooth_coarse < 1 || !(cheb_ratio > 1.0)) FAIL(h, HDG_EINVAL, "hdg_mg_setup: bad smoother");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int b = h->k + 1;
+  const size_t n = (size_t)b * h->nf;
+  if (T->nrows != (int)n || T->ncols != A[0].nrows || Tt->nrows != A[0].nrows || Tt->ncols != (int)n)
+    FAIL(h, HDG_EINVAL, "hdg_mg_setup: transfer operator has the wrong shape");
+  mg_free(h);
+  h->mg = new MgState();
+  MgState* mg = h->mg;
+  mg->nlevels = nlevels;
+  mg->ns_fine = smooth_fine;
+  mg->ns_coarse = smooth_coarse;
+  mg->ratio = cheb_ratio;
+  mg->L.resize(nlevels);
+  int rc;
+  for (int l = 0; l < nlevels; ++l) {
+    MgLevel& L = mg->L[l];
+    L.n = A[l].nrows;
+    L.lmax = lmax[l];
+    if (A[l].nrows != A[l].ncols) FAIL(h, HDG_EINVAL, "hdg_mg_setup: level operator not square");
+    if ((rc = upload_csr(h, A[l], L.A))) return rc;
+    if (l < nlevels - 1) {
+      if (P[l].nrows != A[l].nrows || P[l].ncols != A[l + 1].nrows || R[l].nrows != P[l].ncols ||
+          R[l].ncols != P[l].nrows)
+        FAIL(h, HDG_EINVAL, "hdg_mg_setup: prolongation/restriction shapes inconsistent");
+      if ((rc = upload_csr(h, P[l], L.P))) return rc;
+      if ((rc = upload_csr(h, R[l], L.R))) return rc;
+    }
+    CUDA_TRY(h, dmalloc(&L.dinv, (size_t)L.n));
+    CUDA_TRY(h, dmalloc(&L.x, (size_t)L.n));
+    CUDA_TRY(h, dmalloc(&L.x2, (size_t)L.n));
+    CUDA_TRY(h, dmalloc(&L.b, (size_t)L.n));
+    CUDA_TRY(h, dmalloc(&L.r, (size_t)L.n));
+    CUDA_TRY(h, dmalloc(&L.d, (size_t)L.n));
+    LAUNCH(h, k_csr_diag_inv, small_grid(h, L.n), 256, L.n, L.A.rowptr, L.A.col, L.A.val, L.dinv);
+  }
+  if ((rc = upload_csr(h, *T, mg->T))) return rc;
+  if ((rc = upload_csr(h, *Tt, mg->Tt))) return rc;
+  mg->n_last = A[nlevels - 1].nrows;
+  CUDA_TRY(h, dmalloc(&mg->pinv, (size_t)mg->n_last * mg->n_last));
+  CUDA_TRY(h, cudaMemcpy(mg->pinv, coarsest_pinv, (size_t)mg->n_last * mg->n_last * sizeof(double),
+                         cudaMemcpyHostToDevice));
+  CUDA_TRY(h, dmalloc(&mg->fx, n));
+  CUDA_TRY(h, dmalloc(&mg->fx2, n));
+  CUDA_TRY(h, dmalloc(&mg->fd, n));
+  CUDA_TRY(h, dmalloc(&mg->fr, n));
+  double lam = 2.0;
+  DISPATCH_K(h, rc = mg_fine_lmax<K + 1>(h, &lam));
+  if (rc) return rc;
+  mg->fine_lmax = lam;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  mg->enabled = true;
+  return HDG_OK;
+}
+
+int hdg_mg_enable(hdg_handle h, int on) {
+  if (!h) return HDG_EINVAL;
+  if (!h->mg) FAIL(h, HDG_ESTATE, "hdg_mg_enable: call hdg_mg_setup first");
+  h->mg->enabled = on != 0;
+  return HDG_OK;
+}
+
+int hdg_mg_info(hdg_handle h, int* nlevels, double* fine_lmax) {
+  if (!h) return HDG_EINVAL;
+  if (nlevels) *nlevels = h->mg ? h->mg->nlevels : 0;
+  if (fine_lmax) *fine_lmax = h->mg ? h->mg->fine_lmax : 0.0;
   return HDG_OK;
 }
 

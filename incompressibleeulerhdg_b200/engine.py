@@ -27,6 +27,10 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _vp = C.c_void_p
 
+class hdg_csr(C.Structure):
+    _fields_ = [("nrows", C.c_int32), ("ncols", C.c_int32), ("rowptr", _ip), ("col", _ip), ("val", _dp)]
+
+
 #: every symbol of include/hdg_b200.h with (restype, argtypes); tests check the library exports all
 SIGNATURES = {
     "hdg_version": (C.c_char_p, []),
@@ -44,6 +48,10 @@ SIGNATURES = {
                                          C.POINTER(C.c_int)]),
     "hdg_poisson_apply_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                         C.POINTER(C.c_int)]),
+    "hdg_mg_setup": (C.c_int, [_vp, C.c_int, C.POINTER(hdg_csr), C.POINTER(hdg_csr), C.POINTER(hdg_csr),
+                               C.POINTER(hdg_csr), C.POINTER(hdg_csr), _dp, _dp, C.c_int, C.c_int, C.c_double]),
+    "hdg_mg_enable": (C.c_int, [_vp, C.c_int]),
+    "hdg_mg_info": (C.c_int, [_vp, C.POINTER(C.c_int), _dp]),
     "hdg_trace_spmv_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_forward_eliminate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -230,6 +238,44 @@ class HDGEngine:
         self._check(rc, allow=() if check else (HDG_ENOCONV,))
         self.last_iterations = its.value
         return its.value
+
+    # -- multigrid preconditioner -------------------------------------------------------------------
+    def mg_setup(self, hierarchy=None, smooth_fine=1, smooth_coarse=1, cheb_ratio=10.0):
+        """build (host, scipy) and upload the GTMG hierarchy; the trace solve becomes MG-PCG"""
+        from . import multigrid
+
+        H = multigrid.build_hierarchy(self.mesh, self.k) if hierarchy is None else hierarchy
+        keep = []
+
+        def conv(M):
+            M = M.tocsr()
+            M.sort_indices()
+            rp = np.ascontiguousarray(M.indptr, dtype=np.int32)
+            ci = np.ascontiguousarray(M.indices, dtype=np.int32)
+            va = np.ascontiguousarray(M.data, dtype=np.float64)
+            keep.extend([rp, ci, va])
+            return hdg_csr(M.shape[0], M.shape[1], rp.ctypes.data_as(_ip), ci.ctypes.data_as(_ip), va.ctypes.data_as(_dp))
+
+        nl = H.nlevels
+        A = (hdg_csr * nl)(*[conv(a) for a in H.A])
+        P = (hdg_csr * max(nl - 1, 1))(*[conv(p) for p in H.P]) if nl > 1 else None
+        R = (hdg_csr * max(nl - 1, 1))(*[conv(p.T) for p in H.P]) if nl > 1 else None
+        T = conv(H.T)
+        Tt = conv(H.T.T)
+        lmax = np.ascontiguousarray(H.lmax, dtype=np.float64)
+        pinv = np.ascontiguousarray(H.pinv, dtype=np.float64)
+        self._check(self.lib.hdg_mg_setup(self._h, nl, A, P, R, C.byref(T), C.byref(Tt), _ptr(lmax), _ptr(pinv),
+                                          int(smooth_fine), int(smooth_coarse), float(cheb_ratio)))
+        self.hierarchy = H
+        return H
+
+    def mg_enable(self, on=True):
+        self._check(self.lib.hdg_mg_enable(self._h, int(on)))
+
+    def mg_info(self):
+        nl, lm = C.c_int(0), C.c_double(0.0)
+        self._check(self.lib.hdg_mg_info(self._h, C.byref(nl), C.byref(lm)))
+        return nl.value, lm.value
 
     def trace_spmv_dev(self, x, y):
         self._check(self.lib.hdg_trace_spmv_dev(self._h, _dev(x), _dev(y)))

@@ -218,6 +218,7 @@ def UnitDiskMesh(refinement_level: int = 0) -> Mesh:
     cells = [(0, 1 + i, 1 + (i + 1) % 8) for i in range(8)]
     verts = np.array(verts)
     cells = np.array(cells, dtype=np.int64)
+    prolongations = []  # nested P1 spaces, used by the multigrid setup (finest first)
     for _ in range(refinement_level):
         nv = verts.shape[0]
         e = np.concatenate([cells[:, [1, 2]], cells[:, [2, 0]], cells[:, [0, 1]]])
@@ -235,8 +236,15 @@ def UnitDiskMesh(refinement_level: int = 0) -> Mesh:
             np.stack([v0, m2, m1], 1), np.stack([v1, m0, m2], 1), np.stack([v2, m1, m0], 1), np.stack([m0, m1, m2], 1)
         ])
         verts = np.concatenate([verts, mid])
+        import scipy.sparse as sp
+
+        ne = uniq.size
+        rows = np.concatenate([np.arange(nv), nv + np.arange(ne), nv + np.arange(ne)])
+        cols = np.concatenate([np.arange(nv), a, b])
+        vals = np.concatenate([np.ones(nv), np.full(ne, 0.5), np.full(ne, 0.5)])
+        prolongations.insert(0, sp.coo_matrix((vals, (rows, cols)), shape=(nv + ne, nv)).tocsr())
     m = Mesh.from_cells(cells, vert_xy=verts, name=f"UnitDiskMesh({refinement_level})")
-    m.meta.update(periodic=False)
+    m.meta.update(periodic=False, p1_prolongations=prolongations)
     return m
 
 

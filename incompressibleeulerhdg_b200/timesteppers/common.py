@@ -22,7 +22,7 @@ class IncompressibleEuler(ABC):
     """Abstract base class; owns the engine and the three function spaces
     [DG_{k+1}]^2, DG_k, DGT_k (`hdg_imex.py:65-69`)."""
 
-    def __init__(self, mesh, degree, dt, label=None, device=0, tau=1.0, krylov_rtol=None):
+    def __init__(self, mesh, degree, dt, label=None, device=0, tau=1.0, preconditioner="gtmg"):
         self._mesh = mesh
         self.degree = degree
         self._dt = dt
@@ -38,6 +38,18 @@ class IncompressibleEuler(ABC):
         self.domain_volume = mesh.volume
         # K1-K3 once: the mixed-Poisson operator does not depend on dt, Q* or t
         self.engine.setup_poisson()
+        # trace preconditioner: "gtmg" = P1 coarse space + Chebyshev/facet-block-Jacobi smoothing
+        # (the reference's firedrake.GTMGPC, hdg_imex.py:138-169); "jacobi" = facet-block-Jacobi only
+        assert preconditioner in ("gtmg", "jacobi")
+        self.preconditioner = preconditioner
+        if preconditioner == "gtmg":
+            try:
+                self.engine.mg_setup()
+            except ValueError as exc:  # no nested P1 hierarchy for this mesh
+                import warnings
+
+                warnings.warn(f"falling back to facet-block-Jacobi CG: {exc}")
+                self.preconditioner = "jacobi"
 
     def get_timesteps(self, t_final, warmup):
         """number of timesteps (`common.py:75-84`)"""

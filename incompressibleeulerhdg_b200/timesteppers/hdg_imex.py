@@ -56,8 +56,9 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
     """Abstract base class for the IMEX timesteppers (`hdg_imex.py:22-660`)"""
 
     def __init__(self, mesh, degree, dt, flux="upwind", use_projection_method=True, n_richardson=2, label=None,
-                 callbacks=None, device=0, krylov_rtol=1e-12, tentative_rtol=None, progress=False):
-        super().__init__(mesh, degree, dt, label, device=device)
+                 callbacks=None, device=0, krylov_rtol=1e-12, tentative_rtol=None, progress=False,
+                 preconditioner="gtmg"):
+        super().__init__(mesh, degree, dt, label, device=device, preconditioner=preconditioner)
         self.flux = flux
         self.use_projection_method = use_projection_method
         assert self.flux in ["upwind", "centered"]

@@ -30,8 +30,8 @@ __all__ = ["IncompressibleEulerHDGImplicit"]
 
 class IncompressibleEulerHDGImplicit(IncompressibleEuler):
     def __init__(self, mesh, degree, dt, flux="upwind", use_projection_method=True, callbacks=None, device=0,
-                 krylov_rtol=1e-12, progress=False):
-        super().__init__(mesh, degree, dt, label="HDG Implicit", device=device)
+                 krylov_rtol=1e-12, progress=False, preconditioner="gtmg"):
+        super().__init__(mesh, degree, dt, label="HDG Implicit", device=device, preconditioner=preconditioner)
         self.flux = flux
         assert self.flux in ["upwind", "centered"]
         self.use_projection_method = use_projection_method

@@ -126,3 +126,47 @@ def test_poisson_properties_large():
     eng.trace_spmv_dev(ones, Px)
     eng.synchronize()
     assert float(Px.abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+@pytest.mark.parametrize("mesh_fn", [lambda: UnitSquareMesh(16, perturb=0.15), lambda: PeriodicSquareMesh(12, L=2 * np.pi),
+                                      lambda: UnitDiskMesh(3)])
+def test_multigrid_pcg_matches_oracle(k, mesh_fn):
+    """GTMG-preconditioned CG reaches the same solution in O(1) iterations"""
+    require_degree(k)
+    m = mesh_fn()
+    o = HDGOracle(m, k)
+    eng = HDGEngine(m, k)
+    eng.setup_poisson()
+    rng = np.random.default_rng(12)
+    Ru = rng.standard_normal((m.nc, 2, o.nQ1))
+    Rp = rng.standard_normal((m.nc, o.np_))
+    Rl = rng.standard_normal((m.nf, k + 1))
+    _, _, _, its_jac = eng.poisson_apply_host(Ru, Rp, Rl, rtol=1e-13, maxit=20000)
+    H = eng.mg_setup()
+    nl, lmax = eng.mg_info()
+    assert nl == H.nlevels and 1.0 < lmax < 3.0
+    Q, p, l, its = eng.poisson_apply_host(Ru, Rp, Rl, rtol=1e-13, maxit=200)
+    Qo, po, lo = o.solve_condensed(Ru, Rp, Rl)
+    assert its < 40 and its < its_jac
+    assert rel(Q, Qo) < RTOL and rel(p, po) < RTOL and rel(l, lo) < RTOL
+
+
+def test_p1_stiffness_is_galerkin_coarse_operator():
+    """T^T (-S) T equals the P1 stiffness matrix (so rediscretisation == Galerkin, hdg_imex.py:101-106)"""
+    import scipy.sparse.linalg as spla
+
+    from incompressibleeulerhdg_b200 import multigrid
+
+    k = 2
+    m = UnitSquareMesh(6, perturb=0.2)
+    eng = HDGEngine(m, k)
+    eng.setup_poisson()
+    val, col = eng.get_trace_matrix()
+    P = ell_to_dense(val, col, m.nf, k + 1)  # AoS numbering f*b+m
+    b = k + 1
+    perm = (np.arange(m.nf)[None, :] * b + np.arange(b)[:, None]).ravel()  # SoA index -> AoS index
+    T = multigrid.trace_transfer(m, k).toarray()
+    A = multigrid.p1_stiffness(m).toarray()
+    G = T.T @ P[np.ix_(perm, perm)] @ T
+    assert np.abs(G - A).max() < 1e-11 * np.abs(A).max()

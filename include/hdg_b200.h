@@ -149,9 +149,15 @@ int hdg_fimpl_apply_dev(hdg_handle h, const double* Qstar, const double* X, doub
                         double* Y);
 /* tentative velocity (hdg_imex.py:233-255,274-281; hdg_implicit.py:103-129), in Riesz form:
  *   (I - adt M^-1 f_impl(.;Qstar)) x = rhs     by BiCGStab, relative residual tolerance rtol.
- * zero_guess != 0 starts from x = 0, otherwise from the incoming x. */
+ * zero_guess != 0 starts from x = 0, otherwise from the incoming x.  Converged when
+ * ||rhs - A x||_2 <= rtol ||rhs||_2 (the PETSc convention of hdg_imex.py:224-228). */
 int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int upwind, const double* rhs, double* x,
                             double rtol, int maxit, int zero_guess, int* iters);
+/* Krylov strategy of hdg_tentative_solve_dev: mode 0 = plain BiCGStab, mode 1 (default) = BiCGStab on
+ * the facet-multiplier formulation of the normal-jump penalty, right-preconditioned by the
+ * advection-free operator whose facet Schur complement is inverted by `sweeps` Chebyshev /
+ * facet-block-Jacobi sweeps (mesh-independent iteration counts; see csrc/hdg_tent.cuh). */
+int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps);
 /* dual vector on the pressure space: mode 0  scale * int psi div Q dx      (hdg_implicit.py:145)
  *                                    mode 1  scale * _weak_divergence      (hdg_imex.py:353-365) */
 int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mode, double* Rp);

@@ -23,6 +23,7 @@
 #include "../../include/hdg_b200.h"
 #include "hdg_local.cuh"
 #include "hdg_flow.cuh"
+#include "hdg_tent.cuh"
 
 #define HDG_VERSION "hdg_b200 0.1 (sm_100a)"
 
@@ -70,6 +71,16 @@ struct hdg_engine {
   int *cell_nbr = nullptr, *cell_nbr_e = nullptr;            // [3][nc]
   double* bdm_fm = nullptr;                                  // [2*(K+2)][nf]
   double* bi[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // BiCGStab work: r, rhat, p, v, s, t
+  size_t bi_len = 0;
+  // penalty-robust tentative-velocity solver (hdg_tent.cuh)
+  int tent_mode = 1;          // 0 plain BiCGStab, 1 facet-multiplier formulation
+  int tent_sweeps = 6;        // Chebyshev sweeps on the facet Schur complement
+  double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
+  double *tent_c = nullptr;   // [6][nf]
+  int *tent_col = nullptr, *tent_bits = nullptr;  // [4][nf], [nf]
+  double *tent_cm = nullptr;  // [3*NM][nc]
+  double *tent_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // facet work [NM][nf]: t, nyx, mu, mu2, d
+  double *tent_xh = nullptr, *tent_y = nullptr;  // [2*NQ1][nc]; [n_aug]
   // work vectors
   double *gK = nullptr;                                      // [NL][nc]
   double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
@@ -750,9 +761,9 @@ __global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, const double* __restri
   }
 }
 
-// r = b - t (t = A x0, or r = b if t == nullptr); rhat = r; p = r; partial <r,r>
-__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* __restrict__ b, const double* __restrict__ t,
-                                                   double* __restrict__ r, double* __restrict__ rhat,
+// r = b - t (t = A x0, or r = b if t == nullptr; b may alias r); rhat = r; p = r; partial <r,r>
+__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* b, const double* __restrict__ t,
+                                                   double* r, double* __restrict__ rhat,
                                                    double* __restrict__ p, double* __restrict__ part) {
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -765,17 +776,21 @@ __global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* __res
   s = block_reduce(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
-__global__ void k_bi_start(BiScalars* s, const double* __restrict__ part, int n, double rtol, int maxit) {
+// part: partial sums of the initial <r,r>; part_ref (optional): partial sums of the squared norm the
+// tolerance refers to (||b||^2, the PETSc convention); convergence: <r,r> <= rtol^2 * reference
+__global__ void k_bi_start(BiScalars* s, const double* __restrict__ part, const double* __restrict__ part_ref, int n,
+                           double rtol, int maxit) {
   double rr = reduce_partials(part, n);
+  double ref = part_ref ? reduce_partials(part_ref, n) : rr;
   if (threadIdx.x == 0) {
     s->rho = rr;
-    s->rr0 = rr;
+    s->rr0 = ref;
     s->rr = rr;
     s->tol2 = rtol * rtol;
     s->iters = 0;
     s->maxit = maxit;
     s->ticket = 0;
-    s->done = (rr <= 0.0 || maxit <= 0) ? 1 : 0;
+    s->done = (rr <= rtol * rtol * ref || maxit <= 0) ? 1 : 0;
   }
 }
 // s = r - alpha v, alpha = rho / <rhat, v>
@@ -859,49 +874,41 @@ __global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restri
 
 template <int K>
 static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const double* X, double c0, double c1,
-                         double* Y) {
+                         double* Y, const double* Z = nullptr, double alpha = -1.0) {
   int grid = cdiv(h->nc, 128);
+  if (alpha < 0.0) alpha = h->alpha;
   if (upwind)
-    LAUNCH(h, (k_fimpl<K, true>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, h->alpha, Qstar, X, c0, c1,
+    LAUNCH(h, (k_fimpl<K, true>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, alpha, Qstar, X, Z, c0, c1,
            Y);
   else
-    LAUNCH(h, (k_fimpl<K, false>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, h->alpha, Qstar, X, c0,
+    LAUNCH(h, (k_fimpl<K, false>), grid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, alpha, Qstar, X, Z, c0,
            c1, Y);
 }
 
-template <int K>
-static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
-                        double rtol, int maxit, bool zero_guess, int* iters) {
+// generic driver: op(in, out) applies the (preconditioned) operator to a vector of length n.
+// On entry r0 (the initial residual) sits in bi[0]; the solution update is accumulated in y.
+template <class Op>
+static int bicgstab_loop(hdg_engine* h, size_t n, Op op, double* y, const double* part_ref, double rtol, int maxit,
+                         int* iters) {
   const int G = h->grid;
-  const size_t n = 2 * (size_t)Dims<K>::NQ1 * h->nc;
-  for (int i = 0; i < 6; ++i)
-    if (!h->bi[i]) CUDA_TRY(h, dmalloc(&h->bi[i], n));
   double *r = h->bi[0], *rhat = h->bi[1], *p = h->bi[2], *v = h->bi[3], *sv = h->bi[4], *t = h->bi[5];
   double* P = h->partial;
   double *p_rv = P, *p_ts = P + G, *p_tt = P + 2 * (size_t)G, *p_rho = P + 3 * (size_t)G, *p_rr = P + 4 * (size_t)G;
-  if (zero_guess) {
-    CUDA_TRY(h, cudaMemsetAsync(x, 0, n * sizeof(double), h->stream));
-    LAUNCH(h, k_bi_init, G, BLOCK, n, b, (const double*)nullptr, r, rhat, p, p_rr);
-  } else {
-    launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, t);
-    LAUNCH(h, k_bi_init, G, BLOCK, n, b, (const double*)t, r, rhat, p, p_rr);
-  }
-  LAUNCH(h, k_bi_start, 1, BLOCK, h->bscal, p_rr, G, rtol, maxit);
+  // rhat = p = r, partial <r,r>
+  LAUNCH(h, k_bi_init, G, BLOCK, n, (const double*)r, (const double*)nullptr, r, rhat, p, p_rr);
+  LAUNCH(h, k_bi_start, 1, BLOCK, h->bscal, p_rr, part_ref, G, rtol, maxit);
   const int chunk = 4;
   int launched = 0;
   bool finished = false;
   while (!finished) {
     int m = std::min(chunk, std::max(1, maxit - launched));
     for (int i = 0; i < m; ++i) {
-      {
-        ScopedTimer tf(h, T_FIMPL);
-        launch_fimpl<K>(h, upwind, Qstar, p, 1.0, -adt, v);
-      }
+      op(p, v);
       LAUNCH(h, k_dot2, G, BLOCK, n, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
       LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
-      launch_fimpl<K>(h, upwind, Qstar, sv, 1.0, -adt, t);
+      op(sv, t);
       LAUNCH(h, k_dot2, G, BLOCK, n, t, sv, (const double*)t, p_ts, p_tt);
-      LAUNCH(h, k_bi_xr, G, BLOCK, n, p, sv, t, rhat, x, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+      LAUNCH(h, k_bi_xr, G, BLOCK, n, p, sv, t, rhat, y, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
       LAUNCH(h, k_bi_p, G, BLOCK, n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
     }
     launched += m;
@@ -911,6 +918,177 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
   }
   if (iters) *iters = h->bscal_host->iters;
   return h->bscal_host->done == 1 ? HDG_OK : HDG_ENOCONV;
+}
+
+static int bicgstab_alloc(hdg_engine* h, size_t n) {
+  if (h->bi_len >= n) return HDG_OK;
+  for (int i = 0; i < 6; ++i) {
+    if (h->bi[i]) cudaFree(h->bi[i]);
+    h->bi[i] = nullptr;
+  }
+  h->bi_len = 0;
+  for (int i = 0; i < 6; ++i) CUDA_TRY(h, dmalloc(&h->bi[i], n));
+  h->bi_len = n;
+  return HDG_OK;
+}
+
+// plain BiCGStab on the primal system (no preconditioner)
+template <int K>
+static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
+                        double rtol, int maxit, bool zero_guess, int* iters) {
+  const int G = h->grid;
+  const size_t n = 2 * (size_t)Dims<K>::NQ1 * h->nc;
+  int rc = bicgstab_alloc(h, n);
+  if (rc) return rc;
+  double* part_bb = h->partial + 5 * (size_t)G;
+  LAUNCH(h, k_dot2, G, BLOCK, n, b, b, (const double*)nullptr, part_bb, (double*)nullptr);
+  if (zero_guess) {
+    CUDA_TRY(h, cudaMemsetAsync(x, 0, n * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->bi[0], b, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
+    const double cf[2] = {1.0, -1.0};
+    LinComb lc;
+    lc.n = 2;
+    lc.c[0] = cf[0];
+    lc.c[1] = cf[1];
+    lc.x[0] = b;
+    lc.x[1] = h->bi[5];
+    LAUNCH(h, k_lincomb, G, BLOCK, n, lc, h->bi[0]);
+  }
+  auto op = [&](const double* in, double* out) {
+    ScopedTimer tf(h, T_FIMPL);
+    launch_fimpl<K>(h, upwind, Qstar, in, 1.0, -adt, out);
+  };
+  return bicgstab_loop(h, n, op, x, part_bb, rtol, maxit, iters);
+}
+
+// ---- facet-multiplier formulation (hdg_tent.cuh) --------------------------------------------------
+template <int K>
+static int tent_setup(hdg_engine* h) {
+  constexpr int NM = TentDims<K>::NM;
+  const size_t nf = h->nf, nc = h->nc;
+  if (!h->tent_c) {
+    CUDA_TRY(h, dmalloc(&h->tent_c, 6 * nf));
+    CUDA_TRY(h, dmalloc(&h->tent_col, 4 * nf));
+    CUDA_TRY(h, dmalloc(&h->tent_bits, nf));
+    CUDA_TRY(h, dmalloc(&h->tent_cm, 3 * (size_t)NM * nc));
+    for (int i = 0; i < 5; ++i) CUDA_TRY(h, dmalloc(&h->tent_f[i], (size_t)NM * nf));
+    CUDA_TRY(h, dmalloc(&h->tent_xh, 2 * (size_t)Dims<K>::NQ1 * nc));
+    CUDA_TRY(h, dmalloc(&h->tent_y, 2 * (size_t)Dims<K>::NQ1 * nc + (size_t)NM * nf));
+    LAUNCH(h, k_tent_setup, h->grid, BLOCK, h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local,
+           h->nc, h->nf, h->tent_c, h->tent_col, h->tent_bits);
+  }
+  if (h->tent_lmax <= 0.0) {
+    // lambda_max(D^-1 G) by power iteration in the strong-penalty limit (an upper bound for every a)
+    const int G = h->grid;
+    const size_t n = (size_t)NM * nf;
+    std::vector<double> v0(n);
+    uint64_t st = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < n; ++i) {
+      st ^= st << 13;
+      st ^= st >> 7;
+      st ^= st << 17;
+      v0[i] = (double)(st >> 11) / 9007199254740992.0 - 0.5;
+    }
+    double *x = h->tent_f[2], *x2 = h->tent_f[3];
+    CUDA_TRY(h, cudaMemcpyAsync(x, v0.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> part(G);
+    double lam = 2.0;
+    for (int it = 0; it < 30; ++it) {
+      LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+             0.0, (const double*)nullptr, (const double*)nullptr, (const double*)x, (double*)nullptr, x2, 0.0, 0.0, 0,
+             2);
+      LAUNCH(h, k_dot2, G, BLOCK, n, x2, x2, (const double*)nullptr, h->partial, (double*)nullptr);
+      CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      double s = 0.0;
+      for (double p : part) s += p;
+      lam = std::sqrt(s);
+      LAUNCH(h, k_scale, G, 256, n, 1.0 / lam, x2);
+      std::swap(x, x2);
+    }
+    h->tent_f[2] = x;
+    h->tent_f[3] = x2;
+    h->tent_lmax = lam;
+  }
+  return HDG_OK;
+}
+
+// mu = Cheb_d(X)^-1 t ; returns the buffer that holds mu
+template <int K>
+static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* t) {
+  std::vector<ChebCoef> cc;
+  cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
+  double *x = h->tent_f[2], *x2 = h->tent_f[3];
+  for (int j = 0; j < h->tent_sweeps; ++j) {
+    LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+           inv_aalpha, t, (const double*)nullptr, (const double*)x, h->tent_f[4], x2, cc[j].cd, cc[j].cr,
+           j == 0 ? 1 : 0, 0);
+    std::swap(x, x2);
+  }
+  h->tent_f[2] = x;
+  h->tent_f[3] = x2;
+  return x;
+}
+
+template <int K>
+static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
+                             double rtol, int maxit, bool zero_guess, int* iters) {
+  constexpr int NM = TentDims<K>::NM;
+  const int G = h->grid;
+  const size_t nx = 2 * (size_t)Dims<K>::NQ1 * h->nc, nmu = (size_t)NM * h->nf, n = nx + nmu;
+  int rc = tent_setup<K>(h);
+  if (rc) return rc;
+  rc = bicgstab_alloc(h, n);
+  if (rc) return rc;
+  const double inv_aalpha = 1.0 / (adt * h->alpha);
+  const int cgrid = cdiv(h->nc, 128), fgrid = cdiv(h->nf, 256);
+  double* part_bb = h->partial + 5 * (size_t)G;
+  LAUNCH(h, k_dot2, G, BLOCK, nx, b, b, (const double*)nullptr, part_bb, (double*)nullptr);
+  // initial residual of the augmented system with mu0 = a alpha N x0:  (b - A x0, 0)
+  double* r = h->bi[0];
+  CUDA_TRY(h, cudaMemsetAsync(r + nx, 0, nmu * sizeof(double), h->stream));
+  if (zero_guess) {
+    CUDA_TRY(h, cudaMemsetAsync(x, 0, nx * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(r, b, nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
+    LinComb lc;
+    lc.n = 2;
+    lc.c[0] = 1.0;
+    lc.c[1] = -1.0;
+    lc.x[0] = b;
+    lc.x[1] = h->bi[5];
+    LAUNCH(h, k_lincomb, G, BLOCK, nx, lc, r);
+  }
+  // out = A_aug Phat^-1 in
+  auto precond_x = [&](const double* in, bool with_mu) -> double* {
+    LAUNCH(h, k_tent_moments<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->nc, in, h->tent_cm);
+    LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf,
+           with_mu ? in + nx : (const double*)nullptr, h->tent_f[0], h->tent_f[1]);
+    return tent_schur_solve<K>(h, inv_aalpha, h->tent_f[0]);
+  };
+  auto op = [&](const double* in, double* out) {
+    double* mu = precond_x(in, true);
+    LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, in, mu, h->tent_xh, 0);
+    {
+      ScopedTimer tf(h, T_FIMPL);
+      launch_fimpl<K>(h, upwind, Qstar, h->tent_xh, 1.0, -adt, out, in, 0.0);  // out_x = in_x - a F0(xhat)
+    }
+    // out_mu = N in_x - X mu
+    LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+           inv_aalpha, (const double*)h->tent_f[1], (const double*)nullptr, (const double*)mu, (double*)nullptr,
+           out + nx, 0.0, 0.0, 0, 1);
+  };
+  double* y = h->tent_y;
+  CUDA_TRY(h, cudaMemsetAsync(y, 0, n * sizeof(double), h->stream));
+  int brc = bicgstab_loop(h, n, op, y, part_bb, rtol, maxit, iters);
+  if (brc == HDG_ECUDA) return brc;
+  // x += [Phat^-1 y]_x
+  double* mu = precond_x(y, true);
+  LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, y, mu, x, 1);
+  return brc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1106,7 +1284,9 @@ int hdg_destroy(hdg_handle h) {
   void* ptrs[] = {h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local, h->SK, h->ell_val,
                   h->dinv, h->ell_col, h->gK, h->cg_x, h->cg_r, h->cg_z, h->cg_p, h->cg_q, h->partial, h->scal,
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
-                  h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal};
+                  h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
+                  h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
+                  h->tent_xh, h->tent_y};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->scal_host) cudaFreeHost(h->scal_host);
@@ -1534,6 +1714,13 @@ int hdg_set_penalty(hdg_handle h, double alpha) {
   return HDG_OK;
 }
 
+int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps) {
+  if (!h || mode < 0 || mode > 1 || sweeps < 1 || sweeps > 64) return HDG_EINVAL;
+  h->tent_mode = mode;
+  h->tent_sweeps = sweeps;
+  return HDG_OK;
+}
+
 int hdg_project_bdm_dev(hdg_handle h, const double* Q, double* Qstar) {
   if (!h || !Q || !Qstar) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1566,7 +1753,11 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
   int rc;
   {
     ScopedTimer t(h, T_TENT);
-    DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
+    if (h->tent_mode == 1 && h->alpha > 0.0 && adt > 0.0) {
+      DISPATCH_K(h, rc = run_tentative_aug<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
+    } else {
+      DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
+    }
   }
   if (rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "tentative-velocity BiCGStab did not converge within maxit");
   return rc;

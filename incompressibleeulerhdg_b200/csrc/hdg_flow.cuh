@@ -170,7 +170,7 @@ __device__ __forceinline__ void nbr_trace(const double* __restrict__ X, int nc, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// y = c0 * x + c1 * M^-1 f_impl(., x; Q*)     (hdg_imex.py:313-331)
+// y = c0 * z + c1 * M^-1 f_impl(., x; Q*)     (hdg_imex.py:313-331), z = x unless Z is given
 // Per cell K (outward normal n, s = Q*.n which is single valued for BDM Q*):
 //   - int_K w_c (Q*.grad) x_c
 //   + int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr).w - alpha/h_F ((x_K - x_nbr).n)(w.n)
@@ -229,7 +229,8 @@ template <int K, bool UPWIND>
 __global__ void __launch_bounds__(128) k_fimpl(const double* __restrict__ xy, const int* __restrict__ nbr,
                                                const int* __restrict__ nbr_e, int nc, double alpha,
                                                const double* __restrict__ Qstar, const double* __restrict__ X,
-                                               double c0, double c1, double* __restrict__ Y) {
+                                               const double* __restrict__ Z, double c0, double c1,
+                                               double* __restrict__ Y) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
@@ -280,8 +281,10 @@ __global__ void __launch_bounds__(128) k_fimpl(const double* __restrict__ xy, co
     HDG_UNROLL
     for (int c = 0; c < 2; ++c)
       HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i)
-        Y[(size_t)(c * NQ1 + i) * nc + cell] = c0 * x[c][i] + c1 * acc[c][i];
+      for (int i = 0; i < NQ1; ++i) {
+        size_t idx = (size_t)(c * NQ1 + i) * nc + cell;
+        Y[idx] = c0 * (Z ? Z[idx] : x[c][i]) + c1 * acc[c][i];
+      }
   }
 }
 

@@ -1,0 +1,277 @@
+// Penalty-robust solver for the tentative-velocity system
+//     (I - a M^-1 f_impl(.;Q*)) x = b ,   a = a_ii dt        (hdg_imex.py:233-255, hdg_implicit.py:103-129)
+// which the reference hands to GMRES+ILU / a direct LU.
+//
+// f_impl contains the normal-jump penalty  -alpha/h_F int_F [[x.n]][[w.n]]  (hdg_imex.py:319-323).
+// With L2-orthonormal Legendre moments on every facet,  N x |_F,j = int_0^1 [[x.n]] l_j ds
+// (j <= k+1, exact for the degree-(k+1) normal trace), the penalty is exactly  alpha N^T N  because
+// h_F = |F| (common.py:36-57).  Its weight relative to the mass matrix grows like a/h^2, which is
+// what makes an unpreconditioned Krylov method stall on fine meshes.  The stiff term is removed by
+// introducing the facet multiplier  mu = a alpha N x:
+//
+//     [ I - a F0     M^-1 N^T      ] [ x  ]   [ b ]        F0 = M^-1 f_impl with alpha = 0
+//     [ N           -1/(a alpha) I ] [ mu ] = [ 0 ]
+//
+// and right-preconditioning BiCGStab with the same matrix without the advection part, whose Schur
+// complement  X = 1/(a alpha) I + N M^-1 N^T  is a facet "mass" matrix: symmetric positive
+// definite, 5 blocks of (k+2)^2 per row, spectrum of the facet-block-Jacobi preconditioned X inside
+// [0.25, 1.8] independently of h, k, a (checked in tests).  X^-1 is replaced by a fixed number of
+// Chebyshev/facet-block-Jacobi sweeps, applied matrix-free: every block is a compile-time reference
+// table GG scaled by (n_e . n_e') / detJ.  In this formulation an inexact X only perturbs the
+// preconditioner by O(eps); the stiffness never multiplies the error.
+#pragma once
+#include "hdg_local.cuh"
+
+template <int K>
+struct TentDims {
+  static constexpr int NM = K + 2;                 // normal-moment modes per facet
+  static constexpr int NMH = NM * (NM + 1) / 2;
+};
+
+// per-facet geometric coefficients of X (setup, geometry only):
+//   tc[(3 s + j) nf + f] = (n_e . n_{(e+j)%3}) / detJ  of the cell on side s (0 on a missing side)
+//   tcol[(2 s + j - 1) nf + f] = facet (e+j)%3 of that cell, j = 1, 2        (f itself if missing)
+//   tbits[f] bit (3 s + j) = orientation flip of facet (e+j)%3 in that cell
+__global__ void k_tent_setup(const double* __restrict__ xy, const int* __restrict__ cell_facet,
+                             const int* __restrict__ cell_flip, const int* __restrict__ facet_cell,
+                             const int* __restrict__ facet_local, int nc, int nf, double* __restrict__ tc,
+                             int* __restrict__ tcol, int* __restrict__ tbits) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    int bits = 0;
+    for (int s = 0; s < 2; ++s) {
+      int cell = facet_cell[(size_t)s * nf + f];
+      int e = facet_local[(size_t)s * nf + f];
+      if (cell < 0) {
+        for (int j = 0; j < 3; ++j) tc[(size_t)(3 * s + j) * nf + f] = 0.0;
+        for (int j = 1; j < 3; ++j) tcol[(size_t)(2 * s + j - 1) * nf + f] = f;
+        continue;
+      }
+      Geo g = make_geo(xy, nc, cell);
+      for (int j = 0; j < 3; ++j) {
+        int e2 = (e + j) % 3;
+        tc[(size_t)(3 * s + j) * nf + f] = (g.n[e][0] * g.n[e2][0] + g.n[e][1] * g.n[e2][1]) * g.idetJ;
+        if (cell_flip[(size_t)e2 * nc + cell]) bits |= 1 << (3 * s + j);
+        if (j > 0) tcol[(size_t)(2 * s + j - 1) * nf + f] = cell_facet[(size_t)e2 * nc + cell];
+      }
+    }
+    tbits[f] = bits;
+  }
+}
+
+// cm[(e NM + j) nc + cell] = sigma int_0^1 (y . n_e) l_j ds  in the global facet orientation
+template <int K>
+__global__ void __launch_bounds__(128) k_tent_moments(const double* __restrict__ xy, const int* __restrict__ flip,
+                                                      int nc, const double* __restrict__ Y,
+                                                      double* __restrict__ cm) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NM = TentDims<K>::NM;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double y[2][NQ1];
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) y[c][i] = Y[(size_t)(c * NQ1 + i) * nc + cell];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int fl = flip[(size_t)e * nc + cell];
+      double m[NM];
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) m[j] = 0.0;
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) {
+        double yn = g.n[e][0] * y[0][i] + g.n[e][1] * y[1][i];
+        HDG_UNROLL
+        for (int j = 0; j < NM; ++j)
+          if (T::BF(e, j, i) != 0.0) m[j] = fma(T::BF(e, j, i), yn, m[j]);
+      }
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) cm[(size_t)(e * NM + j) * nc + cell] = flip_sign(fl, j) * m[j];
+    }
+  }
+}
+
+// t = N y_x - y_mu  (y_mu may be null); optionally also sum = N y_x
+template <int K>
+__global__ void __launch_bounds__(256) k_tent_trhs(const double* __restrict__ cm, const int* __restrict__ facet_cell,
+                                                   const int* __restrict__ facet_local, int nc, int nf,
+                                                   const double* __restrict__ ymu, double* __restrict__ t,
+                                                   double* __restrict__ nyx) {
+  constexpr int NM = TentDims<K>::NM;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    int c0 = facet_cell[f], c1 = facet_cell[(size_t)nf + f];
+    int e0 = facet_local[f], e1 = facet_local[(size_t)nf + f];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      double v = cm[(size_t)(e0 * NM + j) * nc + c0];
+      if (c1 >= 0) v += cm[(size_t)(e1 * NM + j) * nc + c1];
+      if (nyx) nyx[(size_t)j * nf + f] = v;
+      if (ymu) v -= ymu[(size_t)j * nf + f];
+      t[(size_t)j * nf + f] = v;
+    }
+  }
+}
+
+// contribution of the cell on one side of facet f to (G mu)_f and to the diagonal block
+template <int K, int E>
+__device__ __forceinline__ void tent_side(int nf, int f, int s, int bits, const double* __restrict__ tc,
+                                          const int* __restrict__ tcol, const double* __restrict__ mu,
+                                          const double (&own)[TentDims<K>::NM], bool offdiag,
+                                          double (&acc)[TentDims<K>::NM], double (&D)[TentDims<K>::NMH]) {
+  using T = RefTables<K>;
+  constexpr int NM = TentDims<K>::NM;
+  const double c0 = tc[(size_t)(3 * s) * nf + f];
+  const int fl0 = (bits >> (3 * s)) & 1;
+  // diagonal block (also part of G mu)
+  HDG_UNROLL
+  for (int j = 0; j < NM; ++j) {
+    HDG_UNROLL
+    for (int l = 0; l <= j; ++l) {
+      if (T::GG(E, E, j, l) != 0.0) {
+        double v = c0 * T::GG(E, E, j, l) * flip_sign(fl0, j) * flip_sign(fl0, l);
+        D[tri(j, l)] += v;
+      }
+    }
+  }
+  if (!offdiag) return;
+  HDG_UNROLL
+  for (int jj = 1; jj < 3; ++jj) {
+    const int E2 = (E + jj) % 3;
+    const double c = tc[(size_t)(3 * s + jj) * nf + f];
+    const int fl = (bits >> (3 * s + jj)) & 1;
+    const int col = tcol[(size_t)(2 * s + jj - 1) * nf + f];
+    double v[NM];
+    HDG_UNROLL
+    for (int l = 0; l < NM; ++l) v[l] = flip_sign(fl, l) * mu[(size_t)l * nf + col];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      double sum = 0.0;
+      HDG_UNROLL
+      for (int l = 0; l < NM; ++l)
+        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), v[l], sum);
+      acc[j] = fma(c * flip_sign(fl0, j), sum, acc[j]);
+    }
+  }
+}
+
+// One sweep on X = inv_aalpha I + G, matrix-free.
+//   mode 0: Chebyshev / facet-block-Jacobi:  r = rhs - X x (x == 0 if zero), d = cd d + cr D^-1 r,
+//           xout = x + d                                                  (xout must not alias x)
+//   mode 1: residual  xout = rhs + rhs2 - X x
+//   mode 2: xout = D^-1 X x   (power iteration for the spectral bound)
+template <int K>
+__global__ void __launch_bounds__(128) k_tent_sweep(int nf, const int* __restrict__ facet_local,
+                                                    const double* __restrict__ tc, const int* __restrict__ tcol,
+                                                    const int* __restrict__ tbits, double inv_aalpha,
+                                                    const double* __restrict__ rhs, const double* __restrict__ rhs2,
+                                                    const double* __restrict__ x, double* __restrict__ d,
+                                                    double* __restrict__ xout, double cd, double cr, int zero,
+                                                    int mode) {
+  constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    const int bits = tbits[f];
+    double own[NM], acc[NM], D[NMH];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      own[j] = zero ? 0.0 : x[(size_t)j * nf + f];
+      acc[j] = 0.0;
+    }
+    HDG_UNROLL
+    for (int i = 0; i < NMH; ++i) D[i] = 0.0;
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) D[tri(j, j)] = inv_aalpha;
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      int e = facet_local[(size_t)s * nf + f];
+      if (e < 0) continue;
+      switch (e) {
+        case 0: tent_side<K, 0>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
+        case 1: tent_side<K, 1>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
+        default: tent_side<K, 2>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
+      }
+    }
+    // X x = D own + off-diagonal part
+    double r[NM];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      double v = acc[j];
+      if (!zero) {
+        HDG_UNROLL
+        for (int l = 0; l < NM; ++l) v = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], v);
+      }
+      r[j] = v;
+    }
+    if (mode != 2) {
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) {
+        double b = rhs[(size_t)j * nf + f];
+        if (mode == 1 && rhs2) b += rhs2[(size_t)j * nf + f];
+        r[j] = b - r[j];
+      }
+    }
+    if (mode == 1) {
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = r[j];
+      continue;
+    }
+    cholesky<NM>(D);
+    chol_solve<NM>(D, r);
+    if (mode == 2) {
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = r[j];
+      continue;
+    }
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      double di = cr * r[j];
+      if (cd != 0.0) di = fma(cd, d[(size_t)j * nf + f], di);
+      d[(size_t)j * nf + f] = di;
+      xout[(size_t)j * nf + f] = own[j] + di;
+    }
+  }
+}
+
+// xh = y - M^-1 N^T mu   (mode 0)   or   xh += y - M^-1 N^T mu   (mode 1, final recovery)
+template <int K>
+__global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy, const int* __restrict__ flip,
+                                                   const int* __restrict__ cell_facet, int nc, int nf,
+                                                   const double* __restrict__ Y, const double* __restrict__ mu,
+                                                   double* __restrict__ Xh, int mode) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NM = TentDims<K>::NM;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double a0[NQ1], a1[NQ1];
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) a0[i] = a1[i] = 0.0;
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int f = cell_facet[(size_t)e * nc + cell];
+      int fl = flip[(size_t)e * nc + cell];
+      double m[NM];
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) m[j] = flip_sign(fl, j) * mu[(size_t)j * nf + f];
+      double cx = g.idetJ * g.n[e][0], cy = g.idetJ * g.n[e][1];
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) {
+        double v = 0.0;
+        HDG_UNROLL
+        for (int j = 0; j < NM; ++j)
+          if (T::BF(e, j, i) != 0.0) v = fma(T::BF(e, j, i), m[j], v);
+        a0[i] = fma(cx, v, a0[i]);
+        a1[i] = fma(cy, v, a1[i]);
+      }
+    }
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) {
+      size_t i0 = (size_t)i * nc + cell, i1 = (size_t)(NQ1 + i) * nc + cell;
+      double v0 = Y[i0] - a0[i], v1 = Y[i1] - a1[i];
+      if (mode == 1) {
+        v0 += Xh[i0];
+        v1 += Xh[i1];
+      }
+      Xh[i0] = v0;
+      Xh[i1] = v1;
+    }
+  }
+}

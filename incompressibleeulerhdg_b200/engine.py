@@ -56,6 +56,7 @@ SIGNATURES = {
     "hdg_forward_eliminate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hdg_set_penalty": (C.c_int, [_vp, C.c_double]),
+    "hdg_set_tentative_solver": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hdg_project_bdm_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_fimpl_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
     "hdg_tentative_solve_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_int, _vp, _vp, C.c_double, C.c_int, C.c_int,
@@ -289,6 +290,10 @@ class HDGEngine:
     # -- velocity side -----------------------------------------------------------------------------------
     def set_penalty(self, alpha: float):
         self._check(self.lib.hdg_set_penalty(self._h, float(alpha)))
+
+    def set_tentative_solver(self, mode: int = 1, sweeps: int = 6):
+        """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps"""
+        self._check(self.lib.hdg_set_tentative_solver(self._h, int(mode), int(sweeps)))
 
     def project_bdm_dev(self, Q, Qstar):
         self._check(self.lib.hdg_project_bdm_dev(self._h, _dev(Q), _dev(Qstar)))

@@ -88,10 +88,13 @@ def test_reconstruct_trace_and_shift(k, mesh_fn):
     assert rel(eng.download(1, dp), ps) < 1e-11 and rel(eng.download(2, dl), ls) < 1e-11
 
 
-@pytest.mark.parametrize("mesh_fn", MESHES[:2])
-def test_tentative_solve(k, mesh_fn):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mesh_fn", MESHES)
+def test_tentative_solve(k, mesh_fn, mode):
+    """mode 0: plain BiCGStab; mode 1: facet-multiplier formulation (csrc/hdg_tent.cuh)"""
     m = mesh_fn()
     o, eng = HDGOracle(m, k), HDGEngine(m, k)
+    eng.set_tentative_solver(mode)
     rng = np.random.default_rng(5)
     # a rough random Q* with adt * |div Q*| >> 1 makes I - adt M^-1 F indefinite (cond ~ 1e4, no
     # Krylov method converges); keep the advecting field in the regime of a resolved flow
@@ -103,9 +106,44 @@ def test_tentative_solve(k, mesh_fn):
     A = (Mdiag - adt * o.f_impl_matrix(Qs)).tocsc()
     ref = spla.splu(A).solve((Mdiag @ b.ravel())).reshape(b.shape)
     dx = eng.empty(0)
-    its = eng.tentative_solve_dev(eng.upload(0, Qs), adt, eng.upload(0, b), dx, rtol=1e-13, maxit=500)
+    its = eng.tentative_solve_dev(eng.upload(0, Qs), adt, eng.upload(0, b), dx, rtol=1e-13, maxit=800)
     assert its > 0
     assert rel(eng.download(0, dx), ref) < 1e-10
+    # warm start from a perturbed solution converges to the same answer in fewer iterations
+    dx2 = eng.upload(0, ref + 1e-4 * rng.standard_normal(ref.shape))
+    its2 = eng.tentative_solve_dev(eng.upload(0, Qs), adt, eng.upload(0, b), dx2, rtol=1e-13, maxit=800,
+                                   zero_guess=False)
+    assert its2 <= its
+    assert rel(eng.download(0, dx2), ref) < 1e-10
+
+
+def test_tentative_solve_is_mesh_robust():
+    """the stiff normal-jump penalty (weight ~ dt/h^2) must not drive the iteration count: the
+    facet-multiplier formulation needs O(50) iterations where plain BiCGStab needs many hundreds"""
+    k = 2
+    counts = {}
+    for nx in (16, 48):
+        m = UnitSquareMesh(nx, perturb=0.1)
+        eng = HDGEngine(m, k)
+        o = HDGOracle(m, k)
+        S, C, pi = np.sin, np.cos, np.pi
+        Q = o.interpolate_cell(lambda x, y: (-C((x - 0.5) * pi) * S((y - 0.5) * pi), S((x - 0.5) * pi) * C((y - 0.5) * pi)),
+                               "Q")
+        dQ = eng.upload(0, Q)
+        dQs = eng.empty(0)
+        eng.project_bdm_dev(dQ, dQs)
+        dt = 0.32 / nx
+        for mode in (1, 0):
+            eng.set_tentative_solver(mode)
+            dx = eng.empty(0)
+            its = eng.tentative_solve_dev(dQs, dt, dQ, dx, rtol=1e-11, maxit=5000, check=False)
+            counts[(nx, mode)] = its
+            if mode == 1:
+                x1 = eng.download(0, dx)
+            else:
+                assert rel(eng.download(0, dx), x1) < 1e-8
+    assert counts[(16, 1)] < 90 and counts[(48, 1)] < 90, counts
+    assert counts[(48, 1)] < counts[(48, 0)] // 3, counts
 
 
 def test_lincomb_and_mass():

@@ -17,6 +17,8 @@ reference triangle with the orthonormal Dubiner / Legendre bases of ``refelem.py
   TT[e][a][b]     = F_e^T F_e                                    (tau-stabilisation on facet e)
   LL[e][d][m][a]  = E_e D_d^T                                    (E M^-1 B^T building blocks)
   NN[e][f][m][n]  = E_e E_f^T                                    (E M^-1 E^T building blocks)
+  BF[e][j][i]     = int_0^1 phi_i(x_e(s)) l_j(s) ds, j <= k+1    (facet normal-moment functionals)
+  GG[e][f][j][l]  = BF_e BF_f^T                                  (N M^-1 N^T building blocks)
 
 plus tabulations at quadrature points for the advection operator f_impl (`hdg_imex.py:313-331`)
 and the BDM projection (`common.py:91-108`):
@@ -123,6 +125,9 @@ def tables(k):
     leg2 = R.legendre01(k + 1, s2)
     out["BF"] = np.array(
         [np.einsum("q,jq,iq->ji", w2, leg2, R.dubiner(k + 1, R.facet_points(e, s2).astype(LD))) for e in range(3)])
+    # Gram blocks of the facet normal-moment functionals (penalty Schur complement of the tentative
+    # velocity solver): GG[e][f][j][l] = sum_i BF[e][j][i] BF[f][l][i]
+    out["GG"] = np.array([[out["BF"][e] @ out["BF"][f].T for f in range(3)] for e in range(3)])
     # BDM interior functionals: BI[w][d][i] = int_T^ ned_w[d] phi_i
     xb, wb = R.triangle_quadrature(2 * k + 3, LD)
     ned = nedelec_ref(k, xb)

@@ -1,0 +1,89 @@
+"""Golden vectors (tests/golden/golden_v1.npz, made by tests/golden/make_golden.py from the oracle).
+
+CPU part: the oracle still reproduces them (regression pin; PARITY UNPINNED against the reference
+itself).  GPU part: the CUDA engine, called through the C-ABI, reproduces them to
+the 1e-10 relative tolerance BASELINE.json's north_star states.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import require_degree
+from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+RTOL = 1e-10
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---- CPU: oracle vs golden ------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2])
+def test_oracle_poisson_golden(k):
+    from oracle.hdg_oracle import HDGOracle
+
+    m = UnitSquareMesh(4, perturb=0.15)
+    g = lambda n: GOLD[f"poisson_k{k}/{n}"]
+    Q, p, l = HDGOracle(m, k).solve_condensed(g("Ru"), g("Rp"), g("Rl"))
+    assert rel(Q, g("Q")) < 1e-12 and rel(p, g("p")) < 1e-12 and rel(l, g("l")) < 1e-12
+
+
+def test_oracle_chorin_golden():
+    from oracle.timesteppers import ChorinOracle, TaylorGreenOracle
+
+    m = UnitSquareMesh(4, perturb=0.1)
+    Q, p = ChorinOracle(m, 2, 0.02).solve(TaylorGreenOracle("exponential", 0.5), 0.04)
+    assert rel(Q, GOLD["chorin_k2/Q"]) < 1e-12 and rel(p, GOLD["chorin_k2/p"]) < 1e-12
+
+
+def test_golden_config0_is_accurate():
+    """BASELINE.json configs[0]: the stored fully implicit k=1 16x16 solution stays close to the exact
+    stationary Taylor-Green velocity (`model_problems.py:56-66`) after 10 steps"""
+    assert float(GOLD["implicit_k1_nx16/err_Q"]) < 5e-3
+
+
+# ---- GPU: engine vs golden ------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 2])
+def test_engine_poisson_golden(k):
+    from incompressibleeulerhdg_b200.engine import HDGEngine
+
+    require_degree(k)
+    m = UnitSquareMesh(4, perturb=0.15)
+    g = lambda n: GOLD[f"poisson_k{k}/{n}"]
+    eng = HDGEngine(m, k)
+    eng.setup_poisson()
+    Q, p, l, its = eng.poisson_apply_host(g("Ru"), g("Rp"), g("Rl"), rtol=1e-13)
+    assert its > 0
+    assert rel(Q, g("Q")) < RTOL and rel(p, g("p")) < RTOL and rel(l, g("l")) < RTOL
+
+
+@pytest.mark.gpu
+def test_engine_chorin_golden():
+    from incompressibleeulerhdg_b200 import timesteppers as TS
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+
+    require_degree(2)
+    m = UnitSquareMesh(4, perturb=0.1)
+    ts = TS.IncompressibleEulerHDGImplicit(m, 2, 0.02, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), 0.04)
+    assert rel(Q.to_host(), GOLD["chorin_k2/Q"]) < RTOL and rel(p.to_host(), GOLD["chorin_k2/p"]) < RTOL
+
+
+@pytest.mark.gpu
+def test_engine_imex_golden():
+    from incompressibleeulerhdg_b200 import timesteppers as TS
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+
+    require_degree(1)
+    m = UnitSquareMesh(5, perturb=0.1)
+    ts = TS.IncompressibleEulerHDGIMEXSSP2_332(m, 1, 0.02, n_richardson=2, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), 0.02)
+    assert rel(Q.to_host(), GOLD["imex_ssp2_k1/Q"]) < RTOL and rel(p.to_host(), GOLD["imex_ssp2_k1/p"]) < RTOL

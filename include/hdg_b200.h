@@ -24,7 +24,7 @@
  *     thread-per-entity kernel is perfectly coalesced:
  *         Q[(c*NQ1+i)*nc + cell]   p[a*nc + cell]   lam[m*nf + facet]
  *   * One handle drives one GPU (one process per GPU); multi-GPU runs create one handle per rank
- *     on that rank's partition and join them with hdg_comm_init().
+ *     on that rank's local mesh and join them with hdg_comm_init() (see the multi-GPU section).
  *   * Calls are asynchronous on the engine stream unless stated; *_host entry points and
  *     functions returning scalars synchronise before returning.
  */
@@ -176,6 +176,38 @@ int hdg_lincomb_dev(hdg_handle h, int64_t n, double* out, int nterms, const doub
                     const double* const* ptrs);
 /* y = M x (inverse == 0) or M^-1 x for a cell field (kind 0 velocity, 1 pressure); M = detJ I */
 int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch ---------------------
+ * Replaces what Firedrake/PETSc do implicitly under mpiexec (DMPlex partition, PyOP2/PetscSF halo
+ * exchanges, MPI_Allreduce in every KSP; the reference itself only names COMM_WORLD at
+ * hdg_imex.py:110).  Each rank creates its handle on its *local mesh* (owned cells + ghost layer,
+ * owned entities numbered first; partition.py), then:
+ *   hdg_comm_unique_id   rank 0 obtains a 128-byte ncclUniqueId and broadcasts it out of band
+ *   hdg_comm_init        collective: joins the handle to the communicator
+ *   hdg_set_partition    owned counts, global facet count and global volume (reductions run over
+ *                        owned entities only and are summed over ranks)
+ *   hdg_set_halo_plan    exchange plan of one entity kind: 0 cells, 1 facets, 2+l P1 level l.
+ *                        Peer j sends the owned entities send_idx[send_ptr[j]..send_ptr[j+1]) and
+ *                        fills the ghost block [recv_off[j], recv_off[j]+recv_cnt[j]); ghost blocks
+ *                        are contiguous, ordered by peer and cover [n_owned, n_local).
+ * Afterwards every entry point refreshes the ghost entries of the inputs whose neighbours it reads
+ * (inputs are const except for their ghost entries) and all Krylov reductions are global. */
+int hdg_comm_unique_id(void* id128);
+int hdg_comm_init(hdg_handle h, int rank, int nranks, const void* id128);
+int hdg_set_partition(hdg_handle h, int nc_owned, int nf_owned, int64_t nf_global, double global_volume);
+int hdg_set_halo_plan(hdg_handle h, int kind, int n_owned, int n_local, int npeers, const int32_t* peer_rank,
+                      const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_off,
+                      const int32_t* recv_cnt);
+/* refresh the ghost entries of an SoA device field [ndof][n_local] (asynchronous on the engine stream) */
+int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field);
+/* in-place sum over ranks of n <= 16 device doubles */
+int hdg_allreduce_sum_dev(hdg_handle h, double* values, int n);
+/* multigrid levels l < repl_level are row-distributed (their CSR blocks passed to hdg_mg_setup hold
+ * the owned rows with local column numbering and need halo plan 2+l); levels >= repl_level are
+ * replicated.  gather_counts[q] / gather_gid: rows of level repl_level owned by rank q and their
+ * global ids (rank-major), used to all-gather the restricted residual at the interface. */
+int hdg_mg_set_distribution(hdg_handle h, int repl_level, const int32_t* gather_counts, const int32_t* gather_gid);
+int hdg_comm_stats(hdg_handle h, int* rank, int* nranks, int64_t* exchanges, int64_t* allreduces);
 
 /* ---- layout conversion / buffer helpers -------------------------------------------------------- */
 

@@ -48,10 +48,17 @@ struct BiScalars {
 };
 
 struct MgState;
+struct Comm;
 
 struct hdg_engine {
   MgState* mg = nullptr;
   int k = 0, nc = 0, nf = 0, device = 0;
+  // partition (multi-GPU, hdg_comm.cuh): nc/nf count the local entities (owned first, then ghosts);
+  // reductions run over the owned prefix only.  Single GPU: everything is owned, comm == nullptr.
+  int nc_own = 0, nf_own = 0;
+  double nf_glob = 0.0;  // global number of facets (constant-mode projection of the trace rhs)
+  Comm* comm = nullptr;
+  int comm_rc = 0;       // sticky NCCL failure, reported by the next C-ABI return
   double tau = 1.0;
   double volume = 0.0;
   cudaStream_t stream = nullptr;
@@ -178,6 +185,19 @@ struct ScopedTimer {
 // ------------------------------------------------------------------------------------------------
 constexpr int BLOCK = 256;
 
+// which entries of a flat SoA vector belong to owned entities.  The vector is one or two segments
+// [ndof][stride] (cells then facets for the augmented tentative system); entity = index % stride.
+struct OwnMask {
+  int all;                 // 1: single GPU, everything owned
+  unsigned long long n1;   // length of segment 1
+  int stride1, own1, stride2, own2;
+};
+__device__ __forceinline__ bool is_owned(const OwnMask& m, size_t i) {
+  if (m.all) return true;
+  if (i < m.n1) return (int)(i % (size_t)m.stride1) < m.own1;
+  return (int)((i - m.n1) % (size_t)m.stride2) < m.own2;
+}
+
 // deterministic block reduction (fixed tree); result valid in thread 0
 __device__ __forceinline__ double block_reduce(double v) {
   __shared__ double sm[BLOCK / 32];
@@ -206,7 +226,96 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
   return res;
 }
 
+#include "hdg_comm.cuh"
 #include "hdg_mg.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU helpers (no-ops on a single GPU)
+// ------------------------------------------------------------------------------------------------
+enum { PLAN_CELLS = 0, PLAN_FACETS = 1, PLAN_P1 = 2 };
+
+static void comm_fail(hdg_engine* h, const char* what, ncclResult_t r) {
+  if (!h->comm_rc) {
+    h->comm_rc = HDG_ENCCL;
+    h->err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+  }
+}
+#define NCCL_DO(h, expr)                              \
+  do {                                                \
+    ncclResult_t _r = (expr);                         \
+    if (_r != ncclSuccess) comm_fail((h), #expr, _r); \
+  } while (0)
+
+static bool comm_grow(double** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return true;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  size_t n = need + need / 2 + 1024;
+  if (cudaMalloc((void**)buf, n * sizeof(double)) != cudaSuccess) return false;
+  *cap = n;
+  return true;
+}
+
+// refresh the ghost entries of an SoA field [ndof][n_local] of entity kind `kind`
+static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfield) {
+  Comm* c = h->comm;
+  if (!c || c->nranks == 1 || !cfield) return;
+  HaloPlanDev& pl = c->plans[kind];
+  if (!pl.set) {
+    if (!h->comm_rc) {
+      h->comm_rc = HDG_ESTATE;
+      h->err = "halo exchange requested for entity kind " + std::to_string(kind) + " without a plan";
+    }
+    return;
+  }
+  double* field = const_cast<double*>(cfield);  // only the ghost entries are written
+  if (!comm_grow(&c->sendbuf, &c->send_cap, (size_t)pl.total_send * ndof) ||
+      !comm_grow(&c->recvbuf, &c->recv_cap, (size_t)pl.total_recv * ndof)) {
+    h->comm_rc = HDG_ECUDA;
+    h->err = "halo exchange: out of device memory for the staging buffers";
+    return;
+  }
+  if (pl.total_send > 0)
+    LAUNCH(h, k_halo_pack, std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_send * ndof, 256))), 256,
+           pl.total_send, ndof, pl.n_local, pl.send_idx, (const double*)field, c->sendbuf);
+  NCCL_DO(h, g_nccl.GroupStart());
+  for (size_t j = 0; j < pl.peers.size(); ++j) {
+    int ns = pl.send_ptr[j + 1] - pl.send_ptr[j];
+    if (ns > 0)
+      NCCL_DO(h, g_nccl.Send(c->sendbuf + (size_t)pl.send_ptr[j] * ndof, (size_t)ns * ndof, ncclDouble, pl.peers[j],
+                             c->nccl, h->stream));
+    if (pl.recv_cnt[j] > 0)
+      NCCL_DO(h, g_nccl.Recv(c->recvbuf + (size_t)(pl.recv_off[j] - pl.n_owned) * ndof, (size_t)pl.recv_cnt[j] * ndof,
+                             ncclDouble, pl.peers[j], c->nccl, h->stream));
+  }
+  NCCL_DO(h, g_nccl.GroupEnd());
+  if (pl.total_recv > 0)
+    LAUNCH(h, k_halo_unpack, std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_recv * ndof, 256))), 256,
+           pl.total_recv, ndof, pl.n_local, pl.n_owned, (const double*)c->recvbuf, field);
+  c->exchanges++;
+}
+
+// sum the partial-sum slots part[0..nslots)[G] over all ranks (in place; consumers stay unchanged)
+static void allreduce_slots(hdg_engine* h, double* part, int nslots) {
+  Comm* c = h->comm;
+  if (!c || c->nranks == 1) return;
+  LAUNCH(h, k_part_finish, nslots, BLOCK, (const double*)part, h->grid, c->red);
+  NCCL_DO(h, g_nccl.AllReduce(c->red, c->red, (size_t)nslots, ncclDouble, ncclSum, c->nccl, h->stream));
+  LAUNCH(h, k_part_spread, nslots, BLOCK, part, h->grid, (const double*)c->red);
+  c->allreduces++;
+}
+
+static inline bool all_owned(const hdg_engine* h) { return h->nc_own == h->nc && h->nf_own == h->nf; }
+static OwnMask mask_cells(const hdg_engine* h, int ndof) {
+  return OwnMask{all_owned(h) ? 1 : 0, (unsigned long long)ndof * h->nc, h->nc, h->nc_own, 1, 1};
+}
+static OwnMask mask_facets(const hdg_engine* h, int ndof) {
+  return OwnMask{all_owned(h) ? 1 : 0, (unsigned long long)ndof * h->nf, h->nf, h->nf_own, 1, 1};
+}
+static OwnMask mask_aug(const hdg_engine* h, int ndof_cell, int ndof_facet) {
+  return OwnMask{all_owned(h) ? 1 : 0, (unsigned long long)ndof_cell * h->nc, h->nc, h->nc_own, h->nf, h->nf_own};
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1+K2: local operator build + static condensation, one thread per cell
@@ -404,7 +513,8 @@ template <int K>
 __global__ void __launch_bounds__(BLOCK) k_trace_rhs(const double* __restrict__ gK, const double* __restrict__ Rl,
                                                      const int* __restrict__ facet_cell,
                                                      const int* __restrict__ facet_local, int nc, int nf,
-                                                     double* __restrict__ b, double* __restrict__ partial) {
+                                                     int nf_own, double* __restrict__ b,
+                                                     double* __restrict__ partial) {
   constexpr int NL1 = Dims<K>::NL1;
   double acc = 0.0;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
@@ -416,7 +526,7 @@ __global__ void __launch_bounds__(BLOCK) k_trace_rhs(const double* __restrict__ 
       if (c1 >= 0) v += gK[(size_t)(e1 * NL1 + m) * nc + c1];
       if (Rl) v -= Rl[(size_t)m * nf + f];
       b[(size_t)m * nf + f] = v;
-      if (m == 0) acc += v;
+      if (m == 0 && f < nf_own) acc += v;
     }
   }
   acc = block_reduce(acc);
@@ -429,11 +539,12 @@ __global__ void __launch_bounds__(BLOCK) k_trace_rhs(const double* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // init: r = b - mean0(b) on mode 0 (projection onto range(S)), x = 0, z = Dinv r, p = z, <r,z>
 template <int b>
-__global__ void __launch_bounds__(BLOCK) k_cg_init(int nf, const double* __restrict__ dinv,
+__global__ void __launch_bounds__(BLOCK) k_cg_init(int nf, int nf_own, double inv_nf_glob,
+                                                   const double* __restrict__ dinv,
                                                    const double* __restrict__ part_mean, double* __restrict__ r,
                                                    double* __restrict__ x, double* __restrict__ z,
                                                    double* __restrict__ p, double* __restrict__ part_rz) {
-  double mean = reduce_partials(part_mean, gridDim.x) / (double)nf;
+  double mean = reduce_partials(part_mean, gridDim.x) * inv_nf_glob;
   double acc = 0.0;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     double rv[b], zv[b];
@@ -447,7 +558,7 @@ __global__ void __launch_bounds__(BLOCK) k_cg_init(int nf, const double* __restr
       HDG_UNROLL
       for (int j = 0; j < b; ++j) s = fma(dinv[(size_t)(i * b + j) * nf + f], rv[j], s);
       zv[i] = s;
-      acc = fma(s, rv[i], acc);
+      if (f < nf_own) acc = fma(s, rv[i], acc);
     }
     HDG_UNROLL
     for (int m = 0; m < b; ++m) {
@@ -474,7 +585,8 @@ __global__ void k_cg_start(CgScalars* s, const double* __restrict__ part_rz, int
 
 // A: q = P p, partial <p,q>
 template <int b>
-__global__ void __launch_bounds__(BLOCK) k_cg_spmv(int nf, const double* __restrict__ val, const int* __restrict__ col,
+__global__ void __launch_bounds__(BLOCK) k_cg_spmv(int nf, int nf_own, const double* __restrict__ val,
+                                                   const int* __restrict__ col,
                                                    const double* __restrict__ p, double* __restrict__ q,
                                                    double* __restrict__ part_pq, const CgScalars* __restrict__ s) {
   if (s && s->done) return;
@@ -497,7 +609,7 @@ __global__ void __launch_bounds__(BLOCK) k_cg_spmv(int nf, const double* __restr
     HDG_UNROLL
     for (int i = 0; i < b; ++i) {
       q[(size_t)i * nf + f] = y[i];
-      if (part_pq) acc = fma(y[i], p[(size_t)i * nf + f], acc);
+      if (part_pq && f < nf_own) acc = fma(y[i], p[(size_t)i * nf + f], acc);
     }
   }
   if (part_pq) {
@@ -508,7 +620,7 @@ __global__ void __launch_bounds__(BLOCK) k_cg_spmv(int nf, const double* __restr
 
 // B: alpha = <r,z>/<p,q>; x += alpha p; r -= alpha q; z = Dinv r; partial <r,z>
 template <int b>
-__global__ void __launch_bounds__(BLOCK) k_cg_update(int nf, const double* __restrict__ dinv,
+__global__ void __launch_bounds__(BLOCK) k_cg_update(int nf, int nf_own, const double* __restrict__ dinv,
                                                      const double* __restrict__ p, const double* __restrict__ q,
                                                      double* __restrict__ x, double* __restrict__ r,
                                                      double* __restrict__ z, const double* __restrict__ part_pq,
@@ -532,7 +644,7 @@ __global__ void __launch_bounds__(BLOCK) k_cg_update(int nf, const double* __res
       HDG_UNROLL
       for (int j = 0; j < b; ++j) v = fma(dinv[(size_t)(i * b + j) * nf + f], rv[j], v);
       z[(size_t)i * nf + f] = v;
-      acc = fma(v, rv[i], acc);
+      if (f < nf_own) acc = fma(v, rv[i], acc);
     }
   }
   acc = block_reduce(acc);
@@ -626,10 +738,10 @@ __global__ void __launch_bounds__(128) k_back(const double* __restrict__ xy, con
 // a7/a8: _shift_pressure  (hdg_imex.py:471-478):  p -= mean(p), lam -= mean(p)
 // int_K p dx = detJ * p_0 / sqrt(2)  (Dubiner mode 0 is the constant sqrt(2))
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_pmean_partial(const double* __restrict__ xy, int nc,
+__global__ void __launch_bounds__(BLOCK) k_pmean_partial(const double* __restrict__ xy, int nc, int nc_own,
                                                          const double* __restrict__ p, double* __restrict__ partial) {
   double acc = 0.0;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc_own; cell += gridDim.x * blockDim.x) {
     double x0 = xy[cell], y0 = xy[(size_t)nc + cell];
     double x1 = xy[2 * (size_t)nc + cell], y1 = xy[3 * (size_t)nc + cell];
     double x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];
@@ -744,12 +856,13 @@ static cudaError_t dmalloc(Tp** p, size_t count) {
 // hdg_imex.py:233-247 / hdg_implicit.py:103-129; the reference uses GMRES+ILU resp. direct LU).
 // Five kernels per iteration, reductions deterministic as in the CG.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, const double* __restrict__ a, const double* __restrict__ b,
-                                                const double* __restrict__ c, double* __restrict__ p_ab,
-                                                double* __restrict__ p_cc) {
-  // partial <a,b> and (optionally) <c,c>
+__global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, OwnMask own, const double* __restrict__ a,
+                                                const double* __restrict__ b, const double* __restrict__ c,
+                                                double* __restrict__ p_ab, double* __restrict__ p_cc) {
+  // partial <a,b> and (optionally) <c,c> over the owned entries
   double s0 = 0.0, s1 = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!is_owned(own, i)) continue;
     s0 = fma(a[i], b[i], s0);
     if (c) s1 = fma(c[i], c[i], s1);
   }
@@ -762,7 +875,7 @@ __global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, const double* __restri
 }
 
 // r = b - t (t = A x0, or r = b if t == nullptr; b may alias r); rhat = r; p = r; partial <r,r>
-__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* b, const double* __restrict__ t,
+__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, OwnMask own, const double* b, const double* __restrict__ t,
                                                    double* r, double* __restrict__ rhat,
                                                    double* __restrict__ p, double* __restrict__ part) {
   double s = 0.0;
@@ -771,7 +884,7 @@ __global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, const double* b, co
     r[i] = v;
     rhat[i] = v;
     p[i] = v;
-    s = fma(v, v, s);
+    if (is_owned(own, i)) s = fma(v, v, s);
   }
   s = block_reduce(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
@@ -803,7 +916,8 @@ __global__ void __launch_bounds__(BLOCK) k_bi_s(size_t n, const double* __restri
     sv[i] = fma(-alpha, v[i], r[i]);
 }
 // omega = <t,s>/<t,t>; x += alpha p + omega s; r = s - omega t; partials <rhat,r>, <r,r>
-__global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, const double* __restrict__ p, const double* __restrict__ sv,
+__global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, OwnMask own, const double* __restrict__ p,
+                                                 const double* __restrict__ sv,
                                                  const double* __restrict__ t, const double* __restrict__ rhat,
                                                  double* __restrict__ x, double* __restrict__ r,
                                                  const double* __restrict__ p_rv, const double* __restrict__ p_ts,
@@ -819,8 +933,10 @@ __global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, const double* __restr
     x[i] += alpha * p[i] + omega * si;
     double ri = fma(-omega, t[i], si);
     r[i] = ri;
-    a0 = fma(rhat[i], ri, a0);
-    a1 = fma(ri, ri, a1);
+    if (is_owned(own, i)) {
+      a0 = fma(rhat[i], ri, a0);
+      a1 = fma(ri, ri, a1);
+    }
   }
   a0 = block_reduce(a0);
   if (threadIdx.x == 0) p_rho[blockIdx.x] = a0;
@@ -888,14 +1004,15 @@ static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const 
 // generic driver: op(in, out) applies the (preconditioned) operator to a vector of length n.
 // On entry r0 (the initial residual) sits in bi[0]; the solution update is accumulated in y.
 template <class Op>
-static int bicgstab_loop(hdg_engine* h, size_t n, Op op, double* y, const double* part_ref, double rtol, int maxit,
-                         int* iters) {
+static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, double* y, const double* part_ref, double rtol,
+                         int maxit, int* iters) {
   const int G = h->grid;
   double *r = h->bi[0], *rhat = h->bi[1], *p = h->bi[2], *v = h->bi[3], *sv = h->bi[4], *t = h->bi[5];
   double* P = h->partial;
   double *p_rv = P, *p_ts = P + G, *p_tt = P + 2 * (size_t)G, *p_rho = P + 3 * (size_t)G, *p_rr = P + 4 * (size_t)G;
   // rhat = p = r, partial <r,r>
-  LAUNCH(h, k_bi_init, G, BLOCK, n, (const double*)r, (const double*)nullptr, r, rhat, p, p_rr);
+  LAUNCH(h, k_bi_init, G, BLOCK, n, own, (const double*)r, (const double*)nullptr, r, rhat, p, p_rr);
+  allreduce_slots(h, p_rr, 1);
   LAUNCH(h, k_bi_start, 1, BLOCK, h->bscal, p_rr, part_ref, G, rtol, maxit);
   const int chunk = 4;
   int launched = 0;
@@ -904,11 +1021,14 @@ static int bicgstab_loop(hdg_engine* h, size_t n, Op op, double* y, const double
     int m = std::min(chunk, std::max(1, maxit - launched));
     for (int i = 0; i < m; ++i) {
       op(p, v);
-      LAUNCH(h, k_dot2, G, BLOCK, n, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
+      LAUNCH(h, k_dot2, G, BLOCK, n, own, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
+      allreduce_slots(h, p_rv, 1);
       LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
       op(sv, t);
-      LAUNCH(h, k_dot2, G, BLOCK, n, t, sv, (const double*)t, p_ts, p_tt);
-      LAUNCH(h, k_bi_xr, G, BLOCK, n, p, sv, t, rhat, y, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+      LAUNCH(h, k_dot2, G, BLOCK, n, own, t, sv, (const double*)t, p_ts, p_tt);
+      allreduce_slots(h, p_ts, 2);
+      LAUNCH(h, k_bi_xr, G, BLOCK, n, own, p, sv, t, rhat, y, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+      allreduce_slots(h, p_rho, 2);
       LAUNCH(h, k_bi_p, G, BLOCK, n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
     }
     launched += m;
@@ -941,11 +1061,14 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
   int rc = bicgstab_alloc(h, n);
   if (rc) return rc;
   double* part_bb = h->partial + 5 * (size_t)G;
-  LAUNCH(h, k_dot2, G, BLOCK, n, b, b, (const double*)nullptr, part_bb, (double*)nullptr);
+  const OwnMask own = mask_cells(h, 2 * Dims<K>::NQ1);
+  LAUNCH(h, k_dot2, G, BLOCK, n, own, b, b, (const double*)nullptr, part_bb, (double*)nullptr);
+  allreduce_slots(h, part_bb, 1);
   if (zero_guess) {
     CUDA_TRY(h, cudaMemsetAsync(x, 0, n * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->bi[0], b, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   } else {
+    halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, x);
     launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
     const double cf[2] = {1.0, -1.0};
     LinComb lc;
@@ -957,10 +1080,11 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
     LAUNCH(h, k_lincomb, G, BLOCK, n, lc, h->bi[0]);
   }
   auto op = [&](const double* in, double* out) {
+    halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, in);
     ScopedTimer tf(h, T_FIMPL);
     launch_fimpl<K>(h, upwind, Qstar, in, 1.0, -adt, out);
   };
-  return bicgstab_loop(h, n, op, x, part_bb, rtol, maxit, iters);
+  return bicgstab_loop(h, n, own, op, x, part_bb, rtol, maxit, iters);
 }
 
 // ---- facet-multiplier formulation (hdg_tent.cuh) --------------------------------------------------
@@ -996,10 +1120,12 @@ static int tent_setup(hdg_engine* h) {
     std::vector<double> part(G);
     double lam = 2.0;
     for (int it = 0; it < 30; ++it) {
+      halo_exchange(h, PLAN_FACETS, NM, x);
       LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
              0.0, (const double*)nullptr, (const double*)nullptr, (const double*)x, (double*)nullptr, x2, 0.0, 0.0, 0,
              2);
-      LAUNCH(h, k_dot2, G, BLOCK, n, x2, x2, (const double*)nullptr, h->partial, (double*)nullptr);
+      LAUNCH(h, k_dot2, G, BLOCK, n, mask_facets(h, NM), x2, x2, (const double*)nullptr, h->partial, (double*)nullptr);
+      allreduce_slots(h, h->partial, 1);
       CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CUDA_TRY(h, cudaStreamSynchronize(h->stream));
       double s = 0.0;
@@ -1022,11 +1148,13 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
   cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
   double *x = h->tent_f[2], *x2 = h->tent_f[3];
   for (int j = 0; j < h->tent_sweeps; ++j) {
+    if (j > 0) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);
     LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
            inv_aalpha, t, (const double*)nullptr, (const double*)x, h->tent_f[4], x2, cc[j].cd, cc[j].cr,
            j == 0 ? 1 : 0, 0);
     std::swap(x, x2);
   }
+  halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);  // consumers read mu on ghost facets
   h->tent_f[2] = x;
   h->tent_f[3] = x2;
   return x;
@@ -1045,7 +1173,10 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   const double inv_aalpha = 1.0 / (adt * h->alpha);
   const int cgrid = cdiv(h->nc, 128), fgrid = cdiv(h->nf, 256);
   double* part_bb = h->partial + 5 * (size_t)G;
-  LAUNCH(h, k_dot2, G, BLOCK, nx, b, b, (const double*)nullptr, part_bb, (double*)nullptr);
+  const OwnMask own = mask_aug(h, 2 * Dims<K>::NQ1, NM);
+  LAUNCH(h, k_dot2, G, BLOCK, nx, mask_cells(h, 2 * Dims<K>::NQ1), b, b, (const double*)nullptr, part_bb,
+         (double*)nullptr);
+  allreduce_slots(h, part_bb, 1);
   // initial residual of the augmented system with mu0 = a alpha N x0:  (b - A x0, 0)
   double* r = h->bi[0];
   CUDA_TRY(h, cudaMemsetAsync(r + nx, 0, nmu * sizeof(double), h->stream));
@@ -1053,6 +1184,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     CUDA_TRY(h, cudaMemsetAsync(x, 0, nx * sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(r, b, nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   } else {
+    halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, x);
     launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
     LinComb lc;
     lc.n = 2;
@@ -1064,6 +1196,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   }
   // out = A_aug Phat^-1 in
   auto precond_x = [&](const double* in, bool with_mu) -> double* {
+    halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, in);  // moments and xhat are evaluated on ghost cells too
     LAUNCH(h, k_tent_moments<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->nc, in, h->tent_cm);
     LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf,
            with_mu ? in + nx : (const double*)nullptr, h->tent_f[0], h->tent_f[1]);
@@ -1083,7 +1216,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   };
   double* y = h->tent_y;
   CUDA_TRY(h, cudaMemsetAsync(y, 0, n * sizeof(double), h->stream));
-  int brc = bicgstab_loop(h, n, op, y, part_bb, rtol, maxit, iters);
+  int brc = bicgstab_loop(h, n, own, op, y, part_bb, rtol, maxit, iters);
   if (brc == HDG_ECUDA) return brc;
   // x += [Phat^-1 y]_x
   double* mu = precond_x(y, true);
@@ -1113,9 +1246,11 @@ static void mg_free(hdg_engine* h) {
   }
   free_csr(mg->T);
   free_csr(mg->Tt);
-  double* v[] = {mg->pinv, mg->fx, mg->fx2, mg->fd, mg->fr};
+  double* v[] = {mg->pinv, mg->fx, mg->fx2, mg->fd, mg->fr, mg->gsend, mg->gbuf};
   for (double* p : v)
     if (p) cudaFree(p);
+  if (mg->gptr) cudaFree(mg->gptr);
+  if (mg->ggid) cudaFree(mg->ggid);
   delete mg;
   h->mg = nullptr;
 }
@@ -1139,15 +1274,31 @@ static void csr_spmv(hdg_engine* h, const DevCsr& A, const double* x, const doub
   LAUNCH(h, k_csr_spmv, small_grid(h, A.nrows), 256, A.nrows, A.rowptr, A.col, A.val, x, b, y, mode);
 }
 
+static inline bool mg_dist(const hdg_engine* h, int l) {
+  return h->comm && h->comm->nranks > 1 && l < h->mg->repl;
+}
+
 // smooth on CSR level l: result ends in L.x (x and x2 ping-pong)
-static void mg_smooth_csr(hdg_engine* h, MgLevel& L, int ns, double ratio, bool zero) {
+static void mg_smooth_csr(hdg_engine* h, int l, int ns, double ratio, bool zero) {
+  MgLevel& L = h->mg->L[l];
   std::vector<ChebCoef> cc;
   cheb_coefs(L.lmax, ratio, ns, cc);
   for (int j = 0; j < ns; ++j) {
-    LAUNCH(h, k_csr_cheb, small_grid(h, L.n), 256, L.n, L.A.rowptr, L.A.col, L.A.val, L.dinv, L.b, L.x, L.d, L.x2,
-           cc[j].cd, cc[j].cr, (zero && j == 0) ? 1 : 0);
+    const bool z = zero && j == 0;
+    if (!z && mg_dist(h, l)) halo_exchange(h, PLAN_P1 + l, 1, L.x);
+    LAUNCH(h, k_csr_cheb, small_grid(h, L.nrows), 256, L.nrows, L.A.rowptr, L.A.col, L.A.val, L.dinv, L.b, L.x, L.d,
+           L.x2, cc[j].cd, cc[j].cr, z ? 1 : 0);
     std::swap(L.x, L.x2);
   }
+}
+
+// owned rows of the first replicated level -> full vector on every rank
+static void mg_allgather(hdg_engine* h, double* out) {
+  MgState* mg = h->mg;
+  Comm* c = h->comm;
+  NCCL_DO(h, g_nccl.AllGather(mg->gsend, mg->gbuf, (size_t)mg->gmax, ncclDouble, c->nccl, h->stream));
+  LAUNCH(h, k_gather_scatter, small_grid(h, mg->L[mg->repl].n), 256, c->nranks, mg->gmax, (const int*)mg->gptr,
+         (const int*)mg->ggid, (const double*)mg->gbuf, out);
 }
 
 static void mg_vcycle(hdg_engine* h, int l) {
@@ -1158,12 +1309,17 @@ static void mg_vcycle(hdg_engine* h, int l) {
     return;
   }
   MgLevel& C = mg->L[l + 1];
-  mg_smooth_csr(h, L, mg->ns_coarse, mg->ratio, true);
+  const bool dist = mg_dist(h, l), to_repl = dist && (l + 1 == mg->repl);
+  mg_smooth_csr(h, l, mg->ns_coarse, mg->ratio, true);
+  if (dist) halo_exchange(h, PLAN_P1 + l, 1, L.x);
   csr_spmv(h, L.A, L.x, L.b, L.r, 2);       // r = b - A x
-  csr_spmv(h, L.R, L.r, nullptr, C.b, 0);   // b_c = R r
+  if (dist) halo_exchange(h, PLAN_P1 + l, 1, L.r);
+  csr_spmv(h, L.R, L.r, nullptr, to_repl ? mg->gsend : C.b, 0);   // b_c = R r
+  if (to_repl) mg_allgather(h, C.b);
   mg_vcycle(h, l + 1);
+  if (mg_dist(h, l + 1)) halo_exchange(h, PLAN_P1 + l + 1, 1, C.x);
   csr_spmv(h, L.P, C.x, nullptr, L.x, 1);   // x += P x_c
-  mg_smooth_csr(h, L, mg->ns_coarse, mg->ratio, false);
+  mg_smooth_csr(h, l, mg->ns_coarse, mg->ratio, false);
 }
 
 // z = M^-1 r: symmetric V-cycle (Chebyshev/block-Jacobi, P1 coarse correction, Chebyshev/block-Jacobi)
@@ -1171,21 +1327,29 @@ template <int b>
 static void mg_apply(hdg_engine* h, const double* r, double* z) {
   MgState* mg = h->mg;
   const int G = h->grid;
+  const bool multi = h->comm && h->comm->nranks > 1;
   std::vector<ChebCoef> cc;
   cheb_coefs(mg->fine_lmax, mg->ratio, mg->ns_fine, cc);
   double *x = mg->fx, *x2 = mg->fx2;
   for (int j = 0; j < mg->ns_fine; ++j) {
+    if (j > 0) halo_exchange(h, PLAN_FACETS, b, x);
     LAUNCH(h, k_ell_cheb<b>, G, 256, h->nf, h->ell_val, h->ell_col, h->dinv, r, x, mg->fd, x2, cc[j].cd, cc[j].cr,
            j == 0 ? 1 : 0);
     std::swap(x, x2);
   }
+  halo_exchange(h, PLAN_FACETS, b, x);
   LAUNCH(h, k_ell_residual<b>, G, 256, h->nf, h->ell_val, h->ell_col, r, x, mg->fr);
+  halo_exchange(h, PLAN_FACETS, b, mg->fr);
   MgLevel& L0 = mg->L[0];
-  csr_spmv(h, mg->Tt, mg->fr, nullptr, L0.b, 0);
+  const bool gather0 = multi && mg->repl == 0;
+  csr_spmv(h, mg->Tt, mg->fr, nullptr, gather0 ? mg->gsend : L0.b, 0);
+  if (gather0) mg_allgather(h, L0.b);
   mg_vcycle(h, 0);
+  if (mg_dist(h, 0)) halo_exchange(h, PLAN_P1, 1, L0.x);
   csr_spmv(h, mg->T, L0.x, nullptr, x, 1);
   for (int j = 0; j < mg->ns_fine; ++j) {
     double* out = (j == mg->ns_fine - 1) ? z : x2;
+    if (j > 0) halo_exchange(h, PLAN_FACETS, b, x);
     LAUNCH(h, k_ell_cheb<b>, G, 256, h->nf, h->ell_val, h->ell_col, h->dinv, r, x, mg->fd, out, cc[j].cd, cc[j].cr, 0);
     if (j != mg->ns_fine - 1) std::swap(x, x2);
   }
@@ -1201,23 +1365,29 @@ static int run_pcg_mg(hdg_engine* h, double rtol, int maxit, int* iters) {
   double* part_pq = h->partial + G;
   double* part_rz = h->partial + 2 * (size_t)G;
   // r = b - mean (mode 0), x = 0; k_cg_init also writes a block-Jacobi z/p which we overwrite
-  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z, h->cg_p, part_rz);
+  const OwnMask own = mask_facets(h, b);
+  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->nf_own, 1.0 / h->nf_glob, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z,
+         h->cg_p, part_rz);
   mg_apply<b>(h, h->cg_r, h->cg_z);
   CUDA_TRY(h, cudaMemcpyAsync(h->cg_p, h->cg_z, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  LAUNCH(h, k_dot2, G, BLOCK, n, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+  LAUNCH(h, k_dot2, G, BLOCK, n, own, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+  allreduce_slots(h, part_rz, 1);
   LAUNCH(h, k_cg_start, 1, BLOCK, h->scal, part_rz, G, rtol, maxit);
   int it = 0;
   while (true) {
     CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (h->scal_host->done || it >= maxit) break;
+    halo_exchange(h, PLAN_FACETS, b, h->cg_p);
     {
       ScopedTimer ts(h, T_SPMV);
-      LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+      LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
     }
+    allreduce_slots(h, part_pq, 1);
     LAUNCH(h, k_cg_update_plain, G, 256, n, h->cg_p, h->cg_q, h->cg_x, h->cg_r, part_pq, h->scal);
     mg_apply<b>(h, h->cg_r, h->cg_z);
-    LAUNCH(h, k_dot2, G, BLOCK, n, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+    LAUNCH(h, k_dot2, G, BLOCK, n, own, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
+    allreduce_slots(h, part_rz, 1);
     LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);
     ++it;
   }
@@ -1243,10 +1413,13 @@ static int mg_fine_lmax(hdg_engine* h, double* lmax_out) {
   std::vector<double> part(G);
   double lam = 1.0;
   for (int it = 0; it < 25; ++it) {
-    LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, mg->fx, mg->fr, (double*)nullptr,
+    halo_exchange(h, PLAN_FACETS, b, mg->fx);
+    LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, mg->fx, mg->fr, (double*)nullptr,
            (const CgScalars*)nullptr);
     LAUNCH(h, k_blockjac<b>, G, 256, h->nf, h->dinv, mg->fr, mg->fx);
-    LAUNCH(h, k_dot2, G, BLOCK, n, mg->fx, mg->fx, (const double*)nullptr, h->partial, (double*)nullptr);
+    LAUNCH(h, k_dot2, G, BLOCK, n, mask_facets(h, b), mg->fx, mg->fx, (const double*)nullptr, h->partial,
+           (double*)nullptr);
+    allreduce_slots(h, h->partial, 1);
     CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     double s = 0.0;
@@ -1289,6 +1462,17 @@ int hdg_destroy(hdg_handle h) {
                   h->tent_xh, h->tent_y};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  if (h->comm) {
+    Comm* c = h->comm;
+    for (auto& pl : c->plans)
+      if (pl.send_idx) cudaFree(pl.send_idx);
+    if (c->sendbuf) cudaFree(c->sendbuf);
+    if (c->recvbuf) cudaFree(c->recvbuf);
+    if (c->red) cudaFree(c->red);
+    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+    delete c;
+    h->comm = nullptr;
+  }
   if (h->scal_host) cudaFreeHost(h->scal_host);
   if (h->bscal_host) cudaFreeHost(h->bscal_host);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -1325,6 +1509,9 @@ int hdg_create(int k, double tau, int nc, int nf, const double* cell_xy, const i
   h->k = k;
   h->nc = nc;
   h->nf = nf;
+  h->nc_own = nc;
+  h->nf_own = nf;
+  h->nf_glob = (double)nf;
   h->tau = tau;
   h->device = device;
 #define CREATE_TRY(expr)                                                          \
@@ -1510,7 +1697,9 @@ int hdg_trace_spmv_dev(hdg_handle h, const double* x, double* y) {
   if (!h || !x || !y) return HDG_EINVAL;
   if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_trace_spmv_dev: call hdg_setup_poisson first");
   // y = S x = -(P x)
-  DISPATCH_K(h, LAUNCH(h, k_cg_spmv<K + 1>, h->grid, BLOCK, h->nf, h->ell_val, h->ell_col, x, y, nullptr, nullptr));
+  halo_exchange(h, PLAN_FACETS, h->k + 1, x);
+  DISPATCH_K(h, LAUNCH(h, k_cg_spmv<K + 1>, h->grid, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, x, y, nullptr,
+                       nullptr));
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
 }
@@ -1520,11 +1709,19 @@ int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* r
   if (!h || !r_l) return HDG_EINVAL;
   if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_forward_eliminate_dev: call hdg_setup_poisson first");
   ScopedTimer t(h, T_FWD);
+  {
+    // the condensed rhs of a cut facet sums the contributions of an owned and a ghost cell
+    int nq1, np, nl1;
+    dims_of(h->k, nq1, np, nl1);
+    halo_exchange(h, PLAN_CELLS, 2 * nq1, rhs_Q);
+    halo_exchange(h, PLAN_CELLS, np, rhs_p);
+  }
   DISPATCH_K(h, {
     LAUNCH(h, k_forward<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, rhs_Q, rhs_p, h->gK);
-    LAUNCH(h, k_trace_rhs<K>, h->grid, BLOCK, h->gK, rhs_l, h->facet_cell, h->facet_local, h->nc, h->nf, r_l,
-           h->partial);
+    LAUNCH(h, k_trace_rhs<K>, h->grid, BLOCK, h->gK, rhs_l, h->facet_cell, h->facet_local, h->nc, h->nf, h->nf_own,
+           r_l, h->partial);
   });
+  allreduce_slots(h, h->partial, 1);
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
 }
@@ -1533,6 +1730,7 @@ int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs
                             double* p) {
   if (!h || !l || !Q || !p) return HDG_EINVAL;
   ScopedTimer t(h, T_BACK);
+  halo_exchange(h, PLAN_FACETS, h->k + 1, l);
   DISPATCH_K(h, {
     LAUNCH(h, k_back<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
            rhs_p, l, Q, p);
@@ -1550,7 +1748,9 @@ static int run_cg(hdg_engine* h, double rtol, int maxit, int* iters) {
   double* part_pq = h->partial + G;
   double* part_rz = h->partial + 2 * (size_t)G;
   // b already sits in cg_r (written by k_trace_rhs), its mode-0 partial sums in part_mean
-  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z, h->cg_p, part_rz);
+  LAUNCH(h, k_cg_init<b>, G, BLOCK, h->nf, h->nf_own, 1.0 / h->nf_glob, h->dinv, part_mean, h->cg_r, h->cg_x, h->cg_z,
+         h->cg_p, part_rz);
+  allreduce_slots(h, part_rz, 1);
   LAUNCH(h, k_cg_start, 1, BLOCK, h->scal, part_rz, G, rtol, maxit);
   const int chunk = 20;
   int launched = 0;
@@ -1559,14 +1759,17 @@ static int run_cg(hdg_engine* h, double rtol, int maxit, int* iters) {
     int n = std::min(chunk, maxit - launched);
     if (n <= 0) n = 1;
     for (int i = 0; i < n; ++i) {
+      halo_exchange(h, PLAN_FACETS, b, h->cg_p);
       if (((launched + i) & 15) == 0) {
         // sampled per-launch timing of the dominant kernel (every 16th SpMV) for bench.py's roofline
         ScopedTimer ts(h, T_SPMV);
-        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
       } else
-        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
-      LAUNCH(h, k_cg_update<b>, G, BLOCK, h->nf, h->dinv, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->cg_z, part_pq,
-             part_rz, h->scal);
+        LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, h->cg_p, h->cg_q, part_pq, h->scal);
+      allreduce_slots(h, part_pq, 1);
+      LAUNCH(h, k_cg_update<b>, G, BLOCK, h->nf, h->nf_own, h->dinv, h->cg_p, h->cg_q, h->cg_x, h->cg_r, h->cg_z,
+             part_pq, part_rz, h->scal);
+      allreduce_slots(h, part_rz, 1);
       LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);
     }
     launched += n;
@@ -1602,10 +1805,12 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   rc = hdg_back_substitute_dev(h, rhs_Q, rhs_p, l, Q, p);
   if (rc) return rc;
   if (shift) {
-    LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, p, h->partial);
+    LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, h->nc_own, p, h->partial);
+    allreduce_slots(h, h->partial, 1);
     LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
   }
   CUDA_TRY(h, cudaGetLastError());
+  if (h->comm_rc) return h->comm_rc;
   if (cg_rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "trace CG did not converge within maxit");
   return HDG_OK;
 }
@@ -1726,6 +1931,7 @@ int hdg_project_bdm_dev(hdg_handle h, const double* Q, double* Qstar) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (!h->bdm_fm) CUDA_TRY(h, dmalloc(&h->bdm_fm, 2 * (size_t)(h->k + 2) * h->nf));
   ScopedTimer t(h, T_BDM);
+  halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), Q);
   DISPATCH_K(h, {
     LAUNCH(h, k_bdm_moments<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_facet, h->facet_cell, h->nc, h->nf, Q,
            h->bdm_fm);
@@ -1741,6 +1947,7 @@ int hdg_fimpl_apply_dev(hdg_handle h, const double* Qstar, const double* X, doub
   if (!h || !Qstar || !X || !Y) return HDG_EINVAL;
   if (X == Y) FAIL(h, HDG_EINVAL, "hdg_fimpl_apply_dev: X and Y must not alias (neighbour gathers)");
   CUDA_TRY(h, cudaSetDevice(h->device));
+  halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), X);
   DISPATCH_K(h, launch_fimpl<K>(h, upwind != 0, Qstar, X, c0, c1, Y));
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
@@ -1759,6 +1966,7 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
       DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
     }
   }
+  if (h->comm_rc) return h->comm_rc;
   if (rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "tentative-velocity BiCGStab did not converge within maxit");
   return rc;
 }
@@ -1766,6 +1974,7 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
 int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mode, double* Rp) {
   if (!h || !Q || !Rp || mode < 0 || mode > 1) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  if (mode == 1) halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), Q);
   DISPATCH_K(h, LAUNCH(h, k_weak_div<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, Q,
                        scale, mode, Rp));
   CUDA_TRY(h, cudaGetLastError());
@@ -1775,6 +1984,7 @@ int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mod
 int hdg_pressure_gradient_dev(hdg_handle h, const double* p, const double* l, double c0, double c1, double* Y) {
   if (!h || !p || !l || !Y) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
+  halo_exchange(h, PLAN_FACETS, h->k + 1, l);
   DISPATCH_K(h, LAUNCH(h, k_pgrad<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, p,
                        l, c0, c1, Y));
   CUDA_TRY(h, cudaGetLastError());
@@ -1785,6 +1995,8 @@ int hdg_reconstruct_trace_dev(hdg_handle h, const double* Q, const double* p, do
   if (!h || !Q || !p || !l) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (!h->gK) CUDA_TRY(h, dmalloc(&h->gK, (size_t)3 * (h->k + 1) * h->nc));
+  halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), Q);
+  halo_exchange(h, PLAN_CELLS, (h->k + 1) * (h->k + 2) / 2, p);
   DISPATCH_K(h, {
     LAUNCH(h, k_trace_moments<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, Q, p, h->gK);
     LAUNCH(h, k_trace_avg<K>, h->grid, BLOCK, h->gK, h->facet_cell, h->facet_local, h->nc, h->nf, l);
@@ -1796,7 +2008,8 @@ int hdg_reconstruct_trace_dev(hdg_handle h, const double* Q, const double* p, do
 int hdg_shift_pressure_dev(hdg_handle h, double* p, double* l) {
   if (!h || !p) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, p, h->partial);
+  LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, h->nc_own, p, h->partial);
+  allreduce_slots(h, h->partial, 1);
   LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
@@ -1832,6 +2045,8 @@ int hdg_reconstruction_rhs_dev(hdg_handle h, const double* Q, const double* b, d
   if (!h || !Q || !b || !Rp || !Rl) return HDG_EINVAL;
   CUDA_TRY(h, cudaSetDevice(h->device));
   CUDA_TRY(h, cudaMemsetAsync(Rl, 0, (size_t)(h->k + 1) * h->nf * sizeof(double), h->stream));
+  halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), Q);
+  halo_exchange(h, PLAN_CELLS, (h->k + 2) * (h->k + 3), b);
   DISPATCH_K(h, LAUNCH(h, k_recon_rhs<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e,
                        h->cell_facet, h->cell_flip, h->nc, h->nf, Q, b, Rp, Rl));
   CUDA_TRY(h, cudaGetLastError());
@@ -1844,7 +2059,8 @@ int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, d
   int ent, ndof;
   field_len(h, kind, n, ent, ndof);
   CUDA_TRY(h, cudaSetDevice(h->device));
-  LAUNCH(h, k_l2_inner, h->grid, 256, h->cell_xy, h->nc, ndof, x, y, h->partial);
+  LAUNCH(h, k_l2_inner, h->grid, 256, h->cell_xy, h->nc, h->nc_own, ndof, x, y, h->partial);
+  allreduce_slots(h, h->partial, 1);
   std::vector<double> part(h->grid);
   CUDA_TRY(h, cudaMemcpyAsync(part.data(), h->partial, h->grid * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1865,7 +2081,8 @@ int hdg_mg_setup(hdg_handle h, int nlevels, const hdg_csr* A, const hdg_csr* P, 
   CUDA_TRY(h, cudaSetDevice(h->device));
   const int b = h->k + 1;
   const size_t n = (size_t)b * h->nf;
-  if (T->nrows != (int)n || T->ncols != A[0].nrows || Tt->nrows != A[0].nrows || Tt->ncols != (int)n)
+  // row-distributed levels hold their owned rows only: nrows <= ncols = local vector length
+  if (T->nrows != (int)n || T->ncols != A[0].ncols || Tt->nrows > A[0].ncols || Tt->ncols != (int)n)
     FAIL(h, HDG_EINVAL, "hdg_mg_setup: transfer operator has the wrong shape");
   mg_free(h);
   h->mg = new MgState();
@@ -1878,13 +2095,14 @@ int hdg_mg_setup(hdg_handle h, int nlevels, const hdg_csr* A, const hdg_csr* P, 
   int rc;
   for (int l = 0; l < nlevels; ++l) {
     MgLevel& L = mg->L[l];
-    L.n = A[l].nrows;
+    L.n = A[l].ncols;
+    L.nrows = A[l].nrows;
     L.lmax = lmax[l];
-    if (A[l].nrows != A[l].ncols) FAIL(h, HDG_EINVAL, "hdg_mg_setup: level operator not square");
+    if (A[l].nrows > A[l].ncols) FAIL(h, HDG_EINVAL, "hdg_mg_setup: level operator has more rows than columns");
     if ((rc = upload_csr(h, A[l], L.A))) return rc;
     if (l < nlevels - 1) {
-      if (P[l].nrows != A[l].nrows || P[l].ncols != A[l + 1].nrows || R[l].nrows != P[l].ncols ||
-          R[l].ncols != P[l].nrows)
+      if (P[l].nrows != A[l].nrows || P[l].ncols != A[l + 1].ncols || R[l].nrows > A[l + 1].ncols ||
+          R[l].ncols != A[l].ncols)
         FAIL(h, HDG_EINVAL, "hdg_mg_setup: prolongation/restriction shapes inconsistent");
       if ((rc = upload_csr(h, P[l], L.P))) return rc;
       if ((rc = upload_csr(h, R[l], L.R))) return rc;
@@ -1895,11 +2113,17 @@ int hdg_mg_setup(hdg_handle h, int nlevels, const hdg_csr* A, const hdg_csr* P, 
     CUDA_TRY(h, dmalloc(&L.b, (size_t)L.n));
     CUDA_TRY(h, dmalloc(&L.r, (size_t)L.n));
     CUDA_TRY(h, dmalloc(&L.d, (size_t)L.n));
-    LAUNCH(h, k_csr_diag_inv, small_grid(h, L.n), 256, L.n, L.A.rowptr, L.A.col, L.A.val, L.dinv);
+    CUDA_TRY(h, cudaMemsetAsync(L.x, 0, (size_t)L.n * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(L.x2, 0, (size_t)L.n * sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(L.r, 0, (size_t)L.n * sizeof(double), h->stream));
+    LAUNCH(h, k_csr_diag_inv, small_grid(h, L.nrows), 256, L.nrows, L.A.rowptr, L.A.col, L.A.val, L.dinv);
   }
   if ((rc = upload_csr(h, *T, mg->T))) return rc;
   if ((rc = upload_csr(h, *Tt, mg->Tt))) return rc;
   mg->n_last = A[nlevels - 1].nrows;
+  mg->repl = 0;
+  if (A[nlevels - 1].nrows != A[nlevels - 1].ncols)
+    FAIL(h, HDG_EINVAL, "hdg_mg_setup: the coarsest level must be replicated (square)");
   CUDA_TRY(h, dmalloc(&mg->pinv, (size_t)mg->n_last * mg->n_last));
   CUDA_TRY(h, cudaMemcpy(mg->pinv, coarsest_pinv, (size_t)mg->n_last * mg->n_last * sizeof(double),
                          cudaMemcpyHostToDevice));
@@ -1921,6 +2145,154 @@ int hdg_mg_enable(hdg_handle h, int on) {
   if (!h) return HDG_EINVAL;
   if (!h->mg) FAIL(h, HDG_ESTATE, "hdg_mg_enable: call hdg_mg_setup first");
   h->mg->enabled = on != 0;
+  return HDG_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------
+int hdg_comm_unique_id(void* id128) {
+  if (!id128) return HDG_EINVAL;
+  if (!nccl_load()) {
+    g_create_err = g_nccl.err;
+    return HDG_ENCCL;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) {
+    g_create_err = "ncclGetUniqueId failed";
+    return HDG_ENCCL;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  memcpy(id128, &id, sizeof(id));
+  return HDG_OK;
+}
+
+int hdg_comm_init(hdg_handle h, int rank, int nranks, const void* id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return HDG_EINVAL;
+  if (h->comm) FAIL(h, HDG_ESTATE, "hdg_comm_init: communicator already initialised");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (!nccl_load()) FAIL(h, HDG_ENCCL, g_nccl.err);
+  Comm* c = new Comm();
+  c->rank = rank;
+  c->nranks = nranks;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclResult_t r = g_nccl.CommInitRank(&c->nccl, nranks, id, rank);
+  if (r != ncclSuccess) {
+    h->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+    delete c;
+    return HDG_ENCCL;
+  }
+  if (cudaMalloc((void**)&c->red, 16 * sizeof(double)) != cudaSuccess) {
+    delete c;
+    FAIL(h, HDG_ECUDA, "hdg_comm_init: cudaMalloc failed");
+  }
+  h->comm = c;
+  return HDG_OK;
+}
+
+int hdg_set_partition(hdg_handle h, int nc_owned, int nf_owned, int64_t nf_global, double global_volume) {
+  if (!h || nc_owned < 0 || nc_owned > h->nc || nf_owned < 0 || nf_owned > h->nf || nf_global < nf_owned ||
+      !(global_volume > 0))
+    return HDG_EINVAL;
+  h->nc_own = nc_owned;
+  h->nf_own = nf_owned;
+  h->nf_glob = (double)nf_global;
+  h->volume = global_volume;
+  return HDG_OK;
+}
+
+int hdg_set_halo_plan(hdg_handle h, int kind, int n_owned, int n_local, int npeers, const int32_t* peer_rank,
+                      const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_off,
+                      const int32_t* recv_cnt) {
+  if (!h || kind < 0 || kind >= HDG_MAX_PLANS || n_owned < 0 || n_local < n_owned || npeers < 0) return HDG_EINVAL;
+  if (!h->comm) FAIL(h, HDG_ESTATE, "hdg_set_halo_plan: call hdg_comm_init first");
+  if (npeers > 0 && (!peer_rank || !send_ptr || !recv_off || !recv_cnt)) return HDG_EINVAL;
+  if ((kind == PLAN_CELLS && n_local != h->nc) || (kind == PLAN_FACETS && n_local != h->nf))
+    FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: n_local does not match the engine's mesh");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  HaloPlanDev& pl = h->comm->plans[kind];
+  if (pl.send_idx) cudaFree(pl.send_idx);
+  pl = HaloPlanDev();
+  pl.n_owned = n_owned;
+  pl.n_local = n_local;
+  int ghosts = 0;
+  for (int j = 0; j < npeers; ++j) {
+    if (peer_rank[j] < 0 || peer_rank[j] >= h->comm->nranks || peer_rank[j] == h->comm->rank)
+      FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: bad peer rank");
+    if (send_ptr[j + 1] < send_ptr[j] || recv_cnt[j] < 0) FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: bad counts");
+    if (recv_cnt[j] > 0 && recv_off[j] != n_owned + ghosts)
+      FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: ghost blocks must be contiguous and ordered by peer");
+    ghosts += recv_cnt[j];
+    pl.peers.push_back(peer_rank[j]);
+    pl.recv_off.push_back(recv_off[j]);
+    pl.recv_cnt.push_back(recv_cnt[j]);
+  }
+  if (ghosts != n_local - n_owned) FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: ghost blocks do not cover the ghost range");
+  pl.send_ptr.assign(send_ptr ? send_ptr : nullptr, send_ptr ? send_ptr + npeers + 1 : nullptr);
+  if (pl.send_ptr.empty()) pl.send_ptr.push_back(0);
+  pl.total_send = pl.send_ptr.back();
+  pl.total_recv = ghosts;
+  for (int i = 0; i < pl.total_send; ++i)
+    if (send_idx[i] < 0 || send_idx[i] >= n_owned) FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: send index not owned");
+  if (pl.total_send > 0) {
+    CUDA_TRY(h, dmalloc(&pl.send_idx, (size_t)pl.total_send));
+    CUDA_TRY(h, cudaMemcpy(pl.send_idx, send_idx, (size_t)pl.total_send * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  pl.set = true;
+  return HDG_OK;
+}
+
+int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field) {
+  if (!h || !field || ndof < 1 || kind < 0 || kind >= HDG_MAX_PLANS) return HDG_EINVAL;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  halo_exchange(h, kind, ndof, field);
+  CUDA_TRY(h, cudaGetLastError());
+  return h->comm_rc;
+}
+
+int hdg_allreduce_sum_dev(hdg_handle h, double* values, int n) {
+  if (!h || !values || n < 1 || n > 16) return HDG_EINVAL;
+  if (!h->comm || h->comm->nranks == 1) return HDG_OK;
+  NCCL_DO(h, g_nccl.AllReduce(values, values, (size_t)n, ncclDouble, ncclSum, h->comm->nccl, h->stream));
+  return h->comm_rc;
+}
+
+int hdg_mg_set_distribution(hdg_handle h, int repl_level, const int32_t* gather_counts, const int32_t* gather_gid) {
+  if (!h || !gather_counts || !gather_gid) return HDG_EINVAL;
+  if (!h->mg) FAIL(h, HDG_ESTATE, "hdg_mg_set_distribution: call hdg_mg_setup first");
+  if (!h->comm) FAIL(h, HDG_ESTATE, "hdg_mg_set_distribution: call hdg_comm_init first");
+  MgState* mg = h->mg;
+  if (repl_level < 0 || repl_level >= mg->nlevels) FAIL(h, HDG_EINVAL, "hdg_mg_set_distribution: bad level");
+  for (int l = 0; l < repl_level; ++l)
+    if (!h->comm->plans[PLAN_P1 + l].set || h->comm->plans[PLAN_P1 + l].n_local != mg->L[l].n)
+      FAIL(h, HDG_ESTATE, "hdg_mg_set_distribution: halo plan of a distributed level is missing or inconsistent");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int nr = h->comm->nranks;
+  std::vector<int> ptr(nr + 1, 0);
+  int gmax = 0;
+  for (int q = 0; q < nr; ++q) {
+    if (gather_counts[q] < 0) return HDG_EINVAL;
+    ptr[q + 1] = ptr[q] + gather_counts[q];
+    gmax = std::max(gmax, gather_counts[q]);
+  }
+  if (ptr[nr] != mg->L[repl_level].n) FAIL(h, HDG_EINVAL, "hdg_mg_set_distribution: counts do not sum to the level size");
+  mg->repl = repl_level;
+  mg->gmax = std::max(gmax, 1);
+  CUDA_TRY(h, dmalloc(&mg->gptr, (size_t)nr + 1));
+  CUDA_TRY(h, dmalloc(&mg->ggid, (size_t)std::max(ptr[nr], 1)));
+  CUDA_TRY(h, dmalloc(&mg->gsend, (size_t)mg->gmax));
+  CUDA_TRY(h, dmalloc(&mg->gbuf, (size_t)mg->gmax * nr));
+  CUDA_TRY(h, cudaMemset(mg->gsend, 0, (size_t)mg->gmax * sizeof(double)));
+  CUDA_TRY(h, cudaMemcpy(mg->gptr, ptr.data(), ((size_t)nr + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(mg->ggid, gather_gid, (size_t)ptr[nr] * sizeof(int), cudaMemcpyHostToDevice));
+  return HDG_OK;
+}
+
+int hdg_comm_stats(hdg_handle h, int* rank, int* nranks, int64_t* exchanges, int64_t* allreduces) {
+  if (!h) return HDG_EINVAL;
+  if (rank) *rank = h->comm ? h->comm->rank : 0;
+  if (nranks) *nranks = h->comm ? h->comm->nranks : 1;
+  if (exchanges) *exchanges = h->comm ? h->comm->exchanges : 0;
+  if (allreduces) *allreduces = h->comm ? h->comm->allreduces : 0;
   return HDG_OK;
 }
 

@@ -579,11 +579,11 @@ __global__ void __launch_bounds__(128) k_recon_rhs(const double* __restrict__ xy
 }
 
 // mass-weighted inner product of two cell fields: partial sums of detJ * x . y
-__global__ void __launch_bounds__(256) k_l2_inner(const double* __restrict__ xy, int nc, int ndof,
+__global__ void __launch_bounds__(256) k_l2_inner(const double* __restrict__ xy, int nc, int nc_own, int ndof,
                                                   const double* __restrict__ x, const double* __restrict__ y,
                                                   double* __restrict__ partial) {
   double acc = 0.0;
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc_own; cell += gridDim.x * blockDim.x) {
     double x0 = xy[cell], y0 = xy[(size_t)nc + cell];
     double x1 = xy[2 * (size_t)nc + cell], y1 = xy[3 * (size_t)nc + cell];
     double x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];

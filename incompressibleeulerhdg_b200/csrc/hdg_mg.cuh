@@ -16,7 +16,8 @@ struct DevCsr {
 };
 
 struct MgLevel {
-  int n = 0;
+  int n = 0;      // vector length (local entries: owned + ghost on a distributed level)
+  int nrows = 0;  // rows this rank computes (owned entries; == n on replicated levels / single GPU)
   DevCsr A, P, R;  // P: level l+1 -> l (n_l x n_{l+1}), R = P^T
   double* dinv = nullptr;
   double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr, *d = nullptr;
@@ -34,6 +35,12 @@ struct MgState {
   double ratio = 10.0;
   double fine_lmax = 2.0;
   double *fx = nullptr, *fx2 = nullptr, *fd = nullptr, *fr = nullptr;  // fine work vectors [b*nf]
+  // multi-GPU: levels l < repl are row-distributed (halo plan PLAN_P1 + l), levels >= repl replicated;
+  // the owned rows of level `repl` are all-gathered (padded to gmax per rank) and scattered by gid
+  int repl = 0;
+  int gmax = 0;
+  int *gptr = nullptr, *ggid = nullptr;  // device [nranks+1], [sum counts]
+  double *gsend = nullptr, *gbuf = nullptr;
 };
 
 struct ChebCoef {

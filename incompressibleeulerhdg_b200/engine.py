@@ -12,7 +12,8 @@ import os
 
 import numpy as np
 
-__all__ = ["HDGEngine", "HDGError", "load_library", "LIB_PATH", "TIMER_LABELS"]
+__all__ = ["HDGEngine", "HDGError", "load_library", "LIB_PATH", "TIMER_LABELS", "nccl_unique_id",
+           "broadcast_unique_id"]
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdg_b200.so")
 
@@ -69,6 +70,15 @@ SIGNATURES = {
     "hdg_l2_inner_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
     "hdg_lincomb_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _dp, C.POINTER(_vp)]),
     "hdg_mass_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "hdg_comm_unique_id": (C.c_int, [_vp]),
+    "hdg_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "hdg_set_partition": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_double]),
+    "hdg_set_halo_plan": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "hdg_halo_exchange_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "hdg_allreduce_sum_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "hdg_mg_set_distribution": (C.c_int, [_vp, C.c_int, _ip, _ip]),
+    "hdg_comm_stats": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64)]),
     "hdg_field_size": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int64)]),
     "hdg_upload": (C.c_int, [_vp, C.c_int, _dp, _vp]),
     "hdg_download": (C.c_int, [_vp, C.c_int, _vp, _dp]),
@@ -119,13 +129,40 @@ def _dev(t):
     return C.c_void_p(t.data_ptr())
 
 
-class HDGEngine:
-    """One engine per GPU.  Mirrors the role of the SCPC python context of `hdg_imex.py:128-133`."""
+def nccl_unique_id() -> bytes:
+    """a fresh 128-byte ncclUniqueId (call on one rank, broadcast to the others)"""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.hdg_comm_unique_id(buf)
+    if rc != HDG_OK:
+        raise HDGError(rc, lib.hdg_last_error(None).decode())
+    return buf.raw
 
-    def __init__(self, mesh, k: int, tau: float = 1.0, device: int = 0, torch_stream: bool = True):
+
+def broadcast_unique_id() -> bytes:
+    """rank 0 creates the ncclUniqueId, torch.distributed carries it to the other ranks"""
+    import torch.distributed as dist
+
+    box = [nccl_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+class HDGEngine:
+    """One engine per GPU.  Mirrors the role of the SCPC python context of `hdg_imex.py:128-133`.
+
+    `mesh` is either a complete :class:`mesh.Mesh` (single GPU) or a :class:`partition.LocalMesh`
+    (one rank of a partitioned mesh; `comm_id` is then the broadcast ncclUniqueId)."""
+
+    def __init__(self, mesh, k: int, tau: float = 1.0, device: int = 0, torch_stream: bool = True,
+                 comm_id: bytes | None = None):
         self.lib = load_library()
         if not (self.lib.hdg_supported_degrees() >> int(k)) & 1:
             raise HDGError(HDG_EINVAL, f"degree k={k} is not compiled into {LIB_PATH}")
+        self.part = None
+        if hasattr(mesh, "cells") and hasattr(mesh, "mesh"):  # partition.LocalMesh
+            self.part = mesh
+            mesh = mesh.mesh
         self.mesh = mesh
         self.k = int(k)
         self.tau = float(tau)
@@ -146,6 +183,46 @@ class HDGEngine:
         if torch_stream:
             # order engine work with torch's current stream so that torch-owned buffers are safe to share
             self.use_torch_stream()
+        if self.part is not None and self.part.nranks > 1:
+            if comm_id is None:
+                comm_id = broadcast_unique_id()
+            self.comm_init(self.part.rank, self.part.nranks, comm_id)
+            pt = self.part
+            self._check(self.lib.hdg_set_partition(self._h, pt.nc_owned, pt.nf_owned, pt.global_nf, pt.global_volume))
+            self.set_halo_plan(0, pt.cells)
+            self.set_halo_plan(1, pt.facets)
+
+    # -- multi-GPU ----------------------------------------------------------------------------------
+    @property
+    def nranks(self):
+        return 1 if self.part is None else self.part.nranks
+
+    @property
+    def rank(self):
+        return 0 if self.part is None else self.part.rank
+
+    def comm_init(self, rank: int, nranks: int, comm_id: bytes):
+        assert len(comm_id) == 128
+        buf = C.create_string_buffer(comm_id, 128)
+        self._check(self.lib.hdg_comm_init(self._h, int(rank), int(nranks), buf))
+
+    def set_halo_plan(self, kind: int, plan):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        peers, sptr, sidx, roff, rcnt = (i32(a) for a in (plan.peers, plan.send_ptr, plan.send_idx, plan.recv_off,
+                                                           plan.recv_cnt))
+        if sidx.size == 0:
+            sidx = np.zeros(1, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(_ip)
+        self._check(self.lib.hdg_set_halo_plan(self._h, int(kind), int(plan.n_owned), int(plan.n_local), int(peers.size),
+                                               p(peers), p(sptr), p(sidx), p(roff), p(rcnt)))
+
+    def halo_exchange_dev(self, kind: int, field, ndof: int):
+        self._check(self.lib.hdg_halo_exchange_dev(self._h, int(kind), int(ndof), _dev(field)))
+
+    def comm_stats(self):
+        r, n, e, a = C.c_int(0), C.c_int(1), C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.hdg_comm_stats(self._h, C.byref(r), C.byref(n), C.byref(e), C.byref(a)))
+        return {"rank": r.value, "nranks": n.value, "exchanges": e.value, "allreduces": a.value}
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _check(self, rc, allow=()):
@@ -241,10 +318,27 @@ class HDGEngine:
         return its.value
 
     # -- multigrid preconditioner -------------------------------------------------------------------
-    def mg_setup(self, hierarchy=None, smooth_fine=1, smooth_coarse=1, cheb_ratio=10.0):
-        """build (host, scipy) and upload the GTMG hierarchy; the trace solve becomes MG-PCG"""
+    def mg_setup(self, hierarchy=None, smooth_fine=1, smooth_coarse=1, cheb_ratio=10.0, global_mesh=None,
+                 repl_threshold=100_000):
+        """build (host, scipy) and upload the GTMG hierarchy; the trace solve becomes MG-PCG.
+
+        On a partitioned mesh `global_mesh` is the complete mesh: the hierarchy is built on it and
+        split with :func:`partition.partition_hierarchy` (`hierarchy` may then be a ready
+        :class:`partition.LocalHierarchy`)."""
         from . import multigrid
 
+        dist = self.part is not None and self.part.nranks > 1
+        if dist:
+            from . import partition
+
+            if hierarchy is None or not hasattr(hierarchy, "repl"):
+                if global_mesh is None:
+                    raise ValueError("mg_setup on a partitioned mesh needs global_mesh")
+                Hg = multigrid.build_hierarchy(global_mesh, self.k) if hierarchy is None else hierarchy
+                hierarchy = partition.partition_hierarchy(Hg, global_mesh, self.part, self.k,
+                                                          repl_threshold=repl_threshold)
+            for l, plan in enumerate(hierarchy.plans):
+                self.set_halo_plan(2 + l, plan)
         H = multigrid.build_hierarchy(self.mesh, self.k) if hierarchy is None else hierarchy
         keep = []
 
@@ -260,13 +354,19 @@ class HDGEngine:
         nl = H.nlevels
         A = (hdg_csr * nl)(*[conv(a) for a in H.A])
         P = (hdg_csr * max(nl - 1, 1))(*[conv(p) for p in H.P]) if nl > 1 else None
-        R = (hdg_csr * max(nl - 1, 1))(*[conv(p.T) for p in H.P]) if nl > 1 else None
+        Rs = H.R if dist else [p.T for p in H.P]
+        R = (hdg_csr * max(nl - 1, 1))(*[conv(r) for r in Rs]) if nl > 1 else None
         T = conv(H.T)
-        Tt = conv(H.T.T)
+        Tt = conv(H.Tt if dist else H.T.T)
         lmax = np.ascontiguousarray(H.lmax, dtype=np.float64)
         pinv = np.ascontiguousarray(H.pinv, dtype=np.float64)
         self._check(self.lib.hdg_mg_setup(self._h, nl, A, P, R, C.byref(T), C.byref(Tt), _ptr(lmax), _ptr(pinv),
                                           int(smooth_fine), int(smooth_coarse), float(cheb_ratio)))
+        if dist:
+            cnt = np.ascontiguousarray(H.gather_counts, dtype=np.int32)
+            gid = np.ascontiguousarray(H.gather_gid, dtype=np.int32)
+            self._check(self.lib.hdg_mg_set_distribution(self._h, int(H.repl), cnt.ctypes.data_as(_ip),
+                                                         gid.ctypes.data_as(_ip)))
         self.hierarchy = H
         return H
 

@@ -15,20 +15,46 @@ import numpy as np
 from ..engine import HDGEngine
 from ..functions import Function, FunctionSpace
 
-__all__ = ["IncompressibleEuler"]
+__all__ = ["IncompressibleEuler", "AUTO_PARTITION"]
+
+#: partition the mesh over the ranks of an initialised torch.distributed group (tests switch this off
+#: to build a single-GPU comparison engine inside a multi-rank job)
+AUTO_PARTITION = True
 
 
 class IncompressibleEuler(ABC):
     """Abstract base class; owns the engine and the three function spaces
     [DG_{k+1}]^2, DG_k, DGT_k (`hdg_imex.py:65-69`)."""
 
-    def __init__(self, mesh, degree, dt, label=None, device=0, tau=1.0, preconditioner="gtmg"):
+    def __init__(self, mesh, degree, dt, label=None, device=0, tau=1.0, preconditioner="gtmg", cell_rank=None):
+        """`mesh` is the complete mesh, exactly as in the reference.  When the process is one rank of
+        an initialised ``torch.distributed`` group (one process per GPU, `torchrun`), the mesh is
+        partitioned here -- the analogue of Firedrake distributing a mesh over COMM_WORLD -- with
+        `cell_rank` (default: contiguous strips, :func:`partition.strip_partition`) and this rank
+        keeps its local part only."""
         self._mesh = mesh
         self.degree = degree
         self._dt = dt
         self._label = label
         self.tau = tau
-        self.engine = HDGEngine(mesh, degree, tau=tau, device=device)
+        self.local_mesh = None
+        rank, world = 0, 1
+        try:
+            import torch.distributed as dist
+
+            if AUTO_PARTITION and dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        if world > 1:
+            from .. import partition
+
+            if cell_rank is None:
+                cell_rank = partition.strip_partition(mesh, world)
+            self.local_mesh = partition.partition_mesh(mesh, cell_rank, rank, world)
+            self.engine = HDGEngine(self.local_mesh, degree, tau=tau, device=device)
+        else:
+            self.engine = HDGEngine(mesh, degree, tau=tau, device=device)
         self._V_Q = FunctionSpace(self.engine, "Q")
         self._V_p = FunctionSpace(self.engine, "p")
         self._V_q = FunctionSpace(self.engine, "p")
@@ -44,7 +70,7 @@ class IncompressibleEuler(ABC):
         self.preconditioner = preconditioner
         if preconditioner == "gtmg":
             try:
-                self.engine.mg_setup()
+                self.engine.mg_setup(global_mesh=mesh if self.local_mesh is not None else None)
             except ValueError as exc:  # no nested P1 hierarchy for this mesh
                 import warnings
 

@@ -123,7 +123,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    target_cells = 2 * args.nx * args.nx
+    nxm, nym, _ = mesh_shape(args, max(1, args.gpus))
+    target_cells = 2 * nxm * nym
     t_all = []
     base = None
     for s in range(args.warmup + args.steps):
@@ -135,9 +136,9 @@ def run_reference(args):
     base["value"] = val
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args),
+        "config": workload_config(args, max(1, args.gpus)),
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -147,14 +148,28 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(args):
+def mesh_shape(args, world):
+    """(nx, ny, height): strong scaling partitions the named nx x nx unit-square mesh; weak scaling
+    stacks `world` such squares into [0,1] x [0,world] so that every GPU keeps 2 nx^2 triangles"""
+    if args.scaling == "weak":
+        return args.nx, args.nx * world, float(world)
+    return args.nx, args.nx, 1.0
+
+
+def workload_config(args, world=1):
+    nx, ny, height = mesh_shape(args, world)
+    if world == 1:
+        part = "single GPU"
+    else:
+        part = (f"{world} horizontal strips of {ny // world} rows of squares, one per GPU; vertex-adjacent ghost "
+                "layer; NCCL halo exchange per neighbour-reading kernel, all-reduce per Krylov dot product")
     return {
         "workload": f"HDG Chorin projection (hdg_implicit.py, use_projection_method=True), k={args.degree}, "
-                    f"UnitSquareMesh({args.nx},{args.nx}) = {2 * args.nx * args.nx} triangles per GPU, upwind flux, "
+                    f"{nx}x{ny} squares on [0,1]x[0,{height:g}] = {2 * nx * ny} triangles in total, upwind flux, "
                     f"Taylor-Green kappa=0.5, dt=0.32/nx, Krylov rtol {args.rtol:g}",
-        "nx": args.nx, "degree": args.degree, "dt": 0.32 / args.nx, "mesh_perturbation": 0.1,
-        "cache": "inputs (>=1.1 GB trace matrix, 0.3 GB velocity fields) exceed the 126 MB L2",
-        "partition": "one mesh replica per GPU (weak scaling, no data-path collective yet)",
+        "nx": nx, "ny": ny, "degree": args.degree, "dt": 0.32 / args.nx, "mesh_perturbation": 0.1,
+        "cache": "inputs (>=1.1 GB trace matrix, 0.3 GB velocity fields per 2 nx^2 cells) exceed the 126 MB L2",
+        "partition": part,
     }
 
 
@@ -180,10 +195,15 @@ def run_ours(args):
 
     nx, k = args.nx, args.degree
     dt = 0.32 / nx
-    mesh = UnitSquareMesh(nx, perturb=0.1)
+    nxm, nym, height = mesh_shape(args, world)
+    mesh = UnitSquareMesh(nxm, nym, perturb=0.1)
+    if height != 1.0:  # weak scaling: [0,1] x [0,world]; the Taylor-Green field stays a no-flow solution there
+        mesh.cell_xy[..., 1] *= height
+    # torch.distributed is initialised => the timestepper partitions the mesh over the ranks
     ts = IncompressibleEulerHDGImplicit(mesh, k, dt, flux="upwind", use_projection_method=True, device=local,
                                         krylov_rtol=args.rtol)
     eng = ts.engine
+    work_units = float(world) if args.scaling == "weak" else 1.0  # 2 nx^2-cell timesteps per global step
     prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
     Q0, p0 = prob.initial_condition()
     f_rhs = prob.f_rhs()
@@ -222,7 +242,7 @@ def run_ours(args):
     launches = eng.launch_count - l0
     timers = eng.timers()
     its_p, its_t = ts.niter_pressure.value, ts.niter_tentative.value
-    value = world * args.steps / (ms / 1e3)
+    value = work_units * args.steps / (ms / 1e3)
 
     # ---- end-to-end arm: forcing from pinned host memory each step, (Q, p) back to the host ----
     from incompressibleeulerhdg_b200.functions import Function
@@ -252,13 +272,14 @@ def run_ours(args):
         step_no += 1
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * e2e_steps / e2e_s
+    e2e_value = work_units * e2e_steps / e2e_s
 
     if rank == 0:
         peak, peak_src = load_peaks()
         b = k + 1
-        nblocks = 5 * mesh.nf
-        spmv_bytes = nblocks * b * b * 8 + nblocks * 4 + 2 * b * mesh.nf * 8
+        nf_loc = eng.nf  # facets this rank's SpMV runs over (owned + ghost)
+        nblocks = 5 * nf_loc
+        spmv_bytes = nblocks * b * b * 8 + nblocks * 4 + 2 * b * nf_loc * 8
         spmv_ms, spmv_n = timers["spmv_sampled"]
         ach = spmv_bytes / (spmv_ms / max(spmv_n, 1)) / 1e6 if spmv_ms > 0 else None
         roofline = {
@@ -272,9 +293,10 @@ def run_ours(args):
             cpu, _ = cpu_chorin_sample(args.cpu_nx, k, 1, mesh.nc)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
+            "config": workload_config(args, world),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.prod(sQ)) * 8,
                     "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps},
@@ -282,6 +304,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t},
+            "comm": eng.comm_stats(),
             "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
                                       ("bdm_projection", "tentative_velocity_solve", "forward_elimination",
                                        "trace_solve", "back_substitution")},
@@ -303,6 +326,9 @@ def main():
     ap.add_argument("--cpu-nx", type=int, default=16, help="mesh size of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the named nx x nx mesh partitioned over the GPUs (BASELINE.json configs[2]); "
+                         "weak: nx x (nx*gpus) squares, 2 nx^2 triangles per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

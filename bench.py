@@ -188,6 +188,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; this program prints ONE line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
     from incompressibleeulerhdg_b200.model_problems import TaylorGreen
@@ -274,6 +276,24 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = work_units * e2e_steps / e2e_s
 
+    # ---- roofline of the dominant trace-solve kernel: back-to-back launches between two CUDA events on
+    # the engine stream (the in-loop samples below also contain the host enqueue gap after the
+    # per-iteration convergence check, so they under-report the kernel)
+    xs, ys = eng.empty(2).normal_(), eng.empty(2)
+    for _ in range(3):
+        eng.trace_spmv_dev(xs, ys)
+    torch.cuda.synchronize()
+    n_spmv = 20
+    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sa.record()
+    for _ in range(n_spmv):
+        eng.trace_spmv_dev(xs, ys)
+    sb.record()
+    torch.cuda.synchronize()
+    spmv_b2b_ms = sa.elapsed_time(sb) / n_spmv
+    if world > 1:
+        barrier()
+
     if rank == 0:
         peak, peak_src = load_peaks()
         b = k + 1
@@ -281,12 +301,17 @@ def run_ours(args):
         nblocks = 5 * nf_loc
         spmv_bytes = nblocks * b * b * 8 + nblocks * 4 + 2 * b * nf_loc * 8
         spmv_ms, spmv_n = timers["spmv_sampled"]
-        ach = spmv_bytes / (spmv_ms / max(spmv_n, 1)) / 1e6 if spmv_ms > 0 else None
+        ach = spmv_bytes / spmv_b2b_ms / 1e6
         roofline = {
-            "kernel": "k_cg_spmv<3> (blocked-ELL trace SpMV inside the CG)",
-            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
-            "launch_ms": spmv_ms / max(spmv_n, 1), "sampled_launches": int(spmv_n),
+            "kernel": f"k_cg_spmv<{b}> (blocked-ELL trace SpMV of the CG; with N > 1 the launch includes this "
+                      "rank's NCCL facet-halo exchange)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at
+            # nx=1024, k=2 on one GPU (profiles/ncu_r1b_cg_spmv_raw.csv.gz): 1.279 GB + 74.4 MB
+            "traffic": 1353474384 if (world == 1 and nx == 1024 and k == 2) else None,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
+            "launch_ms": spmv_b2b_ms, "launches_timed": n_spmv,
+            "in_loop_sampled_ms": spmv_ms / max(spmv_n, 1), "in_loop_samples": int(spmv_n),
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

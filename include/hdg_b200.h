@@ -98,6 +98,11 @@ int hdg_get_trace_matrix(hdg_handle h, double* val_host, int32_t* col_host);
 int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
                            double* Q, double* p, double* l, double rtol, int maxit, int shift,
                            int* iters);
+/* on != 0: the trace Krylov iteration of hdg_poisson_apply_dev starts from the incoming content of
+ * `l` (e.g. the trace of the previous timestep; the analogue of ksp_initial_guess_nonzero) instead of
+ * zero.  The tolerance then refers to the preconditioned norm of the right-hand side, so the
+ * converged result does not depend on the guess.  Default off (the reference starts from zero). */
+int hdg_set_initial_guess(hdg_handle h, int on);
 /* Same with device pointers in SoA layout; asynchronous except for the iteration-count read. */
 int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
                           double* Q, double* p, double* l, double rtol, int maxit, int shift,
@@ -169,6 +174,12 @@ int hdg_shift_pressure_dev(hdg_handle h, double* p, double* l);
 /* pressure-reconstruction right-hand side (hdg_imex.py:204-207):
  *   Rp = _weak_divergence(psi, -b + (grad Q) Q),   Rl = - mu n.b ds  (zero on interior facets) */
 int hdg_reconstruction_rhs_dev(hdg_handle h, const double* Q, const double* b, double* Rp, double* Rl);
+/* constraint rows of the mixed operator applied to a state, Gamma(psi, mu; Q, p, l) of
+ * hdg_imex.py:342-351, as dual vectors Rp [pressure space] and Rl [trace space]: the (psi, mu) part of
+ * the monolithic residual of the fully implicit stage (hdg_imex.py:602-610, hdg_implicit.py:172-183) */
+int hdg_gamma_apply_dev(hdg_handle h, const double* Q, const double* p, const double* l, double* Rp, double* Rl);
+/* *result = sum_i x_i y_i over the owned entries of two fields of `kind` (summed over ranks; synchronous) */
+int hdg_dot_dev(hdg_handle h, int kind, const double* x, const double* y, double* result);
 /* *result = int_Omega x . y dx for two cell fields of the same kind (synchronous) */
 int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, double* result);
 /* out = sum_t coefs[t] * ptrs[t]  over n doubles (nterms <= 8; out may alias any input) */
@@ -220,9 +231,12 @@ int hdg_download(hdg_handle h, int kind, const double* dev_soa, double* host_aos
 /* labels: 0 setup_poisson, 1 forward_elimination, 2 trace_solve, 3 back_substitution,
  *         4 bdm_projection, 5 tentative_velocity_solve, 6 h2d, 7 d2h,
  *         8 spmv_sampled (every 16th trace SpMV of the CG, per-launch events),
- *         9 fimpl_sampled (first f_impl application of every BiCGStab iteration) */
+ *         9 fimpl_sampled (first f_impl application of every BiCGStab iteration),
+ *         10 condense (k_condense inside setup_poisson), 11 assemble (k_assemble inside setup_poisson) */
 int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n);
 int hdg_reset_timers(hdg_handle h);
+/* Measured FP64 FMA throughput of the device in TFLOP/s (denominator of "% of FP64 peak"). */
+int hdg_measure_fp64_peak(hdg_handle h, double* tflops);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */
 int64_t hdg_launch_count(hdg_handle h);
 

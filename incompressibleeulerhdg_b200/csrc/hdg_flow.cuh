@@ -432,6 +432,87 @@ __global__ void __launch_bounds__(256) k_trace_avg(const double* __restrict__ gK
 }
 
 // ------------------------------------------------------------------------------------------------
+// Constraint rows of the mixed operator applied to a state (the monolithic residual of the fully
+// implicit stage, hdg_imex.py:602-610 / hdg_implicit.py:172-183):  Gamma(psi, mu; u, phi, lambda)
+// (hdg_imex.py:342-351) as dual vectors
+//   Rp = B u + T phi - tau F^T lambda                      (per cell)
+//   Rl = sum_{K in f} (E u + tau F phi - tau |f| lambda)    (per facet; pass 2 = k_facet_sum)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128) k_gamma_cell(const double* __restrict__ xy, const int* __restrict__ flip,
+                                                    const int* __restrict__ cell_facet, int nc, int nf, double tau,
+                                                    const double* __restrict__ Q, const double* __restrict__ p,
+                                                    const double* __restrict__ lamg, double* __restrict__ Rp,
+                                                    double* __restrict__ gK) {
+  using T = RefTables<K>;
+  using D = Dims<K>;
+  constexpr int NQ1 = D::NQ1, NP = D::NP, NL1 = D::NL1;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double u[2][NQ1], phi[NP], lam[3][NL1], out[3][NL1], rp[NP];
+    load_Q<K>(Q, nc, cell, u);
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) {
+      phi[a] = p[(size_t)a * nc + cell];
+      rp[a] = 0.0;
+    }
+    int fl[3];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int f = cell_facet[(size_t)e * nc + cell];
+      fl[e] = flip[(size_t)e * nc + cell];
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) {
+        lam[e][m] = flip_sign(fl[e], m) * lamg[(size_t)m * nf + f];
+        out[e][m] = 0.0;
+      }
+    }
+    apply_B_over_detJ<K>(g, u, g.detJ, rp);
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      double c = tau * g.le[e];
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a) {
+        double v = 0.0;
+        HDG_UNROLL
+        for (int b = 0; b < NP; ++b) {
+          const double t = (b <= a) ? T::TT(e, a, b) : T::TT(e, b, a);
+          if (t != 0.0) v = fma(t, phi[b], v);
+        }
+        rp[a] = fma(c, v, rp[a]);
+      }
+    }
+    apply_Ft<K>(g, lam, -tau, rp);
+    apply_E<K>(g, u, 1.0, out);
+    apply_F<K>(g, phi, tau, out);
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) Rp[(size_t)a * nc + cell] = rp[a];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e)
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m)
+        gK[(size_t)(e * NL1 + m) * nc + cell] = flip_sign(fl[e], m) * (out[e][m] - tau * g.le[e] * lam[e][m]);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_facet_sum(const double* __restrict__ gK, const int* __restrict__ facet_cell,
+                                                   const int* __restrict__ facet_local, int nc, int nf,
+                                                   double* __restrict__ out) {
+  constexpr int NL1 = Dims<K>::NL1;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    int c0 = facet_cell[f], c1 = facet_cell[(size_t)nf + f];
+    int e0 = facet_local[f], e1 = facet_local[(size_t)nf + f];
+    HDG_UNROLL
+    for (int m = 0; m < NL1; ++m) {
+      double v = gK[(size_t)(e0 * NL1 + m) * nc + c0];
+      if (c1 >= 0) v += gK[(size_t)(e1 * NL1 + m) * nc + c1];
+      out[(size_t)m * nf + f] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // pressure-reconstruction right-hand side (hdg_imex.py:204-207):
 //   Rp = _weak_divergence(psi, X),  X = -b + (grad Q) Q;      Rl = - mu n.b ds
 // integrated by parts (identity for piecewise polynomials):

@@ -18,7 +18,7 @@ __all__ = ["HDGEngine", "HDGError", "load_library", "LIB_PATH", "TIMER_LABELS", 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdg_b200.so")
 
 TIMER_LABELS = ("setup_poisson", "forward_elimination", "trace_solve", "back_substitution", "bdm_projection",
-                "tentative_velocity_solve", "h2d", "d2h", "spmv_sampled", "fimpl_sampled")
+                "tentative_velocity_solve", "h2d", "d2h", "spmv_sampled", "fimpl_sampled", "condense", "assemble")
 
 HDG_OK, HDG_EINVAL, HDG_ECUDA, HDG_ENOGPU, HDG_ESTATE, HDG_ENCCL, HDG_ENOCONV = range(7)
 
@@ -49,6 +49,7 @@ SIGNATURES = {
                                          C.POINTER(C.c_int)]),
     "hdg_poisson_apply_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                         C.POINTER(C.c_int)]),
+    "hdg_set_initial_guess": (C.c_int, [_vp, C.c_int]),
     "hdg_mg_setup": (C.c_int, [_vp, C.c_int, C.POINTER(hdg_csr), C.POINTER(hdg_csr), C.POINTER(hdg_csr),
                                C.POINTER(hdg_csr), C.POINTER(hdg_csr), _dp, _dp, C.c_int, C.c_int, C.c_double]),
     "hdg_mg_enable": (C.c_int, [_vp, C.c_int]),
@@ -67,6 +68,8 @@ SIGNATURES = {
     "hdg_reconstruct_trace_dev": (C.c_int, [_vp, _vp, _vp, _vp]),
     "hdg_shift_pressure_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_reconstruction_rhs_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "hdg_gamma_apply_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hdg_dot_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
     "hdg_l2_inner_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
     "hdg_lincomb_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _dp, C.POINTER(_vp)]),
     "hdg_mass_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
@@ -84,6 +87,7 @@ SIGNATURES = {
     "hdg_download": (C.c_int, [_vp, C.c_int, _vp, _dp]),
     "hdg_get_timers": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "hdg_reset_timers": (C.c_int, [_vp]),
+    "hdg_measure_fp64_peak": (C.c_int, [_vp, _dp]),
     "hdg_launch_count": (C.c_int64, [_vp]),
 }
 
@@ -309,6 +313,10 @@ class HDGEngine:
         self.last_iterations = its.value
         return Q, p, l, its.value
 
+    def set_initial_guess(self, on: bool = True):
+        """start the trace Krylov solve from the incoming trace vector instead of zero"""
+        self._check(self.lib.hdg_set_initial_guess(self._h, int(bool(on))))
+
     def poisson_apply_dev(self, rhs_Q, rhs_p, rhs_l, Q, p, l, rtol=1e-12, maxit=10000, shift=True, check=True):
         its = C.c_int(0)
         rc = self.lib.hdg_poisson_apply_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(rhs_l), _dev(Q), _dev(p), _dev(l),
@@ -391,7 +399,7 @@ class HDGEngine:
     def set_penalty(self, alpha: float):
         self._check(self.lib.hdg_set_penalty(self._h, float(alpha)))
 
-    def set_tentative_solver(self, mode: int = 1, sweeps: int = 6):
+    def set_tentative_solver(self, mode: int = 1, sweeps: int = 8):
         """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps"""
         self._check(self.lib.hdg_set_tentative_solver(self._h, int(mode), int(sweeps)))
 
@@ -424,6 +432,15 @@ class HDGEngine:
     def reconstruction_rhs_dev(self, Q, b, Rp, Rl):
         self._check(self.lib.hdg_reconstruction_rhs_dev(self._h, _dev(Q), _dev(b), _dev(Rp), _dev(Rl)))
 
+    def gamma_apply_dev(self, Q, p, l, Rp, Rl):
+        """(Rp, Rl) = Gamma(psi, mu; Q, p, l), the constraint rows of the monolithic operator"""
+        self._check(self.lib.hdg_gamma_apply_dev(self._h, _dev(Q), _dev(p), _dev(l), _dev(Rp), _dev(Rl)))
+
+    def dot_dev(self, kind, x, y):
+        out = C.c_double(0.0)
+        self._check(self.lib.hdg_dot_dev(self._h, int(kind), _dev(x), _dev(y), C.byref(out)))
+        return out.value
+
     def l2_inner_dev(self, kind, x, y):
         out = C.c_double(0.0)
         self._check(self.lib.hdg_l2_inner_dev(self._h, int(kind), _dev(x), _dev(y), C.byref(out)))
@@ -448,6 +465,12 @@ class HDGEngine:
         cnt = (C.c_int64 * n)()
         self._check(self.lib.hdg_get_timers(self._h, ms, cnt, n))
         return {lab: (ms[i], cnt[i]) for i, lab in enumerate(TIMER_LABELS)}
+
+    def measure_fp64_peak(self) -> float:
+        """measured FP64 FMA throughput in TFLOP/s"""
+        out = C.c_double(0.0)
+        self._check(self.lib.hdg_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
 
     def reset_timers(self):
         self._check(self.lib.hdg_reset_timers(self._h))

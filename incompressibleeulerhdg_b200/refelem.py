@@ -323,3 +323,68 @@ def nodal_to_modal_facet(k: int, nodes=None):
     nodes = lagrange_nodes_facet(k) if nodes is None else nodes
     V = legendre01(k, nodes).T
     return np.linalg.inv(V)
+
+
+# ---- symmetric (Dunavant-type) rules: fewer points than the collapsed tensor rules ---------------------
+_SYM_SEEDS = {
+    # degree: (centroid weight or None, [(a, w) S21 orbits], [(a, b, w) S111 orbits]); weights sum to 1
+    5: (0.225, [(0.470142064105115, 0.132394152788506), (0.101286507323456, 0.125939180544827)], []),
+    8: (0.144315607677787,
+        [(0.459292588292723, 0.095091634267285), (0.170569307751760, 0.103217370534718),
+         (0.050547228317031, 0.032458497623198)],
+        [(0.008394777409958, 0.263112829634638, 0.027230314174435)]),
+}
+
+
+def _sym_expand(params, n21, n111, has_c):
+    pts, wts = [], []
+    i = 0
+    if has_c:
+        pts.append((1 / 3, 1 / 3))
+        wts.append(params[0])
+        i = 1
+    for _ in range(n21):
+        a, w = params[i], params[i + 1]
+        i += 2
+        b = 1 - 2 * a
+        pts += [(a, a), (a, b), (b, a)]
+        wts += [w] * 3
+    for _ in range(n111):
+        a, b, w = params[i], params[i + 1], params[i + 2]
+        i += 3
+        c = 1 - a - b
+        pts += [(a, b), (b, a), (a, c), (c, a), (b, c), (c, b)]
+        wts += [w] * 6
+    return np.array(pts), np.array(wts)
+
+
+_SYM_CACHE = {}
+
+
+def triangle_quadrature_sym(degree: int, dtype=np.float64):
+    """fully symmetric rule on T^ exact for total degree <= `degree` (7 points for 5, 16 for 8), Newton-
+    refined to round-off from the classical Dunavant parameters by enforcing orthogonality of the
+    Dubiner modes against the constant.  Returns None when no rule is tabulated for `degree`.
+    Weights sum to 1/2."""
+    key = min((d for d in _SYM_SEEDS if d >= degree), default=None)
+    if key is None:
+        return None
+    if key not in _SYM_CACHE:
+        from scipy.optimize import least_squares
+
+        cw, s21, s111 = _SYM_SEEDS[key]
+        p0 = ([cw] if cw is not None else []) + [v for o in s21 for v in o] + [v for o in s111 for v in o]
+        target = np.zeros(ncell(key))
+        target[0] = 1.0 / dubiner(0, np.array([[1 / 3, 1 / 3]]))[0, 0]  # int phi_0 = 1/phi_0 (orthonormal)
+
+        def resid(p):
+            x, w = _sym_expand(p, len(s21), len(s111), cw is not None)
+            return dubiner(key, x) @ (0.5 * w) - target
+
+        sol = least_squares(resid, np.array(p0), xtol=3e-16, ftol=None, gtol=None, max_nfev=200)
+        assert np.abs(resid(sol.x)).max() < 5e-16, np.abs(resid(sol.x)).max()
+        x, w = _sym_expand(sol.x, len(s21), len(s111), cw is not None)
+        assert np.all(w > 0) and np.all(x > 0) and np.all(x.sum(axis=1) < 1)
+        _SYM_CACHE[key] = (x, 0.5 * w)
+    x, w = _SYM_CACHE[key]
+    return x.astype(dtype), w.astype(dtype)

@@ -257,7 +257,8 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                             eng.lincomb_dev(st.l.data, [(1.0, st.l.data), (1.0, up.l.data)])  # :594-599
                     else:
                         with PerformanceLog("unsplit_solve"):  # :601-620
-                            self._monolithic.solve(self._Qstar[i - 1], adt, self._rho[i], st.Q, st.p, st.l)
+                            self._monolithic.solve(self._Qstar[i - 1], adt, self._rho[i], st.Q, st.p, st.l,
+                                                   rtol=self.krylov_rtol, upwind=(self.flux == "upwind"))
                     self._shift_pressure(st)  # :621
                 its = self.pressure_solve("final_stage")  # :624
                 self.niter_final_pressure.update(its)

@@ -2,21 +2,163 @@
 GMRES+MUMPS solve (`hdg_imex.py:600-620`; `hdg_implicit.py:153-186`).
 
 The fully implicit operator is not cell-locally condensable: the momentum block
-couples neighbouring cells directly.  The engine therefore runs a flexible outer Krylov iteration
-on the monolithic (u, phi, lambda) operator, preconditioned by exactly the projection pair the
-reference itself defines (tentative-velocity solve + statically condensed mixed Poisson,
-`hdg_imex.py:572-599`), so that condensation and the trace solve appear inside the preconditioner.
+couples neighbouring cells directly.  The engine therefore runs a flexible GMRES on the monolithic
+(u, phi, lambda) system
+
+    u - a F(u; Q*) - a G(phi, lambda) = rho          (velocity row, Riesz form: M^-1 applied)
+    Gamma(psi, mu; u, phi, lambda)    = 0            (constraint rows, dual form, hdg_imex.py:342-351)
+
+with F = M^-1 f_impl (`hdg_imex.py:313-331`), G = M^-1 g (`:333-340`), a = a_ii dt, right-preconditioned
+by exactly the projection pair the reference itself defines (`hdg_imex.py:572-599`): a
+tentative-velocity solve d1 = (I - a F)^-1 r_u followed by the statically condensed mixed-Poisson
+solve for the constraint defect r_Gamma - Gamma(d1, 0, 0), whose pressure and trace are scaled by
+1/a.  Condensation and the trace solve thus appear inside the preconditioner; the inner solves run at
+a loose tolerance (FGMRES tolerates a varying preconditioner) and the outer iteration is converged to
+``rtol`` so that the result matches the direct solve of the reference to ~1e-10.
+
+The system is singular along (0, 1, 1) (`hdg_imex.py:480-489`); the caller fixes the constant with
+`_shift_pressure`.
 """
 
 from __future__ import annotations
 
+import numpy as np
+
 __all__ = ["MonolithicStage"]
 
 
-class MonolithicStage:
-    def __init__(self, timestepper):
-        self.ts = timestepper
+class _Vec:
+    """(Q, p, l) triple of device tensors"""
 
-    def solve(self, Q_star, adt, rho, Q, p, lmbda):
-        raise NotImplementedError(
-            "the fully implicit (unsplit) stage solve is not implemented yet; use use_projection_method=True")
+    def __init__(self, ts, zero=False):
+        eng = ts.engine
+        self.Q, self.p, self.l = eng.empty(0), eng.empty(1), eng.empty(2)
+        if zero:
+            self.Q.zero_(), self.p.zero_(), self.l.zero_()
+
+    def parts(self):
+        return ((0, self.Q), (1, self.p), (2, self.l))
+
+
+class MonolithicStage:
+    def __init__(self, timestepper, restart=30, inner_rtol=1e-3, maxit=300):
+        self.ts = timestepper
+        self.eng = timestepper.engine
+        self.restart = restart
+        self.inner_rtol = inner_rtol
+        self.maxit = maxit
+        self.last_iterations = 0
+        self.last_inner = (0, 0)
+        self._V = self._Z = None
+        self._w = self._t = self._x = self._zero_p = self._zero_l = None
+
+    # -- small vector algebra on triples (all on the device, through the C-ABI) -----------------------
+    def _dot(self, x, y):
+        return sum(self.eng.dot_dev(kind, a, b) for (kind, a), (_, b) in zip(x.parts(), y.parts()))
+
+    def _lincomb(self, out, terms):
+        for i, (_, o) in enumerate(out.parts()):
+            self.eng.lincomb_dev(o, [(c, v.parts()[i][1]) for c, v in terms])
+
+    def _alloc(self):
+        if self._V is None:
+            m = self.restart
+            self._V = [_Vec(self.ts) for _ in range(m + 1)]
+            self._Z = [_Vec(self.ts) for _ in range(m)]
+            self._w, self._t, self._x = _Vec(self.ts), _Vec(self.ts), _Vec(self.ts)
+            self._zero_p, self._zero_l = self.eng.zeros(1), self.eng.zeros(2)
+            self._gp, self._gl = self.eng.empty(1), self.eng.empty(2)
+
+    # -- operator and preconditioner ------------------------------------------------------------------
+    def _apply(self, Q_star, adt, upwind, x, out):
+        """out = W K x with the row weight W = diag(I, omega, omega): the constraint rows are dual
+        vectors (O(h^2) entries) that act on the pressure through ~1/a, so they are weighted by
+        omega = 1 / (a * mean cell Jacobian) to balance the residual norm GMRES minimises"""
+        eng = self.eng
+        eng.fimpl_apply_dev(Q_star.data, x.Q, out.Q, c0=1.0, c1=-adt, upwind=upwind)  # u - a F(u)
+        eng.pressure_gradient_dev(x.p, x.l, out.Q, c0=1.0, c1=-adt)  # - a G(phi, lambda)
+        eng.gamma_apply_dev(x.Q, x.p, x.l, out.p, out.l)
+        eng.lincomb_dev(out.p, [(self._omega, out.p)])
+        eng.lincomb_dev(out.l, [(self._omega, out.l)])
+
+    def _precondition(self, Q_star, adt, upwind, r, z):
+        """z = P^-1 r: tentative velocity, then mixed Poisson on the remaining constraint defect"""
+        eng = self.eng
+        it_t = eng.tentative_solve_dev(Q_star.data, adt, r.Q, z.Q, upwind=upwind, rtol=self.inner_rtol, maxit=500,
+                                       zero_guess=True, check=False)
+        eng.gamma_apply_dev(z.Q, self._zero_p, self._zero_l, self._gp, self._gl)
+        eng.lincomb_dev(self._gp, [(1.0 / self._omega, r.p), (-1.0, self._gp)])
+        eng.lincomb_dev(self._gl, [(1.0 / self._omega, r.l), (-1.0, self._gl)])
+        t = self._t
+        it_p = eng.poisson_apply_dev(None, self._gp, self._gl, t.Q, t.p, t.l, rtol=self.inner_rtol, maxit=500,
+                                     shift=False, check=False)
+        eng.lincomb_dev(z.Q, [(1.0, z.Q), (1.0, t.Q)])
+        eng.lincomb_dev(z.p, [(1.0 / adt, t.p)])
+        eng.lincomb_dev(z.l, [(1.0 / adt, t.l)])
+        self.last_inner = (self.last_inner[0] + it_t, self.last_inner[1] + it_p)
+
+    # -- FGMRES(m) -------------------------------------------------------------------------------------
+    def solve(self, Q_star, adt, rho, Q, p, lmbda, rtol=1e-12, upwind=True):
+        """solve the fully implicit stage for right-hand side (rho, 0, 0); (Q, p, lmbda) hold the
+        initial guess on entry and the solution on exit.  Returns the number of outer iterations."""
+        eng = self.eng
+        self._alloc()
+        mesh, part = self.ts._mesh, eng.part
+        mean_detJ = 2.0 * (part.global_volume / part.global_nc if part is not None else mesh.volume / mesh.nc)
+        self._omega = 1.0 / (adt * mean_detJ)
+        guess_was = None
+        # inner trace solves always start from zero
+        eng.set_initial_guess(False)
+        x = self._x
+        x.Q, x.p, x.l = Q.data, p.data, lmbda.data
+        V, Z, w = self._V, self._Z, self._w
+        m = self.restart
+        self.last_inner = (0, 0)
+        total = 0
+        bnorm = np.sqrt(eng.dot_dev(0, rho.data, rho.data))
+        if bnorm == 0.0:
+            bnorm = 1.0
+        while True:
+            # r = b - K x
+            self._apply(Q_star, adt, upwind, x, w)
+            eng.lincomb_dev(V[0].Q, [(1.0, rho.data), (-1.0, w.Q)])
+            eng.lincomb_dev(V[0].p, [(-1.0, w.p)])
+            eng.lincomb_dev(V[0].l, [(-1.0, w.l)])
+            beta = np.sqrt(self._dot(V[0], V[0]))
+            if beta <= rtol * bnorm or total >= self.maxit:
+                break
+            self._lincomb(V[0], [(1.0 / beta, V[0])])
+            H = np.zeros((m + 1, m))
+            g = np.zeros(m + 1)
+            g[0] = beta
+            cs, sn = np.zeros(m), np.zeros(m)
+            j_used = 0
+            for j in range(m):
+                self._precondition(Q_star, adt, upwind, V[j], Z[j])
+                self._apply(Q_star, adt, upwind, Z[j], w)
+                for i in range(j + 1):  # modified Gram-Schmidt
+                    H[i, j] = self._dot(w, V[i])
+                    self._lincomb(w, [(1.0, w), (-H[i, j], V[i])])
+                H[j + 1, j] = np.sqrt(self._dot(w, w))
+                if H[j + 1, j] > 0:
+                    self._lincomb(V[j + 1], [(1.0 / H[j + 1, j], w)])
+                for i in range(j):  # previous Givens rotations
+                    t0 = cs[i] * H[i, j] + sn[i] * H[i + 1, j]
+                    H[i + 1, j] = -sn[i] * H[i, j] + cs[i] * H[i + 1, j]
+                    H[i, j] = t0
+                den = np.hypot(H[j, j], H[j + 1, j])
+                cs[j], sn[j] = H[j, j] / den, H[j + 1, j] / den
+                H[j, j] = den
+                H[j + 1, j] = 0.0
+                g[j + 1] = -sn[j] * g[j]
+                g[j] = cs[j] * g[j]
+                total += 1
+                j_used = j + 1
+                if abs(g[j + 1]) <= rtol * bnorm or total >= self.maxit:
+                    break
+            y = np.linalg.solve(np.triu(H[:j_used, :j_used]), g[:j_used])
+            for i in range(j_used):
+                self._lincomb(x, [(1.0, x), (y[i], Z[i])])
+        self.last_iterations = total
+        del guess_was
+        return total

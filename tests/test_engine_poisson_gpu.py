@@ -170,3 +170,40 @@ def test_p1_stiffness_is_galerkin_coarse_operator():
     A = multigrid.p1_stiffness(m).toarray()
     G = T.T @ P[np.ix_(perm, perm)] @ T
     assert np.abs(G - A).max() < 1e-11 * np.abs(A).max()
+
+
+@pytest.mark.parametrize("pc", ["jacobi", "gtmg"])
+def test_initial_guess_does_not_change_the_result(pc):
+    """hdg_set_initial_guess: starting the trace Krylov solve from a guess (here: the exact trace, a
+    perturbed one and garbage) gives the zero-guess result to the solver tolerance; the tolerance is
+    relative to the right-hand side, so a good guess only saves iterations"""
+    import torch
+
+    k = 2
+    require_degree(k)
+    m = UnitSquareMesh(12, perturb=0.15)
+    eng = HDGEngine(m, k)
+    eng.setup_poisson()
+    if pc == "gtmg":
+        eng.mg_setup()
+    rng = np.random.default_rng(11)
+    sQ, sp_, sl = eng.shapes()
+    Rp = eng.upload(1, rng.standard_normal(sp_))
+    Q, p, l = eng.empty(0), eng.empty(1), eng.empty(2)
+    its0 = eng.poisson_apply_dev(None, Rp, None, Q, p, l, rtol=1e-13)
+    Qz, pz, lz = Q.clone(), p.clone(), l.clone()
+    eng.set_initial_guess(True)
+    its_exact = eng.poisson_apply_dev(None, Rp, None, Q, p, l, rtol=1e-13)  # l holds the solution
+    assert its_exact <= 1
+    assert rel(p.cpu().numpy(), pz.cpu().numpy()) < 1e-11
+    l.copy_(lz + 1e-6 * torch.randn_like(lz))
+    its_near = eng.poisson_apply_dev(None, Rp, None, Q, p, l, rtol=1e-13)
+    assert its_near < its0
+    for a, b_ in ((Q, Qz), (p, pz), (l, lz)):
+        assert rel(a.cpu().numpy(), b_.cpu().numpy()) < RTOL
+    l.copy_(100.0 * torch.randn_like(lz))
+    eng.poisson_apply_dev(None, Rp, None, Q, p, l, rtol=1e-13, maxit=100000)
+    for a, b_ in ((Q, Qz), (p, pz), (l, lz)):
+        assert rel(a.cpu().numpy(), b_.cpu().numpy()) < RTOL
+    eng.set_initial_guess(False)
+    assert eng.poisson_apply_dev(None, Rp, None, Q, p, l, rtol=1e-13) == its0

@@ -87,3 +87,19 @@ def test_engine_imex_golden():
     Q0, p0 = prob.initial_condition()
     Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), 0.02)
     assert rel(Q.to_host(), GOLD["imex_ssp2_k1/Q"]) < RTOL and rel(p.to_host(), GOLD["imex_ssp2_k1/p"]) < RTOL
+
+
+@pytest.mark.gpu
+def test_engine_config0_fully_implicit_golden():
+    """BASELINE.json configs[0]: HDG fully implicit, k=1, 16x16, stationary solution, 10 steps"""
+    from incompressibleeulerhdg_b200 import timesteppers as TS
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+
+    require_degree(1)
+    m = UnitSquareMesh(16)
+    ts = TS.IncompressibleEulerHDGImplicit(m, 1, 0.1, use_projection_method=False, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.0)  # kappa = 0: zero forcing
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), 1.0)
+    assert rel(Q.to_host(), GOLD["implicit_k1_nx16/Q"]) < RTOL
+    assert rel(p.to_host(), GOLD["implicit_k1_nx16/p"]) < 1e-9

@@ -66,3 +66,60 @@ def test_imex_k2_ssp2():
     Qo, po = orc.solve(TaylorGreenOracle("constant", 0.5), nt * dt)
     assert rel(Q.to_host(), Qo) < 1e-10
     assert rel(p.to_host(), po) < 1e-10
+
+
+# ---- fully implicit (unsplit) stage: FGMRES on the monolithic system, hdg_implicit.py:153-186 ----------
+def test_gamma_rows_are_consistent_with_the_poisson_solve():
+    """Gamma(Q, p, l) applied to the solution of the condensed mixed-Poisson solve returns the
+    constraint right-hand sides the solve was given (hdg_imex.py:342-351 vs :123-127)"""
+    from incompressibleeulerhdg_b200.engine import HDGEngine
+    from oracle.hdg_oracle import HDGOracle
+
+    k = 2
+    require_degree(k)
+    m = UnitSquareMesh(6, perturb=0.15)
+    o = HDGOracle(m, k)
+    eng = HDGEngine(m, k)
+    eng.setup_poisson()
+    rng = np.random.default_rng(3)
+    Ru = rng.standard_normal((m.nc, 2, o.nQ1))
+    Rp = rng.standard_normal((m.nc, o.np_))
+    Rl = rng.standard_normal((m.nf, k + 1))
+    Rl[:, 0] -= o.consistency_defect(Ru, Rp, Rl) / m.nf  # consistent data: nothing is projected away
+    dRu, dRp, dRl = eng.upload(0, Ru), eng.upload(1, Rp), eng.upload(2, Rl)
+    Q, p, l = eng.empty(0), eng.empty(1), eng.empty(2)
+    eng.poisson_apply_dev(dRu, dRp, dRl, Q, p, l, rtol=1e-14, shift=False)
+    gp, gl = eng.empty(1), eng.empty(2)
+    eng.gamma_apply_dev(Q, p, l, gp, gl)
+    assert rel(eng.download(1, gp), Rp) < 1e-9
+    assert rel(eng.download(2, gl), Rl) < 1e-9
+
+
+@pytest.mark.parametrize("k,nx", [(1, 6), (2, 4)])
+def test_fully_implicit_matches_oracle(k, nx):
+    require_degree(k)
+    m = UnitSquareMesh(nx, perturb=0.1)
+    dt, nt = 0.02, 2
+    ts = TS.IncompressibleEulerHDGImplicit(m, k, dt, flux="upwind", use_projection_method=False, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), nt * dt)
+    orc = ChorinOracle(m, k, dt, flux="upwind", use_projection_method=False)
+    Qo, po = orc.solve(TaylorGreenOracle("exponential", 0.5), nt * dt)
+    assert ts._monolithic.last_iterations > 0
+    assert rel(Q.to_host(), Qo) < 1e-10
+    assert rel(p.to_host(), po) < 1e-9  # the pressure enters the velocity row scaled by dt
+
+
+def test_imex_unsplit_matches_oracle():
+    k, nx, dt = 1, 5, 0.02
+    require_degree(k)
+    m = UnitSquareMesh(nx, perturb=0.1)
+    ts = TS.IncompressibleEulerHDGIMEXSSP2_332(m, k, dt, use_projection_method=False, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), dt)
+    orc = IMEXOracle(m, k, dt, tableau="imex_ssp2_332", use_projection_method=False)
+    Qo, po = orc.solve(TaylorGreenOracle("exponential", 0.5), dt)
+    assert rel(Q.to_host(), Qo) < 1e-10
+    assert rel(p.to_host(), po) < 1e-9

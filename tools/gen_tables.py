@@ -106,7 +106,8 @@ def tables(k):
     out = dict(D=D, E=E, F=F, KK=KK, TT=TT, LL=LL, NN=NN)
     # ---- advection / BDM tabulations -------------------------------------------------------
     # cell rule exact for degree 3k+2 (w in P_{k+1}, Q* in P_{k+1}, grad Q in P_k)
-    xa, wa = R.triangle_quadrature_gj(3 * k + 2, LD)
+    sym = R.triangle_quadrature_sym(3 * k + 2, LD)  # 7 / 16 points for k = 1 / 2 instead of 9 / 25
+    xa, wa = sym if sym is not None else R.triangle_quadrature_gj(3 * k + 2, LD)
     out["WQ"] = wa
     out["PHI"] = R.dubiner(k + 1, xa).T  # [q][i]
     out["DPHI"] = np.moveaxis(R.dubiner_grad(k + 1, xa), [0, 1, 2], [2, 1, 0])  # [d][q][i]

@@ -39,10 +39,11 @@ def main():
     ap.add_argument("--mg", nargs="*", default=["1,1", "1,2", "2,2", "1,3", "2,1"])
     ap.add_argument("--ratio", type=float, nargs="*", default=[10.0])
     ap.add_argument("--rtol", type=float, default=1e-12)
+    ap.add_argument("--cold", action="store_true", help="no warm starts (zero / Q^n initial guesses)")
     args = ap.parse_args()
     nx = args.nx
     mesh = UnitSquareMesh(nx, perturb=0.1)
-    ts = IncompressibleEulerHDGImplicit(mesh, args.k, 0.32 / nx, krylov_rtol=args.rtol)
+    ts = IncompressibleEulerHDGImplicit(mesh, args.k, 0.32 / nx, krylov_rtol=args.rtol, warm_start=not args.cold)
     prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
     Q0, p0 = prob.initial_condition()
     ts.initialise(Q0, p0)
@@ -51,7 +52,11 @@ def main():
     step = 1
     for sw in args.sweeps:
         ts.engine.set_tentative_solver(1, sw)
-        r = run(ts, f, args.steps, step)
+        try:
+            r = run(ts, f, args.steps, step)
+        except Exception as exc:  # too few sweeps: BiCGStab stalls
+            r = {"error": repr(exc)[:200]}
+            ts.initialise(Q0, p0)
         step += args.steps
         print(json.dumps({"nx": nx, "tent_sweeps": sw, **r}), flush=True)
     ts.engine.set_tentative_solver(1, 6)
@@ -60,7 +65,11 @@ def main():
         sf, sc = (int(v) for v in spec.split(","))
         for ratio in args.ratio:
             ts.engine.mg_setup(hierarchy=H, smooth_fine=sf, smooth_coarse=sc, cheb_ratio=ratio)
-            r = run(ts, f, args.steps, step)
+            try:
+                r = run(ts, f, args.steps, step)
+            except Exception as exc:
+                r = {"error": repr(exc)[:200]}
+                ts.initialise(Q0, p0)
             step += args.steps
             print(json.dumps({"nx": nx, "mg": [sf, sc], "ratio": ratio, **r}), flush=True)
 

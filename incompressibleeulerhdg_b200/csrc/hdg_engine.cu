@@ -1573,7 +1573,9 @@ int hdg_create(int k, double tau, int nc, int nf, const double* cell_xy, const i
   cudaDeviceProp prop;
   CREATE_TRY(cudaGetDeviceProperties(&prop, device));
   h->num_sms = prop.multiProcessorCount;
-  h->grid = h->num_sms * 8;
+  // persistent grid of the grid-stride kernels: 6 CTAs of 256 threads are co-resident per SM for the
+  // widest of them (k_cg_spmv: 40 registers), so 6 per SM is exactly one wave without a tail
+  h->grid = h->num_sms * 6;
   CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   int nq1, np, nl1;

@@ -280,9 +280,10 @@ def run_ours(args):
     # the engine stream (the in-loop samples below also contain the host enqueue gap after the
     # per-iteration convergence check, so they under-report the kernel)
     xs, ys = eng.empty(2).normal_(), eng.empty(2)
+    barrier()  # the e2e phase leaves the ranks skewed; the exchange inside the SpMV would wait for the slowest
     for _ in range(3):
         eng.trace_spmv_dev(xs, ys)
-    torch.cuda.synchronize()
+    barrier()
     n_spmv = 20
     sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sa.record()
@@ -291,6 +292,7 @@ def run_ours(args):
     sb.record()
     torch.cuda.synchronize()
     spmv_b2b_ms = sa.elapsed_time(sb) / n_spmv
+    fp64_peak = eng.measure_fp64_peak()  # TFLOP/s, 8 independent DFMA chains per thread
     if world > 1:
         barrier()
 
@@ -313,6 +315,16 @@ def run_ours(args):
             "launch_ms": spmv_b2b_ms, "launches_timed": n_spmv,
             "in_loop_sampled_ms": spmv_ms / max(spmv_n, 1), "in_loop_samples": int(spmv_n),
         }
+        # second-hottest kernel family (tentative velocity): k_fimpl is FP64-issue bound, not HBM bound
+        fimpl_ms, fimpl_n = timers["fimpl_sampled"]
+        dfma_per_cell = {1: 7 * 48 + 3 * 220, 2: 16 * 80 + 3 * 350, 3: 36 * 120 + 3 * 735, 4: 64 * 168 + 3 * 1176}[k]
+        other = {}
+        if fimpl_n:
+            t = fimpl_ms / fimpl_n
+            other["k_fimpl"] = {
+                "launch_ms": t, "bound": "fp64", "dfma_per_cell": dfma_per_cell,
+                "achieved_tflops": 2.0 * dfma_per_cell * eng.nc / t / 1e9, "peak_tflops_measured": fp64_peak,
+                "frac": 2.0 * dfma_per_cell * eng.nc / t / 1e9 / fp64_peak, "sampled_launches": int(fimpl_n)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_chorin_sample(args.cpu_nx, k, 1, mesh.nc)
@@ -327,8 +339,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "other_kernels": other,
             "cpu_baseline": cpu,
-            "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t},
+            "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t,
+                           "per_step_tentative_pressure": ts.iteration_history},
             "comm": eng.comm_stats(),
             "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
                                       ("bdm_projection", "tentative_velocity_solve", "forward_elimination",

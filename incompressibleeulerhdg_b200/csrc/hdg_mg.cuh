@@ -106,12 +106,14 @@ __global__ void k_csr_cheb(int n, const int* __restrict__ rowptr, const int* __r
   }
 }
 
-// x = pinv b on the coarsest level (dense, row per thread)
+// x = pinv b on the coarsest level (dense, row per thread).  The pseudo-inverse of the symmetric
+// coarse operator is symmetric, so row i is read as column i: consecutive threads touch consecutive
+// addresses (coalesced) and the summation order over j stays fixed.
 __global__ void k_dense_matvec(int n, const double* __restrict__ M, const double* __restrict__ b,
                                double* __restrict__ x) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int j = 0; j < n; ++j) s = fma(M[(size_t)i * n + j], b[j], s);
+    for (int j = 0; j < n; ++j) s = fma(M[(size_t)j * n + i], b[j], s);
     x[i] = s;
   }
 }

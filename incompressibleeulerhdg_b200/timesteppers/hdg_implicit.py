@@ -76,6 +76,7 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self._lmbda_prev = self._V_trace.zeros()
         self._dQt = self._V_Q.zeros()  # Q~ - Q of the previous step
         self._nsteps = 0
+        self.iteration_history = []  # (tentative its, pressure its) per step
         self.engine.set_initial_guess(bool(self.warm_start) and self.use_projection_method)
         self.niter_tentative.reset()
         self.niter_pressure.reset()
@@ -101,12 +102,14 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
                 else:
                     self._Q_tentative.assign(Q)
                 its = self.tentative_velocity_solve(self._Q_star, self._rhs, self._Q_tentative, zero_guess=False)  # :129
+                its_t = its
                 self.niter_tentative.update(its)
                 if self.warm_start:
                     eng.lincomb_dev(self._dQt.data, [(1.0, self._Q_tentative.data), (-1.0, Q.data)])
                 eng.weak_divergence_dev(self._Q_tentative.data, self._Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
                 its = self.pressure_solve(self._Rp, self._u, self._phi, self._lmbda)  # :146
                 self.niter_pressure.update(its)
+                self.iteration_history.append((its_t, its))
                 eng.lincomb_dev(Q.data, [(1.0, self._Q_tentative.data), (self._dt, self._u.data)])  # :150
                 self._nsteps += 1
             else:

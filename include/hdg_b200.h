@@ -163,6 +163,12 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
  * advection-free operator whose facet Schur complement is inverted by `sweeps` Chebyshev /
  * facet-block-Jacobi sweeps (mesh-independent iteration counts; see csrc/hdg_tent.cuh). */
 int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps);
+/* multi-GPU only.  local_sweeps != 0 (default): the Chebyshev sweeps of the facet Schur preconditioner
+ * run without halo exchanges in between (restricted overlapping Schwarz on owned + ghost facets; the
+ * preconditioner stays a fixed linear operator and the converged velocity is unchanged to the solver
+ * tolerance, but iterates differ from the single-GPU run in the last digits).  0: exchange before every
+ * sweep, which reproduces the single-GPU iteration exactly. */
+int hdg_set_tentative_comm(hdg_handle h, int local_sweeps);
 /* dual vector on the pressure space: mode 0  scale * int psi div Q dx      (hdg_implicit.py:145)
  *                                    mode 1  scale * _weak_divergence      (hdg_imex.py:353-365) */
 int hdg_weak_divergence_dev(hdg_handle h, const double* Q, double scale, int mode, double* Rp);

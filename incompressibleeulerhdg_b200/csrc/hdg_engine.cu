@@ -86,6 +86,7 @@ struct hdg_engine {
   int tent_sweeps = 8;        // Chebyshev sweeps on the facet Schur complement (8: fewest ms per solve in
                               // the nx=512 probe, profiles/probe_params_r1e.jsonl)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
+  bool tent_local_sweeps = true;  // multi-GPU: no halo exchange between the Chebyshev sweeps (see hdg_set_tentative_comm)
   double *tent_c = nullptr;   // [6][nf]
   int *tent_col = nullptr, *tent_bits = nullptr;  // [4][nf], [nf]
   double *tent_cm = nullptr;  // [3*NM][nc]
@@ -1176,7 +1177,11 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
   cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
   double *x = h->tent_f[2], *x2 = h->tent_f[3];
   for (int j = 0; j < h->tent_sweeps; ++j) {
-    if (j > 0) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);
+    // With local sweeps every rank iterates on its own facets plus the ghost layer without refreshing
+    // the ghosts: a restricted overlapping Schwarz version of the same polynomial.  X is a facet "mass"
+    // matrix (condition ~7 after block-Jacobi), its inverse decays geometrically across the overlap, so
+    // the preconditioner is perturbed only at the partition cuts -- and it stays a fixed linear operator.
+    if (j > 0 && !h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);
     LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
            inv_aalpha, t, (const double*)nullptr, (const double*)x, h->tent_f[4], x2, cc[j].cd, cc[j].cr,
            j == 0 ? 1 : 0, 0);
@@ -2003,6 +2008,12 @@ int hdg_set_penalty(hdg_handle h, double alpha) {
 int hdg_set_initial_guess(hdg_handle h, int on) {
   if (!h) return HDG_EINVAL;
   h->use_guess = on != 0;
+  return HDG_OK;
+}
+
+int hdg_set_tentative_comm(hdg_handle h, int local_sweeps) {
+  if (!h) return HDG_EINVAL;
+  h->tent_local_sweeps = local_sweeps != 0;
   return HDG_OK;
 }
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hdg_set_penalty": (C.c_int, [_vp, C.c_double]),
     "hdg_set_tentative_solver": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "hdg_set_tentative_comm": (C.c_int, [_vp, C.c_int]),
     "hdg_project_bdm_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_fimpl_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
     "hdg_tentative_solve_dev": (C.c_int, [_vp, _vp, C.c_double, C.c_int, _vp, _vp, C.c_double, C.c_int, C.c_int,
@@ -402,6 +403,10 @@ class HDGEngine:
     def set_tentative_solver(self, mode: int = 1, sweeps: int = 8):
         """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps"""
         self._check(self.lib.hdg_set_tentative_solver(self._h, int(mode), int(sweeps)))
+
+    def set_tentative_comm(self, local_sweeps: bool = True):
+        """multi-GPU: skip (True) or perform (False) the halo exchanges between Schur sweeps"""
+        self._check(self.lib.hdg_set_tentative_comm(self._h, int(bool(local_sweeps))))
 
     def project_bdm_dev(self, Q, Qstar):
         self._check(self.lib.hdg_project_bdm_dev(self._h, _dev(Q), _dev(Qstar)))

@@ -65,10 +65,11 @@ def poisson_case(rank, world, local, mesh, k, pc, thr, name):
                               getattr(eng.hierarchy, "repl", None), "comm": eng.comm_stats()})
 
 
-def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name):
+def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, local_sweeps=True):
     def run(auto):
         ts_common.AUTO_PARTITION = auto
         ts = getattr(TS, cls)(mesh, k, dt, device=local, krylov_rtol=1e-13, **kwargs)
+        ts.engine.set_tentative_comm(local_sweeps)
         prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
         Q0, p0 = prob.initial_condition()
         Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), nt * dt)
@@ -79,7 +80,8 @@ def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name):
     lm = ts.local_mesh
     cg, nco = lm.cells.local_gid, lm.nc_owned
     errs = {"Q": rel(Q1[:nco], Q0[cg[:nco]]), "p": rel(p1[:nco], p0[cg[:nco]])}
-    report(rank, name, errs, {"comm": ts.engine.comm_stats()})
+    report(rank, name, errs, {"comm": ts.engine.comm_stats(), "local_sweeps": local_sweeps,
+                              "its_tentative": ts.niter_tentative.value})
 
 
 def main():
@@ -94,6 +96,10 @@ def main():
     poisson_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "gtmg", 60, "poisson_k1_gtmg_distributed")
     poisson_case(rank, world, local, UnitDiskMesh(3), 3, "jacobi", 0, "poisson_k3_disk_jacobi")
     timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2")
+    timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2,
+                     "chorin_k2_exchange_every_sweep", local_sweeps=False)
+    timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGImplicit",
+                     {"use_projection_method": False}, 0.02, 1, "fully_implicit_k1")
     timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
                      {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1")
     dist.barrier()

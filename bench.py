@@ -368,7 +368,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t,
                            "per_step_tentative_pressure": ts.iteration_history},
-            "comm": eng.comm_stats(),
+            "comm": {**eng.comm_stats(), "transport": ("nvlink-p2p" if getattr(eng, "p2p", False) else "nccl")
+                     if world > 1 else "none", "p2p_timeouts": eng.p2p_status()},
             "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
                                       ("bdm_projection", "tentative_velocity_solve", "forward_elimination",
                                        "trace_solve", "back_substitution")},

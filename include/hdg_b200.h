@@ -163,11 +163,12 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
  * advection-free operator whose facet Schur complement is inverted by `sweeps` Chebyshev /
  * facet-block-Jacobi sweeps (mesh-independent iteration counts; see csrc/hdg_tent.cuh). */
 int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps);
-/* multi-GPU only.  local_sweeps != 0 (default): the Chebyshev sweeps of the facet Schur preconditioner
- * run without halo exchanges in between (restricted overlapping Schwarz on owned + ghost facets; the
- * preconditioner stays a fixed linear operator and the converged velocity is unchanged to the solver
- * tolerance, but iterates differ from the single-GPU run in the last digits).  0: exchange before every
- * sweep, which reproduces the single-GPU iteration exactly. */
+/* multi-GPU only.  local_sweeps == 0 (default): the ghost facets are refreshed before every Chebyshev
+ * sweep of the facet Schur preconditioner, which reproduces the single-GPU iteration exactly.
+ * local_sweeps != 0: the sweeps run without halo exchanges in between (restricted overlapping Schwarz
+ * on owned + ghost facets; still a fixed linear preconditioner, the converged velocity is unchanged to
+ * the solver tolerance).  Measured on 2 B200: 3 instead of 10 exchanges per operator application but
+ * ~+40 % BiCGStab iterations, so it only pays when exchanges dominate. */
 int hdg_set_tentative_comm(hdg_handle h, int local_sweeps);
 /* dual vector on the pressure space: mode 0  scale * int psi div Q dx      (hdg_implicit.py:145)
  *                                    mode 1  scale * _weak_divergence      (hdg_imex.py:353-365) */
@@ -215,6 +216,18 @@ int hdg_set_partition(hdg_handle h, int nc_owned, int nf_owned, int64_t nf_globa
 int hdg_set_halo_plan(hdg_handle h, int kind, int n_owned, int n_local, int npeers, const int32_t* peer_rank,
                       const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_off,
                       const int32_t* recv_cnt);
+/* Peer-memory transport (NVLink P2P through CUDA IPC, csrc/hdg_comm.cuh): halo exchanges become a push
+ * kernel that stores straight into the peers' mailboxes plus a wait/unpack kernel, and all-reduces one
+ * single-CTA kernel; NCCL is then only used for the multigrid all-gather.
+ *   hdg_p2p_alloc   allocates this rank's mailbox (slab_doubles per sender and parity; must hold the
+ *                   largest halo block times its dofs) and returns its 64-byte cudaIpcMemHandle
+ *   hdg_p2p_attach  handles[nranks][64]: maps every peer's mailbox and switches the transport on
+ *   hdg_p2p_enable  0 = back to NCCL send/recv + all-reduce, 1 = peer memory (collective: same on all ranks)
+ *   hdg_p2p_status  *error != 0 if a bounded flag wait timed out (a peer died or fell out of step) */
+int hdg_p2p_alloc(hdg_handle h, int64_t slab_doubles, void* handle64);
+int hdg_p2p_attach(hdg_handle h, const void* handles);
+int hdg_p2p_enable(hdg_handle h, int on);
+int hdg_p2p_status(hdg_handle h, int* error);
 /* refresh the ghost entries of an SoA device field [ndof][n_local] (asynchronous on the engine stream) */
 int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field);
 /* in-place sum over ranks of n <= 16 device doubles */

@@ -75,6 +75,62 @@ struct HaloPlanDev {
 };
 
 constexpr int HDG_MAX_PLANS = 2 + 16;  // cells, facets, P1 levels
+constexpr int HDG_MAX_RANKS = 8;       // GPUs of one box (NVSwitch domain)
+constexpr int HDG_RED_MAX = 8;         // doubles per all-reduce
+
+// ---- peer-memory transport (NVLink P2P through CUDA IPC; one process per GPU) -------------------------
+// Every rank owns one device buffer laid out as P2PLayout and maps the buffers of all peers.  A halo
+// exchange is a *push*: the pack kernel stores the owned entries a peer needs straight into that
+// peer's mailbox slab (remote stores over NVLink), then raises a flag in the peer's memory; the
+// receiver's unpack kernel spins on its local flags and copies the slabs into the ghost entries.  An
+// all-reduce is one single-CTA kernel: every rank stores its partial result into all peers' reduction
+// boxes, waits for theirs and sums in rank order (bitwise identical on all ranks).  Slabs and boxes are
+// double-buffered by a per-pair / per-reduction counter, which is sufficient because peer sets are
+// symmetric and each side can only be one exchange ahead of the other (its next push needs the
+// peer's previous one).  Spins are bounded: on a timeout the kernel sets `error` and proceeds.
+struct P2PHeader {
+  unsigned long long halo_flag[HDG_MAX_RANKS];  // halo_flag[q]: number of pushes received from rank q
+  unsigned long long red_flag[HDG_MAX_RANKS];   // red_flag[q]: number of reductions rank q contributed to
+  double red_box[2][HDG_MAX_RANKS][HDG_RED_MAX];
+  int error;                                    // set by a kernel whose bounded spin ran out
+  unsigned int ticket;                          // last-block detection of the push kernel
+  int pad[14];
+};
+
+struct P2P {
+  bool enabled = false;
+  size_t slab = 0;                          // doubles per (parity, sender) slab
+  char* base = nullptr;                     // own buffer: P2PHeader, then mbox[2][nranks][slab]
+  char* peer_base[HDG_MAX_RANKS] = {};      // mapped peer buffers (own entry = base)
+  unsigned long long pair_count[HDG_MAX_RANKS] = {};  // exchanges done with each peer
+  unsigned long long red_count = 0;
+};
+
+__host__ __device__ inline P2PHeader* p2p_header(char* base) { return reinterpret_cast<P2PHeader*>(base); }
+__host__ __device__ inline double* p2p_slab(char* base, size_t slab, int nranks, int parity, int sender) {
+  return reinterpret_cast<double*>(base + sizeof(P2PHeader)) + ((size_t)parity * nranks + sender) * slab;
+}
+
+struct P2PPeers {  // kernel argument: the peers of one exchange
+  int npeers;
+  int rank[HDG_MAX_RANKS];
+  int send_ptr[HDG_MAX_RANKS + 1];
+  int recv_ptr[HDG_MAX_RANKS + 1];          // ghost blocks relative to n_owned
+  char* peer_base[HDG_MAX_RANKS];
+  unsigned long long count[HDG_MAX_RANKS];  // value of the pair counter for this exchange (after increment)
+};
+
+constexpr long long HDG_SPIN_CYCLES = 4000000000ll;  // ~2 s at 1.9 GHz
+
+__device__ __forceinline__ void p2p_wait(volatile unsigned long long* flag, unsigned long long want, int* error) {
+  const long long t0 = clock64();
+  while (*flag < want) {
+    if (clock64() - t0 > HDG_SPIN_CYCLES) {
+      *error = 1;
+      break;
+    }
+  }
+}
 
 struct Comm {
   ncclComm_t nccl = nullptr;
@@ -84,6 +140,7 @@ struct Comm {
   size_t send_cap = 0, recv_cap = 0;
   double* red = nullptr;  // device [16] reduction scratch
   int64_t exchanges = 0, allreduces = 0;
+  P2P p2p;
 };
 
 // sendbuf[i*ndof + d] = field[d*n_local + send_idx[i]]
@@ -104,6 +161,102 @@ __global__ void k_halo_unpack(int total, int ndof, int n_local, int n_owned, con
     int d = (int)(t / total);
     int g = (int)(t - (size_t)d * total);
     field[(size_t)d * n_local + n_owned + g] = buf[(size_t)g * ndof + d];
+  }
+}
+
+// push: slab[(i - send_ptr[j]) * ndof + d] on peer j = field[d*n_local + send_idx[i]], then signal
+__global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int nranks, size_t slab, int ndof,
+                                                  int n_local, const int* __restrict__ send_idx,
+                                                  const double* __restrict__ field, char* own_base) {
+  const int total = pp.send_ptr[pp.npeers];
+  const size_t n = (size_t)total * ndof;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    int d = (int)(t / total);
+    int i = (int)(t - (size_t)d * total);
+    int j = 0;
+    while (i >= pp.send_ptr[j + 1]) ++j;
+    double* dst = p2p_slab(pp.peer_base[j], slab, nranks, (int)(pp.count[j] & 1ull), myrank);
+    dst[(size_t)(i - pp.send_ptr[j]) * ndof + d] = field[(size_t)d * n_local + send_idx[i]];
+  }
+  // the last CTA to finish publishes the data: all remote stores of this grid precede the flags
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    P2PHeader* own = p2p_header(own_base);
+    unsigned int tk = atomicAdd(&own->ticket, 1u);
+    if (tk == gridDim.x - 1) {
+      own->ticket = 0;
+      __threadfence_system();
+      for (int j = 0; j < pp.npeers; ++j) {
+        volatile unsigned long long* f = &p2p_header(pp.peer_base[j])->halo_flag[myrank];
+        *f = pp.count[j];
+      }
+      __threadfence_system();
+    }
+  }
+}
+
+// wait for every peer's push of this exchange, then field[d*n_local + n_owned + g] = slab_q[(g - recv_ptr[q])*ndof + d]
+__global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks, size_t slab, int ndof, int n_local,
+                                                         int n_owned, char* own_base, double* __restrict__ field) {
+  P2PHeader* own = p2p_header(own_base);
+  if (threadIdx.x < pp.npeers)
+    p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], pp.count[threadIdx.x], &own->error);
+  __syncthreads();
+  __threadfence_system();
+  const int total = pp.recv_ptr[pp.npeers];
+  const size_t n = (size_t)total * ndof;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    int d = (int)(t / total);
+    int g = (int)(t - (size_t)d * total);
+    int j = 0;
+    while (g >= pp.recv_ptr[j + 1]) ++j;
+    const double* src = p2p_slab(own_base, slab, nranks, (int)(pp.count[j] & 1ull), pp.rank[j]);
+    field[(size_t)d * n_local + n_owned + g] = __ldcv(&src[(size_t)(g - pp.recv_ptr[j]) * ndof + d]);
+  }
+}
+
+struct P2PAll {  // kernel argument of the all-reduce: every rank of the communicator
+  char* base[HDG_MAX_RANKS];
+};
+
+// in-place all-reduce of the partial-sum slots part[0..nslots)[G] over all ranks, one CTA:
+// finish the slots, store them into every peer's box, wait, sum in rank order, spread back
+__global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, int nranks, unsigned long long count,
+                                                       double* __restrict__ part, int G, int nslots) {
+  __shared__ double mine[HDG_RED_MAX];
+  __shared__ double total[HDG_RED_MAX];
+  for (int s = 0; s < nslots; ++s) {
+    const double* p = part + (size_t)s * G;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) v += p[i];
+    v = block_reduce(v);
+    if (threadIdx.x == 0) mine[s] = v;
+    __syncthreads();
+  }
+  const int parity = (int)(count & 1ull);
+  if (threadIdx.x < nranks) {
+    const int q = threadIdx.x;
+    double* box = p2p_header(all.base[q])->red_box[parity][myrank];
+    for (int s = 0; s < nslots; ++s) box[s] = mine[s];
+    __threadfence_system();
+    volatile unsigned long long* f = &p2p_header(all.base[q])->red_flag[myrank];
+    *f = count;
+  }
+  __syncthreads();
+  P2PHeader* own = p2p_header(all.base[myrank]);
+  if (threadIdx.x < nranks) p2p_wait(&own->red_flag[threadIdx.x], count, &own->error);
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x < nslots) {
+    double v = 0.0;
+    for (int q = 0; q < nranks; ++q) v += __ldcv(&own->red_box[parity][q][threadIdx.x]);
+    total[threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int s = 0; s < nslots; ++s) {
+    double* p = part + (size_t)s * G;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) p[i] = (i == 0) ? total[s] : 0.0;
   }
 }
 

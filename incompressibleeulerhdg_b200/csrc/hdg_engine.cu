@@ -86,7 +86,8 @@ struct hdg_engine {
   int tent_sweeps = 8;        // Chebyshev sweeps on the facet Schur complement (8: fewest ms per solve in
                               // the nx=512 probe, profiles/probe_params_r1e.jsonl)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
-  bool tent_local_sweeps = true;  // multi-GPU: no halo exchange between the Chebyshev sweeps (see hdg_set_tentative_comm)
+  bool tent_local_sweeps = false;  // multi-GPU: skip the halo exchanges between the Chebyshev sweeps
+                                   // (hdg_set_tentative_comm; costs ~+40 % BiCGStab iterations, profiles/summary_r1.md)
   double *tent_c = nullptr;   // [6][nf]
   int *tent_col = nullptr, *tent_bits = nullptr;  // [4][nf], [nf]
   double *tent_cm = nullptr;  // [3*NM][nc]
@@ -274,6 +275,43 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
     return;
   }
   double* field = const_cast<double*>(cfield);  // only the ghost entries are written
+  if (c->p2p.enabled) {
+    // push over NVLink peer memory: pack kernel stores into the peers' mailbox slabs and raises their
+    // flags; the unpack kernel waits on the local flags (hdg_comm.cuh)
+    P2PPeers pp;
+    pp.npeers = (int)pl.peers.size();
+    size_t need = 0;
+    for (int j = 0; j < pp.npeers; ++j) {
+      const int q = pl.peers[j];
+      pp.rank[j] = q;
+      pp.send_ptr[j] = pl.send_ptr[j];
+      pp.recv_ptr[j] = pl.recv_off[j] - pl.n_owned;
+      if (pl.recv_cnt[j] == 0) pp.recv_ptr[j] = (j == 0) ? 0 : pp.recv_ptr[j - 1] + pl.recv_cnt[j - 1];
+      pp.peer_base[j] = c->p2p.peer_base[q];
+      pp.count[j] = ++c->p2p.pair_count[q];
+      need = std::max(need, (size_t)std::max(pl.send_ptr[j + 1] - pl.send_ptr[j], pl.recv_cnt[j]) * ndof);
+    }
+    pp.send_ptr[pp.npeers] = pl.total_send;
+    pp.recv_ptr[pp.npeers] = pl.total_recv;
+    if (need > c->p2p.slab) {
+      if (!h->comm_rc) {
+        h->comm_rc = HDG_EINVAL;
+        h->err = "halo exchange: a block of " + std::to_string(need) + " doubles exceeds the P2P mailbox slab (" +
+                 std::to_string(c->p2p.slab) + "); pass a larger slab to hdg_p2p_alloc";
+      }
+      return;
+    }
+    if (pp.npeers > 0) {
+      const int gs = std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_send * ndof, 256)));
+      LAUNCH(h, k_p2p_push, gs, 256, pp, c->rank, c->nranks, c->p2p.slab, ndof, pl.n_local, (const int*)pl.send_idx,
+             (const double*)field, c->p2p.base);
+      const int gr = std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_recv * ndof, 256)));
+      LAUNCH(h, k_p2p_wait_unpack, gr, 256, pp, c->nranks, c->p2p.slab, ndof, pl.n_local, pl.n_owned, c->p2p.base,
+             field);
+    }
+    c->exchanges++;
+    return;
+  }
   if (!comm_grow(&c->sendbuf, &c->send_cap, (size_t)pl.total_send * ndof) ||
       !comm_grow(&c->recvbuf, &c->recv_cap, (size_t)pl.total_recv * ndof)) {
     h->comm_rc = HDG_ECUDA;
@@ -304,6 +342,13 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
 static void allreduce_slots(hdg_engine* h, double* part, int nslots) {
   Comm* c = h->comm;
   if (!c || c->nranks == 1) return;
+  if (c->p2p.enabled && nslots <= HDG_RED_MAX) {
+    P2PAll all;
+    for (int q = 0; q < c->nranks; ++q) all.base[q] = c->p2p.peer_base[q];
+    LAUNCH(h, k_p2p_allreduce, 1, BLOCK, all, c->rank, c->nranks, ++c->p2p.red_count, part, h->grid, nslots);
+    c->allreduces++;
+    return;
+  }
   LAUNCH(h, k_part_finish, nslots, BLOCK, (const double*)part, h->grid, c->red);
   NCCL_DO(h, g_nccl.AllReduce(c->red, c->red, (size_t)nslots, ncclDouble, ncclSum, c->nccl, h->stream));
   LAUNCH(h, k_part_spread, nslots, BLOCK, part, h->grid, (const double*)c->red);
@@ -1230,6 +1275,9 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   // out = A_aug Phat^-1 in
   auto precond_x = [&](const double* in, bool with_mu) -> double* {
     halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, in);  // moments and xhat are evaluated on ghost cells too
+    // local sweeps iterate on the ghost facets as well, so their right-hand side must be the true one:
+    // the multiplier part of a Krylov vector is garbage on ghost facets until it is refreshed
+    if (with_mu && h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, NM, in + nx);
     LAUNCH(h, k_tent_moments<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->nc, in, h->tent_cm);
     LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf,
            with_mu ? in + nx : (const double*)nullptr, h->tent_f[0], h->tent_f[1]);
@@ -1520,6 +1568,9 @@ int hdg_destroy(hdg_handle h) {
     if (c->sendbuf) cudaFree(c->sendbuf);
     if (c->recvbuf) cudaFree(c->recvbuf);
     if (c->red) cudaFree(c->red);
+    for (int q = 0; q < c->nranks && q < HDG_MAX_RANKS; ++q)
+      if (q != c->rank && c->p2p.peer_base[q]) cudaIpcCloseMemHandle(c->p2p.peer_base[q]);
+    if (c->p2p.base) cudaFree(c->p2p.base);
     if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
     delete c;
     h->comm = nullptr;
@@ -2318,6 +2369,65 @@ int hdg_comm_init(hdg_handle h, int rank, int nranks, const void* id128) {
     FAIL(h, HDG_ECUDA, "hdg_comm_init: cudaMalloc failed");
   }
   h->comm = c;
+  return HDG_OK;
+}
+
+int hdg_p2p_alloc(hdg_handle h, int64_t slab_doubles, void* handle64) {
+  if (!h || !handle64 || slab_doubles < 1) return HDG_EINVAL;
+  if (!h->comm) FAIL(h, HDG_ESTATE, "hdg_p2p_alloc: call hdg_comm_init first");
+  Comm* c = h->comm;
+  if (c->nranks > HDG_MAX_RANKS) FAIL(h, HDG_EINVAL, "hdg_p2p_alloc: more ranks than one NVSwitch box holds");
+  if (c->p2p.base) FAIL(h, HDG_ESTATE, "hdg_p2p_alloc: already allocated");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t bytes = sizeof(P2PHeader) + 2 * (size_t)c->nranks * (size_t)slab_doubles * sizeof(double);
+  CUDA_TRY(h, cudaMalloc((void**)&c->p2p.base, bytes));
+  CUDA_TRY(h, cudaMemset(c->p2p.base, 0, bytes));
+  c->p2p.slab = (size_t)slab_doubles;
+  c->p2p.peer_base[c->rank] = c->p2p.base;
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(h, cudaIpcGetMemHandle(&hd, c->p2p.base));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  memcpy(handle64, &hd, sizeof(hd));
+  return HDG_OK;
+}
+
+int hdg_p2p_attach(hdg_handle h, const void* handles) {
+  if (!h || !handles) return HDG_EINVAL;
+  if (!h->comm || !h->comm->p2p.base) FAIL(h, HDG_ESTATE, "hdg_p2p_attach: call hdg_p2p_alloc first");
+  Comm* c = h->comm;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  for (int q = 0; q < c->nranks; ++q) {
+    if (q == c->rank) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)handles + 64 * (size_t)q, sizeof(hd));
+    void* ptr = nullptr;
+    CUDA_TRY(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    c->p2p.peer_base[q] = (char*)ptr;
+  }
+  c->p2p.enabled = true;
+  return HDG_OK;
+}
+
+int hdg_p2p_enable(hdg_handle h, int on) {
+  if (!h || !h->comm) return HDG_EINVAL;
+  Comm* c = h->comm;
+  if (on) {
+    for (int q = 0; q < c->nranks; ++q)
+      if (!c->p2p.peer_base[q]) FAIL(h, HDG_ESTATE, "hdg_p2p_enable: peers are not attached");
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  c->p2p.enabled = on != 0;
+  return HDG_OK;
+}
+
+// 0 if no bounded spin of the peer-memory transport has timed out on this rank
+int hdg_p2p_status(hdg_handle h, int* error) {
+  if (!h || !error) return HDG_EINVAL;
+  *error = 0;
+  if (!h->comm || !h->comm->p2p.base) return HDG_OK;
+  CUDA_TRY(h, cudaMemcpyAsync(error, &p2p_header(h->comm->p2p.base)->error, sizeof(int), cudaMemcpyDeviceToHost,
+                              h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return HDG_OK;
 }
 

@@ -226,7 +226,7 @@ __device__ __forceinline__ void fimpl_facet(const Geo& g, double alpha, int nc, 
 }
 
 template <int K, bool UPWIND>
-__global__ void __launch_bounds__(128) k_fimpl(const double* __restrict__ xy, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(128, (K <= 2 ? 3 : 1)) k_fimpl(const double* __restrict__ xy, const int* __restrict__ nbr,
                                                const int* __restrict__ nbr_e, int nc, double alpha,
                                                const double* __restrict__ Qstar, const double* __restrict__ X,
                                                const double* __restrict__ Z, double c0, double c1,

@@ -112,44 +112,36 @@ __global__ void __launch_bounds__(256) k_tent_trhs(const double* __restrict__ cm
   }
 }
 
-// contribution of the cell on one side of facet f to (G mu)_f and to the diagonal block
+// contribution of the cell on one side of facet f to (G mu)_f and to the diagonal block.  All global
+// loads (geometric coefficients c[0..2], neighbour values v[0..1][.]) are issued by the caller *before*
+// the switch over the local facet index, so that the divergent part is arithmetic only and the ~22
+// independent loads of a facet are in flight together (the kernel is latency bound: ncu r1h shows 50 %
+// long-scoreboard stalls at 52 % occupancy with DRAM traffic already at the algorithmic minimum).
 template <int K, int E>
-__device__ __forceinline__ void tent_side(int nf, int f, int s, int bits, const double* __restrict__ tc,
-                                          const int* __restrict__ tcol, const double* __restrict__ mu,
-                                          const double (&own)[TentDims<K>::NM], bool offdiag,
+__device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const double (&c)[3],
+                                          const double (&v)[2][TentDims<K>::NM], bool offdiag,
                                           double (&acc)[TentDims<K>::NM], double (&D)[TentDims<K>::NMH]) {
   using T = RefTables<K>;
   constexpr int NM = TentDims<K>::NM;
-  const double c0 = tc[(size_t)(3 * s) * nf + f];
-  const int fl0 = (bits >> (3 * s)) & 1;
   // diagonal block (also part of G mu)
   HDG_UNROLL
   for (int j = 0; j < NM; ++j) {
     HDG_UNROLL
     for (int l = 0; l <= j; ++l) {
-      if (T::GG(E, E, j, l) != 0.0) {
-        double v = c0 * T::GG(E, E, j, l) * flip_sign(fl0, j) * flip_sign(fl0, l);
-        D[tri(j, l)] += v;
-      }
+      if (T::GG(E, E, j, l) != 0.0) D[tri(j, l)] += c[0] * T::GG(E, E, j, l) * flip_sign(fl0, j) * flip_sign(fl0, l);
     }
   }
   if (!offdiag) return;
   HDG_UNROLL
   for (int jj = 1; jj < 3; ++jj) {
     const int E2 = (E + jj) % 3;
-    const double c = tc[(size_t)(3 * s + jj) * nf + f];
-    const int fl = (bits >> (3 * s + jj)) & 1;
-    const int col = tcol[(size_t)(2 * s + jj - 1) * nf + f];
-    double v[NM];
-    HDG_UNROLL
-    for (int l = 0; l < NM; ++l) v[l] = flip_sign(fl, l) * mu[(size_t)l * nf + col];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
       double sum = 0.0;
       HDG_UNROLL
       for (int l = 0; l < NM; ++l)
-        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), v[l], sum);
-      acc[j] = fma(c * flip_sign(fl0, j), sum, acc[j]);
+        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), flip_sign(fl[jj - 1], l) * v[jj - 1][l], sum);
+      acc[j] = fma(c[jj] * flip_sign(fl0, j), sum, acc[j]);
     }
   }
 }
@@ -169,45 +161,63 @@ __global__ void __launch_bounds__(128) k_tent_sweep(int nf, const int* __restric
                                                     int mode) {
   constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    // ---- all loads first ------------------------------------------------------------------------
     const int bits = tbits[f];
-    double own[NM], acc[NM], D[NMH];
+    int e[2], col[2][2];
+    double c[2][3], v[2][2][NM], own[NM], b[NM], dprev[NM];
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      e[s] = facet_local[(size_t)s * nf + f];
+      HDG_UNROLL
+      for (int j = 0; j < 3; ++j) c[s][j] = tc[(size_t)(3 * s + j) * nf + f];  // zero on a missing side
+      HDG_UNROLL
+      for (int jj = 0; jj < 2; ++jj) col[s][jj] = tcol[(size_t)(2 * s + jj) * nf + f];  // f itself if missing
+    }
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
       own[j] = zero ? 0.0 : x[(size_t)j * nf + f];
-      acc[j] = 0.0;
+      b[j] = 0.0;
+      if (mode != 2) {
+        b[j] = rhs[(size_t)j * nf + f];
+        if (mode == 1 && rhs2) b[j] += rhs2[(size_t)j * nf + f];
+      }
+      dprev[j] = (mode == 0 && cd != 0.0) ? d[(size_t)j * nf + f] : 0.0;
     }
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s)
+      HDG_UNROLL
+      for (int jj = 0; jj < 2; ++jj)
+        HDG_UNROLL
+        for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0 : x[(size_t)l * nf + col[s][jj]];
+    // ---- arithmetic -----------------------------------------------------------------------------
+    double acc[NM], D[NMH];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) acc[j] = 0.0;
     HDG_UNROLL
     for (int i = 0; i < NMH; ++i) D[i] = 0.0;
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) D[tri(j, j)] = inv_aalpha;
     HDG_UNROLL
     for (int s = 0; s < 2; ++s) {
-      int e = facet_local[(size_t)s * nf + f];
-      if (e < 0) continue;
-      switch (e) {
-        case 0: tent_side<K, 0>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
-        case 1: tent_side<K, 1>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
-        default: tent_side<K, 2>(nf, f, s, bits, tc, tcol, x, own, !zero, acc, D); break;
+      if (e[s] < 0) continue;
+      const int fl0 = (bits >> (3 * s)) & 1;
+      const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
+      switch (e[s]) {
+        case 0: tent_side<K, 0>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+        case 1: tent_side<K, 1>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+        default: tent_side<K, 2>(fl0, fl, c[s], v[s], !zero, acc, D); break;
       }
     }
     // X x = D own + off-diagonal part
     double r[NM];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
-      double v = acc[j];
+      double w = acc[j];
       if (!zero) {
         HDG_UNROLL
-        for (int l = 0; l < NM; ++l) v = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], v);
+        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], w);
       }
-      r[j] = v;
-    }
-    if (mode != 2) {
-      HDG_UNROLL
-      for (int j = 0; j < NM; ++j) {
-        double b = rhs[(size_t)j * nf + f];
-        if (mode == 1 && rhs2) b += rhs2[(size_t)j * nf + f];
-        r[j] = b - r[j];
-      }
+      r[j] = (mode != 2) ? b[j] - w : w;
     }
     if (mode == 1) {
       HDG_UNROLL
@@ -223,8 +233,7 @@ __global__ void __launch_bounds__(128) k_tent_sweep(int nf, const int* __restric
     }
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
-      double di = cr * r[j];
-      if (cd != 0.0) di = fma(cd, d[(size_t)j * nf + f], di);
+      double di = fma(cd, dprev[j], cr * r[j]);
       d[(size_t)j * nf + f] = di;
       xout[(size_t)j * nf + f] = own[j] + di;
     }

@@ -78,6 +78,10 @@ SIGNATURES = {
     "hdg_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hdg_set_partition": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_double]),
     "hdg_set_halo_plan": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "hdg_p2p_alloc": (C.c_int, [_vp, C.c_int64, _vp]),
+    "hdg_p2p_attach": (C.c_int, [_vp, _vp]),
+    "hdg_p2p_enable": (C.c_int, [_vp, C.c_int]),
+    "hdg_p2p_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "hdg_halo_exchange_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hdg_allreduce_sum_dev": (C.c_int, [_vp, _vp, C.c_int]),
     "hdg_mg_set_distribution": (C.c_int, [_vp, C.c_int, _ip, _ip]),
@@ -185,6 +189,7 @@ class HDGEngine:
         if rc != HDG_OK:
             raise HDGError(rc, self.lib.hdg_last_error(None).decode())
         self.last_iterations = 0
+        self.p2p = False
         if torch_stream:
             # order engine work with torch's current stream so that torch-owned buffers are safe to share
             self.use_torch_stream()
@@ -196,6 +201,8 @@ class HDGEngine:
             self._check(self.lib.hdg_set_partition(self._h, pt.nc_owned, pt.nf_owned, pt.global_nf, pt.global_volume))
             self.set_halo_plan(0, pt.cells)
             self.set_halo_plan(1, pt.facets)
+            if os.environ.get("HDG_P2P", "1") != "0":
+                self.p2p_setup()
 
     # -- multi-GPU ----------------------------------------------------------------------------------
     @property
@@ -220,6 +227,40 @@ class HDGEngine:
         p = lambda a: a.ctypes.data_as(_ip)
         self._check(self.lib.hdg_set_halo_plan(self._h, int(kind), int(plan.n_owned), int(plan.n_local), int(peers.size),
                                                p(peers), p(sptr), p(sidx), p(roff), p(rcnt)))
+
+    def p2p_setup(self, slab_doubles: int | None = None):
+        """switch halo exchanges and all-reduces to the NVLink peer-memory transport: allocate this
+        rank's mailbox, gather the CUDA IPC handles over torch.distributed, map the peers"""
+        import torch.distributed as dist
+
+        if slab_doubles is None:
+            pt = self.part
+
+            def biggest(plan):
+                send = np.diff(plan.send_ptr).max(initial=0)
+                return int(max(send, plan.recv_cnt.max(initial=0)))
+
+            need = max(biggest(pt.cells) * 2 * self.nQ1, biggest(pt.facets) * (self.k + 2), biggest(pt.verts))
+            box = [need]
+            gathered = [None] * self.nranks
+            dist.all_gather_object(gathered, box[0])
+            slab_doubles = int(max(gathered)) + 1024  # the same on every rank
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.hdg_p2p_alloc(self._h, int(slab_doubles), buf))
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, buf.raw)
+        blob = C.create_string_buffer(b"".join(handles), 64 * self.nranks)
+        self._check(self.lib.hdg_p2p_attach(self._h, blob))
+        dist.barrier()  # nobody pushes before everybody has mapped everybody
+        self.p2p = True
+
+    def p2p_enable(self, on: bool = True):
+        self._check(self.lib.hdg_p2p_enable(self._h, int(bool(on))))
+
+    def p2p_status(self) -> int:
+        err = C.c_int(0)
+        self._check(self.lib.hdg_p2p_status(self._h, C.byref(err)))
+        return err.value
 
     def halo_exchange_dev(self, kind: int, field, ndof: int):
         self._check(self.lib.hdg_halo_exchange_dev(self._h, int(kind), int(ndof), _dev(field)))
@@ -404,7 +445,7 @@ class HDGEngine:
         """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps"""
         self._check(self.lib.hdg_set_tentative_solver(self._h, int(mode), int(sweeps)))
 
-    def set_tentative_comm(self, local_sweeps: bool = True):
+    def set_tentative_comm(self, local_sweeps: bool = False):
         """multi-GPU: skip (True) or perform (False) the halo exchanges between Schur sweeps"""
         self._check(self.lib.hdg_set_tentative_comm(self._h, int(bool(local_sweeps))))
 

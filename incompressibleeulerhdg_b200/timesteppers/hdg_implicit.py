@@ -39,8 +39,9 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self.alpha = 1  # penalty parameter (:41)
         self.engine.set_penalty(self.alpha)
         self.krylov_rtol = krylov_rtol
-        # warm_start: both Krylov solves start from time-extrapolated guesses (tentative velocity:
-        # Q^n + (Q~^{n-1} - Q^{n-1}); trace: 2 lambda^{n-1} - lambda^{n-2}) instead of Q^n / zero.  The
+        # warm_start: both Krylov solves start from time-extrapolated guesses instead of Q^n / zero:
+        # tentative velocity Q^n + 2 d^{n-1} - d^{n-2} with d = Q~ - Q (linear extrapolation of the
+        # increment), trace 3 lambda^{n-1} - 3 lambda^{n-2} + lambda^{n-3} (quadratic).  The
         # tolerances refer to the right-hand side norms, so the converged fields are the same; only the
         # iteration counts drop.  (The reference solves both systems directly, hdg_implicit.py:129,146.)
         self.warm_start = warm_start
@@ -74,7 +75,9 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self._Rp, self._phi = Function(self._V_p), Function(self._V_p)
         self._lmbda = self._V_trace.zeros()
         self._lmbda_prev = self._V_trace.zeros()
+        self._lmbda_prev2 = self._V_trace.zeros()
         self._dQt = self._V_Q.zeros()  # Q~ - Q of the previous step
+        self._dQt_prev = self._V_Q.zeros()  # ... and of the one before
         self._nsteps = 0
         self.iteration_history = []  # (tentative its, pressure its) per step
         self.engine.set_initial_guess(bool(self.warm_start) and self.use_projection_method)
@@ -93,18 +96,28 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
             eng.lincomb_dev(self._rhs.data, [(1.0, Q.data), (self._dt, f.data)])  # :126 / :182 in Riesz form
             if self.use_projection_method:
                 if self.warm_start:
-                    eng.lincomb_dev(self._Q_tentative.data, [(1.0, Q.data), (1.0, self._dQt.data)])
-                    if self._nsteps >= 2:  # lambda <- 2 lambda^{n-1} - lambda^{n-2}, lambda_prev <- lambda^{n-1}
-                        eng.lincomb_dev(self._lmbda_prev.data, [(2.0, self._lmbda.data), (-1.0, self._lmbda_prev.data)])
-                        self._lmbda, self._lmbda_prev = self._lmbda_prev, self._lmbda
+                    n = self._nsteps
+                    if n >= 2:
+                        eng.lincomb_dev(self._Q_tentative.data, [(1.0, Q.data), (2.0, self._dQt.data),
+                                                                  (-1.0, self._dQt_prev.data)])
                     else:
-                        self._lmbda_prev.assign(self._lmbda)
+                        eng.lincomb_dev(self._Q_tentative.data, [(1.0, Q.data), (1.0, self._dQt.data)])
+                    # the guess goes into the oldest trace buffer, which then becomes the current one
+                    l1, l2, l3 = self._lmbda, self._lmbda_prev, self._lmbda_prev2
+                    if n >= 3:
+                        eng.lincomb_dev(l3.data, [(3.0, l1.data), (-3.0, l2.data), (1.0, l3.data)])
+                    elif n == 2:
+                        eng.lincomb_dev(l3.data, [(2.0, l1.data), (-1.0, l2.data)])
+                    else:
+                        l3.assign(l1)
+                    self._lmbda, self._lmbda_prev, self._lmbda_prev2 = l3, l1, l2
                 else:
                     self._Q_tentative.assign(Q)
                 its = self.tentative_velocity_solve(self._Q_star, self._rhs, self._Q_tentative, zero_guess=False)  # :129
                 its_t = its
                 self.niter_tentative.update(its)
-                if self.warm_start:
+                if self.warm_start:  # d^{n-2} <- d^{n-1}, d^{n-1} <- Q~ - Q
+                    self._dQt, self._dQt_prev = self._dQt_prev, self._dQt
                     eng.lincomb_dev(self._dQt.data, [(1.0, self._Q_tentative.data), (-1.0, Q.data)])
                 eng.weak_divergence_dev(self._Q_tentative.data, self._Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
                 its = self.pressure_solve(self._Rp, self._u, self._phi, self._lmbda)  # :146

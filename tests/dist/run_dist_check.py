@@ -42,12 +42,14 @@ def report(rank, name, errs, extra=None):
         failures.append(name)
 
 
-def poisson_case(rank, world, local, mesh, k, pc, thr, name):
+def poisson_case(rank, world, local, mesh, k, pc, thr, name, p2p=True):
     cr = partition.strip_partition(mesh, world)
     lm = partition.partition_mesh(mesh, cr, rank, world)
     ref = HDGEngine(mesh, k, device=local)
     ref.setup_poisson()
     eng = HDGEngine(lm, k, device=local)
+    if not p2p:
+        eng.p2p_enable(False)  # NCCL send/recv + all-reduce instead of the peer-memory transport
     eng.setup_poisson()
     if pc == "gtmg":
         H = multigrid.build_hierarchy(mesh, k)
@@ -62,10 +64,11 @@ def poisson_case(rank, world, local, mesh, k, pc, thr, name):
     nco, nfo = lm.nc_owned, lm.nf_owned
     errs = {"Q": rel(Q1[:nco], Q0[cg[:nco]]), "p": rel(p1[:nco], p0[cg[:nco]]), "l": rel(l1[:nfo], l0[fg[:nfo]])}
     report(rank, name, errs, {"its_single": it0, "its_dist": it1, "repl": getattr(eng, "hierarchy", None) and
-                              getattr(eng.hierarchy, "repl", None), "comm": eng.comm_stats()})
+                              getattr(eng.hierarchy, "repl", None), "comm": eng.comm_stats(), "p2p": p2p,
+                              "p2p_timeouts": eng.p2p_status()})
 
 
-def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, local_sweeps=True):
+def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, local_sweeps=False):
     def run(auto):
         ts_common.AUTO_PARTITION = auto
         ts = getattr(TS, cls)(mesh, k, dt, device=local, krylov_rtol=1e-13, **kwargs)
@@ -81,7 +84,7 @@ def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, loc
     cg, nco = lm.cells.local_gid, lm.nc_owned
     errs = {"Q": rel(Q1[:nco], Q0[cg[:nco]]), "p": rel(p1[:nco], p0[cg[:nco]])}
     report(rank, name, errs, {"comm": ts.engine.comm_stats(), "local_sweeps": local_sweeps,
-                              "its_tentative": ts.niter_tentative.value})
+                              "its_tentative": ts.niter_tentative.value, "p2p_timeouts": ts.engine.p2p_status()})
 
 
 def main():
@@ -93,11 +96,12 @@ def main():
     poisson_case(rank, world, local, m16, 2, "jacobi", 0, "poisson_k2_jacobi")
     poisson_case(rank, world, local, m16, 2, "gtmg", 100000, "poisson_k2_gtmg_replicated")
     poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels")
+    poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels_nccl", p2p=False)
     poisson_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "gtmg", 60, "poisson_k1_gtmg_distributed")
     poisson_case(rank, world, local, UnitDiskMesh(3), 3, "jacobi", 0, "poisson_k3_disk_jacobi")
     timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2")
     timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2,
-                     "chorin_k2_exchange_every_sweep", local_sweeps=False)
+                     "chorin_k2_local_sweeps", local_sweeps=True)
     timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGImplicit",
                      {"use_projection_method": False}, 0.02, 1, "fully_implicit_k1")
     timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",

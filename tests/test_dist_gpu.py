@@ -22,4 +22,4 @@ def test_one_vs_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     cases = [l for l in res.stdout.splitlines() if l.startswith('{"case"')]
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert len(cases) >= 9 and all('"ok": true' in c for c in cases), "\n".join(cases)
+    assert len(cases) >= 10 and all('"ok": true' in c for c in cases), "\n".join(cases)

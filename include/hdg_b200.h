@@ -256,6 +256,12 @@ int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n);
 int hdg_reset_timers(hdg_handle h);
 /* Measured FP64 FMA throughput of the device in TFLOP/s (denominator of "% of FP64 peak"). */
 int hdg_measure_fp64_peak(hdg_handle h, double* tflops);
+/* The iteration bodies of the three Krylov loops (BiCGStab chunk of the tentative solve, one
+ * multigrid-PCG iteration, Jacobi-CG chunk) are captured once into CUDA graphs and replayed, which
+ * removes the per-kernel launch cost that dominates at small per-GPU sizes (strong scaling).  On by
+ * default on one GPU and with the peer-memory transport; hdg_set_graphs(h, 0) launches kernel by kernel. */
+int hdg_set_graphs(hdg_handle h, int on);
+int hdg_graph_replays(hdg_handle h, int64_t* replays);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */
 int64_t hdg_launch_count(hdg_handle h);
 

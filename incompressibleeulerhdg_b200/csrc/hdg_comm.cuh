@@ -92,9 +92,14 @@ struct P2PHeader {
   unsigned long long halo_flag[HDG_MAX_RANKS];  // halo_flag[q]: number of pushes received from rank q
   unsigned long long red_flag[HDG_MAX_RANKS];   // red_flag[q]: number of reductions rank q contributed to
   double red_box[2][HDG_MAX_RANKS][HDG_RED_MAX];
+  // exchange / reduction counters live on the device (not in kernel arguments) so that a captured
+  // CUDA graph of a Krylov iteration can be replayed: every kernel derives "this exchange" from them
+  unsigned long long pair_cnt[HDG_MAX_RANKS];   // completed exchanges with rank q
+  unsigned long long red_cnt;                   // completed all-reduces
   int error;                                    // set by a kernel whose bounded spin ran out
   unsigned int ticket;                          // last-block detection of the push kernel
-  int pad[14];
+  unsigned int ticket2;                         // ... and of the wait/unpack kernel
+  int pad[13];
 };
 
 struct P2P {
@@ -102,8 +107,6 @@ struct P2P {
   size_t slab = 0;                          // doubles per (parity, sender) slab
   char* base = nullptr;                     // own buffer: P2PHeader, then mbox[2][nranks][slab]
   char* peer_base[HDG_MAX_RANKS] = {};      // mapped peer buffers (own entry = base)
-  unsigned long long pair_count[HDG_MAX_RANKS] = {};  // exchanges done with each peer
-  unsigned long long red_count = 0;
 };
 
 __host__ __device__ inline P2PHeader* p2p_header(char* base) { return reinterpret_cast<P2PHeader*>(base); }
@@ -117,7 +120,6 @@ struct P2PPeers {  // kernel argument: the peers of one exchange
   int send_ptr[HDG_MAX_RANKS + 1];
   int recv_ptr[HDG_MAX_RANKS + 1];          // ghost blocks relative to n_owned
   char* peer_base[HDG_MAX_RANKS];
-  unsigned long long count[HDG_MAX_RANKS];  // value of the pair counter for this exchange (after increment)
 };
 
 constexpr long long HDG_SPIN_CYCLES = 4000000000ll;  // ~2 s at 1.9 GHz
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int n
     int i = (int)(t - (size_t)d * total);
     int j = 0;
     while (i >= pp.send_ptr[j + 1]) ++j;
-    double* dst = p2p_slab(pp.peer_base[j], slab, nranks, (int)(pp.count[j] & 1ull), myrank);
+    const unsigned long long cnt = p2p_header(own_base)->pair_cnt[pp.rank[j]] + 1ull;  // this exchange
+    double* dst = p2p_slab(pp.peer_base[j], slab, nranks, (int)(cnt & 1ull), myrank);
     dst[(size_t)(i - pp.send_ptr[j]) * ndof + d] = field[(size_t)d * n_local + send_idx[i]];
   }
   // the last CTA to finish publishes the data: all remote stores of this grid precede the flags
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int n
       __threadfence_system();
       for (int j = 0; j < pp.npeers; ++j) {
         volatile unsigned long long* f = &p2p_header(pp.peer_base[j])->halo_flag[myrank];
-        *f = pp.count[j];
+        *f = own->pair_cnt[pp.rank[j]] + 1ull;
       }
       __threadfence_system();
     }
@@ -200,8 +203,11 @@ __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int n
 __global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks, size_t slab, int ndof, int n_local,
                                                          int n_owned, char* own_base, double* __restrict__ field) {
   P2PHeader* own = p2p_header(own_base);
-  if (threadIdx.x < pp.npeers)
-    p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], pp.count[threadIdx.x], &own->error);
+  __shared__ unsigned long long cnt[HDG_MAX_RANKS];
+  if (threadIdx.x < pp.npeers) {
+    cnt[threadIdx.x] = own->pair_cnt[pp.rank[threadIdx.x]] + 1ull;  // this exchange
+    p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], cnt[threadIdx.x], &own->error);
+  }
   __syncthreads();
   __threadfence_system();
   const int total = pp.recv_ptr[pp.npeers];
@@ -211,8 +217,19 @@ __global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks
     int g = (int)(t - (size_t)d * total);
     int j = 0;
     while (g >= pp.recv_ptr[j + 1]) ++j;
-    const double* src = p2p_slab(own_base, slab, nranks, (int)(pp.count[j] & 1ull), pp.rank[j]);
+    const double* src = p2p_slab(own_base, slab, nranks, (int)(cnt[j] & 1ull), pp.rank[j]);
     field[(size_t)d * n_local + n_owned + g] = __ldcv(&src[(size_t)(g - pp.recv_ptr[j]) * ndof + d]);
+  }
+  // the last CTA to finish closes the exchange: every CTA has read the counters by then
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int tk = atomicAdd(&own->ticket2, 1u);
+    if (tk == gridDim.x - 1) {
+      own->ticket2 = 0;
+      for (int j = 0; j < pp.npeers; ++j) own->pair_cnt[pp.rank[j]] = cnt[j];
+      __threadfence();
+    }
   }
 }
 
@@ -222,10 +239,11 @@ struct P2PAll {  // kernel argument of the all-reduce: every rank of the communi
 
 // in-place all-reduce of the partial-sum slots part[0..nslots)[G] over all ranks, one CTA:
 // finish the slots, store them into every peer's box, wait, sum in rank order, spread back
-__global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, int nranks, unsigned long long count,
-                                                       double* __restrict__ part, int G, int nslots) {
+__global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, int nranks, double* __restrict__ part,
+                                                       int G, int nslots) {
   __shared__ double mine[HDG_RED_MAX];
   __shared__ double total[HDG_RED_MAX];
+  const unsigned long long count = p2p_header(all.base[myrank])->red_cnt + 1ull;  // this reduction
   for (int s = 0; s < nslots; ++s) {
     const double* p = part + (size_t)s * G;
     double v = 0.0;
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, i
     double* p = part + (size_t)s * G;
     for (int i = threadIdx.x; i < G; i += blockDim.x) p[i] = (i == 0) ? total[s] : 0.0;
   }
+  if (threadIdx.x == 0) own->red_cnt = count;
 }
 
 // red[slot] = sum of the G partials of slot `slot` (one block per slot, fixed tree)

@@ -93,6 +93,8 @@ SIGNATURES = {
     "hdg_get_timers": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "hdg_reset_timers": (C.c_int, [_vp]),
     "hdg_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+    "hdg_set_graphs": (C.c_int, [_vp, C.c_int]),
+    "hdg_graph_replays": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_launch_count": (C.c_int64, [_vp]),
 }
 
@@ -193,6 +195,8 @@ class HDGEngine:
         if torch_stream:
             # order engine work with torch's current stream so that torch-owned buffers are safe to share
             self.use_torch_stream()
+        if os.environ.get("HDG_GRAPHS", "1") == "0":
+            self.set_graphs(False)
         if self.part is not None and self.part.nranks > 1:
             if comm_id is None:
                 comm_id = broadcast_unique_id()
@@ -517,6 +521,16 @@ class HDGEngine:
         out = C.c_double(0.0)
         self._check(self.lib.hdg_measure_fp64_peak(self._h, C.byref(out)))
         return out.value
+
+    def set_graphs(self, on: bool = True):
+        """replay the Krylov iteration bodies as CUDA graphs (default) or launch kernel by kernel"""
+        self._check(self.lib.hdg_set_graphs(self._h, int(bool(on))))
+
+    @property
+    def graph_replays(self) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.hdg_graph_replays(self._h, C.byref(n)))
+        return n.value
 
     def reset_timers(self):
         self._check(self.lib.hdg_reset_timers(self._h))

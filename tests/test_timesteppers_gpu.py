@@ -123,3 +123,23 @@ def test_imex_unsplit_matches_oracle():
     Qo, po = orc.solve(TaylorGreenOracle("exponential", 0.5), dt)
     assert rel(Q.to_host(), Qo) < 1e-10
     assert rel(p.to_host(), po) < 1e-9
+
+
+def test_cuda_graph_replay_is_bitwise_identical():
+    """the Krylov iteration bodies replayed as CUDA graphs (default) give bit-for-bit the fields and
+    iteration counts of the kernel-by-kernel launches (hdg_set_graphs)"""
+    k = 2
+    require_degree(k)
+    m = UnitSquareMesh(10, perturb=0.1)
+    dt, nt = 0.02, 3
+    out = []
+    for graphs in (True, False):
+        ts = TS.IncompressibleEulerHDGImplicit(m, k, dt, krylov_rtol=1e-12)
+        ts.engine.set_graphs(graphs)
+        prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+        Q0, p0 = prob.initial_condition()
+        Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), nt * dt)
+        out.append((Q.to_host(), p.to_host(), list(ts.iteration_history), ts.engine.graph_replays))
+    assert out[0][3] > 0 and out[1][3] == 0
+    assert out[0][2] == out[1][2]
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])

@@ -103,6 +103,9 @@ int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_
  * zero.  The tolerance then refers to the preconditioned norm of the right-hand side, so the
  * converged result does not depend on the guess.  Default off (the reference starts from zero). */
 int hdg_set_initial_guess(hdg_handle h, int on);
+/* warm-started trace solves that did not converge within their iteration cap and were repeated from a
+ * zero guess (robustness fallback; counted for diagnostics) */
+int hdg_guess_restarts(hdg_handle h, int64_t* restarts);
 /* Same with device pointers in SoA layout; asynchronous except for the iteration-count read. */
 int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
                           double* Q, double* p, double* l, double rtol, int maxit, int shift,
@@ -260,7 +263,13 @@ int hdg_measure_fp64_peak(hdg_handle h, double* tflops);
  * multigrid-PCG iteration, Jacobi-CG chunk) are captured once into CUDA graphs and replayed, which
  * removes the per-kernel launch cost that dominates at small per-GPU sizes (strong scaling).  On by
  * default on one GPU and with the peer-memory transport; hdg_set_graphs(h, 0) launches kernel by kernel. */
+/* diagnostics: the Krylov scalars of the last trace CG (out[0..4]: reference <b,M^-1 b>, <r,z>, rtol^2,
+ * iterations, done) and of the last BiCGStab (out[5..9]: ||b||^2, ||r||^2, rtol^2, iterations, done) */
+int hdg_debug_scalars(hdg_handle h, double* out10);
 int hdg_set_graphs(hdg_handle h, int on);
+/* tuning knobs that do not change results: "sweep_minblocks" in {5, 6, 8} selects the register-allocation
+ * variant of k_tent_sweep (96 / 80 / 64 registers per thread at k = 2; default 5) */
+int hdg_set_tuning(hdg_handle h, const char* name, int value);
 int hdg_graph_replays(hdg_handle h, int64_t* replays);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */
 int64_t hdg_launch_count(hdg_handle h);

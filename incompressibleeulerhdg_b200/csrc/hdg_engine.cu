@@ -69,6 +69,7 @@ struct hdg_engine {
   Comm* comm = nullptr;
   int comm_rc = 0;       // sticky NCCL failure, reported by the next C-ABI return
   bool use_guess = false;  // trace solve starts from the incoming trace vector (hdg_set_initial_guess)
+  int64_t guess_restarts = 0;  // warm-started solves that had to be repeated from zero
   // CUDA graphs of the Krylov iteration bodies (launch-bound at small per-GPU sizes, hdg_set_graphs)
   bool use_graphs = true;
   bool capturing = false;
@@ -103,6 +104,7 @@ struct hdg_engine {
   int tent_sweeps = 8;        // Chebyshev sweeps on the facet Schur complement (8: fewest ms per solve in
                               // the nx=512 probe, profiles/probe_params_r1e.jsonl)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
+  int tune_sweep = 5;         // register-allocation variant of k_tent_sweep (hdg_set_tuning)
   bool tent_local_sweeps = false;  // multi-GPU: skip the halo exchanges between the Chebyshev sweeps
                                    // (hdg_set_tentative_comm; costs ~+40 % BiCGStab iterations, profiles/summary_r1.md)
   double *tent_c = nullptr;   // [6][nf]
@@ -1285,6 +1287,17 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
 }
 
 // ---- facet-multiplier formulation (hdg_tent.cuh) --------------------------------------------------
+#define LAUNCH_SWEEP(h, K, ...)                                                                  \
+  do {                                                                                           \
+    const int _g = cdiv((h)->nf, 128);                                                           \
+    if ((h)->tune_sweep >= 8)                                                                    \
+      LAUNCH(h, (k_tent_sweep<K, 8>), _g, 128, __VA_ARGS__);                                     \
+    else if ((h)->tune_sweep >= 6)                                                               \
+      LAUNCH(h, (k_tent_sweep<K, 6>), _g, 128, __VA_ARGS__);                                     \
+    else                                                                                         \
+      LAUNCH(h, (k_tent_sweep<K, 5>), _g, 128, __VA_ARGS__);                                     \
+  } while (0)
+
 template <int K>
 static int tent_setup(hdg_engine* h) {
   constexpr int NM = TentDims<K>::NM;
@@ -1316,9 +1329,9 @@ static int tent_setup(hdg_engine* h) {
     CUDA_TRY(h, cudaMemcpyAsync(x, v0.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     std::vector<double> part(G);
     double lam = 2.0;
-    for (int it = 0; it < 30; ++it) {
+    for (int it = 0; it < 80; ++it) {  // power iteration: an under-estimate would make the Chebyshev sweeps amplify
       halo_exchange(h, PLAN_FACETS, NM, x);
-      LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+      LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
              0.0, (const double*)nullptr, (const double*)nullptr, (const double*)x, (double*)nullptr, x2, 0.0, 0.0, 0,
              2);
       LAUNCH(h, k_dot2, G, BLOCK, n, mask_facets(h, NM), x2, x2, (const double*)nullptr, h->partial, (double*)nullptr);
@@ -1350,7 +1363,7 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
     // matrix (condition ~7 after block-Jacobi), its inverse decays geometrically across the overlap, so
     // the preconditioner is perturbed only at the partition cuts -- and it stays a fixed linear operator.
     if (j > 0 && !h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);
-    LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
            inv_aalpha, t, (const double*)nullptr, (const double*)x, h->tent_f[4], x2, cc[j].cd, cc[j].cr,
            j == 0 ? 1 : 0, 0);
     std::swap(x, x2);
@@ -1414,7 +1427,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
       launch_fimpl<K>(h, upwind, Qstar, h->tent_xh, 1.0, -adt, out, in, 0.0);  // out_x = in_x - a F0(xhat)
     }
     // out_mu = N in_x - X mu
-    LAUNCH(h, k_tent_sweep<K>, cdiv(h->nf, 128), 128, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
            inv_aalpha, (const double*)h->tent_f[1], (const double*)nullptr, (const double*)mu, (double*)nullptr,
            out + nx, 0.0, 0.0, 0, 1);
   };
@@ -1654,7 +1667,7 @@ static int mg_fine_lmax(hdg_engine* h, double* lmax_out) {
   CUDA_TRY(h, cudaMemcpyAsync(mg->fx, v0.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   std::vector<double> part(G);
   double lam = 1.0;
-  for (int it = 0; it < 25; ++it) {
+  for (int it = 0; it < 100; ++it) {  // see tent_setup: the bound has to be safe, the smoother must stay SPD
     halo_exchange(h, PLAN_FACETS, b, mg->fx);
     LAUNCH(h, k_cg_spmv<b>, G, BLOCK, h->nf, h->nf_own, h->ell_val, h->ell_col, mg->fx, mg->fr, (double*)nullptr,
            (const CgScalars*)nullptr);
@@ -2070,18 +2083,36 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   int rc = hdg_forward_eliminate_dev(h, rhs_Q, rhs_p, rhs_l, h->cg_r);
   if (rc) return rc;
   int cg_rc = HDG_EINVAL;
+  bool used_guess = h->use_guess;
   {
     ScopedTimer t(h, T_SOLVE);
     const double* guess = h->use_guess ? l : nullptr;
+    // a warm-started solve is capped: if the correction equation has not converged after a few hundred
+    // iterations the guess was useless (or its residual sits in round-off) and the solve is repeated
+    // from zero, which is the reference behaviour
+    const int cap = guess ? std::min(maxit, h->mg && h->mg->enabled ? 150 : 3000) : maxit;
     if (h->mg && h->mg->enabled) {
-      DISPATCH_K(h, cg_rc = run_pcg_mg<K + 1>(h, rtol, maxit, guess, iters));
+      DISPATCH_K(h, cg_rc = run_pcg_mg<K + 1>(h, rtol, cap, guess, iters));
     } else {
-      DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, maxit, guess, iters));
+      DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, cap, guess, iters));
+    }
+    if (guess && cg_rc == HDG_ENOCONV && !h->comm_rc) {
+      h->guess_restarts++;
+      used_guess = false;
+      int its0 = iters ? *iters : 0;
+      rc = hdg_forward_eliminate_dev(h, rhs_Q, rhs_p, rhs_l, h->cg_r);
+      if (rc) return rc;
+      if (h->mg && h->mg->enabled) {
+        DISPATCH_K(h, cg_rc = run_pcg_mg<K + 1>(h, rtol, maxit, (const double*)nullptr, iters));
+      } else {
+        DISPATCH_K(h, cg_rc = run_cg<K + 1>(h, rtol, maxit, (const double*)nullptr, iters));
+      }
+      if (iters) *iters += its0;
     }
   }
   if (cg_rc == HDG_ECUDA) return cg_rc;
   int b = h->k + 1;
-  if (h->use_guess) {  // the CG solved for the correction of the guess held in l
+  if (used_guess) {  // the CG solved for the correction of the guess held in l
     LinComb lc;
     lc.n = 2;
     lc.c[0] = 1.0;
@@ -2212,6 +2243,31 @@ int hdg_set_penalty(hdg_handle h, double alpha) {
   return HDG_OK;
 }
 
+int hdg_set_tuning(hdg_handle h, const char* name, int value) {
+  if (!h || !name) return HDG_EINVAL;
+  if (!strcmp(name, "sweep_minblocks")) {
+    h->tune_sweep = value;
+    // the variant is baked into the captured BiCGStab graph
+    if (h->g_bicg.exec) {
+      cudaGraphExecDestroy(h->g_bicg.exec);
+      h->g_bicg.exec = nullptr;
+    }
+    return HDG_OK;
+  }
+  FAIL(h, HDG_EINVAL, std::string("hdg_set_tuning: unknown knob ") + name);
+}
+
+// last Krylov scalars seen by the host: out[0..4] = trace CG (reference <b,M^-1 b>, <r,z>, rtol^2, iterations,
+// done flag), out[5..9] = BiCGStab (||b||^2, ||r||^2, rtol^2, iterations, done flag)
+int hdg_debug_scalars(hdg_handle h, double* out10) {
+  if (!h || !out10) return HDG_EINVAL;
+  const CgScalars* c = h->scal_host;
+  const BiScalars* b = h->bscal_host;
+  out10[0] = c->rz0; out10[1] = c->rz; out10[2] = c->tol2; out10[3] = c->iters; out10[4] = c->done;
+  out10[5] = b->rr0; out10[6] = b->rr; out10[7] = b->tol2; out10[8] = b->iters; out10[9] = b->done;
+  return HDG_OK;
+}
+
 int hdg_set_graphs(hdg_handle h, int on) {
   if (!h) return HDG_EINVAL;
   h->use_graphs = on != 0;
@@ -2221,6 +2277,12 @@ int hdg_set_graphs(hdg_handle h, int on) {
 int hdg_graph_replays(hdg_handle h, int64_t* replays) {
   if (!h || !replays) return HDG_EINVAL;
   *replays = h->graph_replays;
+  return HDG_OK;
+}
+
+int hdg_guess_restarts(hdg_handle h, int64_t* restarts) {
+  if (!h || !restarts) return HDG_EINVAL;
+  *restarts = h->guess_restarts;
   return HDG_OK;
 }
 

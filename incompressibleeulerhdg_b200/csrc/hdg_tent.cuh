@@ -151,8 +151,11 @@ __device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const dou
 //           xout = x + d                                                  (xout must not alias x)
 //   mode 1: residual  xout = rhs + rhs2 - X x
 //   mode 2: xout = D^-1 X x   (power iteration for the spectral bound)
-template <int K>
-__global__ void __launch_bounds__(128) k_tent_sweep(int nf, const int* __restrict__ facet_local,
+// MINB = resident CTAs per SM the register allocation is tuned for (5: 96 registers at
+// k = 2; 6: 80 registers; 8: 64 registers with a 120-byte spill) -- selected at run time by
+// hdg_set_tuning("sweep_minblocks") so that the variants can be compared on the same box.
+template <int K, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __restrict__ facet_local,
                                                     const double* __restrict__ tc, const int* __restrict__ tcol,
                                                     const int* __restrict__ tbits, double inv_aalpha,
                                                     const double* __restrict__ rhs, const double* __restrict__ rhs2,

@@ -93,8 +93,11 @@ SIGNATURES = {
     "hdg_get_timers": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "hdg_reset_timers": (C.c_int, [_vp]),
     "hdg_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+    "hdg_debug_scalars": (C.c_int, [_vp, _dp]),
     "hdg_set_graphs": (C.c_int, [_vp, C.c_int]),
+    "hdg_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
     "hdg_graph_replays": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "hdg_guess_restarts": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_launch_count": (C.c_int64, [_vp]),
 }
 
@@ -522,6 +525,17 @@ class HDGEngine:
         self._check(self.lib.hdg_measure_fp64_peak(self._h, C.byref(out)))
         return out.value
 
+    def set_tuning(self, name: str, value: int):
+        """result-neutral tuning knobs, e.g. ("sweep_minblocks", 6)"""
+        self._check(self.lib.hdg_set_tuning(self._h, name.encode(), int(value)))
+
+    def debug_scalars(self):
+        out = (C.c_double * 10)()
+        self._check(self.lib.hdg_debug_scalars(self._h, out))
+        v = list(out)
+        return {"cg": {"ref": v[0], "rz": v[1], "tol2": v[2], "iters": int(v[3]), "done": int(v[4])},
+                "bicgstab": {"bb": v[5], "rr": v[6], "tol2": v[7], "iters": int(v[8]), "done": int(v[9])}}
+
     def set_graphs(self, on: bool = True):
         """replay the Krylov iteration bodies as CUDA graphs (default) or launch kernel by kernel"""
         self._check(self.lib.hdg_set_graphs(self._h, int(bool(on))))
@@ -530,6 +544,12 @@ class HDGEngine:
     def graph_replays(self) -> int:
         n = C.c_int64(0)
         self._check(self.lib.hdg_graph_replays(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def guess_restarts(self) -> int:
+        n = C.c_int64(0)
+        self._check(self.lib.hdg_guess_restarts(self._h, C.byref(n)))
         return n.value
 
     def reset_timers(self):

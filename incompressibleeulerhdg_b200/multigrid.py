@@ -110,7 +110,7 @@ class Hierarchy:
         return len(self.A)
 
 
-def _lmax_jacobi(A, iters=30, seed=0):
+def _lmax_jacobi(A, iters=100, seed=0):
     """power-iteration estimate of lambda_max(D^-1 A)"""
     d = A.diagonal()
     v = np.random.default_rng(seed).standard_normal(A.shape[0])

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--ratio", type=float, nargs="*", default=[10.0])
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--cold", action="store_true", help="no warm starts (zero / Q^n initial guesses)")
+    ap.add_argument("--minblocks", type=int, nargs="*", default=[])
     args = ap.parse_args()
     nx = args.nx
     mesh = UnitSquareMesh(nx, perturb=0.1)
@@ -59,7 +60,13 @@ def main():
             ts.initialise(Q0, p0)
         step += args.steps
         print(json.dumps({"nx": nx, "tent_sweeps": sw, **r}), flush=True)
-    ts.engine.set_tentative_solver(1, 6)
+    ts.engine.set_tentative_solver(1, 8)
+    for mb in args.minblocks:
+        ts.engine.set_tuning("sweep_minblocks", mb)
+        r = run(ts, f, args.steps, step)
+        step += args.steps
+        print(json.dumps({"nx": nx, "sweep_minblocks": mb, **r}), flush=True)
+    ts.engine.set_tuning("sweep_minblocks", 5)
     H = ts.engine.hierarchy
     for spec in args.mg:
         sf, sc = (int(v) for v in spec.split(","))

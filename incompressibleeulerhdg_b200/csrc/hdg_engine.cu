@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -833,11 +834,33 @@ __global__ void __launch_bounds__(BLOCK) k_cg_update(int nf, int nf_own, const d
   if (threadIdx.x == 0) part_rz[blockIdx.x] = acc;
 }
 
+// partial sums of the mode-0 coefficients of a trace vector over the owned facets
+__global__ void __launch_bounds__(BLOCK) k_mode0_partial(int nf_own, const double* __restrict__ z,
+                                                         double* __restrict__ part) {
+  double acc = 0.0;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf_own; f += gridDim.x * blockDim.x) acc += z[f];
+  acc = block_reduce(acc);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+// x_mode0 -= mean0 (the constant null vector of P has coefficient 1 in mode 0 of every facet)
+__global__ void __launch_bounds__(BLOCK) k_sub_mode0(int nf, const double* __restrict__ part, double inv_nf_glob,
+                                                     double* __restrict__ x) {
+  const double mean = reduce_partials(part, gridDim.x) * inv_nf_glob;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) x[f] -= mean;
+}
+
 // C: beta = <r,z>_new / <r,z>_old; p = z + beta p; convergence bookkeeping.
 // Every block derives the same decision from the same partials; block 0 publishes it.
+// part_z0 (optional): partial sums of the mode-0 coefficients of z.  The multigrid preconditioner does not
+// keep z orthogonal to the constant null vector of P; left alone, the search directions accumulate a
+// constant component that P annihilates but that swamps <p, P p> with round-off once the residual is
+// small (the CG then diverges again from ~1e-10, profiles/debug_cg_trace_r1o.log).  So the constant is
+// removed from z before it enters p:  p = (z - mean0(z) n) + beta p.
 template <int b>
 __global__ void __launch_bounds__(BLOCK) k_cg_pupdate(int nf, const double* __restrict__ z, double* __restrict__ p,
-                                                      const double* __restrict__ part_rz, CgScalars* s) {
+                                                      const double* __restrict__ part_rz, CgScalars* s,
+                                                      const double* __restrict__ part_z0 = nullptr,
+                                                      double inv_nf_glob = 0.0) {
   __shared__ int done_in;
   __shared__ double rz_old, rz0, tol2;
   __shared__ int it, maxit;
@@ -856,9 +879,10 @@ __global__ void __launch_bounds__(BLOCK) k_cg_pupdate(int nf, const double* __re
   bool stop = conv || (it + 1 >= maxit);
   if (!stop) {
     double beta = rz_new / rz_old;
+    const double zmean = part_z0 ? reduce_partials(part_z0, gridDim.x) * inv_nf_glob : 0.0;
     size_t n = (size_t)b * nf;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-      p[i] = fma(beta, p[i], z[i]);
+      p[i] = fma(beta, p[i], z[i] - (i < (size_t)nf ? zmean : 0.0));
   }
   // publish after all blocks have read the old scalars: a grid-wide ordering is not available, so
   // the *last* block to arrive writes (ticket counter in s->pad)
@@ -1609,12 +1633,25 @@ static int run_pcg_mg(hdg_engine* h, double rtol, int maxit, const double* guess
     allreduce_slots(h, part_rz, 1);
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->cg_p, h->cg_z, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // first search direction without its constant component (see k_cg_pupdate)
+  LAUNCH(h, k_mode0_partial, G, BLOCK, h->nf_own, (const double*)h->cg_z, part_mean);
+  allreduce_slots(h, part_mean, 1);
+  LAUNCH(h, k_sub_mode0, G, BLOCK, h->nf, (const double*)part_mean, 1.0 / h->nf_glob, h->cg_p);
   LAUNCH(h, k_cg_start, 1, BLOCK, h->scal, part_rz, guess ? (const double*)part_ref : (const double*)nullptr, G, rtol,
          maxit);
   int it = 0;
+  static const bool cg_trace = getenv("HDG_CG_TRACE") != nullptr;  // per-iteration scalars on stderr (diagnostics)
   while (true) {
     CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (cg_trace) {
+      std::vector<double> pq(G);
+      cudaMemcpy(pq.data(), part_pq, G * sizeof(double), cudaMemcpyDeviceToHost);
+      double spq = 0.0;
+      for (double v : pq) spq += v;
+      fprintf(stderr, "[hdg cg] it %d guess %d rz %.6e ref %.6e last<p,Pp> %.6e done %d\n", it, guess ? 1 : 0,
+              h->scal_host->rz, h->scal_host->rz0, spq, h->scal_host->done);
+    }
     if (h->scal_host->done || it >= maxit) break;
     auto body = [&]() {
       halo_exchange(h, PLAN_FACETS, b, h->cg_p);
@@ -1624,11 +1661,18 @@ static int run_pcg_mg(hdg_engine* h, double rtol, int maxit, const double* guess
                h->scal);
       }
       allreduce_slots(h, part_pq, 1);
-      LAUNCH(h, k_cg_update_plain, G, 256, n, h->cg_p, h->cg_q, h->cg_x, h->cg_r, part_pq, h->scal);
+      double* part_q0 = h->partial + 4 * (size_t)G;
+      LAUNCH(h, k_mode0_partial, G, BLOCK, h->nf_own, (const double*)h->cg_q, part_q0);
+      allreduce_slots(h, part_q0, 1);
+      LAUNCH(h, k_cg_update_plain, G, 256, n, h->cg_p, h->cg_q, h->cg_x, h->cg_r, part_pq, h->scal,
+             (const double*)part_q0, 1.0 / h->nf_glob, (size_t)h->nf);
       mg_apply<b>(h, h->cg_r, h->cg_z);
       LAUNCH(h, k_dot2, G, BLOCK, n, own, h->cg_r, h->cg_z, (const double*)nullptr, part_rz, (double*)nullptr);
       allreduce_slots(h, part_rz, 1);
-      LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal);
+      LAUNCH(h, k_mode0_partial, G, BLOCK, h->nf_own, (const double*)h->cg_z, part_mean);
+      allreduce_slots(h, part_mean, 1);
+      LAUNCH(h, k_cg_pupdate<b>, G, BLOCK, h->nf, h->cg_z, h->cg_p, part_rz, h->scal, (const double*)part_mean,
+             1.0 / h->nf_glob);
     };
     // the body's scratch pointers (multigrid ping-pong buffers) are part of the key: they are the same
     // at every iteration because each V-cycle swaps them an even number of times or only as scratch
@@ -2087,10 +2131,11 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   {
     ScopedTimer t(h, T_SOLVE);
     const double* guess = h->use_guess ? l : nullptr;
-    // a warm-started solve is capped: if the correction equation has not converged after a few hundred
-    // iterations the guess was useless (or its residual sits in round-off) and the solve is repeated
-    // from zero, which is the reference behaviour
-    const int cap = guess ? std::min(maxit, h->mg && h->mg->enabled ? 150 : 3000) : maxit;
+    // a warm-started solve is capped (healthy ones need 7-35 multigrid-PCG iterations at nx=1024): now and
+    // then the correction equation stalls at its initial residual for reasons not yet understood
+    // (profiles/summary_r1.md, "open issues"); the solve is then repeated from zero, which is the
+    // reference behaviour, and counted in hdg_guess_restarts
+    const int cap = guess ? std::min(maxit, h->mg && h->mg->enabled ? 64 : 3000) : maxit;
     if (h->mg && h->mg->enabled) {
       DISPATCH_K(h, cg_rc = run_pcg_mg<K + 1>(h, rtol, cap, guess, iters));
     } else {

@@ -210,15 +210,24 @@ __global__ void k_scale(size_t n, double c, double* __restrict__ x) {
 }
 
 // x += alpha p ; r -= alpha q   with alpha = <r,z>/<p,q> (plain CG update without preconditioner)
+// part_q0 (optional): partial sums of the mode-0 coefficients of q = P p.  The assembled P annihilates the
+// constants only to ~1e-13 (S_K 1 = 0 holds to the accuracy of the per-cell Cholesky), i.e. it is a
+// slightly perturbed singular matrix; once the residual reaches ~1e-12 CG starts chasing that spurious
+// near-null mode (alpha explodes, the residual bounces).  Removing the constant from q makes the operator
+// the CG sees exactly (I - Pi) P (I - Pi) -- what PETSc's MatNullSpace does for the reference
+// (`nullspace=` at hdg_imex.py:186,196,218).
 __global__ void __launch_bounds__(256) k_cg_update_plain(size_t n, const double* __restrict__ p,
                                                          const double* __restrict__ q, double* __restrict__ x,
                                                          double* __restrict__ r, const double* __restrict__ part_pq,
-                                                         const CgScalars* __restrict__ s) {
+                                                         const CgScalars* __restrict__ s,
+                                                         const double* __restrict__ part_q0 = nullptr,
+                                                         double inv_nf_glob = 0.0, size_t nf = 0) {
   if (s->done) return;
   double pq = reduce_partials(part_pq, gridDim.x);
   double alpha = s->rz / pq;
+  const double qmean = part_q0 ? reduce_partials(part_q0, gridDim.x) * inv_nf_glob : 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     x[i] = fma(alpha, p[i], x[i]);
-    r[i] = fma(-alpha, q[i], r[i]);
+    r[i] = fma(-alpha, q[i] - (i < nf ? qmean : 0.0), r[i]);
   }
 }

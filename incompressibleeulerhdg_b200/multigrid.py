@@ -122,6 +122,20 @@ def _lmax_jacobi(A, iters=100, seed=0):
     return float(lam)
 
 
+def _pinv_semidefinite(A: np.ndarray, rtol: float = 1e-9) -> np.ndarray:
+    """pseudo-inverse of the symmetric positive semi-definite coarsest operator with an explicit,
+    generous cut-off.  The constant null vector shows up as an eigenvalue of relative size ~1e-16, which
+    sits right at numpy's default pinv cut-off (1e-15): when it survived, the coarse solve amplified
+    round-off along the constants by ~1e16, the preconditioned CG directions acquired huge null-space
+    components and <p, P p> lost all accuracy (erratic, occasionally stalling trace solves;
+    profiles/debug_cg_trace_r1o.log)."""
+    A = 0.5 * (A + A.T)
+    w, V = np.linalg.eigh(A)
+    keep = w > rtol * w.max()
+    assert keep.sum() >= A.shape[0] - 1 - 2, "coarsest operator has an unexpectedly large null space"
+    return (V[:, keep] / w[keep]) @ V[:, keep].T
+
+
 def build_hierarchy(mesh, k: int, max_coarsest: int = 1200) -> Hierarchy:
     T = trace_transfer(mesh, k)
     A0 = p1_stiffness(mesh)
@@ -146,6 +160,6 @@ def build_hierarchy(mesh, k: int, max_coarsest: int = 1200) -> Hierarchy:
         raise ValueError(
             f"coarsest P1 level has {n_last} unknowns (> {max_coarsest}): this mesh carries no nested hierarchy; "
             "algebraic coarsening is not implemented yet")
-    pinv = np.linalg.pinv(A[-1].toarray(), hermitian=True)
+    pinv = _pinv_semidefinite(A[-1].toarray())
     lmax = [_lmax_jacobi(a) for a in A]
     return Hierarchy(T, A, P, pinv, lmax)

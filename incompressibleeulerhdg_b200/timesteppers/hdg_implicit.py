@@ -62,7 +62,7 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
     @PerformanceLog("pressure_solve")
     def pressure_solve(self, Rp, u, phi, lmbda):
         return self.engine.poisson_apply_dev(None, Rp.data, None, u.data, phi.data, lmbda.data, rtol=self.krylov_rtol,
-                                             maxit=100000, shift=True)
+                                             maxit=2000 if self.preconditioner == "gtmg" else 100000, shift=True)
 
     def initialise(self, Q_initial, p_initial):
         """interpolate the initial conditions and allocate the per-step work fields (:82-84)"""

@@ -198,6 +198,30 @@ int hdg_lincomb_dev(hdg_handle h, int64_t n, double* out, int nterms, const doub
 /* y = M x (inverse == 0) or M^-1 x for a cell field (kind 0 velocity, 1 pressure); M = detJ I */
 int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y);
 
+/* ---- passive tracer advection (single GPU in this build) ---------------------
+ * Replaces `_tracer_advection(chi, q, u, project_onto_cg=True)` (common.py:110-129) and the tracer
+ * mass solves of hdg_implicit.py:93-96,192-193 and hdg_imex.py:415-448,622-623,638-639.
+ *
+ * hdg_tracer_setup hands over the [CG_{k+1}]^2 space of the velocity projection and the quadrature
+ * tables (all host arrays, copied; NLOC = (k+2)(k+3)/2 Lagrange nodes per cell, NP = (k+1)(k+2)/2):
+ *   cellmap [NLOC][nc]      global CG dof of local node j of every cell
+ *   inc_ptr [ncg+1], inc_idx [NLOC*nc]   incidence CSR of the dofs: entries j*nc + cell in a fixed order
+ *   W [NLOC][NLOC]          modal <- nodal (inverse Vandermonde matrix of the Lagrange nodes)
+ *   dinv [ncg]              inverse diagonal of the CG mass matrix (Jacobi preconditioner)
+ *   tab_cell [nq_cell][1+3NP+3NLOC]    per point: weight, chi, d0 chi, d1 chi, psi, d0 psi, d1 psi
+ *   tab_facet [3][nq_facet][1+NP+NLOC] per local facet and point: weight, chi, psi (symmetric rule)
+ * hdg_project_cg_dev: Qcg = cell-wise [P_{k+1}]^2 representation of the L2 projection of Q onto
+ *   [CG_{k+1}]^2 (`Function(V_CG).project(u)`), Jacobi-PCG on the matrix-free mass matrix to
+ *   <r,z> <= rtol^2 <r0,z0> per component.
+ * hdg_tracer_advection_dev: out = c0 acc + c1 M^-1 [ q div(chi u) dx - (chi+ - chi-)(un+ q+ - un- q-) dS ]
+ *   with u = Qcg, un = (u.n + |u.n|)/2; acc may be NULL when c0 == 0 and may alias out; q must not. */
+int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_t* inc_ptr, const int32_t* inc_idx,
+                     const double* W, const double* dinv, int nq_cell, const double* tab_cell, int nq_facet,
+                     const double* tab_facet);
+int hdg_project_cg_dev(hdg_handle h, const double* Q, double* Qcg, double rtol, int maxit, int* iters);
+int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, double c0, const double* acc,
+                             double c1, double* out);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch ---------------------
  * Replaces what Firedrake/PETSc do implicitly under mpiexec (DMPlex partition, PyOP2/PetscSF halo
  * exchanges, MPI_Allreduce in every KSP; the reference itself only names COMM_WORLD at

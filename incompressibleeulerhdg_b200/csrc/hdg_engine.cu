@@ -51,6 +51,7 @@ struct BiScalars {
 
 struct MgState;
 struct Comm;
+struct TracerState;
 
 // an instantiated CUDA graph of one Krylov iteration body together with the key (pointers, scalars)
 // it was captured for; replayed while the key matches, recaptured otherwise
@@ -62,6 +63,7 @@ struct GraphCache {
 
 struct hdg_engine {
   MgState* mg = nullptr;
+  TracerState* tracer = nullptr;  // passive tracer advection + CG velocity projection (hdg_tracer.cuh)
   int k = 0, nc = 0, nf = 0, device = 0;
   // partition (multi-GPU, hdg_comm.cuh): nc/nf count the local entities (owned first, then ghosts);
   // reductions run over the owned prefix only.  Single GPU: everything is owned, comm == nullptr.
@@ -255,6 +257,19 @@ __device__ __forceinline__ double reduce_partials(const double* __restrict__ par
 
 #include "hdg_comm.cuh"
 #include "hdg_mg.cuh"
+#include "hdg_tracer.cuh"
+
+static void tracer_free(hdg_engine* h) {
+  TracerState* t = h->tracer;
+  if (!t) return;
+  void* ptrs[] = {t->cellmap, t->inc_ptr, t->inc_idx, t->W, t->dinv, t->tab_cell, t->tab_facet, t->yK,
+                  t->x, t->r, t->z, t->p, t->Ap, t->part, t->scal};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (t->scal_host) cudaFreeHost(t->scal_host);
+  delete t;
+  h->tracer = nullptr;
+}
 
 // ------------------------------------------------------------------------------------------------
 // multi-GPU helpers (no-ops on a single GPU)
@@ -1753,6 +1768,7 @@ int hdg_destroy(hdg_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   mg_free(h);
+  tracer_free(h);
   void* ptrs[] = {h->cell_xy, h->cell_facet, h->cell_flip, h->facet_cell, h->facet_local, h->SK, h->ell_val,
                   h->dinv, h->ell_col, h->gK, h->cg_x, h->cg_r, h->cg_z, h->cg_p, h->cg_q, h->partial, h->scal,
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
@@ -2854,6 +2870,113 @@ int hdg_mg_info(hdg_handle h, int* nlevels, double* fine_lmax) {
   if (!h) return HDG_EINVAL;
   if (nlevels) *nlevels = h->mg ? h->mg->nlevels : 0;
   if (fine_lmax) *fine_lmax = h->mg ? h->mg->fine_lmax : 0.0;
+  return HDG_OK;
+}
+
+// ---- passive tracer (hdg_tracer.cuh) ------------------------------------------------------------------
+int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_t* inc_ptr, const int32_t* inc_idx,
+                     const double* W, const double* dinv, int nq_cell, const double* tab_cell, int nq_facet,
+                     const double* tab_facet) {
+  if (!h || ncg <= 0 || !cellmap || !inc_ptr || !inc_idx || !W || !dinv || nq_cell <= 0 || !tab_cell ||
+      nq_facet <= 0 || !tab_facet)
+    return HDG_EINVAL;
+  if (h->comm) FAIL(h, HDG_EINVAL, "tracer advection is single-GPU in this build (no CG-dof halo plan yet)");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  tracer_free(h);
+  int nq1, np, nl1;
+  dims_of(h->k, nq1, np, nl1);
+  TracerState* t = new TracerState();
+  h->tracer = t;
+  t->ncg = ncg;
+  t->nloc = nq1;
+  t->nq_cell = nq_cell;
+  t->nq_facet = nq_facet;
+  const size_t nloc = nq1, nc = h->nc;
+  const size_t sc = 1 + 3 * np + 3 * nq1, sf = 1 + np + nq1;
+  CUDA_TRY(h, dmalloc(&t->cellmap, nloc * nc));
+  CUDA_TRY(h, dmalloc(&t->inc_ptr, (size_t)ncg + 1));
+  CUDA_TRY(h, dmalloc(&t->inc_idx, nloc * nc));
+  CUDA_TRY(h, dmalloc(&t->W, nloc * nloc));
+  CUDA_TRY(h, dmalloc(&t->dinv, (size_t)ncg));
+  CUDA_TRY(h, dmalloc(&t->tab_cell, (size_t)nq_cell * sc));
+  CUDA_TRY(h, dmalloc(&t->tab_facet, (size_t)3 * nq_facet * sf));
+  CUDA_TRY(h, dmalloc(&t->yK, 2 * nloc * nc));
+  for (double** v : {&t->x, &t->r, &t->z, &t->p, &t->Ap}) CUDA_TRY(h, dmalloc(v, 2 * (size_t)ncg));
+  CUDA_TRY(h, dmalloc(&t->part, 2 * (size_t)h->grid));
+  CUDA_TRY(h, dmalloc(&t->scal, 1));
+  CUDA_TRY(h, cudaMallocHost((void**)&t->scal_host, sizeof(TracerScalars)));
+  cudaStream_t st = h->stream;
+  CUDA_TRY(h, cudaMemcpyAsync(t->cellmap, cellmap, nloc * nc * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->inc_ptr, inc_ptr, ((size_t)ncg + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->inc_idx, inc_idx, nloc * nc * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->W, W, nloc * nloc * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->dinv, dinv, (size_t)ncg * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->tab_cell, tab_cell, (size_t)nq_cell * sc * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(t->tab_facet, tab_facet, (size_t)3 * nq_facet * sf * sizeof(double),
+                              cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));  // the host arrays may be released on return
+  return HDG_OK;
+}
+
+}  // extern "C"
+
+template <int K>
+static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rtol, int maxit, int* iters) {
+  constexpr int NLOC = Dims<K>::NQ1;
+  TracerState* t = h->tracer;
+  const int nc = h->nc, ncg = t->ncg, G = h->grid;
+  const int cgrid = cdiv(nc, 128);
+  const size_t cs = (size_t)NLOC * nc;
+  LAUNCH(h, k_cgp_load<NLOC>, cgrid, 128, h->cell_xy, nc, t->W, Q, t->yK);
+  LAUNCH(h, k_cgp_gather<0>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
+         t->Ap, t->part);
+  LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 0, 0, 1);
+  int par = 0, it = 0;
+  const double tol2 = rtol * rtol;
+  bool done = false;
+  while (!done && it < maxit) {
+    ++it;
+    LAUNCH(h, k_cgp_cellop<NLOC>, cgrid, 128, h->cell_xy, nc, ncg, t->cellmap, t->W, t->p, t->yK);
+    LAUNCH(h, k_cgp_gather<1>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
+           t->Ap, t->part);
+    LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 1, par, 0);
+    LAUNCH(h, k_cgp_update, G, BLOCK, ncg, t->scal, par, t->dinv, t->p, t->Ap, t->x, t->r, t->z, t->part);
+    LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 0, par ^ 1, 0);
+    LAUNCH(h, k_cgp_dir, G, BLOCK, ncg, t->scal, par, t->z, t->p);
+    par ^= 1;
+    if (it % 4 == 0 || it == maxit) {
+      CUDA_TRY(h, cudaMemcpyAsync(t->scal_host, t->scal, sizeof(TracerScalars), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      const TracerScalars& s = *t->scal_host;
+      done = s.rz[par][0] <= tol2 * s.rz0[0] && s.rz[par][1] <= tol2 * s.rz0[1];
+    }
+  }
+  LAUNCH(h, k_cgp_tocell<NLOC>, cgrid, 128, nc, ncg, t->cellmap, t->W, t->x, Qcg);
+  CUDA_TRY(h, cudaGetLastError());
+  if (iters) *iters = it;
+  if (!done) FAIL(h, HDG_ENOCONV, "CG velocity projection did not converge");
+  return HDG_OK;
+}
+
+extern "C" {
+
+int hdg_project_cg_dev(hdg_handle h, const double* Q, double* Qcg, double rtol, int maxit, int* iters) {
+  if (!h || !Q || !Qcg || rtol <= 0.0 || maxit < 1) return HDG_EINVAL;
+  if (!h->tracer) FAIL(h, HDG_ESTATE, "hdg_tracer_setup has not been called");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  DISPATCH_K(h, return run_project_cg<K>(h, Q, Qcg, rtol, maxit, iters));
+  return HDG_OK;
+}
+
+int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, double c0, const double* acc,
+                             double c1, double* out) {
+  if (!h || !Qcg || !q || !out || (c0 != 0.0 && !acc) || out == q) return HDG_EINVAL;
+  if (!h->tracer) FAIL(h, HDG_ESTATE, "hdg_tracer_setup has not been called");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  TracerState* t = h->tracer;
+  DISPATCH_K(h, LAUNCH(h, k_tracer_adv<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc,
+                       t->nq_cell, t->tab_cell, t->nq_facet, t->tab_facet, Qcg, q, c0, acc, c1, out));
+  CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
 }
 

@@ -74,6 +74,9 @@ SIGNATURES = {
     "hdg_l2_inner_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
     "hdg_lincomb_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _dp, C.POINTER(_vp)]),
     "hdg_mass_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
+    "hdg_tracer_setup": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int, _dp]),
+    "hdg_project_cg_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_int)]),
+    "hdg_tracer_advection_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, C.c_double, _vp]),
     "hdg_comm_unique_id": (C.c_int, [_vp]),
     "hdg_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hdg_set_partition": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_double]),
@@ -510,6 +513,37 @@ class HDGEngine:
 
     def mass_dev(self, kind, x, y, inverse=False):
         self._check(self.lib.hdg_mass_dev(self._h, int(kind), int(inverse), _dev(x), _dev(y)))
+
+    # -- passive tracer ----------------------------------------------------------
+    def tracer_setup(self, nq_facet: int | None = None):
+        """build the [CG_{k+1}]^2 space of the velocity projection (`common.py:119-122`) and hand it and
+        the quadrature tables of the advection kernel to the engine; idempotent"""
+        if getattr(self, "cg_space", None) is not None:
+            return self.cg_space
+        from . import cgspace
+
+        sp = cgspace.build_cg_space(self.mesh, self.k + 1)
+        tab_cell, tab_facet = cgspace.tracer_tables(self.k, nq_facet)
+        cellmap = np.ascontiguousarray(sp.cellmap.T, dtype=np.int32)  # SoA [nloc][nc]
+        dinv = np.ascontiguousarray(1.0 / sp.diag)
+        self._check(self.lib.hdg_tracer_setup(
+            self._h, sp.ndof, cellmap.ctypes.data_as(_ip), sp.inc_ptr.ctypes.data_as(_ip),
+            sp.inc_idx.ctypes.data_as(_ip), _ptr(sp.W), _ptr(dinv), tab_cell.shape[0], _ptr(tab_cell),
+            tab_facet.shape[1], _ptr(tab_facet)))
+        self.cg_space = sp
+        return sp
+
+    def project_cg_dev(self, Q, Qcg, rtol=1e-13, maxit=500):
+        """Qcg = cell-wise representation of the L2 projection of Q onto [CG_{k+1}]^2; returns the
+        number of PCG iterations"""
+        its = C.c_int(0)
+        self._check(self.lib.hdg_project_cg_dev(self._h, _dev(Q), _dev(Qcg), float(rtol), int(maxit), C.byref(its)))
+        return its.value
+
+    def tracer_advection_dev(self, Qcg, q, out, c0=0.0, acc=None, c1=1.0):
+        """out = c0 acc + c1 M^-1 _tracer_advection(chi, q, Qcg)  (`common.py:110-129`)"""
+        self._check(self.lib.hdg_tracer_advection_dev(self._h, _dev(Qcg), _dev(q), float(c0),
+                                                      _dev(acc) if acc is not None else None, float(c1), _dev(out)))
 
     # -- reporting -----------------------------------------------------------------------------------
     def timers(self):

@@ -12,6 +12,8 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 
+from ..auxilliary.logging import PerformanceLog
+from ..auxilliary.utils import Averager
 from ..engine import HDGEngine
 from ..functions import Function, FunctionSpace
 
@@ -33,6 +35,10 @@ class IncompressibleEuler(ABC):
         `cell_rank` (default: contiguous strips, :func:`partition.strip_partition`) and this rank
         keeps its local part only."""
         self._mesh = mesh
+        self.q_tracer = None
+        #: tolerance of the CG velocity projection (<r,z> relative; Firedrake's `project` default is a
+        #: CG solve to rtol 1e-8 [FD-knowledge] -- tighter here so that results are reproducible to 1e-10)
+        self.cg_projection_rtol = 1e-13
         self.degree = degree
         self._dt = dt
         self._label = label
@@ -91,6 +97,36 @@ class IncompressibleEuler(ABC):
         """H(div)-conforming projection (`common.py:91-108`), kept in the cell-wise DG representation"""
         out = Function(self._V_Q) if out is None else out
         self.engine.project_bdm_dev(Q.data, out.data)
+        return out
+
+    # -- passive tracer (`common.py:110-129`) ----------------------------------------------------------
+    def _tracer_initialise(self, q_initial):
+        """`Function(self._V_q, name="tracer").interpolate(q_initial)` (`hdg_implicit.py:73-77`,
+        `hdg_imex.py:523-527`) plus the engine-side set-up of the [CG_{k+1}]^2 velocity projection;
+        returns None when no tracer is advected"""
+        self.q_tracer = None
+        if q_initial is None or q_initial is False:
+            return None
+        if self.local_mesh is not None:
+            raise NotImplementedError("tracer advection runs on a single GPU in this build "
+                                      "(the CG-dof halo plan of the velocity projection is not built yet)")
+        self.engine.tracer_setup()
+        self.q_tracer = self._V_q.interpolate(q_initial)
+        self.q_tracer.rename("tracer")
+        self.niter_cg_projection = Averager()
+        return self.q_tracer
+
+    def _project_onto_cg(self, Q: Function, out: Function) -> Function:
+        """`Function(V_CG).project(u)` (`common.py:119-122`), kept in the cell-wise representation"""
+        with PerformanceLog("cg_projection"):
+            its = self.engine.project_cg_dev(Q.data, out.data, rtol=self.cg_projection_rtol)
+        self.niter_cg_projection.update(its)
+        return out
+
+    def _tracer_advection(self, q: Function, u_cg: Function, out: Function, c0=0.0, acc=None, c1=1.0):
+        """out = c0 acc + c1 M^-1 _tracer_advection(chi, q, u) for an already projected velocity"""
+        self.engine.tracer_advection_dev(u_cg.data, q.data, out.data, c0=c0,
+                                         acc=None if acc is None else acc.data, c1=c1)
         return out
 
     @abstractmethod

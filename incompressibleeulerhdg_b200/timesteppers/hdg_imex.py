@@ -213,10 +213,12 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
         self.engine.reconstruct_trace_dev(state.Q.data, state.p.data, state.l.data)
 
     def solve(self, Q_initial, p_initial, q_initial, f_rhs, T_final, warmup=False):
-        if q_initial:
-            raise NotImplementedError("passive tracer advection is not on the engine's hot path yet")
         eng = self.engine
         nt = self.get_timesteps(T_final, warmup)
+        q_tracer = self._tracer_initialise(q_initial)  # :523-529
+        if q_tracer is not None:
+            self._q = [Function(self._V_q) for _ in range(self.nstages)]  # :81-85
+            self._u_cg = [Function(self._V_Q) for _ in range(self.nstages)]
         cur = self._current_state
         self._V_Q.interpolate(Q_initial, out=cur.Q)  # :520
         self._V_p.interpolate(p_initial, out=cur.p)  # :521
@@ -229,7 +231,7 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
             a.reset()
         for callback in self.callbacks:
             callback.reset()
-            callback(cur.Q, cur.p, 0, q_tracer=None)
+            callback(cur.Q, cur.p, 0, q_tracer=q_tracer)
         steps = tqdm.tqdm(range(nt)) if self.progress else range(nt)
         for k in steps:
             with PerformanceLog("timestep"):
@@ -237,6 +239,8 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                 for i in range(self.nstages):  # :554-557
                     self._V_Q.interpolate(f_rhs(tn + self._c_expl[i] * self._dt), out=self._b_rhs[i])
                 self._stage_state[0].assign(cur)  # :558
+                if q_tracer is not None:
+                    self._q[0].assign(q_tracer)  # :559-560
                 for i in range(1, self.nstages):
                     st = self._stage_state[i]
                     adt = self._a_impl[i, i] * self._dt
@@ -260,6 +264,8 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                             self._monolithic.solve(self._Qstar[i - 1], adt, self._rho[i], st.Q, st.p, st.l,
                                                    rtol=self.krylov_rtol, upwind=(self.flux == "upwind"))
                     self._shift_pressure(st)  # :621
+                    if q_tracer is not None:  # :622-623
+                        self._tracer_stage(i)
                 its = self.pressure_solve("final_stage")  # :624
                 self.niter_final_pressure.update(its)
                 self._V_Q.interpolate(f_rhs(tn + self._dt), out=self._b_new)  # :629
@@ -268,10 +274,42 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                 cur.p.assign(self._pressure_reconstruction.p)  # :633-636
                 cur.l.assign(self._pressure_reconstruction.l)
                 self._shift_pressure(cur)  # :637
+                if q_tracer is not None:  # :638-639
+                    self._tracer_final(q_tracer)
             for callback in self.callbacks:
-                callback(cur.Q, cur.p, tn + self._dt, q_tracer=None)
+                callback(cur.Q, cur.p, tn + self._dt, q_tracer=q_tracer)
         self.print_iteration_summary()
         return cur.Q, cur.p
+
+    def _tracer_accumulate(self, out, terms):
+        """out = q_0 + sum_t c_t M^-1 adv(q_t, u_t) for terms = [(c, q, u_cg), ...]"""
+        if not terms:
+            return out.assign(self._q[0])
+        acc = self._q[0]
+        for c, q, u in terms:
+            self._tracer_advection(q, u, out, c0=1.0, acc=acc, c1=c)
+            acc = out
+        return out
+
+    @PerformanceLog("tracer_advection")
+    def _tracer_stage(self, i):
+        """`solve(a_tracer == self._tracer_residual(chi, i), self._q[i])` (`hdg_imex.py:415-432,622-623`):
+        q_i = q_0 + dt sum_{j<i} a^E_ij M^-1 adv(q_j, P_CG Q_i) -- every term uses the velocity of
+        stage i, as the reference does"""
+        self._project_onto_cg(self._stage_state[i].Q, self._u_cg[i])
+        terms = [(self._dt * self._a_expl[i, j], self._q[j], self._u_cg[i]) for j in range(i)
+                 if self._a_expl[i, j] != 0]
+        self._tracer_accumulate(self._q[i], terms)
+
+    @PerformanceLog("tracer_advection")
+    def _tracer_final(self, q_tracer):
+        """`solve(a_tracer == self._tracer_final_residual(chi), q_tracer)` (`hdg_imex.py:434-448,638-639`):
+        q^{n+1} = q_0 + dt sum_i b^E_i M^-1 adv(q_i, P_CG Q_i)"""
+        if self._b_expl[0] != 0:  # stage 0 is the state at t_n; stages >= 1 were projected in _tracer_stage
+            self._project_onto_cg(self._stage_state[0].Q, self._u_cg[0])
+        terms = [(self._dt * self._b_expl[i], self._q[i], self._u_cg[i]) for i in range(self.nstages)
+                 if self._b_expl[i] != 0]
+        self._tracer_accumulate(q_tracer, terms)
 
     def print_iteration_summary(self, file=None):
         """:648-659"""

@@ -85,11 +85,22 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self.niter_pressure.reset()
         return self.Q, self.p
 
+    def initialise_tracer(self, q_initial):
+        """`hdg_implicit.py:73-79`; allocates the projected velocity and the second tracer buffer"""
+        q = self._tracer_initialise(q_initial)
+        if q is not None:
+            self._u_cg = Function(self._V_Q)
+            self._q_new = Function(self._V_q, name="tracer")
+        return q
+
     def step(self, k, f_rhs, f_field=None):
         """one timestep t_k -> t_{k+1} (:92-190).  f_field, if given, is an already interpolated
         forcing Function (host-driven forcing); otherwise f_rhs(t_k) is interpolated."""
         eng, Q, p = self.engine, self.Q, self.p
         with PerformanceLog("timestep"):
+            if self.q_tracer is not None:
+                # :93-96 -- `project` runs when the form is built, i.e. on the velocity of time t_k
+                self._project_onto_cg(Q, self._u_cg)
             with PerformanceLog("bdm_projection"):
                 self.project_bdm(Q, out=self._Q_star)  # :98
             f = f_field if f_field is not None else self._V_Q.interpolate(f_rhs(k * self._dt), out=self._f)  # :100
@@ -133,19 +144,23 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
                     self.niter_pressure.update(its)
             p.assign(self._phi)  # :189-190
             eng.shift_pressure_dev(p.data, None)
+            if self.q_tracer is not None:  # :192-193  q <- q + dt M^-1 adv(q, P_CG Q^k), explicit Euler
+                with PerformanceLog("tracer_advection"):
+                    self._tracer_advection(self.q_tracer, self._u_cg, self._q_new, c0=1.0, acc=self.q_tracer,
+                                           c1=self._dt)
+                self.q_tracer.data, self._q_new.data = self._q_new.data, self.q_tracer.data
         return Q, p
 
     def solve(self, Q_initial, p_initial, q_initial, f_rhs, T_final, warmup=False):
-        if q_initial:
-            raise NotImplementedError("passive tracer advection is not on the engine's hot path yet")
         nt = self.get_timesteps(T_final, warmup)
+        q_tracer = self.initialise_tracer(q_initial)
         Q, p = self.initialise(Q_initial, p_initial)
         for callback in self.callbacks:
             callback.reset()
-            callback(Q, p, 0, q_tracer=None)
+            callback(Q, p, 0, q_tracer=q_tracer)
         steps = tqdm.tqdm(range(nt)) if self.progress else range(nt)
         for k in steps:
             self.step(k, f_rhs)
             for callback in self.callbacks:
-                callback(Q, p, (k + 1) * self._dt, q_tracer=None)
+                callback(Q, p, (k + 1) * self._dt, q_tracer=q_tracer)
         return Q, p

@@ -150,11 +150,25 @@ class ChorinOracle(_Base):
         pn = phi - o.integral_p(phi) / self.mesh.volume * o.const_p()  # :189-190
         return Qn, pn
 
-    def solve(self, problem, T_final, warmup=False):
+    def solve(self, problem, T_final, warmup=False, q_initial=None):
+        """with `q_initial` (a callable) the passive tracer is advected as in hdg_implicit.py:73-77,
+        93-96,192-193 -- explicit Euler with the CG-projected velocity of the *old* time level -- and
+        the result is kept in ``self.q_tracer``"""
         nt = 1 if warmup else int(np.round(T_final / self.dt))
         Q, p = self.initial_state(problem)
+        q = None
+        if q_initial is not None:
+            from .tracer import TracerOracle
+
+            tr = TracerOracle(self.o)
+            q = self.interp_p(q_initial)
         for k in range(nt):
+            if q is not None:
+                u_cg = tr.project_cg(Q)  # :93-96 (project runs when the form is built)
             Q, p = self.step(Q, p, problem.f_rhs(k * self.dt))
+            if q is not None:
+                q = q + self.dt * tr.advection(q, u_cg)  # :192-193
+        self.q_tracer = q
         return Q, p
 
 
@@ -216,6 +230,7 @@ class IMEXOracle(_Base):
         # persistent stage state (hdg_imex.py:72-88): never reset between timesteps
         self.stage = [dict(Q=zQ(), p=np.zeros((nc, o.np_)), l=np.zeros((nf, o.nl1))) for _ in range(self.nstages)]
         self.b_rhs = [zQ() for _ in range(self.nstages)]
+        self.tracer, self.q_tracer = None, None
 
     # residual recursions as dual vectors -----------------------------------------------------------
     def residual(self, i):
@@ -269,12 +284,20 @@ class IMEXOracle(_Base):
                 st["p"] = x[offp:offl].reshape(nc, o.np_)
                 st["l"] = x[offl:].reshape(nf, o.nl1)
             st["p"], st["l"] = o.shift_pressure(st["p"], st["l"])  # :621
+            if self.tracer is not None:  # :622-623 with _tracer_residual :415-432 (velocity of stage i throughout)
+                u_i = self.tracer.project_cg(st["Q"])
+                self.q[i] = self.q[0] + sum(dt * self.a_expl[i, j] * self.tracer.advection(self.q[j], u_i)
+                                            for j in range(i) if self.a_expl[i, j] != 0)
         # final stage :624  (rhs in the w-row)
         Qn, _, _ = o.solve_condensed(self.final_residual(), zp, zl)
         # pressure reconstruction :629-637
         b_new = self.interp_Q(problem.f_rhs(tn + dt))
         Rp, Rl = self.reconstruction_rhs(Qn, b_new)
         _, pn, ln = o.solve_condensed(zQ, Rp, Rl)
+        if self.tracer is not None:  # :638-639 with _tracer_final_residual :434-448
+            self.q_tracer = self.q[0] + sum(
+                dt * self.b_expl[i] * self.tracer.advection(self.q[i], self.tracer.project_cg(self.stage[i]["Q"]))
+                for i in range(self.nstages) if self.b_expl[i] != 0)
         return dict(Q=Qn, p=pn, l=ln)
 
     def reconstruction_rhs(self, Qn, b_new):
@@ -301,12 +324,20 @@ class IMEXOracle(_Base):
             np.add.at(Rl, self.mesh.cell_facet[bnd, e], contrib[bnd])
         return Rp, Rl
 
-    def solve(self, problem, T_final, warmup=False):
+    def solve(self, problem, T_final, warmup=False, q_initial=None):
         o = self.o
         nt = 1 if warmup else int(np.round(T_final / self.dt))
         Q, p = self.initial_state(problem)  # :520-522
         lam = o.reconstruct_trace(Q, p)  # :534
         cur = dict(Q=Q, p=p, l=lam)
+        if q_initial is not None:  # :523-527
+            from .tracer import TracerOracle
+
+            self.tracer = TracerOracle(o)
+            self.q_tracer = self.interp_p(q_initial)
+            self.q = [None] * self.nstages
         for k in range(nt):
+            if self.tracer is not None:
+                self.q[0] = self.q_tracer  # :559-560
             cur = self.step(cur, problem, k * self.dt)
         return cur["Q"], cur["p"]

@@ -108,6 +108,10 @@ struct hdg_engine {
                               // the nx=512 probe, profiles/probe_params_r1e.jsonl)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
   int tune_sweep = 5;         // register-allocation variant of k_tent_sweep (hdg_set_tuning)
+  int tune_tracer = 1;        // 1 = tracer advection from the compile-time tables, 0 = runtime tables
+  int tune_condense = 0;      // K >= 3: 0 = fully unrolled thread-per-cell kernel (default, faster),
+                              //         1 = row-loop condensation with the Cholesky factor in shared memory
+                              //             (hdg_set_tuning "condense_rows")
   bool tent_local_sweeps = false;  // multi-GPU: skip the halo exchanges between the Chebyshev sweeps
                                    // (hdg_set_tentative_comm; costs ~+40 % BiCGStab iterations, profiles/summary_r1.md)
   double *tent_c = nullptr;   // [6][nf]
@@ -505,12 +509,28 @@ __device__ __forceinline__ double W_entry(const Geo& g, const double (&nu)[3][2]
   return v * g.le[e];
 }
 
+// W_entry is structurally zero where all three reference tables vanish
+template <int K>
+__device__ __forceinline__ constexpr bool W_nonzero(int e, int m, int a) {
+  using T = RefTables<K>;
+  return T::LL(e, 0, m, a) != 0.0 || T::LL(e, 1, m, a) != 0.0 || T::F(e, m, a) != 0.0;
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) k_condense(const double* __restrict__ xy, const int* __restrict__ flip, int nc,
                                                   double tau, double* __restrict__ SK) {
   using T = RefTables<K>;
   using D = Dims<K>;
   constexpr int NP = D::NP, NL1 = D::NL1, NL = D::NL;
+  // Work reduction, kept per degree where it measured faster (profiles/condense_bench_r1r.jsonl, 10^6 cells):
+  //  * K <= 2: the NL x NP matrix W is built once and kept in registers (54 doubles at k = 2) instead of
+  //    being re-derived from the tables inside every dot product;
+  //  * K <= 3: S_K = S_K^T is computed on and above the diagonal only and mirrored on store
+  //    (k = 3: 0.895 -> 0.525 ms; k = 1: 0.072 -> 0.064 ms; k = 2 unchanged at 0.19 ms: latency bound at
+  //    8 warps/SM, not FP64-issue bound).  At k = 4 the triangular loop nest made the register allocation
+  //    worse (5.8 -> 12.7 ms), so k = 4 keeps the full loop nest.
+  constexpr bool SYM = (K <= 3);
+  constexpr bool CACHE_W = (K <= 2);
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     Geo g = make_geo(xy, nc, cell);
     double L[D::NH];
@@ -524,32 +544,181 @@ __global__ void __launch_bounds__(128) k_condense(const double* __restrict__ xy,
       nu[e][0] = g.Ji[0][0] * g.n[e][0] + g.Ji[0][1] * g.n[e][1];
       nu[e][1] = g.Ji[1][0] * g.n[e][0] + g.Ji[1][1] * g.n[e][1];
     }
+    double Wc[CACHE_W ? NL * NP : 1];
+    if (CACHE_W) {
+      HDG_UNROLL
+      for (int e = 0; e < 3; ++e)
+        HDG_UNROLL
+        for (int m = 0; m < NL1; ++m)
+          HDG_UNROLL
+          for (int a = 0; a < NP; ++a) Wc[CACHE_W ? (e * NL1 + m) * NP + a : 0] = W_entry<K>(g, nu, tau, e, m, a);
+    }
+    auto W = [&](int e, int m, int a) -> double {
+      return CACHE_W ? Wc[CACHE_W ? (e * NL1 + m) * NP + a : 0] : W_entry<K>(g, nu, tau, e, m, a);
+    };
     HDG_UNROLL
     for (int e = 0; e < 3; ++e) {
       HDG_UNROLL
       for (int m = 0; m < NL1; ++m) {
         double v[NP];
         HDG_UNROLL
-        for (int a = 0; a < NP; ++a) v[a] = W_entry<K>(g, nu, tau, e, m, a);
+        for (int a = 0; a < NP; ++a) v[a] = W(e, m, a);
         chol_solve<NP>(L, v);
         double sg = flip_sign(fl[e], m);
         HDG_UNROLL
-        for (int e2 = 0; e2 < 3; ++e2) {
+        for (int e2 = (SYM ? e : 0); e2 < 3; ++e2) {
           double nn = (g.n[e][0] * g.n[e2][0] + g.n[e][1] * g.n[e2][1]) * g.le[e] * g.le[e2] * g.idetJ;
           HDG_UNROLL
-          for (int m2 = 0; m2 < NL1; ++m2) {
+          for (int m2 = (SYM && e2 == e ? m : 0); m2 < NL1; ++m2) {
             double s = 0.0;
             HDG_UNROLL
-            for (int a = 0; a < NP; ++a) s = fma(v[a], W_entry<K>(g, nu, tau, e2, m2, a), s);
+            for (int a = 0; a < NP; ++a)
+              if (W_nonzero<K>(e2, m2, a)) s = fma(v[a], W(e2, m2, a), s);
             if (T::NN(e, e2, m, m2) != 0.0) s = fma(-nn, T::NN(e, e2, m, m2), s);
             if (e == e2 && m == m2) s -= tau * g.le[e];
             s *= sg * flip_sign(fl[e2], m2);
-            SK[(size_t)((e * NL1 + m) * NL + e2 * NL1 + m2) * nc + cell] = s;
+            const int r = e * NL1 + m, c = e2 * NL1 + m2;
+            SK[(size_t)(r * NL + c) * nc + cell] = s;
+            if (SYM && c != r) SK[(size_t)(c * NL + r) * nc + cell] = s;
           }
         }
       }
     }
   }
+}
+
+// Row-loop variant for K >= 3 (optional: hdg_set_tuning(h, "condense_rows", 1)).  Measured SLOWER than the
+// unrolled kernel on B200 (10^6 cells: k = 3 1.43 vs 0.525 ms, k = 4 8.1 vs 5.8 ms; 254 registers leave
+// 8 warps/SM and the 3 table loads per W entry make it LSU/latency bound), so it is not the default; it is
+// kept as the second, independently written implementation that the parity tests compare with.  The fully unrolled kernel above keeps the packed Cholesky factor
+// (55 doubles at k = 3, 120 at k = 4) and the compiler's hoisted W entries in registers and spills
+// 3 - 14 KB per thread (ptxas: 2 920 / 14 352 bytes of spill stores; the k = 4 launch was bound by
+// local-memory traffic through L2).  Here the factor lives in shared memory ([NH][blockDim], bank-
+// conflict free), the loop over the NL rows of S_K and the loop over the columns c >= r are *real*
+// loops, and W entries are formed from the reference tables with warp-uniform (broadcast) loads, so
+// the per-thread register state is the geometry, one solution vector v[NP] and the loop counters.
+template <int K>
+__device__ __forceinline__ double W_entry_dyn(const Geo& g, const double (&nu)[3][2], double tau, int e, int m, int a) {
+  using T = RefTables<K>;
+  double v = tau * T::F(e, m, a);
+  v = fma(nu[e][0], T::LL(e, 0, m, a), v);
+  v = fma(nu[e][1], T::LL(e, 1, m, a), v);
+  return v * g.le[e];
+}
+
+constexpr int CONDENSE_ROWS_BLOCK = 64;
+
+template <int K>
+__global__ void __launch_bounds__(CONDENSE_ROWS_BLOCK) k_condense_rows(const double* __restrict__ xy,
+                                                                       const int* __restrict__ flip, int nc, double tau,
+                                                                       double* __restrict__ SK) {
+  using T = RefTables<K>;
+  using D = Dims<K>;
+  constexpr int NP = D::NP, NL1 = D::NL1, NL = D::NL, BD = CONDENSE_ROWS_BLOCK;
+  extern __shared__ double Lsh[];  // [NH][BD]
+  double* Lt = Lsh + threadIdx.x;
+#define LS(a, b) Lt[tri(a, b) * BD]
+  for (int cell = blockIdx.x * BD + threadIdx.x; cell < nc; cell += gridDim.x * BD) {
+    Geo g = make_geo(xy, nc, cell);
+    {
+      // H = T + B B^T / detJ (build_H) straight into shared memory, then the in-place Cholesky
+      double g00 = g.Ji[0][0] * g.Ji[0][0] + g.Ji[0][1] * g.Ji[0][1];
+      double g01 = g.Ji[0][0] * g.Ji[1][0] + g.Ji[0][1] * g.Ji[1][1];
+      double g11 = g.Ji[1][0] * g.Ji[1][0] + g.Ji[1][1] * g.Ji[1][1];
+      double c0 = g.detJ * g00, c1 = g.detJ * g01, c2 = g.detJ * g11;
+      double t0 = tau * g.le[0], t1 = tau * g.le[1], t2 = tau * g.le[2];
+#pragma unroll 1
+      for (int a = 0; a < NP; ++a)
+#pragma unroll 1
+        for (int b = 0; b <= a; ++b) {
+          double hh = c0 * T::KK(0, a, b);
+          hh = fma(c1, T::KK(1, a, b), hh);
+          hh = fma(c2, T::KK(2, a, b), hh);
+          hh = fma(t0, T::TT(0, a, b), hh);
+          hh = fma(t1, T::TT(1, a, b), hh);
+          hh = fma(t2, T::TT(2, a, b), hh);
+          LS(a, b) = hh;
+        }
+#pragma unroll 1
+      for (int j = 0; j < NP; ++j) {
+        double d = LS(j, j);
+        for (int kk = 0; kk < j; ++kk) d = fma(-LS(j, kk), LS(j, kk), d);
+        double inv = rsqrt(d);
+        LS(j, j) = inv;  // the diagonal holds 1 / L_jj, as in cholesky<N>
+#pragma unroll 1
+        for (int i = j + 1; i < NP; ++i) {
+          double sacc = LS(i, j);
+          for (int kk = 0; kk < j; ++kk) sacc = fma(-LS(i, kk), LS(j, kk), sacc);
+          LS(i, j) = sacc * inv;
+        }
+      }
+    }
+    double nu[3][2];
+    int flbits = 0;
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      if (flip[(size_t)e * nc + cell]) flbits |= 1 << e;
+      nu[e][0] = g.Ji[0][0] * g.n[e][0] + g.Ji[0][1] * g.n[e][1];
+      nu[e][1] = g.Ji[1][0] * g.n[e][0] + g.Ji[1][1] * g.n[e][1];
+    }
+#pragma unroll 1
+    for (int r = 0; r < NL; ++r) {
+      const int e = r / NL1, m = r - e * NL1;
+      double v[NP];
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a) v[a] = W_entry_dyn<K>(g, nu, tau, e, m, a);
+      // v <- (L L^T)^-1 v with L in shared memory (static indices: v stays in registers)
+      HDG_UNROLL
+      for (int i = 0; i < NP; ++i) {
+        double sacc = v[i];
+        HDG_UNROLL
+        for (int kk = 0; kk < i; ++kk) sacc = fma(-LS(i, kk), v[kk], sacc);
+        v[i] = sacc * LS(i, i);
+      }
+      HDG_UNROLL
+      for (int i = NP - 1; i >= 0; --i) {
+        double sacc = v[i];
+        HDG_UNROLL
+        for (int kk = i + 1; kk < NP; ++kk) sacc = fma(-LS(kk, i), v[kk], sacc);
+        v[i] = sacc * LS(i, i);
+      }
+      const double sg = flip_sign((flbits >> e) & 1, m);
+      const double ler = g.le[e] * g.idetJ;
+#pragma unroll 1
+      for (int c = r; c < NL; ++c) {
+        const int e2 = c / NL1, m2 = c - e2 * NL1;
+        double sacc = 0.0;
+        HDG_UNROLL
+        for (int a = 0; a < NP; ++a) sacc = fma(v[a], W_entry_dyn<K>(g, nu, tau, e2, m2, a), sacc);
+        double nn = (g.n[e][0] * g.n[e2][0] + g.n[e][1] * g.n[e2][1]) * ler * g.le[e2];
+        sacc = fma(-nn, T::NN(e, e2, m, m2), sacc);
+        if (c == r) sacc -= tau * g.le[e];
+        sacc *= sg * flip_sign((flbits >> e2) & 1, m2);
+        SK[(size_t)(r * NL + c) * nc + cell] = sacc;
+        if (c != r) SK[(size_t)(c * NL + r) * nc + cell] = sacc;
+      }
+    }
+  }
+#undef LS
+}
+
+template <int K>
+static cudaError_t launch_condense(hdg_engine* h) {
+  if (K >= 3 && h->tune_condense != 0) {
+    const size_t smem = (size_t)Dims<K>::NH * CONDENSE_ROWS_BLOCK * sizeof(double);
+    static bool attr_done = false;  // per template instance
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(k_condense_rows<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_done = true;
+    }
+    k_condense_rows<K><<<cdiv(h->nc, CONDENSE_ROWS_BLOCK), CONDENSE_ROWS_BLOCK, smem, h->stream>>>(
+        h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
+  } else {
+    k_condense<K><<<cdiv(h->nc, 128), 128, 0, h->stream>>>(h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
+  }
+  h->launches++;
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1976,7 +2145,7 @@ int hdg_setup_poisson(hdg_handle h, int keep_local) {
     DISPATCH_K(h, {
       {
         ScopedTimer tc(h, T_CONDENSE);
-        LAUNCH(h, k_condense<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
+        CUDA_TRY(h, launch_condense<K>(h));
       }
       {
         ScopedTimer ta(h, T_ASSEMBLE);
@@ -2313,6 +2482,14 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
       cudaGraphExecDestroy(h->g_bicg.exec);
       h->g_bicg.exec = nullptr;
     }
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tracer_tables")) {
+    h->tune_tracer = value;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "condense_rows")) {
+    h->tune_condense = value;
     return HDG_OK;
   }
   FAIL(h, HDG_EINVAL, std::string("hdg_set_tuning: unknown knob ") + name);
@@ -2915,6 +3092,17 @@ int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_
   CUDA_TRY(h, cudaMemcpyAsync(t->tab_facet, tab_facet, (size_t)3 * nq_facet * sf * sizeof(double),
                               cudaMemcpyHostToDevice, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));  // the host arrays may be released on return
+  // the projection kernels carry W = VINV of the equispaced Lagrange nodes as compile-time constants:
+  // refuse any other node set instead of silently projecting with the wrong basis
+  DISPATCH_K(h, LAUNCH(h, k_cgp_check_w<K>, 1, 1, t->W, t->part));
+  double werr[2] = {0.0, 0.0};
+  CUDA_TRY(h, cudaMemcpyAsync(werr, t->part, sizeof(werr), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (!(werr[0] <= 1e-11 * werr[1])) {
+    tracer_free(h);
+    FAIL(h, HDG_EINVAL, "hdg_tracer_setup: W is not the modal<-nodal map of the equispaced P_{k+1} Lagrange nodes "
+                        "(the only node set compiled into the projection kernels)");
+  }
   return HDG_OK;
 }
 
@@ -2927,7 +3115,7 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
   const int nc = h->nc, ncg = t->ncg, G = h->grid;
   const int cgrid = cdiv(nc, 128);
   const size_t cs = (size_t)NLOC * nc;
-  LAUNCH(h, k_cgp_load<NLOC>, cgrid, 128, h->cell_xy, nc, t->W, Q, t->yK);
+  LAUNCH(h, k_cgp_load<K>, cgrid, 128, h->cell_xy, nc, Q, t->yK);
   LAUNCH(h, k_cgp_gather<0>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
          t->Ap, t->part);
   LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 0, 0, 1);
@@ -2936,7 +3124,7 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
   bool done = false;
   while (!done && it < maxit) {
     ++it;
-    LAUNCH(h, k_cgp_cellop<NLOC>, cgrid, 128, h->cell_xy, nc, ncg, t->cellmap, t->W, t->p, t->yK);
+    LAUNCH(h, k_cgp_cellop<K>, cgrid, 128, h->cell_xy, nc, ncg, t->cellmap, t->p, t->yK);
     LAUNCH(h, k_cgp_gather<1>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
            t->Ap, t->part);
     LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 1, par, 0);
@@ -2951,7 +3139,7 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
       done = s.rz[par][0] <= tol2 * s.rz0[0] && s.rz[par][1] <= tol2 * s.rz0[1];
     }
   }
-  LAUNCH(h, k_cgp_tocell<NLOC>, cgrid, 128, nc, ncg, t->cellmap, t->W, t->x, Qcg);
+  LAUNCH(h, k_cgp_tocell<K>, cgrid, 128, nc, ncg, t->cellmap, t->x, Qcg);
   CUDA_TRY(h, cudaGetLastError());
   if (iters) *iters = it;
   if (!done) FAIL(h, HDG_ENOCONV, "CG velocity projection did not converge");
@@ -2974,8 +3162,16 @@ int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, d
   if (!h->tracer) FAIL(h, HDG_ESTATE, "hdg_tracer_setup has not been called");
   CUDA_TRY(h, cudaSetDevice(h->device));
   TracerState* t = h->tracer;
-  DISPATCH_K(h, LAUNCH(h, k_tracer_adv<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc,
-                       t->nq_cell, t->tab_cell, t->nq_facet, t->tab_facet, Qcg, q, c0, acc, c1, out));
+  // default facet rule: compile-time tables (no table loads); otherwise, or with hdg_set_tuning
+  // ("tracer_tables", 0), the runtime tables handed to hdg_tracer_setup
+  DISPATCH_K(h, {
+    if (h->tune_tracer != 0 && t->nq_facet == RefTables<K>::NQF)
+      LAUNCH(h, k_tracer_adv_t<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, Qcg, q, c0,
+             acc, c1, out);
+    else
+      LAUNCH(h, k_tracer_adv<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, t->nq_cell,
+             t->tab_cell, t->nq_facet, t->tab_facet, Qcg, q, c0, acc, c1, out);
+  });
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
 }

@@ -12,15 +12,17 @@
 // solve is the CG_{k+1} mass matrix of the velocity projection; it is applied matrix-free: with the
 // nodal (Lagrange) basis phi_j = sum_i W[i][j] psi_i of the orthonormal modal basis psi,
 //     M_K = detJ W^T W,       load_K = detJ W^T U_K,       U^cg_K = W x_K
-// (W = inverse Vandermonde matrix, a runtime table), i.e. two small dense products per cell and a
+// (W = inverse Vandermonde matrix of the equispaced Lagrange nodes, the compile-time table VINV), i.e.
+// two small dense products per cell and a
 // deterministic gather over the cells that share a dof (incidence CSR, fixed order, no atomics).
 // Jacobi-PCG with both velocity components advanced together (one alpha/beta per component); all
 // Krylov scalars stay in device memory, the host polls the residual every few iterations.
 //
-// The advection kernel evaluates the volume and interior-facet integrals by quadrature from runtime
-// tables (the non-polynomial |u.n| rules out closed-form reference tensors): one thread per cell, tables
-// are read with warp-uniform addresses (broadcast), the neighbour's tracer trace with the facet
-// parameter reversed (both cells are counter-clockwise).
+// The advection kernel evaluates the volume and interior-facet integrals by quadrature (the non-polynomial
+// |u.n| rules out closed-form reference tensors), one thread per cell, the neighbour's tracer trace with
+// the facet parameter reversed (both cells are counter-clockwise).  Two variants: k_tracer_adv_t reads the
+// compile-time tables of hdg_tables.inc (default facet rule; table entries are immediate operands),
+// k_tracer_adv reads runtime tables with warp-uniform (broadcast) loads for any other facet rule.
 #pragma once
 #include "hdg_local.cuh"
 
@@ -47,9 +49,13 @@ struct TracerState {
 
 // ---- CG projection ------------------------------------------------------------------------------
 // yK[c][j][cell] = detJ sum_i W[i][j] U[c][i][cell]            (load vector, element contributions)
-template <int NLOC>
-__global__ void __launch_bounds__(128) k_cgp_load(const double* __restrict__ xy, int nc, const double* __restrict__ W,
+// W = RefTables<K>::VINV (compile-time: the entries are immediate operands of the DFMAs; the runtime
+// copy handed to hdg_tracer_setup is checked against it on the host)
+template <int K>
+__global__ void __launch_bounds__(128) k_cgp_load(const double* __restrict__ xy, int nc,
                                                   const double* __restrict__ U, double* __restrict__ yK) {
+  using T = RefTables<K>;
+  constexpr int NLOC = Dims<K>::NQ1;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     Geo g = make_geo(xy, nc, cell);
     HDG_UNROLL
@@ -61,18 +67,36 @@ __global__ void __launch_bounds__(128) k_cgp_load(const double* __restrict__ xy,
       for (int j = 0; j < NLOC; ++j) {
         double s = 0.0;
         HDG_UNROLL
-        for (int i = 0; i < NLOC; ++i) s = fma(__ldg(W + i * NLOC + j), u[i], s);
+        for (int i = 0; i < NLOC; ++i)
+          if (T::VINV(i, j) != 0.0) s = fma(T::VINV(i, j), u[i], s);
         yK[(size_t)(c * NLOC + j) * nc + cell] = g.detJ * s;
       }
     }
   }
 }
 
+// out[0] = max |W - VINV|, out[1] = max |VINV|  (set-up check, one thread)
+template <int K>
+__global__ void k_cgp_check_w(const double* __restrict__ W, double* __restrict__ out) {
+  using T = RefTables<K>;
+  constexpr int NLOC = Dims<K>::NQ1;
+  double err = 0.0, mx = 0.0;
+  for (int i = 0; i < NLOC; ++i)
+    for (int j = 0; j < NLOC; ++j) {
+      err = fmax(err, fabs(W[i * NLOC + j] - T::VINV(i, j)));
+      mx = fmax(mx, fabs(T::VINV(i, j)));
+    }
+  out[0] = err;
+  out[1] = mx;
+}
+
 // yK = M_K x_K = detJ W^T (W x_K)  with x_K gathered through the cell -> dof map
-template <int NLOC>
+template <int K>
 __global__ void __launch_bounds__(128) k_cgp_cellop(const double* __restrict__ xy, int nc, int ncg,
-                                                    const int* __restrict__ cellmap, const double* __restrict__ W,
+                                                    const int* __restrict__ cellmap,
                                                     const double* __restrict__ x, double* __restrict__ yK) {
+  using T = RefTables<K>;
+  constexpr int NLOC = Dims<K>::NQ1;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     Geo g = make_geo(xy, nc, cell);
     int dof[NLOC];
@@ -87,14 +111,16 @@ __global__ void __launch_bounds__(128) k_cgp_cellop(const double* __restrict__ x
       for (int i = 0; i < NLOC; ++i) {
         double s = 0.0;
         HDG_UNROLL
-        for (int j = 0; j < NLOC; ++j) s = fma(__ldg(W + i * NLOC + j), xl[j], s);
+        for (int j = 0; j < NLOC; ++j)
+          if (T::VINV(i, j) != 0.0) s = fma(T::VINV(i, j), xl[j], s);
         m[i] = s;
       }
       HDG_UNROLL
       for (int j = 0; j < NLOC; ++j) {
         double s = 0.0;
         HDG_UNROLL
-        for (int i = 0; i < NLOC; ++i) s = fma(__ldg(W + i * NLOC + j), m[i], s);
+        for (int i = 0; i < NLOC; ++i)
+          if (T::VINV(i, j) != 0.0) s = fma(T::VINV(i, j), m[i], s);
         yK[(size_t)(c * NLOC + j) * nc + cell] = g.detJ * s;
       }
     }
@@ -102,10 +128,11 @@ __global__ void __launch_bounds__(128) k_cgp_cellop(const double* __restrict__ x
 }
 
 // cell-wise modal representation of a CG field:  Ucg[c][i][cell] = sum_j W[i][j] x[c][dof_j]
-template <int NLOC>
+template <int K>
 __global__ void __launch_bounds__(128) k_cgp_tocell(int nc, int ncg, const int* __restrict__ cellmap,
-                                                    const double* __restrict__ W, const double* __restrict__ x,
-                                                    double* __restrict__ Ucg) {
+                                                    const double* __restrict__ x, double* __restrict__ Ucg) {
+  using T = RefTables<K>;
+  constexpr int NLOC = Dims<K>::NQ1;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     int dof[NLOC];
     HDG_UNROLL
@@ -119,7 +146,8 @@ __global__ void __launch_bounds__(128) k_cgp_tocell(int nc, int ncg, const int* 
       for (int i = 0; i < NLOC; ++i) {
         double s = 0.0;
         HDG_UNROLL
-        for (int j = 0; j < NLOC; ++j) s = fma(__ldg(W + i * NLOC + j), xl[j], s);
+        for (int j = 0; j < NLOC; ++j)
+          if (T::VINV(i, j) != 0.0) s = fma(T::VINV(i, j), xl[j], s);
         Ucg[(size_t)(c * NLOC + i) * nc + cell] = s;
       }
     }
@@ -328,6 +356,105 @@ __global__ void __launch_bounds__(128) k_tracer_adv(const double* __restrict__ x
         double wf = -w * fscale * flux;
         HDG_UNROLL
         for (int a = 0; a < NP; ++a) res[a] = fma(wf, __ldg(t + 1 + a), res[a]);
+      }
+    }
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) {
+      size_t idx = (size_t)a * nc + cell;
+      out[idx] = (c0 != 0.0 ? c0 * acc[idx] : 0.0) + c1 * res[a];
+    }
+  }
+}
+
+// Same operator from the compile-time tables of hdg_tables.inc (cell rule WQ/PHI/DPHI/DPSI exact to degree
+// 3k+2 >= 3k, facet rule WF/PHIF/PSIF with NQF = ceil((3k+4)/2) Gauss points = the default facet rule):
+// every table entry is an immediate operand, so the kernel issues no table loads at all (the runtime-table
+// kernel above is LSU bound: one broadcast load per DFMA).  The tracer basis is the first NP functions of
+// the hierarchical velocity basis, so chi = PHI[.][a < NP].  Used when nq_facet == NQF; the neighbour's local
+// facet index is a runtime value, so its trace is evaluated for the three candidates and selected.
+template <int K>
+__global__ void __launch_bounds__(128) k_tracer_adv_t(const double* __restrict__ xy, const int* __restrict__ nbr,
+                                                      const int* __restrict__ nbr_e, int nc,
+                                                      const double* __restrict__ U, const double* __restrict__ q,
+                                                      double c0, const double* acc, double c1, double* out) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NP = Dims<K>::NP, NQ = T::NQ, NQF = T::NQF;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double u[2][NQ1], qk[NP], res[NP];
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) u[c][i] = U[(size_t)(c * NQ1 + i) * nc + cell];
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) {
+      qk[a] = q[(size_t)a * nc + cell];
+      res[a] = 0.0;
+    }
+    // contravariant velocity coefficients beta_d = sum_c Ji[d][c] u_c: the volume term only needs beta and
+    // div u = sum_d d_d beta_d
+    double be[2][NQ1];
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) {
+      be[0][i] = g.Ji[0][0] * u[0][i] + g.Ji[0][1] * u[1][i];
+      be[1][i] = g.Ji[1][0] * u[0][i] + g.Ji[1][1] * u[1][i];
+    }
+    HDG_UNROLL
+    for (int qp = 0; qp < NQ; ++qp) {
+      double qv = 0.0;
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a)
+        if (T::PHI(qp, a) != 0.0) qv = fma(T::PHI(qp, a), qk[a], qv);
+      double b0 = 0.0, b1 = 0.0, divu = 0.0;
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) {
+        if (T::PHI(qp, i) != 0.0) {
+          b0 = fma(T::PHI(qp, i), be[0][i], b0);
+          b1 = fma(T::PHI(qp, i), be[1][i], b1);
+        }
+        if (T::DPHI(0, qp, i) != 0.0) divu = fma(T::DPHI(0, qp, i), be[0][i], divu);
+        if (T::DPHI(1, qp, i) != 0.0) divu = fma(T::DPHI(1, qp, i), be[1][i], divu);
+      }
+      const double wq = T::WQ(qp) * qv;
+      const double w0 = wq * b0, w1 = wq * b1, wd = wq * divu;
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a) {
+        if (T::DPSI(0, qp, a) != 0.0) res[a] = fma(w0, T::DPSI(0, qp, a), res[a]);
+        if (T::DPSI(1, qp, a) != 0.0) res[a] = fma(w1, T::DPSI(1, qp, a), res[a]);
+        if (T::PHI(qp, a) != 0.0) res[a] = fma(wd, T::PHI(qp, a), res[a]);
+      }
+    }
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      const int nb = nbr[(size_t)e * nc + cell];
+      if (nb < 0) continue;
+      const int ne = nbr_e[(size_t)e * nc + cell];
+      double qn[NP], un_c[NQ1];
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a) qn[a] = q[(size_t)a * nc + nb];
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) un_c[i] = g.n[e][0] * u[0][i] + g.n[e][1] * u[1][i];
+      const double fscale = g.le[e] * g.idetJ;
+      HDG_UNROLL
+      for (int qf = 0; qf < NQF; ++qf) {
+        double un = 0.0;
+        HDG_UNROLL
+        for (int i = 0; i < NQ1; ++i)
+          if (T::PHIF(e, qf, i) != 0.0) un = fma(T::PHIF(e, qf, i), un_c[i], un);
+        double qin = 0.0, o0 = 0.0, o1 = 0.0, o2 = 0.0;
+        HDG_UNROLL
+        for (int a = 0; a < NP; ++a) {
+          if (T::PSIF(e, qf, a) != 0.0) qin = fma(T::PSIF(e, qf, a), qk[a], qin);
+          if (T::PSIF(0, NQF - 1 - qf, a) != 0.0) o0 = fma(T::PSIF(0, NQF - 1 - qf, a), qn[a], o0);
+          if (T::PSIF(1, NQF - 1 - qf, a) != 0.0) o1 = fma(T::PSIF(1, NQF - 1 - qf, a), qn[a], o1);
+          if (T::PSIF(2, NQF - 1 - qf, a) != 0.0) o2 = fma(T::PSIF(2, NQF - 1 - qf, a), qn[a], o2);
+        }
+        const double qout = ne == 0 ? o0 : (ne == 1 ? o1 : o2);
+        const double flux = fmax(un, 0.0) * qin + fmin(un, 0.0) * qout;
+        const double wf = -T::WF(qf) * fscale * flux;
+        HDG_UNROLL
+        for (int a = 0; a < NP; ++a)
+          if (T::PSIF(e, qf, a) != 0.0) res[a] = fma(wf, T::PSIF(e, qf, a), res[a]);
       }
     }
     HDG_UNROLL

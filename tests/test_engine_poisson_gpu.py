@@ -38,6 +38,28 @@ def test_local_schur_matches_oracle(k):
     SK = eng.get_local_schur()
     ref = o.condensed_local()
     assert rel(SK, ref) < 1e-11
+    if k <= 3:  # computed on and above the diagonal and mirrored on store (k = 4 keeps the full loop nest)
+        assert np.array_equal(SK, SK.transpose(0, 2, 1))
+    else:
+        assert rel(SK, SK.transpose(0, 2, 1)) < 1e-12
+
+
+@pytest.mark.parametrize("k", [3, 4])
+def test_condensation_kernel_variants_agree(k):
+    """K >= 3 ships two condensation kernels (fully unrolled thread-per-cell = default; row loop with the
+    Cholesky factor in shared memory, hdg_set_tuning "condense_rows"); both must reproduce the oracle.
+    257 cells leave the last block of either launch partially filled."""
+    require_degree(k)
+    m = RandomAffineCells(257)
+    ref = HDGOracle(m, k).condensed_local()
+    eng = HDGEngine(m, k)
+    out = {}
+    for variant in (0, 1):
+        eng.set_tuning("condense_rows", variant)
+        eng.setup_poisson(keep_local=True)
+        out[variant] = eng.get_local_schur()
+        assert rel(out[variant], ref) < 1e-11, variant
+    assert rel(out[1], out[0]) < 1e-12
 
 
 @pytest.mark.parametrize("k", [1, 2, 3])

@@ -103,3 +103,52 @@ def test_engine_config0_fully_implicit_golden():
     Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), 1.0)
     assert rel(Q.to_host(), GOLD["implicit_k1_nx16/Q"]) < RTOL
     assert rel(p.to_host(), GOLD["implicit_k1_nx16/p"]) < 1e-9
+
+
+# ---- passive tracer (tests/golden/golden_tracer_v1.npz, made by tests/golden/make_golden_tracer.py) ------
+GOLD_T = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_tracer_v1.npz"))
+
+
+def _tracer0(x, y):
+    return np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)
+
+
+def test_oracle_tracer_golden():
+    from oracle.hdg_oracle import HDGOracle
+    from oracle.timesteppers import ChorinOracle, TaylorGreenOracle
+    from oracle.tracer import TracerOracle
+
+    t = TracerOracle(HDGOracle(UnitSquareMesh(4, perturb=0.15), 2))
+    U = t.project_cg(GOLD_T["project_k2/Q"])
+    assert rel(U, GOLD_T["project_k2/U"]) < 1e-12
+    assert rel(t.advection(GOLD_T["advect_k2/q"], U), GOLD_T["advect_k2/adv"]) < 1e-12
+    orc = ChorinOracle(UnitSquareMesh(4, perturb=0.1), 2, 0.02)
+    orc.solve(TaylorGreenOracle("exponential", 0.5), 0.04, q_initial=_tracer0)
+    assert rel(orc.q_tracer, GOLD_T["chorin_k2/q"]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_engine_tracer_golden():
+    from incompressibleeulerhdg_b200.engine import HDGEngine
+    from incompressibleeulerhdg_b200.functions import Expression
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+    from incompressibleeulerhdg_b200.timesteppers import (IncompressibleEulerHDGIMEXSSP2_332,
+                                                          IncompressibleEulerHDGImplicit)
+
+    require_degree(2)
+    eng = HDGEngine(UnitSquareMesh(4, perturb=0.15), 2)
+    eng.tracer_setup()
+    dU, dadv = eng.empty(0), eng.empty(1)
+    eng.project_cg_dev(eng.upload(0, GOLD_T["project_k2/Q"]), dU, rtol=1e-14)
+    assert rel(eng.download(0, dU), GOLD_T["project_k2/U"]) < RTOL
+    eng.tracer_advection_dev(dU, eng.upload(1, GOLD_T["advect_k2/q"]), dadv)
+    assert rel(eng.download(1, dadv), GOLD_T["advect_k2/adv"]) < RTOL
+    ts = IncompressibleEulerHDGImplicit(UnitSquareMesh(4, perturb=0.1), 2, 0.02, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    ts.solve(*prob.initial_condition(), Expression(_tracer0, 0), prob.f_rhs(), 0.04)
+    assert rel(ts.q_tracer.to_host(), GOLD_T["chorin_k2/q"]) < RTOL
+    require_degree(1)
+    ts = IncompressibleEulerHDGIMEXSSP2_332(UnitSquareMesh(5, perturb=0.1), 1, 0.02, n_richardson=2, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    ts.solve(*prob.initial_condition(), Expression(_tracer0, 0), prob.f_rhs(), 0.02)
+    assert rel(ts.q_tracer.to_host(), GOLD_T["imex_ssp2_k1/q"]) < RTOL

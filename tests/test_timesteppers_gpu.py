@@ -68,6 +68,22 @@ def test_imex_k2_ssp2():
     assert rel(p.to_host(), po) < 1e-10
 
 
+def test_imex_k3_ssp2_config3_element():
+    """the element of BASELINE.json configs[3] (k = 3, IMEX SSP2(3,3,2) with the projection-preconditioned
+    Richardson iteration, n_richardson = 2) on a mesh the oracle finishes in seconds"""
+    k, nx, dt, nt = 3, 3, 0.02, 1
+    require_degree(k)
+    m = UnitSquareMesh(nx, perturb=0.1)
+    ts = TS.IncompressibleEulerHDGIMEXSSP2_332(m, k, dt, use_projection_method=True, n_richardson=2, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q0, p0 = prob.initial_condition()
+    Q, p = ts.solve(Q0, p0, None, prob.f_rhs(), nt * dt)
+    orc = IMEXOracle(m, k, dt, tableau="imex_ssp2_332", n_richardson=2)
+    Qo, po = orc.solve(TaylorGreenOracle("exponential", 0.5), nt * dt)
+    assert rel(Q.to_host(), Qo) < 1e-10
+    assert rel(p.to_host(), po) < 1e-10
+
+
 # ---- fully implicit (unsplit) stage: FGMRES on the monolithic system, hdg_implicit.py:153-186 ----------
 def test_gamma_rows_are_consistent_with_the_poisson_solve():
     """Gamma(Q, p, l) applied to the solution of the condensed mixed-Poisson solve returns the

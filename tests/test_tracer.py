@@ -177,3 +177,21 @@ def test_advection_is_conservative_and_consistent():
     # M^-1 adv(1, u) = L2 projection of div u (facet fluxes of a constant cancel the boundary term of the
     # integration by parts only where u.n is continuous, which it is for the CG velocity)
     assert np.abs(adv1).max() < 5e-3
+
+
+def test_compiled_vinv_table_is_the_refelem_map():
+    """the projection kernels carry VINV (csrc/hdg_tables.inc, tools/gen_tables.py) as compile-time
+    constants; it must be the modal <- nodal map that cgspace.build_cg_space hands to hdg_tracer_setup"""
+    import os
+    import re
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "incompressibleeulerhdg_b200", "csrc",
+                        "hdg_tables.inc")
+    txt = open(path).read()
+    for k in (1, 2, 3, 4):
+        ns = txt[txt.index(f"namespace hdg_tab_k{k} {{"):]
+        m = re.search(r"VINV\[(\d+)\]\[(\d+)\] = (\{.*?\});", ns)
+        arr = np.array(eval(m.group(3).replace("{", "[").replace("}", "]")))
+        W = R.nodal_to_modal_cell(k + 1)
+        assert arr.shape == W.shape == (R.ncell(k + 1),) * 2
+        assert np.abs(arr - W).max() < 1e-13 * np.abs(W).max()

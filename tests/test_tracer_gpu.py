@@ -70,13 +70,34 @@ def test_tracer_advection_matches_oracle(k, mesh_fn):
     U = o.interpolate_cell(tg_velocity, "Q") + 0.1 * rng.standard_normal((m.nc, 2, o.nQ1))
     q = rng.standard_normal((m.nc, o.np_))
     acc = rng.standard_normal((m.nc, o.np_))
-    dU, dq, dacc, dout = eng.upload(0, U), eng.upload(1, q), eng.upload(1, acc), eng.empty(1)
-    eng.tracer_advection_dev(dU, dq, dout)
     adv = t.advection(q, U)
-    print(f"k={k} {m.name} rel.err={rel(eng.download(1, dout), adv):.2e}")
-    assert rel(eng.download(1, dout), adv) < TOL
-    eng.tracer_advection_dev(dU, dq, dacc, c0=0.5, acc=dacc, c1=-0.25)  # acc aliases out
-    assert rel(eng.download(1, dacc), 0.5 * acc - 0.25 * adv) < TOL
+    dU, dq, dout = eng.upload(0, U), eng.upload(1, q), eng.empty(1)
+    # 1: compile-time tables (default facet rule), 0: runtime tables
+    for variant in (1, 0):
+        eng.set_tuning("tracer_tables", variant)
+        dout.zero_()
+        eng.tracer_advection_dev(dU, dq, dout)
+        err = rel(eng.download(1, dout), adv)
+        print(f"k={k} {m.name} variant={variant} rel.err={err:.2e}")
+        assert err < TOL
+        dacc = eng.upload(1, acc)
+        eng.tracer_advection_dev(dU, dq, dacc, c0=0.5, acc=dacc, c1=-0.25)  # acc aliases out
+        assert rel(eng.download(1, dacc), 0.5 * acc - 0.25 * adv) < TOL
+
+
+def test_tracer_advection_other_facet_rule():
+    """a facet rule that is not the compiled-in default goes through the runtime-table kernel"""
+    k = 2
+    m = UnitSquareMesh(5, perturb=0.15)
+    o = HDGOracle(m, k, nq_facet=7)
+    eng = HDGEngine(m, k)
+    eng.tracer_setup(nq_facet=7)
+    rng = np.random.default_rng(6)
+    U = o.interpolate_cell(tg_velocity, "Q") + 0.1 * rng.standard_normal((m.nc, 2, o.nQ1))
+    q = rng.standard_normal((m.nc, o.np_))
+    dout = eng.empty(1)
+    eng.tracer_advection_dev(eng.upload(0, U), eng.upload(1, q), dout)
+    assert rel(eng.download(1, dout), TracerOracle(o).advection(q, U)) < TOL
 
 
 def test_tracer_requires_setup():

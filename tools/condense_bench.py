@@ -44,6 +44,19 @@ def main():
                 print(json.dumps({"fp64_fma_peak_tflops_measured": fp64, "hbm_gbs_measured": hbm}), flush=True)
             nQ, np_, b = 2 * eng.nQ1, eng.np_, eng.nl1
             nA, nl = nQ + np_, 3 * b
+            # K >= 3 has two condensation kernels (hdg_set_tuning "condense_rows"): time the optional row-loop
+            # kernel first, then the default unrolled thread-per-cell kernel whose numbers go into the line
+            unrolled_ms = None
+            if k >= 3:
+                eng.set_tuning("condense_rows", 1)
+                eng.setup_poisson(keep_local=True)
+                eng.reset_timers()
+                for _ in range(args.reps):
+                    eng.setup_poisson(keep_local=True)
+                eng.synchronize()
+                tm0 = eng.timers()
+                unrolled_ms = tm0["condense"][0] / tm0["condense"][1]
+                eng.set_tuning("condense_rows", 0)
             eng.setup_poisson(keep_local=True)  # warm-up (allocations)
             eng.reset_timers()
             for _ in range(args.reps):
@@ -75,6 +88,7 @@ def main():
                 "forward_GBs": gbs(by_fwd, t_fwd), "forward_hbm_frac": gbs(by_fwd, t_fwd) / hbm,
                 "back_GBs": gbs(by_back, t_back), "back_hbm_frac": gbs(by_back, t_back) / hbm,
                 "cells_per_s_condense": nc / t_cond * 1e3,
+                "condense_rows_variant_ms": unrolled_ms,
             }
             print(json.dumps(res), flush=True)
             del eng, Ru, Rp, lam, out_l, Q, p

@@ -26,6 +26,7 @@ and the BDM projection (`common.py:91-108`):
   cell rule (exact to degree 3k+2):  WQ[q], PHI[q][i], DPHI[d][q][i]
   facet rule (NQF Gauss points):     WF[q], PHIF[e][q][i], LEG[m][q]  (Legendre of degree <= k+1)
   BDM:  interior-moment test functions NED[w][d][q] at the cell rule points
+  VINV[i][j]      = modal <- nodal map of the equispaced P_{k+1} Lagrange nodes (CG projection, tracer path)
 """
 
 from __future__ import annotations
@@ -153,6 +154,14 @@ def tables(k):
     Ninv = Ninv + Ninv @ (np.eye(2 * nQ1, dtype=LD) - Nl @ Ninv)
     Ninv = Ninv + Ninv @ (np.eye(2 * nQ1, dtype=LD) - Nl @ Ninv)
     out["LIFT"] = Ninv[:, :nfm].reshape(2, nQ1, 3, k + 2)  # [c][i][e][j]
+    # modal <- nodal map of the equispaced Lagrange nodes of P_{k+1} (CG velocity projection of the tracer
+    # path, common.py:119-122): VINV = V^-1 with V[n][i] = phi_i(node_n); two refinement steps in long double
+    nodes = R.lagrange_nodes_cell(k + 1).astype(LD)
+    V = R.dubiner(k + 1, nodes).T
+    Vi = np.linalg.inv(V.astype(np.float64)).astype(LD)
+    Vi = Vi + Vi @ (np.eye(nQ1, dtype=LD) - V @ Vi)
+    Vi = Vi + Vi @ (np.eye(nQ1, dtype=LD) - V @ Vi)
+    out["VINV"] = Vi  # [i][j]
     return {n: snap(v) for n, v in out.items()}, dict(nQ1=nQ1, np_=np_, nl1=nl1, nq=len(wa), nqf=nqf,
                                                        nint=k * (k + 2))
 

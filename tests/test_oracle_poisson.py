@@ -70,3 +70,25 @@ def test_poisson_convergence(k):
         errs.append(o.l2_error_p(p, lambda x, y: np.cos(np.pi * x) * np.cos(np.pi * y)))
     rate = np.log2(errs[0] / errs[1])
     assert rate > k + 1 - 0.35, (errs, rate)
+
+
+def test_timestepper_convergence_rates():
+    """observed rates of the IMEX SSP2(3,3,2) oracle against the exact Taylor-Green solution Psi(t) Q_s
+    (`model_problems.py:56-105`), k = 1, nx = 4 -> 8: velocity -> k+2, pressure -> k+1.  The same run on the
+    engine is `tests/test_driver.py::test_driver_observed_convergence_rates` (nx = 8 -> 16)."""
+    from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+    from oracle.timesteppers import IMEXOracle, TaylorGreenOracle
+
+    prob = TaylorGreenOracle("exponential", 0.5)
+    T, k, errs = 0.05, 1, []
+    for nx in (4, 8):
+        orc = IMEXOracle(UnitSquareMesh(nx), k, 0.0125, tableau="imex_ssp2_332")
+        Q, p = orc.solve(prob, T)
+        o, psi = orc.o, prob.psi(T)
+        Qe = o.interpolate_cell(lambda x, y: tuple(psi * c for c in prob.Q_stationary(x, y)), "Q")
+        pe = o.interpolate_cell(lambda x, y: psi ** 2 * prob.p_stationary(x, y), "p")
+        pe = pe - o.integral_p(pe) * o.const_p()
+        errs.append((o.l2_norm_Q(Q - Qe), float(np.sqrt(np.einsum("n,na->", o.detJ, (p - pe) ** 2)))))
+    rate_Q = np.log2(errs[0][0] / errs[1][0])
+    rate_p = np.log2(errs[0][1] / errs[1][1])
+    assert abs(rate_Q - 2.651) < 0.02 and abs(rate_p - 1.905) < 0.02, (errs, rate_Q, rate_p)

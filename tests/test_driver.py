@@ -188,3 +188,33 @@ def test_driver_observed_convergence_rates(k, rate_Q, rate_p):
     print(f"k={k} errors {errs} rates velocity {got_Q:.3f} pressure {got_p:.3f}")
     assert abs(got_Q - rate_Q) < 0.05 and abs(got_p - rate_p) < 0.05
     assert got_Q > k + 1.5 and got_p > k + 0.8
+
+
+@pytest.mark.parametrize("m", [2, 3])
+def test_vorticity_projector_matches_reference_form(m):
+    """`callbacks.py:44-69`: tau xi dx == -eps:(grad tau (x) Q) dx + tau eps:(n (x) Q) ds on CG_m.  For a
+    continuous velocity whose curl lies in CG_m the weak projection is the curl itself; for a discontinuous
+    velocity it differs from the cell-wise curl (interior jumps are not in the reference's form)."""
+    from incompressibleeulerhdg_b200 import refelem as R
+    from incompressibleeulerhdg_b200.auxilliary.callbacks import VorticityProjector
+    from incompressibleeulerhdg_b200.mesh import UnitDiskMesh
+
+    mesh = UnitDiskMesh(1)
+    nodes = R.lagrange_nodes_cell(m)
+    Vinv = R.nodal_to_modal_cell(m, nodes)
+    x0 = mesh.cell_xy[:, 0]
+    J = np.stack([mesh.cell_xy[:, 1] - x0, mesh.cell_xy[:, 2] - x0], axis=-1)
+    xp = x0[:, None, :] + np.einsum("ncd,qd->nqc", J, nodes)
+
+    def coef(f):
+        return np.einsum("iq,nqc->nci", Vinv, np.stack(f(xp[..., 0], xp[..., 1]), axis=-1))
+
+    P = VorticityProjector(mesh, m)
+    assert np.abs(P.at_vertices(coef(lambda x, y: (-y, x))) - 2.0).max() < 1e-11
+    w = P.at_vertices(coef(lambda x, y: (x * y, x ** 2)))  # curl = x
+    assert np.abs(w - mesh.cell_xy[..., 0]).max() < 1e-11
+    # the mass matrix is the CG mass matrix: constants integrate to the area
+    one = np.ones(P.cg.ndof)
+    rows = np.bincount(P.cg.cellmap.ravel(), weights=(P.detJ[:, None] * (P.cg.W.T @ P.cg.W @ np.ones(P.cg.nloc))[None, :]).ravel(),
+                       minlength=P.cg.ndof)
+    assert abs(one @ rows - mesh.volume) < 1e-12

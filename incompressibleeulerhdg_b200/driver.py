@@ -192,6 +192,8 @@ def main(argv=None, file=None):
     if rank != 0 and file is None:
         file = open(os.devnull, "w")
     outdir = None if args.output == "none" else args.output
+    if outdir is not None:
+        os.makedirs(outdir, exist_ok=True)
     mesh = build_mesh(args)
     callbacks = None
     if args.animation and outdir is not None:

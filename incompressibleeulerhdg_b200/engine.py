@@ -518,7 +518,7 @@ class HDGEngine:
     def tracer_setup(self, nq_facet: int | None = None):
         """build the [CG_{k+1}]^2 space of the velocity projection (`common.py:119-122`) and hand it and
         the quadrature tables of the advection kernel to the engine; idempotent"""
-        if getattr(self, "cg_space", None) is not None:
+        if getattr(self, "cg_space", None) is not None and getattr(self, "_tracer_nq_facet", None) == nq_facet:
             return self.cg_space
         from . import cgspace
 
@@ -531,6 +531,7 @@ class HDGEngine:
             sp.inc_idx.ctypes.data_as(_ip), _ptr(sp.W), _ptr(dinv), tab_cell.shape[0], _ptr(tab_cell),
             tab_facet.shape[1], _ptr(tab_facet)))
         self.cg_space = sp
+        self._tracer_nq_facet = nq_facet
         return sp
 
     def project_cg_dev(self, Q, Qcg, rtol=1e-13, maxit=500):

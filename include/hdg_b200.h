@@ -198,12 +198,16 @@ int hdg_lincomb_dev(hdg_handle h, int64_t n, double* out, int nterms, const doub
 /* y = M x (inverse == 0) or M^-1 x for a cell field (kind 0 velocity, 1 pressure); M = detJ I */
 int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y);
 
-/* ---- passive tracer advection (single GPU in this build) ---------------------
+/* ---- passive tracer advection ------------------------------------------------
  * Replaces `_tracer_advection(chi, q, u, project_onto_cg=True)` (common.py:110-129) and the tracer
  * mass solves of hdg_implicit.py:93-96,192-193 and hdg_imex.py:415-448,622-623,638-639.
  *
  * hdg_tracer_setup hands over the [CG_{k+1}]^2 space of the velocity projection and the quadrature
  * tables (all host arrays, copied; NLOC = (k+2)(k+3)/2 Lagrange nodes per cell, NP = (k+1)(k+2)/2):
+ *   ncg, ncg_owned          CG dofs held by this handle and how many of them it owns (equal on one GPU).  On a
+ *                           partitioned mesh the dofs are numbered owned-first and their halo plan is set
+ *                           beforehand with hdg_set_halo_plan(h, 18, ...) (partition.cg_plan); the multi-GPU
+ *                           path has host-side (gloo) tests only -- it has not run on 2 GPUs yet
  *   cellmap [NLOC][nc]      global CG dof of local node j of every cell
  *   inc_ptr [ncg+1], inc_idx [NLOC*nc]   incidence CSR of the dofs: entries j*nc + cell in a fixed order
  *   W [NLOC][NLOC]          modal <- nodal (inverse Vandermonde matrix of the Lagrange nodes)
@@ -215,9 +219,9 @@ int hdg_mass_dev(hdg_handle h, int kind, int inverse, const double* x, double* y
  *   <r,z> <= rtol^2 <r0,z0> per component.
  * hdg_tracer_advection_dev: out = c0 acc + c1 M^-1 [ q div(chi u) dx - (chi+ - chi-)(un+ q+ - un- q-) dS ]
  *   with u = Qcg, un = (u.n + |u.n|)/2; acc may be NULL when c0 == 0 and may alias out; q must not. */
-int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_t* inc_ptr, const int32_t* inc_idx,
-                     const double* W, const double* dinv, int nq_cell, const double* tab_cell, int nq_facet,
-                     const double* tab_facet);
+int hdg_tracer_setup(hdg_handle h, int ncg, int ncg_owned, const int32_t* cellmap, const int32_t* inc_ptr,
+                     const int32_t* inc_idx, const double* W, const double* dinv, int nq_cell, const double* tab_cell,
+                     int nq_facet, const double* tab_facet);
 int hdg_project_cg_dev(hdg_handle h, const double* Q, double* Qcg, double rtol, int maxit, int* iters);
 int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, double c0, const double* acc,
                              double c1, double* out);
@@ -231,7 +235,8 @@ int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, d
  *   hdg_comm_init        collective: joins the handle to the communicator
  *   hdg_set_partition    owned counts, global facet count and global volume (reductions run over
  *                        owned entities only and are summed over ranks)
- *   hdg_set_halo_plan    exchange plan of one entity kind: 0 cells, 1 facets, 2+l P1 level l.
+ *   hdg_set_halo_plan    exchange plan of one entity kind: 0 cells, 1 facets, 2+l P1 level l (l < 16),
+ *                        18 CG dofs of the tracer path.
  *                        Peer j sends the owned entities send_idx[send_ptr[j]..send_ptr[j+1]) and
  *                        fills the ghost block [recv_off[j], recv_off[j]+recv_cnt[j]); ghost blocks
  *                        are contiguous, ordered by peer and cover [n_owned, n_local).

@@ -59,7 +59,9 @@ def _local_entities(d: int):
     return ents, nint
 
 
-def build_cg_space(mesh, degree: int) -> CGSpace:
+def build_cg_space(mesh, degree: int, perm: np.ndarray | None = None) -> CGSpace:
+    """`perm` (optional) renumbers the dofs: dof l of the numbering above becomes perm[l] (used on a
+    partitioned mesh to put the owned dofs first, ``partition.cg_plan``)"""
     d = int(degree)
     assert d >= 1
     nc, nf, nv = mesh.nc, mesh.nf, mesh.nv
@@ -78,6 +80,9 @@ def build_cg_space(mesh, degree: int) -> CGSpace:
             cellmap[:, j] = nv + nf * (d - 1) + cells * nint + ent[1]
     ndof = nv + nf * (d - 1) + nc * nint
     assert ndof < 2 ** 31 and nc * nloc < 2 ** 31
+    if perm is not None:
+        assert perm.shape == (ndof,)
+        cellmap = np.asarray(perm, dtype=np.int64)[cellmap]
     flat = cellmap.ravel()  # index = cell * nloc + j
     order = np.argsort(flat, kind="stable")
     counts = np.bincount(flat, minlength=ndof)

@@ -74,7 +74,7 @@ struct HaloPlanDev {
   int total_send = 0, total_recv = 0;
 };
 
-constexpr int HDG_MAX_PLANS = 2 + 16;  // cells, facets, P1 levels
+constexpr int HDG_MAX_PLANS = 2 + 16 + 1;  // cells, facets, P1 levels, CG dofs of the tracer path
 constexpr int HDG_MAX_RANKS = 8;       // GPUs of one box (NVSwitch domain)
 constexpr int HDG_RED_MAX = 8;         // doubles per all-reduce
 

@@ -278,7 +278,7 @@ static void tracer_free(hdg_engine* h) {
 // ------------------------------------------------------------------------------------------------
 // multi-GPU helpers (no-ops on a single GPU)
 // ------------------------------------------------------------------------------------------------
-enum { PLAN_CELLS = 0, PLAN_FACETS = 1, PLAN_P1 = 2 };
+enum { PLAN_CELLS = 0, PLAN_FACETS = 1, PLAN_P1 = 2, PLAN_CG = 2 + 16 };
 
 static void comm_fail(hdg_engine* h, const char* what, ncclResult_t r) {
   if (!h->comm_rc) {
@@ -3051,13 +3051,18 @@ int hdg_mg_info(hdg_handle h, int* nlevels, double* fine_lmax) {
 }
 
 // ---- passive tracer (hdg_tracer.cuh) ------------------------------------------------------------------
-int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_t* inc_ptr, const int32_t* inc_idx,
-                     const double* W, const double* dinv, int nq_cell, const double* tab_cell, int nq_facet,
-                     const double* tab_facet) {
-  if (!h || ncg <= 0 || !cellmap || !inc_ptr || !inc_idx || !W || !dinv || nq_cell <= 0 || !tab_cell ||
-      nq_facet <= 0 || !tab_facet)
+int hdg_tracer_setup(hdg_handle h, int ncg, int ncg_owned, const int32_t* cellmap, const int32_t* inc_ptr,
+                     const int32_t* inc_idx, const double* W, const double* dinv, int nq_cell, const double* tab_cell,
+                     int nq_facet, const double* tab_facet) {
+  if (!h || ncg <= 0 || ncg_owned <= 0 || ncg_owned > ncg || !cellmap || !inc_ptr || !inc_idx || !W || !dinv ||
+      nq_cell <= 0 || !tab_cell || nq_facet <= 0 || !tab_facet)
     return HDG_EINVAL;
-  if (h->comm) FAIL(h, HDG_EINVAL, "tracer advection is single-GPU in this build (no CG-dof halo plan yet)");
+  const bool partitioned = h->comm && h->comm->nranks > 1;
+  if (!partitioned && ncg_owned != ncg) FAIL(h, HDG_EINVAL, "hdg_tracer_setup: ghost CG dofs without a communicator");
+  if (partitioned && !h->comm->plans[PLAN_CG].set)
+    FAIL(h, HDG_ESTATE, "hdg_tracer_setup: set the halo plan of the CG dofs first (hdg_set_halo_plan, kind 18)");
+  if (partitioned && (h->comm->plans[PLAN_CG].n_local != ncg || h->comm->plans[PLAN_CG].n_owned != ncg_owned))
+    FAIL(h, HDG_EINVAL, "hdg_tracer_setup: dof counts do not match the CG halo plan");
   CUDA_TRY(h, cudaSetDevice(h->device));
   tracer_free(h);
   int nq1, np, nl1;
@@ -3065,6 +3070,7 @@ int hdg_tracer_setup(hdg_handle h, int ncg, const int32_t* cellmap, const int32_
   TracerState* t = new TracerState();
   h->tracer = t;
   t->ncg = ncg;
+  t->ncg_own = ncg_owned;
   t->nloc = nq1;
   t->nq_cell = nq_cell;
   t->nq_facet = nq_facet;
@@ -3115,20 +3121,28 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
   const int nc = h->nc, ncg = t->ncg, G = h->grid;
   const int cgrid = cdiv(nc, 128);
   const size_t cs = (size_t)NLOC * nc;
+  // multi-GPU (one rank of a partitioned mesh): dots run over the owned dofs and are summed over the ranks
+  // (allreduce_slots), ghost entries of p / x are refreshed before the kernels that read them through the
+  // cell -> dof map (halo_exchange); both are no-ops on a single GPU
+  const int own = t->ncg_own;
   LAUNCH(h, k_cgp_load<K>, cgrid, 128, h->cell_xy, nc, Q, t->yK);
-  LAUNCH(h, k_cgp_gather<0>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
+  LAUNCH(h, k_cgp_gather<0>, G, BLOCK, ncg, own, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
          t->Ap, t->part);
+  allreduce_slots(h, t->part, 2);
   LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 0, 0, 1);
   int par = 0, it = 0;
   const double tol2 = rtol * rtol;
   bool done = false;
   while (!done && it < maxit) {
     ++it;
+    halo_exchange(h, PLAN_CG, 2, t->p);
     LAUNCH(h, k_cgp_cellop<K>, cgrid, 128, h->cell_xy, nc, ncg, t->cellmap, t->p, t->yK);
-    LAUNCH(h, k_cgp_gather<1>, G, BLOCK, ncg, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
+    LAUNCH(h, k_cgp_gather<1>, G, BLOCK, ncg, own, cs, t->inc_ptr, t->inc_idx, t->yK, t->dinv, t->x, t->r, t->z, t->p,
            t->Ap, t->part);
+    allreduce_slots(h, t->part, 2);
     LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 1, par, 0);
-    LAUNCH(h, k_cgp_update, G, BLOCK, ncg, t->scal, par, t->dinv, t->p, t->Ap, t->x, t->r, t->z, t->part);
+    LAUNCH(h, k_cgp_update, G, BLOCK, ncg, own, t->scal, par, t->dinv, t->p, t->Ap, t->x, t->r, t->z, t->part);
+    allreduce_slots(h, t->part, 2);
     LAUNCH(h, k_cgp_finish, 1, BLOCK, t->part, G, t->scal, 0, par ^ 1, 0);
     LAUNCH(h, k_cgp_dir, G, BLOCK, ncg, t->scal, par, t->z, t->p);
     par ^= 1;
@@ -3139,8 +3153,10 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
       done = s.rz[par][0] <= tol2 * s.rz0[0] && s.rz[par][1] <= tol2 * s.rz0[1];
     }
   }
+  halo_exchange(h, PLAN_CG, 2, t->x);
   LAUNCH(h, k_cgp_tocell<K>, cgrid, 128, nc, ncg, t->cellmap, t->x, Qcg);
   CUDA_TRY(h, cudaGetLastError());
+  if (h->comm_rc) return h->comm_rc;
   if (iters) *iters = it;
   if (!done) FAIL(h, HDG_ENOCONV, "CG velocity projection did not converge");
   return HDG_OK;
@@ -3162,6 +3178,7 @@ int hdg_tracer_advection_dev(hdg_handle h, const double* Qcg, const double* q, d
   if (!h->tracer) FAIL(h, HDG_ESTATE, "hdg_tracer_setup has not been called");
   CUDA_TRY(h, cudaSetDevice(h->device));
   TracerState* t = h->tracer;
+  halo_exchange(h, PLAN_CELLS, (h->k + 1) * (h->k + 2) / 2, q);  // the upwind flux reads the neighbours' tracer
   // default facet rule: compile-time tables (no table loads); otherwise, or with hdg_set_tuning
   // ("tracer_tables", 0), the runtime tables handed to hdg_tracer_setup
   DISPATCH_K(h, {

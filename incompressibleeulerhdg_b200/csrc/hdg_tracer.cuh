@@ -16,7 +16,9 @@
 // two small dense products per cell and a
 // deterministic gather over the cells that share a dof (incidence CSR, fixed order, no atomics).
 // Jacobi-PCG with both velocity components advanced together (one alpha/beta per component); all
-// Krylov scalars stay in device memory, the host polls the residual every few iterations.
+// Krylov scalars stay in device memory, the host polls the residual every few iterations.  On a partitioned
+// mesh the dofs are numbered owned-first (partition.cg_plan): dots run over the owned prefix and are summed
+// over the ranks, ghost entries of p and x are refreshed before the kernels that gather through the cell map.
 //
 // The advection kernel evaluates the volume and interior-facet integrals by quadrature (the non-polynomial
 // |u.n| rules out closed-form reference tensors), one thread per cell, the neighbour's tracer trace with
@@ -33,7 +35,7 @@ struct TracerScalars {
 };
 
 struct TracerState {
-  int ncg = 0, nloc = 0, nq_cell = 0, nq_facet = 0;
+  int ncg = 0, ncg_own = 0, nloc = 0, nq_cell = 0, nq_facet = 0;  // ncg_own < ncg on a partitioned mesh
   int *cellmap = nullptr;   // [nloc][nc]
   int *inc_ptr = nullptr;   // [ncg+1]
   int *inc_idx = nullptr;   // [nloc*nc]  entries j*nc + cell
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(128) k_cgp_tocell(int nc, int ncg, const int* 
 // MODE 0: first PCG step  b = out; x = 0; r = b; z = dinv r; p = z; partial <r,z>
 // MODE 1: Ap = out; partial <p,Ap>
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK) k_cgp_gather(int ncg, size_t comp_stride, const int* __restrict__ inc_ptr,
+__global__ void __launch_bounds__(BLOCK) k_cgp_gather(int ncg, int ncg_own, size_t comp_stride,
+                                                      const int* __restrict__ inc_ptr,
                                                       const int* __restrict__ inc_idx,
                                                       const double* __restrict__ yK, const double* __restrict__ dinv,
                                                       double* __restrict__ x, double* __restrict__ r,
@@ -185,13 +188,17 @@ __global__ void __launch_bounds__(BLOCK) k_cgp_gather(int ncg, size_t comp_strid
       z[g1] = z1;
       p[g] = z0;
       p[g1] = z1;
-      acc0 = fma(s0, z0, acc0);
-      acc1 = fma(s1, z1, acc1);
+      if (g < ncg_own) {  // reductions run over the owned dofs only
+        acc0 = fma(s0, z0, acc0);
+        acc1 = fma(s1, z1, acc1);
+      }
     } else {
       Ap[g] = s0;
       Ap[g1] = s1;
-      acc0 = fma(p[g], s0, acc0);
-      acc1 = fma(p[g1], s1, acc1);
+      if (g < ncg_own) {
+        acc0 = fma(p[g], s0, acc0);
+        acc1 = fma(p[g1], s1, acc1);
+      }
     }
   }
   acc0 = block_reduce(acc0);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(BLOCK) k_cgp_finish(const double* __restrict__
 }
 
 // x += alpha p; r -= alpha Ap; z = dinv r; partial <r,z>      (alpha = rz[par] / pAp per component)
-__global__ void __launch_bounds__(BLOCK) k_cgp_update(int ncg, const TracerScalars* __restrict__ s, int par,
+__global__ void __launch_bounds__(BLOCK) k_cgp_update(int ncg, int ncg_own, const TracerScalars* __restrict__ s, int par,
                                                       const double* __restrict__ dinv, const double* __restrict__ p,
                                                       const double* __restrict__ Ap, double* __restrict__ x,
                                                       double* __restrict__ r, double* __restrict__ z,
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(BLOCK) k_cgp_update(int ncg, const TracerScala
       r[i] = rr;
       double zz = d * rr;
       z[i] = zz;
-      acc[c] = fma(rr, zz, acc[c]);
+      if (g < ncg_own) acc[c] = fma(rr, zz, acc[c]);
     }
   }
   double a0 = block_reduce(acc[0]);

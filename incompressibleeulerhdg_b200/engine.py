@@ -74,7 +74,7 @@ SIGNATURES = {
     "hdg_l2_inner_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _dp]),
     "hdg_lincomb_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _dp, C.POINTER(_vp)]),
     "hdg_mass_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
-    "hdg_tracer_setup": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int, _dp]),
+    "hdg_tracer_setup": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_int, _dp]),
     "hdg_project_cg_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "hdg_tracer_advection_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, C.c_double, _vp]),
     "hdg_comm_unique_id": (C.c_int, [_vp]),
@@ -515,21 +515,36 @@ class HDGEngine:
         self._check(self.lib.hdg_mass_dev(self._h, int(kind), int(inverse), _dev(x), _dev(y)))
 
     # -- passive tracer ----------------------------------------------------------
-    def tracer_setup(self, nq_facet: int | None = None):
+    PLAN_CG = 18  # halo-plan kind of the CG dofs (include/hdg_b200.h)
+
+    def tracer_setup(self, nq_facet: int | None = None, global_mesh=None):
         """build the [CG_{k+1}]^2 space of the velocity projection (`common.py:119-122`) and hand it and
-        the quadrature tables of the advection kernel to the engine; idempotent"""
+        the quadrature tables of the advection kernel to the engine; idempotent.  On a partitioned mesh
+        `global_mesh` is the complete mesh: the dofs are renumbered owned-first and their halo plan is
+        installed (``partition.cg_plan``)."""
         if getattr(self, "cg_space", None) is not None and getattr(self, "_tracer_nq_facet", None) == nq_facet:
             return self.cg_space
         from . import cgspace
 
-        sp = cgspace.build_cg_space(self.mesh, self.k + 1)
+        n_owned = None
+        if self.part is not None and self.part.nranks > 1:
+            if global_mesh is None:
+                raise ValueError("tracer_setup on a partitioned mesh needs global_mesh")
+            from . import partition
+
+            plan, perm = partition.cg_plan(global_mesh, self.part, self.k + 1)
+            sp = cgspace.build_cg_space(self.mesh, self.k + 1, perm=perm)
+            self.set_halo_plan(self.PLAN_CG, plan)
+            n_owned = plan.n_owned
+        else:
+            sp = cgspace.build_cg_space(self.mesh, self.k + 1)
         tab_cell, tab_facet = cgspace.tracer_tables(self.k, nq_facet)
         cellmap = np.ascontiguousarray(sp.cellmap.T, dtype=np.int32)  # SoA [nloc][nc]
         dinv = np.ascontiguousarray(1.0 / sp.diag)
         self._check(self.lib.hdg_tracer_setup(
-            self._h, sp.ndof, cellmap.ctypes.data_as(_ip), sp.inc_ptr.ctypes.data_as(_ip),
-            sp.inc_idx.ctypes.data_as(_ip), _ptr(sp.W), _ptr(dinv), tab_cell.shape[0], _ptr(tab_cell),
-            tab_facet.shape[1], _ptr(tab_facet)))
+            self._h, sp.ndof, sp.ndof if n_owned is None else n_owned, cellmap.ctypes.data_as(_ip),
+            sp.inc_ptr.ctypes.data_as(_ip), sp.inc_idx.ctypes.data_as(_ip), _ptr(sp.W), _ptr(dinv), tab_cell.shape[0],
+            _ptr(tab_cell), tab_facet.shape[1], _ptr(tab_facet)))
         self.cg_space = sp
         self._tracer_nq_facet = nq_facet
         return sp

@@ -29,7 +29,7 @@ import scipy.sparse as sp
 from .mesh import Mesh
 
 __all__ = ["strip_partition", "block_partition", "HaloPlan", "LocalMesh", "partition_mesh", "build_plan",
-           "LocalHierarchy", "partition_hierarchy", "exchange_host"]
+           "LocalHierarchy", "partition_hierarchy", "exchange_host", "cg_plan"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,6 +221,48 @@ def partition_mesh(mesh: Mesh, cell_rank: np.ndarray, rank: int, nranks: int | N
     m.meta.update(partitioned=True, periodic=mesh.meta.get("periodic", False))
     return LocalMesh(mesh=m, rank=rank, nranks=nranks, cells=cells, facets=facets, verts=verts, global_nc=mesh.nc,
                      global_nf=mesh.nf, global_nv=mesh.nv, global_volume=mesh.volume, cell_rank=cell_rank)
+
+
+# ------------------------------------------------------------------------------------------------
+# continuous Lagrange dofs (velocity projection of the passive-tracer path, cgspace.py)
+# ------------------------------------------------------------------------------------------------
+def cg_plan(mesh: Mesh, lm: LocalMesh, degree: int):
+    """halo plan of the CG_degree dofs of rank `lm.rank` and the renumbering that makes it usable.
+
+    A CG dof belongs to the owner of the entity it sits on (vertex, facet, cell).  ``cgspace`` numbers the
+    dofs of the *local* mesh as [vertices | facet interiors | cell interiors] in local entity order, which
+    interleaves owned and ghost dofs; the engine's exchange wants owned dofs first and the ghosts of every
+    peer in one block.  Returns ``(plan, perm)`` with ``perm[l]`` = position of local cgspace dof ``l`` in
+    that order (pass it to ``cgspace.build_cg_space(..., perm=perm)``); ``plan.local_gid`` are the ids in the
+    global numbering of ``cgspace`` on the complete mesh, so both ends of an exchange agree on the order.
+    """
+    d = int(degree)
+    ne, nint = d - 1, (d - 1) * (d - 2) // 2
+    NV, NF = mesh.nv, mesh.nf
+    cell_rank = lm.cell_rank
+    facet_owner, vert_owner = _entity_owners(mesh, cell_rank)
+    owner = np.concatenate([vert_owner, np.repeat(facet_owner, ne), np.repeat(cell_rank, nint)]).astype(np.int32)
+
+    def gids(v, f, c):  # global dof ids of global entity id arrays
+        parts = [np.asarray(v, dtype=np.int64)]
+        if ne:
+            parts.append((NV + np.asarray(f, dtype=np.int64)[:, None] * ne + np.arange(ne)).ravel())
+        if nint:
+            parts.append((NV + NF * ne + np.asarray(c, dtype=np.int64)[:, None] * nint + np.arange(nint)).ravel())
+        return np.concatenate(parts)
+
+    local_sets = []
+    for q in range(lm.nranks):
+        c = _local_cells(mesh, cell_rank, q)
+        local_sets.append(gids(np.unique(mesh.cell_vert[c].ravel()), np.unique(mesh.cell_facet[c].ravel()), c))
+    plan = build_plan(owner, local_sets, lm.rank)
+    # global id of every dof in the local cgspace numbering (local entity order)
+    gid_local = gids(lm.verts.local_gid, lm.facets.local_gid, lm.cells.local_gid)
+    order = np.argsort(plan.local_gid)
+    pos = np.searchsorted(plan.local_gid[order], gid_local)
+    assert np.array_equal(plan.local_gid[order][pos], gid_local), "local CG dofs and the plan disagree"
+    perm = order[pos].astype(np.int64)
+    return plan, perm
 
 
 # ------------------------------------------------------------------------------------------------

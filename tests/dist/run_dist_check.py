@@ -87,6 +87,30 @@ def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, loc
                               "its_tentative": ts.niter_tentative.value, "p2p_timeouts": ts.engine.p2p_status()})
 
 
+def tracer_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name):
+    """passive tracer on the partitioned mesh vs the single-GPU run (CG-dof halo plan, owned-only dots).
+    Opt-in (HDG_DIST_TRACER=1): the multi-GPU tracer path has host-side tests only so far."""
+    from incompressibleeulerhdg_b200.functions import Expression
+
+    q0 = Expression(lambda x, y: np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y), 0)
+
+    def run(auto):
+        ts_common.AUTO_PARTITION = auto
+        ts = getattr(TS, cls)(mesh, k, dt, device=local, krylov_rtol=1e-13, **kwargs)
+        prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+        Q0, p0 = prob.initial_condition()
+        Q, p = ts.solve(Q0, p0, q0, prob.f_rhs(), nt * dt)
+        return ts, Q.to_host(), ts.q_tracer.to_host()
+
+    _, Q0, q_single = run(False)
+    ts, Q1, q_dist = run(True)
+    lm = ts.local_mesh
+    cg, nco = lm.cells.local_gid, lm.nc_owned
+    errs = {"Q": rel(Q1[:nco], Q0[cg[:nco]]), "q": rel(q_dist[:nco], q_single[cg[:nco]])}
+    report(rank, name, errs, {"comm": ts.engine.comm_stats(), "cg_projection_its": ts.niter_cg_projection.value,
+                              "p2p_timeouts": ts.engine.p2p_status()})
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -106,6 +130,11 @@ def main():
                      {"use_projection_method": False}, 0.02, 1, "fully_implicit_k1")
     timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
                      {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1")
+    if os.environ.get("HDG_DIST_TRACER", "0") == "1":
+        os.environ["HDG_TRACER_MULTI"] = "1"
+        tracer_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2_tracer")
+        tracer_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
+                    {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1_tracer")
     dist.barrier()
     dist.destroy_process_group()
     if failures:

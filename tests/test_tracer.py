@@ -195,3 +195,116 @@ def test_compiled_vinv_table_is_the_refelem_map():
         W = R.nodal_to_modal_cell(k + 1)
         assert arr.shape == W.shape == (R.ncell(k + 1),) * 2
         assert np.abs(arr - W).max() < 1e-13 * np.abs(W).max()
+
+
+# ---- partitioned mesh: CG-dof halo plan and the distributed projection (host logic of the multi-GPU path) --------
+@pytest.mark.parametrize("world", [2, 3])
+def test_cg_plan_matches_global_space(world):
+    from incompressibleeulerhdg_b200 import partition as PT
+
+    mesh = UnitSquareMesh(6, perturb=0.1)
+    cr = PT.strip_partition(mesh, world)
+    G = cgspace.build_cg_space(mesh, 3)
+    cover = np.zeros(G.ndof, dtype=int)
+    for r in range(world):
+        lm = PT.partition_mesh(mesh, cr, r, world)
+        plan, perm = PT.cg_plan(mesh, lm, 3)
+        L = cgspace.build_cg_space(lm.mesh, 3, perm=perm)
+        assert L.ndof == plan.n_local and np.array_equal(np.sort(perm), np.arange(L.ndof))
+        # the renumbered local cell map names the same global dofs as the global space (incl. facet direction)
+        assert np.array_equal(plan.local_gid[L.cellmap], G.cellmap[lm.cells.local_gid])
+        own = plan.local_gid[:plan.n_owned]
+        assert np.allclose(L.diag[:plan.n_owned], G.diag[own], rtol=1e-14)  # owned rows see all their cells
+        # ghost blocks: contiguous per peer, in the order the owner packs them
+        off = plan.n_owned
+        for j in range(len(plan.peers)):
+            if plan.recv_cnt[j]:
+                assert plan.recv_off[j] == off
+                off += plan.recv_cnt[j]
+        assert off == plan.n_local
+        cover[own] += 1
+    assert np.all(cover == 1)
+
+
+def _dist_project_worker(rank, world, port, out_dir):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    from incompressibleeulerhdg_b200 import partition as PT
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        k = 1
+        mesh = UnitSquareMesh(6, perturb=0.1)
+        lm = PT.partition_mesh(mesh, PT.strip_partition(mesh, world), rank, world)
+        plan, perm = PT.cg_plan(mesh, lm, k + 1)
+        L = cgspace.build_cg_space(lm.mesh, k + 1, perm=perm)
+        no = plan.n_owned
+        og = HDGOracle(mesh, k)
+        Qg = og.interpolate_cell(tg_velocity, "Q") + 0.05 * np.random.default_rng(9).standard_normal((mesh.nc, 2, og.nQ1))
+        Ug = TracerOracle(og).project_cg(Qg)  # global reference, every rank can afford it at this size
+        Ql = Qg[lm.cells.local_gid]
+        detJ = 2.0 * lm.mesh.cell_area()
+
+        def allsum(v):
+            t = torch.tensor(v, dtype=torch.float64)
+            dist.all_reduce(t)
+            return t.numpy()
+
+        def dots(u, v):  # owned dofs only, summed over the ranks: [2]
+            return allsum(np.sum(u[:, :no] * v[:, :no], axis=1))
+
+        def gather(yK):  # yK [2, nc, nloc] -> [2, ndof] (ghost rows incomplete, like k_cgp_gather)
+            return np.stack([np.bincount(L.cellmap.ravel(), weights=yK[c].ravel(), minlength=L.ndof) for c in range(2)])
+
+        def apply_mass(p):  # k_cgp_cellop + k_cgp_gather<1> after the halo exchange of p
+            PT.exchange_host(plan, p, rank)
+            xl = p[:, L.cellmap]  # [2, nc, nloc]
+            return gather(detJ[None, :, None] * ((xl @ L.W.T) @ L.W))
+
+        b = gather(detJ[None, :, None] * (np.swapaxes(Ql, 0, 1) @ L.W))
+        dinv = 1.0 / L.diag
+        x = np.zeros_like(b)
+        r = b.copy()
+        z = dinv * r
+        p = z.copy()
+        rz = rz0 = dots(r, z)
+        its = 0
+        while np.any(rz > 1e-28 * rz0) and its < 300:
+            Ap = apply_mass(p)
+            al = rz / dots(p, Ap)
+            x += al[:, None] * p
+            r -= al[:, None] * Ap
+            z = dinv * r
+            rz_new = dots(r, z)
+            p = z + (rz_new / rz)[:, None] * p
+            rz = rz_new
+            its += 1
+        PT.exchange_host(plan, x, rank)  # before k_cgp_tocell
+        Ul = np.swapaxes(x[:, L.cellmap] @ L.W.T, 0, 1)  # [nc_local, 2, nloc]
+        nco = lm.nc_owned
+        err = np.abs(Ul[:nco] - Ug[lm.cells.local_gid[:nco]]).max() / np.abs(Ug).max()
+        np.save(os.path.join(out_dir, f"proj{rank}.npy"), np.array([err, its]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_distributed_cg_projection_gloo_world2(tmp_path):
+    """the multi-GPU projection algorithm (owned-first dofs, owned-only dots, ghost refresh of p and x) on two
+    gloo ranks reproduces the single-domain oracle projection on every owned cell"""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_dist_project_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        err, its = np.load(tmp_path / f"proj{r}.npy")
+        assert its < 300 and err < 1e-11, (err, its)

@@ -37,40 +37,40 @@ from .model_problems import DoubleLayerShearFlow, KelvinHelmholtz, TaylorGreen
 TIMESTEPPERS = ["implicit", "imex_implicit", "imex_ars2_232", "imex_ars3_443", "imex_ssp2_332", "imex_ssp3_433"]
 
 
+#: the reference's options (`driver.py:26-176`): (name, type, default, choices, what it selects).  Names, types,
+#: defaults and choices are the reference's; `tests/test_driver.py` pins them against a copy of that list.
+_VALUE_OPTIONS = [
+    ("problem", str, "taylorgreen", ["taylorgreen", "kelvinhelmholtz", "shear"], "which model problem"),
+    ("nx", int, 8, None, "cells per direction of the square meshes"),
+    ("refinement", int, 2, None, "refinement level of the disk mesh"),
+    ("degree", int, 1, None, "pressure degree k (velocity k+1, trace k)"),
+    ("tfinal", float, 1.0, None, "end of the simulated interval"),
+    ("kappa", float, 0.5, None, "decay rate of the Taylor-Green amplitude Psi(t)"),
+    ("dt", float, 0.04, None, "time step"),
+    ("discretisation", str, "hdg", ["conforming", "dg", "hdg"], "spatial discretisation (only hdg is built)"),
+    ("richardson", int, 2, None, "Richardson iterations per IMEX stage"),
+    ("flux", str, "upwind", ["upwind", "centered"], "numerical flux of the advection term"),
+    ("timestepper", str, "imex_ssp2_332", TIMESTEPPERS, "time integrator"),
+    ("forcing", str, "exponential", ["exponential", "constant"], "time dependence of the Taylor-Green forcing"),
+]
+_FLAG_OPTIONS = [
+    ("use_projection_method", "split every implicit stage into tentative velocity + pressure correction"),
+    ("test_pressure_solver", "time one condensed mixed-Poisson solve and exit"),
+    ("warmup", "run a single time step only"),
+    ("animation", "write the fields after every step to evolution.pvd"),
+    ("tracer_advection", "advect the passive tracer sin(2 pi x) sin(2 pi y)"),
+]
+
+
 def build_parser() -> argparse.ArgumentParser:
-    """the argument parser of `driver.py:26-176` (same names, types, choices and defaults)"""
+    """argument parser with the reference's option set plus the engine-side ``--device`` / ``--output``"""
     parser = argparse.ArgumentParser("Mesh specifications and polynomial degree")
-    parser.add_argument("--problem", choices=["taylorgreen", "kelvinhelmholtz", "shear"], type=str, action="store",
-                        default="taylorgreen", help="model problem to solve")
-    parser.add_argument("--nx", metavar="nx", type=int, action="store", default=8,
-                        help="number of grid cells in x-direction")
-    parser.add_argument("--refinement", metavar="refinement", type=int, action="store", default=2,
-                        help="refinement level for unit disk mesh")
-    parser.add_argument("--degree", metavar="degree", type=int, action="store", default=1, help="polynomial degree")
-    parser.add_argument("--tfinal", metavar="tfinal", type=float, action="store", default=1.0, help="final time")
-    parser.add_argument("--kappa", type=float, action="store", default=0.5, help="exponential decay factor")
-    parser.add_argument("--dt", type=float, action="store", default=0.04, help="timestep size")
-    parser.add_argument("--discretisation", choices=["conforming", "dg", "hdg"], type=str, action="store",
-                        default="hdg", help="discretisation method")
-    parser.add_argument("--use_projection_method", action="store_true", default=False,
-                        help="use projection method for timestepping")
-    parser.add_argument("--richardson", metavar="richardson", type=int, action="store", default=2,
-                        help="number of Richardson iterations")
-    parser.add_argument("--flux", choices=["upwind", "centered"], type=str, action="store", default="upwind",
-                        help="numerical flux")
-    parser.add_argument("--timestepper", choices=TIMESTEPPERS, type=str, action="store", default="imex_ssp2_332",
-                        help="timestepper")
-    parser.add_argument("--forcing", choices=["exponential", "constant"], type=str, action="store",
-                        default="exponential", help="forcing")
-    parser.add_argument("--test_pressure_solver", action="store_true", default=False,
-                        help="carry out a single solve with the pressure solver for testing")
-    parser.add_argument("--warmup", action="store_true", default=False, help="only perform one timestep")
-    parser.add_argument("--animation", action="store_true", default=False,
-                        help="save velocity and pressure fields at the end of each timestep as an animation")
-    parser.add_argument("--tracer_advection", action="store_true", default=False, help="advect tracer field")
-    # engine-side additions
-    parser.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK or 0)")
-    parser.add_argument("--output", type=str, default=".", help="directory for the .pvd/.vtu files, 'none' to skip")
+    for name, typ, default, choices, text in _VALUE_OPTIONS:
+        parser.add_argument(f"--{name}", type=typ, default=default, choices=choices, help=f"{text} [{default}]")
+    for name, text in _FLAG_OPTIONS:
+        parser.add_argument(f"--{name}", action="store_true", default=False, help=text)
+    parser.add_argument("--device", type=int, default=None, help="CUDA device [LOCAL_RANK, else 0]")
+    parser.add_argument("--output", type=str, default=".", help="directory of the .pvd/.vtu files, 'none' to skip [.]")
     return parser
 
 
@@ -109,31 +109,18 @@ def build_timestepper(args, mesh, callbacks, device):
 
 
 def print_header(args, timestepper, file=None):
-    """`driver.py:285-306`"""
-    p = lambda *a: print(*a, file=file)  # noqa: E731
-    p("+-------------------------------------------------+")
-    p("! timesteppers for incompressible Euler equations !")
-    p("+-------------------------------------------------+")
-    p()
-    p(f"model problem = {args.problem}")
-    if args.problem == "taylorgreen":
-        p(f"mesh size = {args.nx} x {args.nx}")
-        p(f"forcing = {args.forcing}")
-        p(f"kappa = {args.kappa}")
-    elif args.problem == "shear":
-        p(f"mesh size = {args.nx} x {args.nx}")
-    elif args.problem == "kelvinhelmholtz":
-        p(f"mesh refinement = {args.refinement}")
-    p(f"polynomial degree = {args.degree}")
-    p(f"final time = {args.tfinal}")
-    p(f"timestep size = {args.dt}")
-    p(f"discretisation = {args.discretisation}")
-    p(f"numerical flux = {args.flux}")
-    p(f"number of Richardson iterations = {args.richardson}")
-    p(f"use projection method = {args.use_projection_method}")
-    p(f"advect tracer = {args.tracer_advection}")
-    p(f"timestepping method = {timestepper.label}")
-    p()
+    """the banner and run summary the reference prints (`driver.py:285-306`), same labels in the same order"""
+    per_problem = {"taylorgreen": [("mesh size", f"{args.nx} x {args.nx}"), ("forcing", args.forcing), ("kappa", args.kappa)],
+                   "shear": [("mesh size", f"{args.nx} x {args.nx}")],
+                   "kelvinhelmholtz": [("mesh refinement", args.refinement)]}[args.problem]
+    rows = [("model problem", args.problem), *per_problem, ("polynomial degree", args.degree),
+            ("final time", args.tfinal), ("timestep size", args.dt), ("discretisation", args.discretisation),
+            ("numerical flux", args.flux), ("number of Richardson iterations", args.richardson),
+            ("use projection method", args.use_projection_method), ("advect tracer", args.tracer_advection),
+            ("timestepping method", timestepper.label)]
+    title = "! timesteppers for incompressible Euler equations !"
+    rule = "+" + "-" * (len(title) - 2) + "+"
+    print("\n".join([rule, title, rule, ""] + [f"{label} = {value}" for label, value in rows] + [""]), file=file)
 
 
 def test_pressure_solver(timestepper, file=None):

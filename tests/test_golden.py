@@ -152,3 +152,69 @@ def test_engine_tracer_golden():
     prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
     ts.solve(*prob.initial_condition(), Expression(_tracer0, 0), prob.f_rhs(), 0.02)
     assert rel(ts.q_tracer.to_host(), GOLD_T["imex_ssp2_k1/q"]) < RTOL
+
+
+# ---- IMEX tableaux: golden data produced by EXECUTING the reference's own property bodies ------------------------
+# (tests/golden/make_golden_tableaux.py; src/timesteppers/hdg_imex.py:668-1038).  This is the one part of the path
+# that is pinned against the reference itself rather than against the restatement.
+def _tableaux_golden():
+    import json
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tableaux_v1.json")
+    return json.load(open(path))["classes"]
+
+
+ORACLE_KEY = {"IncompressibleEulerHDGIMEXImplicit": "imex_implicit", "IncompressibleEulerHDGIMEXARS2_232": "imex_ars2_232",
+              "IncompressibleEulerHDGIMEXARS3_443": "imex_ars3_443", "IncompressibleEulerHDGIMEXSSP2_332": "imex_ssp2_332",
+              "IncompressibleEulerHDGIMEXSSP3_433": "imex_ssp3_433"}
+
+
+@pytest.mark.parametrize("cls_name", sorted(ORACLE_KEY))
+def test_imex_tableaux_equal_the_reference(cls_name):
+    import incompressibleeulerhdg_b200.timesteppers as TS
+    from oracle.timesteppers import TABLEAUX
+
+    gold = _tableaux_golden()[cls_name]
+    cls = getattr(TS, cls_name)
+    orc = TABLEAUX[ORACLE_KEY[cls_name]]
+    assert cls.nstages.fget(None) == gold["nstages"] == orc["nstages"]
+    for prop in ("_a_expl", "_a_impl", "_b_expl", "_b_impl", "_c_expl"):
+        g = np.asarray(gold[prop], dtype=float)
+        mine = np.asarray(getattr(cls, prop).fget(None), dtype=float)
+        assert mine.shape == g.shape and np.array_equal(mine, g), (cls_name, prop)  # bit-exact
+        assert np.array_equal(np.asarray(orc[prop[1:]], dtype=float), g), (cls_name, prop, "oracle")
+
+
+def test_imex_tableaux_labels_and_order_conditions():
+    """what the reference's tableau data does and does not satisfy -- the quirks are part of the
+    behaviour to reproduce, so they are pinned here rather than "fixed":
+      * ARS3(4,4,3) stores SIX implicit weights for five stages; the loops read the first five,
+        [0, 3/2, -3, 2, 1/2], which sum to one but give b_impl . c = 1/4 instead of 1/2;
+      * SSP2(3,3,2) evaluates the forcing at c_expl = (0, 1, 1/2) although the row sums of A_expl are
+        (0, 1/2, 1)."""
+    import incompressibleeulerhdg_b200.timesteppers as TS
+
+    gold = _tableaux_golden()
+    assert len(gold) == 5
+    for name, g in gold.items():
+        s_ = g["nstages"]
+        ae, ai = np.asarray(g["_a_expl"]), np.asarray(g["_a_impl"])
+        be, bi, ce = np.asarray(g["_b_expl"]), np.asarray(g["_b_impl"]), np.asarray(g["_c_expl"])
+        assert ae.shape == ai.shape == (s_, s_) and be.shape == ce.shape == (s_,)
+        assert bi.shape == ((6,) if name.endswith("ARS3_443") else (s_,))
+        bi = bi[:s_]
+        assert abs(be.sum() - 1) < 1e-14 and abs(bi.sum() - 1) < 1e-14  # consistency (first order)
+        assert np.allclose(np.triu(ae), 0) and np.allclose(np.triu(ai, 1), 0)  # explicit / diagonally implicit
+        assert np.allclose(ae.sum(axis=1), ce, atol=1e-14) == (not name.endswith("SSP2_332"))
+        if "Implicit" in name:
+            continue
+        ci = ai.sum(axis=1)
+        second = [abs(b_ @ c_ - 0.5) < 1e-13 for b_ in (be, bi) for c_ in (ce, ci)]
+        assert second == ([True, True, False, False] if name.endswith("ARS3_443") else [True] * 4), (name, second)
+    # the label is part of the driver's output (`driver.py:305`); instantiating needs a GPU, so compare the
+    # string baked into the factory call instead
+    import inspect
+
+    src = inspect.getsource(TS.hdg_imex)
+    for g in gold.values():
+        assert f'"{g["label"]}"' in src, g["label"]

@@ -51,15 +51,20 @@ class PerformanceLog:
 
 
 def log_summary(file=None):
-    """table of label / calls / total / mean / std, largest total first"""
+    """the table the reference prints (`logging.py:34-60`): one right-aligned row per label with calls, total,
+    mean and standard deviation in seconds, largest total first; nothing at all when no timer ran.  The text is
+    byte-identical to the reference's for the same timings (`tests/test_golden.py`, golden made by running the
+    reference's own module).  Returns the rows."""
     rows = []
     for label, ts in PerformanceLog.records.items():
         a = np.asarray(ts)
-        rows.append((label, a.size, a.sum(), a.mean(), a.std()))
+        rows.append((label, int(a.size), float(a.sum()), float(a.mean()), float(a.std())))
+    if not rows:
+        return rows
     rows.sort(key=lambda r: -r[2])
-    width = max([len(r[0]) for r in rows] + [5])
-    print(f"{'label':<{width}}  {'ncall':>6}  {'total[s]':>10}  {'avg[s]':>10}  {'std[s]':>10}", file=file)
-    print("-" * (width + 44), file=file)
+    cols = ("timer", "ncall", "total", "avg", "std")
+    print("%32s : %6s    %10s %10s %10s" % cols, file=file)
+    print("-" * 77, file=file)
     for label, n, tot, avg, std in rows:
-        print(f"{label:<{width}}  {n:6d}  {tot:10.4f}  {avg:10.4e}  {std:10.4e}", file=file)
+        print("%32s : %6d    %10.4e %10.4e %10.4e" % (label, n, tot, avg, std), file=file)
     return rows

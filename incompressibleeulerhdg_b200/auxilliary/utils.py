@@ -15,11 +15,14 @@ class Averager:
 
     def reset(self):
         self._n = 0
-        self._mean = 0.0
+        self._mean = 0
 
     def update(self, x):
         self._n += 1
-        self._mean += (float(x) - self._mean) / self._n
+        self._mean += (x - self._mean) / self._n
+
+    def __repr__(self):
+        return f"{self.value} (averaged over {self.n_samples} samples)"
 
     @property
     def value(self):

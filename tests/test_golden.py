@@ -218,3 +218,61 @@ def test_imex_tableaux_labels_and_order_conditions():
     src = inspect.getsource(TS.hdg_imex)
     for g in gold.values():
         assert f'"{g["label"]}"' in src, g["label"]
+
+
+# ---- host-side pieces pinned against the reference itself (tests/golden/make_golden_reference_host.py) ----------
+def _host_golden():
+    import json
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_host_v1.json")))
+
+
+def test_log_summary_text_equals_the_reference():
+    import io
+
+    from incompressibleeulerhdg_b200.auxilliary.logging import PerformanceLog, log_summary
+
+    gold = _host_golden()
+    saved = {k: list(v) for k, v in PerformanceLog.records.items()}
+    try:
+        PerformanceLog.reset()
+        out = io.StringIO()
+        assert log_summary(file=out) == [] and out.getvalue() == ""  # the reference prints nothing without timers
+        for label, ts in gold["timings"].items():
+            PerformanceLog.records[label].extend(ts)
+        log_summary(file=out)
+        assert out.getvalue() == gold["log_summary"]
+    finally:
+        PerformanceLog.reset()
+        for k, v in saved.items():
+            PerformanceLog.records[k].extend(v)
+
+
+def test_averager_equals_the_reference():
+    from incompressibleeulerhdg_b200.auxilliary.utils import Averager
+
+    gold = _host_golden()
+    a = Averager()
+    for x, (n, v) in zip(gold["samples"], gold["averager"]["running"]):
+        a.update(x)
+        assert a.n_samples == n and a.value == v  # same recurrence => bit-identical
+    assert repr(a) == gold["averager"]["repr"]
+    a.reset()
+    assert [a.n_samples, float(a.value)] == gold["averager"]["after_reset"]
+
+
+def test_shear_flow_pressure_uses_the_reference_fourier_coefficients():
+    """`model_problems.py:166-187`: p_0 = delta cos(x) sum_k c_k sin((2k+1)(y - pi)) / (1 + (2k+1)^2) with the
+    reference's own quad() coefficients c_k"""
+    from incompressibleeulerhdg_b200.model_problems import DoubleLayerShearFlow
+
+    g = _host_golden()["shear"]
+    prob = DoubleLayerShearFlow(None, None)
+    assert prob.rho == g["rho"] and prob.delta == g["delta"]
+    rng = np.random.default_rng(3)
+    x, y = rng.uniform(0, 2 * np.pi, 50), rng.uniform(0, 2 * np.pi, 50)
+    n = 2 * np.arange(g["kmax"]) + 1
+    series = (np.asarray(g["fourier_coefficient"])[:, None] * np.sin(n[:, None] * (y[None, :] - np.pi))
+              / (1 + n[:, None] ** 2)).sum(axis=0)
+    _, p0 = prob.initial_condition()
+    assert np.abs(p0(x, y) - g["delta"] * np.cos(x) * series).max() < 1e-13

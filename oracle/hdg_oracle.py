@@ -1,11 +1,14 @@
 """CPU oracle for the HDG hot path of eikehmueller/IncompressibleEulerHDG  --  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or recorded outputs
-and its arithmetic lives in Firedrake/Slate/PETSc/MUMPS, none of which is installed here or
-pinned by the reference (`requirements.txt:1-3`).  This file therefore *restates* the reference's
-UFL forms with plain numpy quadrature and is anchored on (i) the analytic Taylor-Green solution
-of `model_problems.py:56-105`, (ii) structural invariants (symmetry, null vector (0,1,1),
-condensed == monolithic), and (iii) observed convergence rates.
+PARITY: the reference ships no tests, golden vectors or recorded outputs and its
+arithmetic lives in Firedrake/Slate/PETSc/MUMPS, none of which is installed here or pinned by the
+reference (`requirements.txt:1-3`), so OUTPUTS of the reference are unavailable ("parity unpinned" in
+that sense).  This file *restates* the reference's UFL forms with plain numpy quadrature.  The forms
+themselves ARE pinned: `oracle/miniufl.py` executes the reference's own form-building code (cut out of
+`hdg_imex.py` / `hdg_implicit.py` / `common.py` with ast) and `tests/test_forms_golden.py` checks every
+operator and right-hand side assembled here against it to round-off.  Further anchors: (i) the analytic
+Taylor-Green solution of `model_problems.py:56-105`, (ii) structural invariants (symmetry, null vector
+(0,1,1), condensed == monolithic), and (iii) observed convergence rates.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline leg may import this
 module.  The product path (``incompressibleeulerhdg_b200``) never does.

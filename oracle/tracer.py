@@ -1,5 +1,7 @@
 """CPU oracle for the passive-tracer path  --  TEST INFRASTRUCTURE ONLY (same rules as hdg_oracle.py:
-only tests/, smoke() and bench.py's cpu_baseline leg may import it).  PARITY UNPINNED (no Firedrake).
+only tests/, smoke() and bench.py's cpu_baseline leg may import it).  No Firedrake outputs to compare with; the
+advection form is pinned against the reference's own `_tracer_advection` executed through oracle/miniufl.py
+(tests/test_forms_golden.py); the CG projection is the standard L2 projection (`Function(V_CG).project(u)`).
 
 Restates (reference file:line)
 

@@ -330,6 +330,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     fimpl_b2b_ms = sa.elapsed_time(sb) / n_fimpl
     del Xf, Yf
+    # the kernel with the largest share of the step (profiles/launches_r1k.md: 39 %): one Chebyshev / facet-block-
+    # Jacobi sweep on the facet Schur complement of the tentative-velocity preconditioner, timed the same way
+    n_sweep, sweep_b2b_ms, sweep_err = 20, None, None
+    try:
+        sweep_b2b_ms = eng.tent_sweep_probe(dt, n_sweep)
+    except Exception as exc:  # a measurement aid must not cost the bench line
+        sweep_err = f"{type(exc).__name__}: {exc}"
     fp64_peak = eng.measure_fp64_peak()  # TFLOP/s, 8 independent DFMA chains per thread
     if world > 1:
         barrier()
@@ -360,6 +367,18 @@ def run_ours(args):
             "launch_ms": t, "bound": "fp64", "dfma_per_cell": dfma_per_cell,
             "achieved_tflops": 2.0 * dfma_per_cell * eng.nc / t / 1e9, "peak_tflops_measured": fp64_peak,
             "frac": 2.0 * dfma_per_cell * eng.nc / t / 1e9 / fp64_peak, "launches_timed": n_fimpl}}
+        # per facet: geometry 6 doubles + 7 ints, and rhs, x, d (read), d, xout (written) of NM = k + 2 doubles each;
+        # the 4 neighbour facets' x are re-reads of the same vector (L2)
+        nm = k + 2
+        sweep_bytes = (6 * 8 + 7 * 4 + 5 * nm * 8) * nf_loc
+        if sweep_b2b_ms:
+            sw = sweep_bytes / sweep_b2b_ms / 1e6
+            other["k_tent_sweep"] = {
+                "launch_ms": sweep_b2b_ms, "bound": "hbm", "algorithmic_bytes_per_launch": sweep_bytes,
+                "achieved": sw, "peak": peak, "unit": "GB/s", "frac": sw / peak, "launches_timed": n_sweep,
+                "share_of_step": "39 % of the device time of a step in profiles/launches_r1k.md"}
+        else:
+            other["k_tent_sweep"] = {"error": sweep_err}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_chorin_sample(args.cpu_nx, k, 1, mesh.nc)
@@ -368,7 +387,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": {**workload_config(args, world), "tuning": dict(getattr(eng, "tuning", {}))},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.prod(sQ)) * 8,
                     "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps},

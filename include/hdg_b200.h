@@ -288,6 +288,10 @@ int hdg_get_timers(hdg_handle h, double* ms, int64_t* ncalls, int n);
 int hdg_reset_timers(hdg_handle h);
 /* Measured FP64 FMA throughput of the device in TFLOP/s (denominator of "% of FP64 peak"). */
 int hdg_measure_fp64_peak(hdg_handle h, double* tflops);
+/* mean duration (ms) of nrep back-to-back launches of one Chebyshev / facet-block-Jacobi sweep on the facet Schur
+ * complement of the tentative-velocity preconditioner (k_tent_sweep, the kernel with the largest share of a Chorin
+ * step) for a = adt; measurement aid of bench.py, no reference counterpart */
+int hdg_tent_sweep_probe(hdg_handle h, double adt, int nrep, double* ms_per_launch);
 /* The iteration bodies of the three Krylov loops (BiCGStab chunk of the tentative solve, one
  * multigrid-PCG iteration, Jacobi-CG chunk) are captured once into CUDA graphs and replayed, which
  * removes the per-kernel launch cost that dominates at small per-GPU sizes (strong scaling).  On by

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdg_b200.so")
 SOURCES = ["hdg_engine.cu"]
-HEADERS = ["hdg_local.cuh", "hdg_flow.cuh", "hdg_mg.cuh", "hdg_tent.cuh", "hdg_comm.cuh", "hdg_tracer.cuh", "hdg_tables.inc",
+HEADERS = ["hdg_local.cuh", "hdg_flow.cuh", "hdg_mg.cuh", "hdg_tent.cuh", "hdg_advblock.cuh", "hdg_comm.cuh", "hdg_tracer.cuh",
+           "hdg_tables.inc",
            os.path.join("..", "..", "include", "hdg_b200.h")]
 STAMP = LIB + ".flags"
 NVCC_FLAGS = [
@@ -37,11 +38,17 @@ def _command() -> list:
     return cmd
 
 
+def _stamp() -> str:
+    """what the library was built with: flags and source names, not the checkout's absolute path (the tree is
+    copied to another directory on the GPU box, which must not make a shipped library look stale)"""
+    return " ".join(os.path.basename(a) if os.sep in a else a for a in _command()[1:])
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     # a library built with other flags (e.g. a development subset of the degrees) is stale
-    if not os.path.exists(STAMP) or open(STAMP).read() != " ".join(_command()):
+    if not os.path.exists(STAMP) or open(STAMP).read() != _stamp():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
@@ -53,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     cmd = _command()
-    stamp = " ".join(cmd)
+    stamp = _stamp()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -25,6 +25,7 @@
 #include "hdg_local.cuh"
 #include "hdg_flow.cuh"
 #include "hdg_tent.cuh"
+#include "hdg_advblock.cuh"
 
 #define HDG_VERSION "hdg_b200 0.1 (sm_100a)"
 
@@ -119,6 +120,10 @@ struct hdg_engine {
   double *tent_cm = nullptr;  // [3*NM][nc]
   double *tent_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // facet work [NM][nf]: t, nyx, mu, mu2, d
   double *tent_xh = nullptr, *tent_y = nullptr;  // [2*NQ1][nc]; [n_aug]
+  // experimental cell-block advection preconditioner (hdg_advblock.cuh); off unless hdg_set_tuning("tent_cellblock", 1)
+  int tune_cellblock = 0;
+  double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*)
+  double *adv_in = nullptr;   // [2*NQ1][nc]    C in_x
   // work vectors
   double *gK = nullptr;                                      // [NL][nc]
   double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
@@ -1582,6 +1587,38 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
   return x;
 }
 
+// back-to-back launches of one Chebyshev / facet-block-Jacobi sweep of the facet Schur complement (k_tent_sweep,
+// mode 0, the kernel with the largest share of a Chorin step) between two events on the engine stream; the
+// scratch vectors of the tentative solver serve as input (their content does not change the work done)
+template <int K>
+static int run_sweep_probe(hdg_engine* h, double adt, int nrep, double* ms_per_launch) {
+  int rc = tent_setup<K>(h);
+  if (rc) return rc;
+  const size_t n = (size_t)TentDims<K>::NM * h->nf;
+  const double inv_aalpha = 1.0 / (adt * h->alpha);
+  for (int i : {0, 2, 4}) CUDA_TRY(h, cudaMemsetAsync(h->tent_f[i], 0, n * sizeof(double), h->stream));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int warm = 3;
+  for (int i = 0; i < warm + nrep; ++i) {
+    if (i == warm) cudaEventRecord(e0, h->stream);
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha,
+                 (const double*)h->tent_f[0], (const double*)nullptr, (const double*)h->tent_f[2], h->tent_f[4],
+                 h->tent_f[3], 0.3, 0.7, 0, 0);
+  }
+  cudaEventRecord(e1, h->stream);
+  cudaError_t err = cudaEventSynchronize(e1);
+  float ms = 0;
+  if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CUDA_TRY(h, err);
+  CUDA_TRY(h, cudaGetLastError());
+  *ms_per_launch = (double)ms / nrep;
+  return HDG_OK;
+}
+
 template <int K>
 static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
                              double rtol, int maxit, bool zero_guess, int* iters) {
@@ -1616,19 +1653,40 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     lc.x[1] = h->bi[5];
     LAUNCH(h, k_lincomb, G, BLOCK, nx, lc, r);
   }
+  // experimental: compose the preconditioner with the inverse cell-diagonal blocks C of I - a F0(Q*)
+  // (hdg_advblock.cuh): Phat^-1 -> Phat^-1 diag(C, I).  Built once per solve (Q*, a change from solve to solve).
+  const bool cellblock = h->tune_cellblock != 0;
+  if (cellblock) {
+    constexpr int NQ1 = Dims<K>::NQ1;
+    if (!h->adv_blk) CUDA_TRY(h, dmalloc(&h->adv_blk, (size_t)NQ1 * NQ1 * h->nc));
+    if (!h->adv_in) CUDA_TRY(h, dmalloc(&h->adv_in, nx));
+    if (upwind)
+      LAUNCH(h, (k_advblock_build<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
+    else
+      LAUNCH(h, (k_advblock_build<K, false>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
+    LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk);
+  }
+  // x part of the vector the multiplier preconditioner sees: C in_x (cell-local, so it is applied before the
+  // ghost refresh inside precond_x) or in_x itself
+  auto scaled_x = [&](const double* in) -> const double* {
+    if (!cellblock) return in;
+    LAUNCH(h, k_advblock_apply<K>, cgrid, 128, h->nc, (const double*)h->adv_blk, in, h->adv_in);
+    return h->adv_in;
+  };
   // out = A_aug Phat^-1 in
-  auto precond_x = [&](const double* in, bool with_mu) -> double* {
+  auto precond_x = [&](const double* in, const double* in_mu) -> double* {
     halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, in);  // moments and xhat are evaluated on ghost cells too
     // local sweeps iterate on the ghost facets as well, so their right-hand side must be the true one:
     // the multiplier part of a Krylov vector is garbage on ghost facets until it is refreshed
-    if (with_mu && h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, NM, in + nx);
+    if (in_mu && h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, NM, in_mu);
     LAUNCH(h, k_tent_moments<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->nc, in, h->tent_cm);
-    LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf,
-           with_mu ? in + nx : (const double*)nullptr, h->tent_f[0], h->tent_f[1]);
+    LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf, in_mu, h->tent_f[0],
+           h->tent_f[1]);
     return tent_schur_solve<K>(h, inv_aalpha, h->tent_f[0]);
   };
-  auto op = [&](const double* in, double* out) {
-    double* mu = precond_x(in, true);
+  auto op = [&](const double* vin, double* out) {
+    const double* in = scaled_x(vin);
+    double* mu = precond_x(in, vin + nx);
     LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, in, mu, h->tent_xh, 0);
     {
       ScopedTimer tf(h, T_FIMPL);
@@ -1643,12 +1701,14 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   CUDA_TRY(h, cudaMemsetAsync(y, 0, n * sizeof(double), h->stream));
   std::vector<uint64_t> key = {2ull, key_of(Qstar), key_of(adt), (uint64_t)upwind, key_of(h->alpha),
                                (uint64_t)h->tent_sweeps, (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax),
-                               key_of(h->tent_f[2]), key_of(h->tent_f[3])};
+                               key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
+                               key_of(h->adv_blk), key_of(h->adv_in)};
   int brc = bicgstab_loop(h, n, own, op, key, y, part_bb, rtol, maxit, iters);
   if (brc == HDG_ECUDA) return brc;
   // x += [Phat^-1 y]_x
-  double* mu = precond_x(y, true);
-  LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, y, mu, x, 1);
+  const double* yx = scaled_x(y);
+  double* mu = precond_x(yx, y + nx);
+  LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, yx, mu, x, 1);
   return brc;
 }
 
@@ -1943,7 +2003,7 @@ int hdg_destroy(hdg_handle h) {
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
                   h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
                   h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
-                  h->tent_xh, h->tent_y};
+                  h->tent_xh, h->tent_y, h->adv_blk, h->adv_in};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg})
@@ -2479,6 +2539,14 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     h->tune_sweep = value;
     // the variant is baked into the captured BiCGStab graph
     if (h->g_bicg.exec) {
+      cudaGraphExecDestroy(h->g_bicg.exec);
+      h->g_bicg.exec = nullptr;
+    }
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_cellblock")) {
+    h->tune_cellblock = value != 0;
+    if (h->g_bicg.exec) {  // the body of the captured BiCGStab graph changes
       cudaGraphExecDestroy(h->g_bicg.exec);
       h->g_bicg.exec = nullptr;
     }
@@ -3041,6 +3109,15 @@ int hdg_measure_fp64_peak(hdg_handle h, double* tflops) {
   cudaEventDestroy(e1);
   *tflops = best;
   return HDG_OK;
+}
+
+int hdg_tent_sweep_probe(hdg_handle h, double adt, int nrep, double* ms_per_launch) {
+  if (!h || !ms_per_launch || nrep <= 0 || !(adt > 0.0)) return HDG_EINVAL;
+  if (!(h->alpha > 0.0)) FAIL(h, HDG_ESTATE, "hdg_tent_sweep_probe: the facet Schur complement needs alpha > 0");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc;
+  DISPATCH_K(h, rc = run_sweep_probe<K>(h, adt, nrep, ms_per_launch));
+  return rc;
 }
 
 int hdg_mg_info(hdg_handle h, int* nlevels, double* fine_lmax) {

@@ -96,6 +96,7 @@ SIGNATURES = {
     "hdg_get_timers": (C.c_int, [_vp, _dp, C.POINTER(C.c_int64), C.c_int]),
     "hdg_reset_timers": (C.c_int, [_vp]),
     "hdg_measure_fp64_peak": (C.c_int, [_vp, _dp]),
+    "hdg_tent_sweep_probe": (C.c_int, [_vp, C.c_double, C.c_int, _dp]),
     "hdg_debug_scalars": (C.c_int, [_vp, _dp]),
     "hdg_set_graphs": (C.c_int, [_vp, C.c_int]),
     "hdg_set_tuning": (C.c_int, [_vp, C.c_char_p, C.c_int]),
@@ -203,6 +204,12 @@ class HDGEngine:
             self.use_torch_stream()
         if os.environ.get("HDG_GRAPHS", "1") == "0":
             self.set_graphs(False)
+        # result-neutral knobs for A/B runs of the unchanged tests / bench, e.g. HDG_TUNING="tent_cellblock=1"
+        self.tuning = {}
+        for item in filter(None, os.environ.get("HDG_TUNING", "").split(",")):
+            name, _, value = item.partition("=")
+            self.set_tuning(name.strip(), int(value or 1))
+            self.tuning[name.strip()] = int(value or 1)
         if self.part is not None and self.part.nranks > 1:
             if comm_id is None:
                 comm_id = broadcast_unique_id()
@@ -573,6 +580,12 @@ class HDGEngine:
         """measured FP64 FMA throughput in TFLOP/s"""
         out = C.c_double(0.0)
         self._check(self.lib.hdg_measure_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
+    def tent_sweep_probe(self, adt: float, nrep: int = 20) -> float:
+        """mean ms of `nrep` back-to-back k_tent_sweep launches (facet Schur sweep of the tentative solver)"""
+        out = C.c_double(0.0)
+        self._check(self.lib.hdg_tent_sweep_probe(self._h, float(adt), int(nrep), C.byref(out)))
         return out.value
 
     def set_tuning(self, name: str, value: int):

@@ -1,0 +1,46 @@
+"""Experimental knob ``tent_cellblock`` (csrc/hdg_advblock.cuh): the cell-block advection preconditioner of the
+tentative-velocity solve.  Written after the round's GPU budget was spent, so it has never run on a GPU: the
+device arithmetic is checked on the CPU (tests/test_advblock_host.py), the solver integration is not.  The knob
+is off by default and this file only runs with HDG_EXPERIMENTAL=1 -- the first thing to do with it on a B200:
+
+    HDG_EXPERIMENTAL=1 python -m pytest tests/test_zz_cellblock_gpu.py -m gpu -q -s
+    HDG_TUNING=tent_cellblock=1 python bench.py          # against the default line
+"""
+import os
+
+import numpy as np
+import pytest
+
+import incompressibleeulerhdg_b200.timesteppers as TS
+from conftest import require_degree
+from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+from oracle.timesteppers import ChorinOracle, TaylorGreenOracle
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HDG_EXPERIMENTAL", "0") != "1",
+                                 reason="experimental knob, not yet run on a GPU (set HDG_EXPERIMENTAL=1)")]
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("flux", ["upwind", "centered"])
+@pytest.mark.parametrize("k,nx", [(1, 8), (2, 8), (3, 4)])
+def test_cellblock_preconditioner_keeps_the_solution_and_cuts_iterations(k, nx, flux):
+    require_degree(k)
+    mesh, dt, nt = UnitSquareMesh(nx, perturb=0.1), 0.32 / nx, 3
+    runs = {}
+    for on in (0, 1):
+        ts = TS.IncompressibleEulerHDGImplicit(mesh, k, dt, flux=flux, krylov_rtol=1e-13, warm_start=False)
+        ts.engine.set_tuning("tent_cellblock", on)
+        prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+        Q, p = ts.solve(*prob.initial_condition(), None, prob.f_rhs(), nt * dt)
+        runs[on] = (Q.to_host(), p.to_host(), ts.niter_tentative.value)
+    Qo, po = ChorinOracle(mesh, k, dt, flux=flux).solve(TaylorGreenOracle("exponential", 0.5), nt * dt)
+    print(f"k={k} {flux}: BiCGStab iterations per solve {runs[0][2]:.1f} -> {runs[1][2]:.1f}; "
+          f"knob on vs oracle: velocity {rel(runs[1][0], Qo):.2e} pressure {rel(runs[1][1], po):.2e}")
+    assert rel(runs[1][0], Qo) < 1e-10 and rel(runs[1][1], po) < 1e-10
+    assert rel(runs[1][0], runs[0][0]) < 1e-10
+    assert runs[1][2] < 0.8 * runs[0][2]

@@ -9,7 +9,7 @@
 //     Phat^-1  ->  Phat^-1 diag(C, I) ,    C_K = [ (I - a F0)_KK ]^-1        (one NQ1 x NQ1 block per cell,
 //                                                                              the same for both components)
 //
-// halves the iteration count in the CPU model of the solver (tools/experiments/tent_precond_model.py:
+// halves the iteration count in the CPU model of the solver (tests/experiments/tent_precond_model.py:
 // 88 -> 48 cold, 31 -> 16 warm-started at nx = 12, k = 2, CFL 0.32).  C is a right preconditioner: the
 // Krylov residual is still the residual of the unmodified system, so any nonsingular C leaves the converged
 // solution unchanged.

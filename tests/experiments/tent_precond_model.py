@@ -1,7 +1,7 @@
 """CPU model of the tentative-velocity Krylov solve: BiCGStab iteration counts for preconditioner variants,
-on the oracle's matrices (numpy/scipy; development tool, not part of the product or of the tests).
+on the oracle's matrices (numpy/scipy; development tool kept under tests/ because it uses the oracle; not collected by pytest).
 
-    python tools/experiments/tent_precond_model.py [nx=12] [k=2] [cfl=0.32]
+    python tests/experiments/tent_precond_model.py [nx=12] [k=2] [cfl=0.32]
 
 System:  A x = b,  A = M - a f_impl(.;Q*)  (hdg_imex.py:233-235, hdg_implicit.py:103-125), a = cfl / nx,
 Q* = BDM projection of the Taylor-Green velocity, split as  A = M - a F0 + a Pen  with the advection part F0
@@ -28,7 +28,7 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-sys.path.insert(0, __file__.rsplit("/tools/", 1)[0])
+sys.path.insert(0, __file__.rsplit("/tests/", 1)[0])
 from incompressibleeulerhdg_b200.mesh import UnitSquareMesh  # noqa: E402
 from oracle.hdg_oracle import HDGOracle  # noqa: E402
 from oracle.timesteppers import TaylorGreenOracle  # noqa: E402

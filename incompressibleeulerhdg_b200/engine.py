@@ -204,12 +204,16 @@ class HDGEngine:
             self.use_torch_stream()
         if os.environ.get("HDG_GRAPHS", "1") == "0":
             self.set_graphs(False)
-        # result-neutral knobs for A/B runs of the unchanged tests / bench, e.g. HDG_TUNING="tent_cellblock=1"
+        # result-neutral knobs for A/B runs of the unchanged tests / bench, e.g. HDG_TUNING="tent_cellblock=1,tent_sweeps=4"
         self.tuning = {}
         for item in filter(None, os.environ.get("HDG_TUNING", "").split(",")):
             name, _, value = item.partition("=")
-            self.set_tuning(name.strip(), int(value or 1))
-            self.tuning[name.strip()] = int(value or 1)
+            name, value = name.strip(), int(value or 1)
+            if name == "tent_sweeps":  # Chebyshev sweeps on the facet Schur complement of the tentative solve
+                self.set_tentative_solver(1, value)
+            else:
+                self.set_tuning(name, value)
+            self.tuning[name] = value
         if self.part is not None and self.part.nranks > 1:
             if comm_id is None:
                 comm_id = broadcast_unique_id()

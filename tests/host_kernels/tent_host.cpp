@@ -1,0 +1,65 @@
+// TEST INFRASTRUCTURE -- not part of the product (see cuda_shim.h).  The velocity-side kernels of the tentative
+// solve (csrc/hdg_flow.cuh, hdg_tent.cuh, hdg_advblock.cuh) as plain C functions, all arrays in the engine's SoA
+// layouts; tests/test_tent_host.py strings them together the way run_tentative_aug (csrc/hdg_engine.cu) does.
+#include "cuda_shim.h"
+#include "hdg_flow.cuh"
+#include "hdg_tent.cuh"
+#include "hdg_advblock.cuh"
+
+#define BY_K(k, ...)                \
+  switch (k) {                      \
+    case 1: { constexpr int K = 1; __VA_ARGS__; } return 0; \
+    case 2: { constexpr int K = 2; __VA_ARGS__; } return 0; \
+    case 3: { constexpr int K = 3; __VA_ARGS__; } return 0; \
+    case 4: { constexpr int K = 4; __VA_ARGS__; } return 0; \
+    default: return 1;              \
+  }
+
+extern "C" {
+
+int th_setup(int nc, int nf, const double* xy, const int* cell_facet, const int* cell_flip, const int* facet_cell,
+             const int* facet_local, int* nbr, int* nbr_e, double* tc, int* tcol, int* tbits) {
+  k_build_nbr(cell_facet, facet_cell, facet_local, nc, nf, nbr, nbr_e);
+  k_tent_setup(xy, cell_facet, cell_flip, facet_cell, facet_local, nc, nf, tc, tcol, tbits);
+  return 0;
+}
+
+int th_fimpl(int k, int upwind, int nc, const double* xy, const int* nbr, const int* nbr_e, double alpha,
+             const double* Qstar, const double* X, const double* Z, double c0, double c1, double* Y) {
+  BY_K(k, if (upwind) k_fimpl<K, true>(xy, nbr, nbr_e, nc, alpha, Qstar, X, Z, c0, c1, Y);
+          else k_fimpl<K, false>(xy, nbr, nbr_e, nc, alpha, Qstar, X, Z, c0, c1, Y))
+}
+
+int th_moments(int k, int nc, const double* xy, const int* flip, const double* Y, double* cm) {
+  BY_K(k, k_tent_moments<K>(xy, flip, nc, Y, cm))
+}
+
+int th_trhs(int k, int nc, int nf, const double* cm, const int* facet_cell, const int* facet_local, const double* ymu,
+            double* t, double* nyx) {
+  BY_K(k, k_tent_trhs<K>(cm, facet_cell, facet_local, nc, nf, ymu, t, nyx))
+}
+
+int th_sweep(int k, int nf, const int* facet_local, const double* tc, const int* tcol, const int* tbits,
+             double inv_aalpha, const double* rhs, const double* rhs2, const double* x, double* d, double* xout,
+             double cd, double cr, int zero, int mode) {
+  BY_K(k, (k_tent_sweep<K, 5>(nf, facet_local, tc, tcol, tbits, inv_aalpha, rhs, rhs2, x, d, xout, cd, cr, zero, mode)))
+}
+
+int th_xhat(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, const double* Y,
+            const double* mu, double* Xh, int mode) {
+  BY_K(k, k_tent_xhat<K>(xy, flip, cell_facet, nc, nf, Y, mu, Xh, mode))
+}
+
+int th_advblock(int k, int upwind, int nc, const double* xy, const int* nbr, const double* Qstar, double adt,
+                double* blk) {
+  BY_K(k, for (int cell = 0; cell < nc; ++cell) {
+    if (upwind) advblock_build_cell<K, true>(xy, nbr, nc, cell, Qstar, adt, blk);
+    else advblock_build_cell<K, false>(xy, nbr, nc, cell, Qstar, adt, blk);
+    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk);
+  })
+}
+
+int th_advblock_apply(int k, int nc, const double* blk, const double* X, double* Y) {
+  BY_K(k, for (int cell = 0; cell < nc; ++cell) advblock_apply_cell<K>(nc, cell, blk, X, Y))
+}
+}

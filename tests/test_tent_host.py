@@ -1,0 +1,219 @@
+"""CPU execution of the tentative-velocity device kernels (csrc/hdg_flow.cuh, hdg_tent.cuh, hdg_advblock.cuh), compiled
+with g++ through tests/host_kernels (test infrastructure; the engine has no CPU path), and a numpy port of the
+host orchestration of `run_tentative_aug` (csrc/hdg_engine.cu): facet-multiplier formulation, Chebyshev /
+facet-block-Jacobi sweeps on the facet Schur complement, BiCGStab on the augmented system.  Checks
+
+* `k_fimpl` against the oracle's `f_impl` (`hdg_imex.py:313-331`),
+* the solution of the tentative-velocity system `[M - a f_impl(.;Q*)] x = M b` (`hdg_imex.py:233-255`,
+  `hdg_implicit.py:103-129`) against the oracle's sparse-direct solve,
+* that the experimental cell-block advection preconditioner (knob ``tent_cellblock``) leaves the solution
+  unchanged and cuts the iteration count with the real (inexact) sweeps, not only in the idealised model of
+  tests/experiments/tent_precond_model.py.
+
+The same kernels run on the GPU in tests/test_engine_flow_gpu.py / test_timesteppers_gpu.py."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+from oracle.hdg_oracle import HDGOracle
+from oracle.timesteppers import TaylorGreenOracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_kernels"))
+import build as host_build  # noqa: E402
+
+DP, IP = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(DP)
+
+
+def ip(a):
+    return a.ctypes.data_as(IP)
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    return host_build.build("tent_host.cpp", str(tmp_path_factory.mktemp("host_kernels")))
+
+
+def soa(Q):  # [nc, 2, nQ1] -> [2 nQ1][nc]
+    return np.ascontiguousarray(Q.transpose(1, 2, 0).reshape(-1, Q.shape[0]))
+
+
+def aos(Qs, nq1):  # [2 nQ1][nc] -> [nc, 2, nQ1]
+    return np.ascontiguousarray(Qs.reshape(2, nq1, -1).transpose(2, 0, 1))
+
+
+class HostTentative:
+    """numpy port of tent_setup / tent_schur_solve / run_tentative_aug / bicgstab_loop (csrc/hdg_engine.cu)"""
+
+    def __init__(self, lib, mesh, k, alpha=1.0, sweeps=8):
+        self.lib, self.k, self.alpha, self.sweeps = lib, k, alpha, sweeps
+        self.nc, self.nf = nc, nf = mesh.nc, mesh.nf
+        self.nq1, self.nm = (k + 2) * (k + 3) // 2, k + 2
+        i32 = lambda a: np.ascontiguousarray(np.asarray(a).T, dtype=np.int32)  # noqa: E731  AoS [n, m] -> SoA [m][n]
+        self.xy = np.ascontiguousarray(np.asarray(mesh.cell_xy, dtype=np.float64).transpose(1, 2, 0).reshape(6, nc))
+        self.cell_facet, self.cell_flip = i32(mesh.cell_facet), i32(mesh.cell_flip)
+        self.facet_cell, self.facet_local = i32(mesh.facet_cell), i32(mesh.facet_local)
+        self.nbr, self.nbr_e = np.zeros((3, nc), np.int32), np.zeros((3, nc), np.int32)
+        self.tc, self.tcol, self.tbits = np.zeros((6, nf)), np.zeros((4, nf), np.int32), np.zeros(nf, np.int32)
+        assert lib.th_setup(nc, nf, dp(self.xy), ip(self.cell_facet), ip(self.cell_flip), ip(self.facet_cell),
+                            ip(self.facet_local), ip(self.nbr), ip(self.nbr_e), dp(self.tc), ip(self.tcol),
+                            ip(self.tbits)) == 0
+        self.d = np.zeros((self.nm, nf))
+        self.lmax = self._power_iteration()
+        self.cellblock = None
+
+    # -- kernels ---------------------------------------------------------------------------------------------
+    def fimpl(self, upwind, Qstar, X, c0, c1, Z=None, alpha=None):
+        Y = np.zeros_like(X)
+        assert self.lib.th_fimpl(self.k, int(upwind), self.nc, dp(self.xy), ip(self.nbr), ip(self.nbr_e),
+                                 ctypes.c_double(self.alpha if alpha is None else alpha), dp(Qstar), dp(X), dp(Z),
+                                 ctypes.c_double(c0), ctypes.c_double(c1), dp(Y)) == 0
+        return Y
+
+    def sweep(self, inv_aalpha, rhs, x, cd, cr, zero, mode):
+        xout = np.zeros((self.nm, self.nf))
+        assert self.lib.th_sweep(self.k, self.nf, ip(self.facet_local), dp(self.tc), ip(self.tcol), ip(self.tbits),
+                                 ctypes.c_double(inv_aalpha), dp(rhs), None, dp(x), dp(self.d), dp(xout),
+                                 ctypes.c_double(cd), ctypes.c_double(cr), int(zero), int(mode)) == 0
+        return xout
+
+    def _power_iteration(self):
+        x = np.random.default_rng(1).uniform(-0.5, 0.5, (self.nm, self.nf))
+        lam = 2.0
+        for _ in range(80):
+            x = self.sweep(0.0, None, x, 0.0, 0.0, 0, 2)
+            lam = np.linalg.norm(x)
+            x /= lam
+        return lam
+
+    def schur_solve(self, inv_aalpha, t):
+        a, b = self.lmax / 8.0, 1.1 * self.lmax  # cheb_coefs (csrc/hdg_mg.cuh)
+        theta, delta = 0.5 * (b + a), 0.5 * (b - a)
+        sigma = theta / delta
+        rho = 1.0 / sigma
+        coefs = [(0.0, 1.0 / theta)]
+        for _ in range(1, self.sweeps):
+            rho_new = 1.0 / (2.0 * sigma - rho)
+            coefs.append((rho_new * rho, 2.0 * rho_new / delta))
+            rho = rho_new
+        x = np.zeros((self.nm, self.nf))
+        for j, (cd, cr) in enumerate(coefs):
+            x = self.sweep(inv_aalpha, t, x, cd, cr, j == 0, 0)
+        return x
+
+    def precond_x(self, inv_aalpha, in_x, in_mu):
+        cm = np.zeros((3 * self.nm, self.nc))
+        assert self.lib.th_moments(self.k, self.nc, dp(self.xy), ip(self.cell_flip), dp(in_x), dp(cm)) == 0
+        t, nyx = np.zeros((self.nm, self.nf)), np.zeros((self.nm, self.nf))
+        assert self.lib.th_trhs(self.k, self.nc, self.nf, dp(cm), ip(self.facet_cell), ip(self.facet_local), dp(in_mu),
+                                dp(t), dp(nyx)) == 0
+        return self.schur_solve(inv_aalpha, t), nyx
+
+    def xhat(self, Y, mu):
+        Xh = np.zeros_like(Y)
+        assert self.lib.th_xhat(self.k, self.nc, self.nf, dp(self.xy), ip(self.cell_flip), ip(self.cell_facet), dp(Y),
+                                dp(mu), dp(Xh), 0) == 0
+        return Xh
+
+    def scaled_x(self, v):
+        if self.cellblock is None:
+            return v
+        out = np.zeros_like(v)
+        assert self.lib.th_advblock_apply(self.k, self.nc, dp(self.cellblock), dp(v), dp(out)) == 0
+        return out
+
+    # -- run_tentative_aug -----------------------------------------------------------------------------------
+    def solve(self, Qstar, adt, upwind, b, rtol, use_cellblock, maxit=400):
+        nq, nmu = 2 * self.nq1 * self.nc, self.nm * self.nf
+        inv_aalpha = 1.0 / (adt * self.alpha)
+        self.cellblock = None
+        if use_cellblock:
+            self.cellblock = np.zeros((self.nq1 * self.nq1, self.nc))
+            assert self.lib.th_advblock(self.k, int(upwind), self.nc, dp(self.xy), ip(self.nbr), dp(Qstar),
+                                        ctypes.c_double(adt), dp(self.cellblock)) == 0
+
+        def split(v):
+            return (np.ascontiguousarray(v[:nq].reshape(2 * self.nq1, self.nc)),
+                    np.ascontiguousarray(v[nq:].reshape(self.nm, self.nf)))
+
+        def op(v):
+            vx, vmu = split(v)
+            in_x = self.scaled_x(vx)
+            mu, nyx = self.precond_x(inv_aalpha, in_x, vmu)
+            xh = self.xhat(in_x, mu)
+            out_x = self.fimpl(upwind, Qstar, xh, 1.0, -adt, Z=in_x, alpha=0.0)  # in_x - a F0(xhat)
+            out_mu = self.sweep(inv_aalpha, nyx, mu, 0.0, 0.0, 0, 1)              # N in_x - X mu
+            return np.concatenate([out_x.ravel(), out_mu.ravel()])
+
+        # BiCGStab on the augmented system, zero initial guess: r0 = (b, 0)
+        r = np.concatenate([b.ravel(), np.zeros(nmu)])
+        bb = float(b.ravel() @ b.ravel())
+        rhat, p, y = r.copy(), r.copy(), np.zeros(nq + nmu)
+        rho, its = float(rhat @ r), 0
+        while float(r @ r) > rtol * rtol * bb and its < maxit:
+            its += 1
+            v = op(p)
+            al = rho / float(rhat @ v)
+            s = r - al * v
+            t = op(s)
+            om = float(t @ s) / float(t @ t)
+            y += al * p + om * s
+            r = s - om * t
+            rho_new = float(rhat @ r)
+            if not np.isfinite(rho_new) or rho == 0.0 or om == 0.0:  # breakdown: report it as not converged
+                its = maxit
+                break
+            p = r + (rho_new / rho) * (al / om) * (p - om * v)
+            rho = rho_new
+        yx, ymu = split(y)
+        in_x = self.scaled_x(yx)
+        mu, _ = self.precond_x(inv_aalpha, in_x, ymu)
+        return self.xhat(in_x, mu), its
+
+
+def _problem(k, nx, flux, cfl=0.32):
+    mesh = UnitSquareMesh(nx, perturb=0.1)
+    o = HDGOracle(mesh, k, alpha_penalty=1.0, flux=flux)
+    prob = TaylorGreenOracle("exponential", 0.5)
+    Q0 = o.interpolate_cell(lambda x, y: prob.Q_stationary(x, y), "Q")
+    return mesh, o, Q0, o.project_bdm(Q0), cfl / nx
+
+
+@pytest.mark.parametrize("flux", ["upwind", "centered"])
+@pytest.mark.parametrize("k,nx", [(1, 4), (2, 3), (3, 2)])
+def test_fimpl_kernel_on_the_host_matches_the_oracle(lib, k, nx, flux):
+    mesh, o, Q0, Qs, _ = _problem(k, nx, flux)
+    ht = HostTentative(lib, mesh, k)
+    X = Q0 + 0.1 * np.random.default_rng(3).standard_normal(Q0.shape)
+    got = aos(ht.fimpl(flux == "upwind", soa(Qs), soa(X), 0.0, 1.0), o.nQ1)       # M^-1 f_impl(., X; Q*)
+    ref = o.f_impl_apply(X, Qs) / o.detJ[:, None, None]
+    assert np.abs(got - ref).max() < 1e-11 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("flux", ["upwind", "centered"])
+@pytest.mark.parametrize("k,nx", [(1, 8), (2, 6)])
+def test_tentative_solver_on_the_host(lib, k, nx, flux):
+    mesh, o, Q0, Qs, adt = _problem(k, nx, flux)
+    ht = HostTentative(lib, mesh, k)
+    assert 1.0 < ht.lmax < 2.0  # spectrum of the block-Jacobi preconditioned facet Schur complement (hdg_tent.cuh)
+    rng = np.random.default_rng(11)
+    b = Q0 + 0.01 * rng.standard_normal(Q0.shape)                                 # Riesz form: (I - a M^-1 f_impl) x = b
+    M = sp.diags(np.repeat(o.detJ, o.nQ))
+    x_ref = spla.spsolve((M - adt * o.f_impl_matrix(Qs)).tocsc(), M @ b.ravel()).reshape(b.shape)
+    res = {}
+    for cb in (False, True):
+        x, its = ht.solve(soa(Qs), adt, flux == "upwind", soa(b), 1e-12, cb)
+        err = np.abs(aos(x, o.nQ1) - x_ref).max() / np.abs(x_ref).max()
+        res[cb] = (its, err)
+        assert err < 1e-9, (cb, its, err)
+    print(f"k={k} nx={nx} {flux}: BiCGStab iterations {res[False][0]} -> {res[True][0]} with the cell blocks")
+    assert res[True][0] <= 0.75 * res[False][0]

@@ -1,12 +1,7 @@
 // TEST INFRASTRUCTURE -- not part of the product.  Compiles the per-cell bodies of csrc/hdg_advblock.cuh with
-// g++ (CUDA qualifiers defined away on the command line, see tests/test_advblock_host.py) so that the arithmetic
+// g++ (CUDA qualifiers defined away on the command line, see cuda_shim.h and build.py) so that the arithmetic
 // of the device code can be checked against the numpy oracle without a GPU.  The engine never loads this.
-#include <cmath>
-#include <cstddef>
-using std::fabs;
-using std::fma;
-using std::sqrt;
-static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }  // CUDA builtin used by hdg_local.cuh
+#include "cuda_shim.h"
 #include "hdg_advblock.cuh"
 
 template <int K>

@@ -1,0 +1,35 @@
+// TEST INFRASTRUCTURE -- not part of the product (see cuda_shim.h).  The per-cell / per-facet kernels of the condensed
+// mixed-Poisson path (csrc/hdg_poisson.cuh) as plain C functions, all arrays in the engine's SoA layouts.
+#include "cuda_shim.h"
+#include "hdg_poisson.cuh"
+
+#define BY_K(k, ...)                \
+  switch (k) {                      \
+    case 1: { constexpr int K = 1; __VA_ARGS__; } return 0; \
+    case 2: { constexpr int K = 2; __VA_ARGS__; } return 0; \
+    case 3: { constexpr int K = 3; __VA_ARGS__; } return 0; \
+    case 4: { constexpr int K = 4; __VA_ARGS__; } return 0; \
+    default: return 1;              \
+  }
+
+extern "C" {
+
+int ph_condense(int k, int nc, const double* xy, const int* flip, double tau, double* SK) {
+  BY_K(k, k_condense<K>(xy, flip, nc, tau, SK))
+}
+
+int ph_assemble(int k, int nc, int nf, const double* SK, const int* cell_facet, const int* facet_cell,
+                const int* facet_local, double* val, int* col, double* dinv) {
+  BY_K(k, k_assemble<K>(SK, cell_facet, facet_cell, facet_local, nc, nf, val, col, dinv))
+}
+
+int ph_forward(int k, int nc, const double* xy, const int* flip, double tau, const double* Ru, const double* Rp,
+               double* gK) {
+  BY_K(k, k_forward<K>(xy, flip, nc, tau, Ru, Rp, gK))
+}
+
+int ph_back(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, double tau,
+            const double* Ru, const double* Rp, const double* lam, double* uo, double* po) {
+  BY_K(k, k_back<K>(xy, flip, cell_facet, nc, nf, tau, Ru, Rp, lam, uo, po))
+}
+}

@@ -4,7 +4,7 @@ qualifiers defined away) and compared with the diagonal blocks of the oracle's f
 (`hdg_imex.py:313-331` with alpha = 0).  This is test infrastructure: the engine itself has no CPU path."""
 import ctypes
 import os
-import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -13,19 +13,13 @@ from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
 from oracle.hdg_oracle import HDGOracle
 from oracle.timesteppers import TaylorGreenOracle
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "incompressibleeulerhdg_b200", "csrc")
-SRC = os.path.join(ROOT, "tests", "host_kernels", "advblock_host.cpp")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_kernels"))
+import build as host_build  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def host_lib(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("host_kernels") / "advblock_host.so")
-    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-D__device__=", "-D__host__=",
-           "-D__forceinline__=inline", "-D__global__=", "-I", CSRC, SRC, "-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr
-    lib = ctypes.CDLL(out)
+    lib = host_build.build("advblock_host.cpp", str(tmp_path_factory.mktemp("host_kernels")))
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
     lib.advblock_host.restype = ctypes.c_int
     lib.advblock_host.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ip, dp, ctypes.c_double, dp,

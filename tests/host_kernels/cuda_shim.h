@@ -21,3 +21,5 @@ static const HostDim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1}, blockIdx = {0, 
 #define __shared__ static
 static inline void __syncthreads() {}
 static inline double __shfl_down_sync(unsigned, double v, int) { return 0.0 * v; }
+template <class T>
+static inline T __ldg(const T* p) { return *p; }

@@ -35,7 +35,6 @@ def test_create_rejects_bad_arguments(engine_lib):
 
 def test_no_cpu_fallback(engine_lib):
     """without a GPU the product path must fail loudly (no silent CPU route)"""
-    import numpy as np
     import pytest
 
     from incompressibleeulerhdg_b200.mesh import UnitSquareMesh

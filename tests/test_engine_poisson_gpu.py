@@ -176,8 +176,6 @@ def test_multigrid_pcg_matches_oracle(k, mesh_fn):
 
 def test_p1_stiffness_is_galerkin_coarse_operator():
     """T^T (-S) T equals the P1 stiffness matrix (so rediscretisation == Galerkin, hdg_imex.py:101-106)"""
-    import scipy.sparse.linalg as spla
-
     from incompressibleeulerhdg_b200 import multigrid
 
     k = 2

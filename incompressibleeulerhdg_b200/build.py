@@ -59,18 +59,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """compile csrc/*.cu -> libhdg_b200.so; returns the library path"""
     if not force and not needs_build():
         return LIB
-    cmd = _command()
-    stamp = _stamp()
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr, file=sys.stderr)
-    with open(STAMP, "w") as fh:
-        fh.write(stamp)
+    import fcntl
+
+    # one build at a time (two pytest sessions, or a test session next to a manual build, would otherwise link into
+    # the same file); whoever waited re-checks whether the work has been done meanwhile
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        cmd = _command()
+        stamp = _stamp()
+        tmp = LIB + f".tmp{os.getpid()}"
+        cmd[cmd.index("-o") + 1] = tmp  # link next to the target, then rename atomically
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr, file=sys.stderr)
+        os.replace(tmp, LIB)
+        with open(STAMP, "w") as fh:
+            fh.write(stamp)
     return LIB
 
 

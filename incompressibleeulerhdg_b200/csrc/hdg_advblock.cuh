@@ -100,8 +100,13 @@ __device__ __forceinline__ void advblock_build_cell(const double* __restrict__ x
 
 // in-place inverse of the N x N block of one cell, Gauss-Jordan without pivoting (see the header comment).
 // N <= 10 (k <= 2): fully unrolled, the block lives in registers; larger blocks: rolled loops on a local array.
+// The inverse is also stored rounded to FP32 (blk32): the apply kernel reads that copy and does its arithmetic in
+// FP64, which halves the bytes of the only HBM-bound kernel of this preconditioner.  Rounding the *entries* of C
+// only replaces C by a slightly different fixed matrix -- the preconditioner stays an exactly linear operator, so
+// right-preconditioned BiCGStab and the converged solution are unaffected (unlike FP32 *vectors*).
 template <int N>
-__device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* __restrict__ blk) {
+__device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* __restrict__ blk,
+                                                     float* __restrict__ blk32) {
   double A[N * N];
   if constexpr (N <= 10) {
     HDG_UNROLL
@@ -122,7 +127,10 @@ __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* _
       }
     }
     HDG_UNROLL
-    for (int i = 0; i < N * N; ++i) blk[(size_t)i * nc + cell] = A[i];
+    for (int i = 0; i < N * N; ++i) {
+      blk[(size_t)i * nc + cell] = A[i];
+      blk32[(size_t)i * nc + cell] = (float)A[i];
+    }
   } else {
     for (int i = 0; i < N * N; ++i) A[i] = blk[(size_t)i * nc + cell];
     for (int p = 0; p < N; ++p) {
@@ -136,13 +144,17 @@ __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* _
         for (int c = 0; c < N; ++c) A[r * N + c] = fma(-f, A[p * N + c], A[r * N + c]);
       }
     }
-    for (int i = 0; i < N * N; ++i) blk[(size_t)i * nc + cell] = A[i];
+    for (int i = 0; i < N * N; ++i) {
+      blk[(size_t)i * nc + cell] = A[i];
+      blk32[(size_t)i * nc + cell] = (float)A[i];
+    }
   }
 }
 
-// Y_c = C_K X_c for both velocity components of one cell (X, Y: SoA velocity fields [2 NQ1][nc]; Y must not alias X)
+// Y_c = C_K X_c for both velocity components of one cell (X, Y: SoA velocity fields [2 NQ1][nc]; Y must not alias X);
+// blk is the FP32-stored inverse, the arithmetic is FP64
 template <int K>
-__device__ __forceinline__ void advblock_apply_cell(int nc, int cell, const double* __restrict__ blk,
+__device__ __forceinline__ void advblock_apply_cell(int nc, int cell, const float* __restrict__ blk,
                                                     const double* __restrict__ X, double* __restrict__ Y) {
   constexpr int NQ1 = Dims<K>::NQ1;
   double x[2][NQ1];
@@ -155,7 +167,7 @@ __device__ __forceinline__ void advblock_apply_cell(int nc, int cell, const doub
     double y0 = 0.0, y1 = 0.0;
     HDG_UNROLL
     for (int j = 0; j < NQ1; ++j) {
-      const double a = blk[(size_t)(i * NQ1 + j) * nc + cell];
+      const double a = (double)blk[(size_t)(i * NQ1 + j) * nc + cell];
       y0 = fma(a, x[0][j], y0);
       y1 = fma(a, x[1][j], y1);
     }
@@ -174,13 +186,13 @@ __global__ void __launch_bounds__(128) k_advblock_build(const double* __restrict
 }
 
 template <int K>
-__global__ void __launch_bounds__(64) k_advblock_invert(int nc, double* __restrict__ blk) {
+__global__ void __launch_bounds__(64) k_advblock_invert(int nc, double* __restrict__ blk, float* __restrict__ blk32) {
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x)
-    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk);
+    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32);
 }
 
 template <int K>
-__global__ void __launch_bounds__(128) k_advblock_apply(int nc, const double* __restrict__ blk,
+__global__ void __launch_bounds__(128) k_advblock_apply(int nc, const float* __restrict__ blk,
                                                         const double* __restrict__ X, double* __restrict__ Y) {
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x)
     advblock_apply_cell<K>(nc, cell, blk, X, Y);

@@ -123,7 +123,8 @@ struct hdg_engine {
   double *tent_xh = nullptr, *tent_y = nullptr;  // [2*NQ1][nc]; [n_aug]
   // experimental cell-block advection preconditioner (hdg_advblock.cuh); off unless hdg_set_tuning("tent_cellblock", 1)
   int tune_cellblock = 0;
-  double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*)
+  double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*) (FP64 work copy)
+  float *adv_blk32 = nullptr; // [NQ1*NQ1][nc]  the same rounded to FP32: what k_advblock_apply reads
   double *adv_in = nullptr;   // [2*NQ1][nc]    C in_x
   // work vectors
   double *gK = nullptr;                                      // [NL][nc]
@@ -1401,18 +1402,19 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   if (cellblock) {
     constexpr int NQ1 = Dims<K>::NQ1;
     if (!h->adv_blk) CUDA_TRY(h, dmalloc(&h->adv_blk, (size_t)NQ1 * NQ1 * h->nc));
+    if (!h->adv_blk32) CUDA_TRY(h, dmalloc(&h->adv_blk32, (size_t)NQ1 * NQ1 * h->nc));
     if (!h->adv_in) CUDA_TRY(h, dmalloc(&h->adv_in, nx));
     if (upwind)
       LAUNCH(h, (k_advblock_build<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
     else
       LAUNCH(h, (k_advblock_build<K, false>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
-    LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk);
+    LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk, h->adv_blk32);
   }
   // x part of the vector the multiplier preconditioner sees: C in_x (cell-local, so it is applied before the
   // ghost refresh inside precond_x) or in_x itself
   auto scaled_x = [&](const double* in) -> const double* {
     if (!cellblock) return in;
-    LAUNCH(h, k_advblock_apply<K>, cgrid, 128, h->nc, (const double*)h->adv_blk, in, h->adv_in);
+    LAUNCH(h, k_advblock_apply<K>, cgrid, 128, h->nc, (const float*)h->adv_blk32, in, h->adv_in);
     return h->adv_in;
   };
   // out = A_aug Phat^-1 in
@@ -1444,7 +1446,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   std::vector<uint64_t> key = {2ull, key_of(Qstar), key_of(adt), (uint64_t)upwind, key_of(h->alpha),
                                (uint64_t)h->tent_sweeps, (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax),
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
-                               key_of(h->adv_blk), key_of(h->adv_in)};
+                               key_of(h->adv_blk32), key_of(h->adv_in)};
   int brc = bicgstab_loop(h, n, own, op, key, y, part_bb, rtol, maxit, iters);
   if (brc == HDG_ECUDA) return brc;
   // x += [Phat^-1 y]_x
@@ -1745,7 +1747,7 @@ int hdg_destroy(hdg_handle h) {
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
                   h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
                   h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
-                  h->tent_xh, h->tent_y, h->adv_blk, h->adv_in};
+                  h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg})

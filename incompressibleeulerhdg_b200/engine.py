@@ -131,6 +131,20 @@ def load_library(path: str | None = None):
     return lib
 
 
+def parse_tuning(spec: str):
+    """``"tent_cellblock=1, tent_sweeps=4"`` -> ``[("tent_cellblock", 1), ("tent_sweeps", 4)]``; a bare name means 1"""
+    out = []
+    for item in spec.split(","):
+        name, _, value = item.strip().partition("=")
+        if not name:
+            continue
+        try:
+            out.append((name.strip(), int(value.strip() or 1)))
+        except ValueError:
+            raise ValueError(f"HDG_TUNING: {item.strip()!r} is not name=integer") from None
+    return out
+
+
 def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
@@ -206,11 +220,11 @@ class HDGEngine:
             self.set_graphs(False)
         # result-neutral knobs for A/B runs of the unchanged tests / bench, e.g. HDG_TUNING="tent_cellblock=1,tent_sweeps=4"
         self.tuning = {}
-        for item in filter(None, os.environ.get("HDG_TUNING", "").split(",")):
-            name, _, value = item.partition("=")
-            name, value = name.strip(), int(value or 1)
+        for name, value in parse_tuning(os.environ.get("HDG_TUNING", "")):
             if name == "tent_sweeps":  # Chebyshev sweeps on the facet Schur complement of the tentative solve
                 self.set_tentative_solver(1, value)
+            elif name == "tent_local_sweeps":  # multi-GPU: no halo exchange between those sweeps
+                self.set_tentative_comm(bool(value))
             else:
                 self.set_tuning(name, value)
             self.tuning[name] = value

@@ -2,7 +2,7 @@
 (tests/test_tent_host.py, real device kernels compiled with g++) against the number of Chebyshev sweeps, with and
 without the cell-block advection preconditioner, and a cost model from the per-kernel times of
 profiles/launches_r1k.md (us per launch at nx = 1024, k = 2: sweep 170, fimpl 721, xhat + moments + trhs 318,
-BiCGStab vector kernels 600 per operator application; cell-block apply ~400 estimated from its 1 120 B/cell).
+BiCGStab vector kernels 600 per operator application; cell-block apply ~250 estimated from its 720 B/cell).
 
     python tests/experiments/tent_host_sweeps.py [nx=8] [k=2] [rtol=1e-6] [alpha=1]
 
@@ -34,7 +34,7 @@ def main():
         for cb in (False, True):
             ht = T.HostTentative(lib, mesh, k, alpha=alpha, sweeps=sweeps)
             _, its = ht.solve(T.soa(Qs), adt, True, T.soa(b), rtol, cb)
-            per_app = 170 * (sweeps + 1) + 721 + 318 + 600 + (400 if cb else 0)
+            per_app = 170 * (sweeps + 1) + 721 + 318 + 600 + (250 if cb else 0)
             print(f"  sweeps {sweeps:2d}  cell blocks {int(cb)}  iterations {its:4d}  model {2 * its * per_app / 1e3:7.1f} ms",
                   flush=True)
 

@@ -51,15 +51,15 @@ int th_xhat(int k, int nc, int nf, const double* xy, const int* flip, const int*
 }
 
 int th_advblock(int k, int upwind, int nc, const double* xy, const int* nbr, const double* Qstar, double adt,
-                double* blk) {
+                double* blk, float* blk32) {
   BY_K(k, for (int cell = 0; cell < nc; ++cell) {
     if (upwind) advblock_build_cell<K, true>(xy, nbr, nc, cell, Qstar, adt, blk);
     else advblock_build_cell<K, false>(xy, nbr, nc, cell, Qstar, adt, blk);
-    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk);
+    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32);
   })
 }
 
-int th_advblock_apply(int k, int nc, const double* blk, const double* X, double* Y) {
-  BY_K(k, for (int cell = 0; cell < nc; ++cell) advblock_apply_cell<K>(nc, cell, blk, X, Y))
+int th_advblock_apply(int k, int nc, const float* blk32, const double* X, double* Y) {
+  BY_K(k, for (int cell = 0; cell < nc; ++cell) advblock_apply_cell<K>(nc, cell, blk32, X, Y))
 }
 }

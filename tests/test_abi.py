@@ -44,3 +44,16 @@ def test_no_cpu_fallback(engine_lib):
     with pytest.raises(engine.HDGError) as ei:
         engine.HDGEngine(UnitSquareMesh(2), 1)
     assert ei.value.code == engine.HDG_ENOGPU
+
+
+def test_tuning_spec_parser():
+    """HDG_TUNING, the environment switch for A/B runs of the unchanged tests and bench"""
+    import pytest
+
+    from incompressibleeulerhdg_b200.engine import parse_tuning
+
+    assert parse_tuning("") == []
+    assert parse_tuning("tent_cellblock") == [("tent_cellblock", 1)]
+    assert parse_tuning(" tent_cellblock=1, tent_sweeps = 4 ,") == [("tent_cellblock", 1), ("tent_sweeps", 4)]
+    with pytest.raises(ValueError):
+        parse_tuning("tent_sweeps=four")

@@ -23,7 +23,7 @@ def host_lib(tmp_path_factory):
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
     lib.advblock_host.restype = ctypes.c_int
     lib.advblock_host.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, ip, dp, ctypes.c_double, dp,
-                                  ctypes.c_int, dp, dp]
+                                  ctypes.POINTER(ctypes.c_float), dp, dp]
     return lib
 
 
@@ -52,7 +52,7 @@ def test_blocks_match_the_oracle_matrix(host_lib, k, nx, flux):
     adt = 0.4 / nx
     blk = np.zeros((n1 * n1, nc))
     assert host_lib.advblock_host(k, int(flux == "upwind"), nc, _ptr(xy), _ptr(nbr, ctypes.c_int32), _ptr(Qsoa), adt,
-                                  _ptr(blk), 0, None, None) == 0
+                                  _ptr(blk), None, None, None) == 0
     F0 = o.f_impl_matrix(Qs).toarray().reshape(nc, 2, n1, nc, 2, n1)
     for cell in range(nc):
         ref = np.eye(n1) - adt * F0[cell, 0, :, cell, 0, :] / o.detJ[cell]
@@ -69,15 +69,17 @@ def test_inverse_and_apply(host_lib, k, nx):
     adt = 0.32 / nx
     args = (k, 1, nc, _ptr(xy), _ptr(nbr, ctypes.c_int32), _ptr(Qsoa), adt)
     blk = np.zeros((n1 * n1, nc))
-    assert host_lib.advblock_host(*args, _ptr(blk), 0, None, None) == 0
+    assert host_lib.advblock_host(*args, _ptr(blk), None, None, None) == 0
     rng = np.random.default_rng(7)
     X = rng.standard_normal((2 * n1, nc))
     Y = np.zeros_like(X)
-    inv = np.zeros_like(blk)
-    assert host_lib.advblock_host(*args, _ptr(inv), 1, _ptr(X), _ptr(Y)) == 0
+    inv, inv32 = np.zeros_like(blk), np.zeros(blk.shape, np.float32)
+    assert host_lib.advblock_host(*args, _ptr(inv), _ptr(inv32, ctypes.c_float), _ptr(X), _ptr(Y)) == 0
     B = blk.T.reshape(nc, n1, n1)
     C = inv.T.reshape(nc, n1, n1)
     assert np.abs(np.einsum("nij,njk->nik", C, B) - np.eye(n1)).max() < 1e-11
+    assert np.array_equal(inv32, inv.astype(np.float32))  # the copy the apply kernel reads (FP32 storage, FP64 arithmetic)
+    C = inv32.astype(np.float64).T.reshape(nc, n1, n1)
     # positive definite symmetric part (I + a int_dK |s| phi phi - a/2 int_K div(Q*) phi phi with div Q* ~ 0): the
     # reason elimination without pivoting is safe
     assert np.linalg.eigvalsh(0.5 * (B + B.transpose(0, 2, 1))).min() > 0.0

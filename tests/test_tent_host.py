@@ -27,7 +27,7 @@ from oracle.timesteppers import TaylorGreenOracle
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_kernels"))
 import build as host_build  # noqa: E402
 
-DP, IP = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+DP, IP, FP = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)
 
 
 def dp(a):
@@ -128,7 +128,7 @@ class HostTentative:
         if self.cellblock is None:
             return v
         out = np.zeros_like(v)
-        assert self.lib.th_advblock_apply(self.k, self.nc, dp(self.cellblock), dp(v), dp(out)) == 0
+        assert self.lib.th_advblock_apply(self.k, self.nc, self.cellblock.ctypes.data_as(FP), dp(v), dp(out)) == 0
         return out
 
     # -- run_tentative_aug -----------------------------------------------------------------------------------
@@ -137,9 +137,10 @@ class HostTentative:
         inv_aalpha = 1.0 / (adt * self.alpha)
         self.cellblock = None
         if use_cellblock:
-            self.cellblock = np.zeros((self.nq1 * self.nq1, self.nc))
+            work = np.zeros((self.nq1 * self.nq1, self.nc))
+            self.cellblock = np.zeros((self.nq1 * self.nq1, self.nc), np.float32)  # what the apply kernel reads
             assert self.lib.th_advblock(self.k, int(upwind), self.nc, dp(self.xy), ip(self.nbr), dp(Qstar),
-                                        ctypes.c_double(adt), dp(self.cellblock)) == 0
+                                        ctypes.c_double(adt), dp(work), self.cellblock.ctypes.data_as(FP)) == 0
 
         def split(v):
             return (np.ascontiguousarray(v[:nq].reshape(2 * self.nq1, self.nc)),

@@ -38,6 +38,20 @@ int fh_pgrad(int k, int nc, int nf, const double* xy, const int* flip, const int
   BY_K(k, k_pgrad<K>(xy, flip, cell_facet, nc, nf, p, lam, c0, c1, Y))
 }
 
+// hdg_gamma_apply_dev: constraint rows Gamma(psi, mu; u, phi, lambda) of the mixed operator; gK is scratch
+int fh_gamma(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, const int* facet_cell,
+             const int* facet_local, double tau, const double* Q, const double* p, const double* lam, double* Rp,
+             double* gK, double* Rl) {
+  BY_K(k, k_gamma_cell<K>(xy, flip, cell_facet, nc, nf, tau, Q, p, lam, Rp, gK);
+          k_facet_sum<K>(gK, facet_cell, facet_local, nc, nf, Rl))
+}
+
+// hdg_reconstruction_rhs_dev: Rl must be zero on entry
+int fh_recon_rhs(int k, int nc, int nf, const double* xy, const int* nbr, const int* nbr_e, const int* cell_facet,
+                 const int* flip, const double* Q, const double* B, double* Rp, double* Rl) {
+  BY_K(k, k_recon_rhs<K>(xy, nbr, nbr_e, cell_facet, flip, nc, nf, Q, B, Rp, Rl))
+}
+
 // hdg_reconstruct_trace_dev: gK is scratch [3 (k + 1)][nc]
 int fh_reconstruct_trace(int k, int nc, int nf, const double* xy, const int* flip, const int* facet_cell,
                          const int* facet_local, double tau, const double* Q, const double* p, double* gK,

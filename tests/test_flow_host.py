@@ -70,3 +70,41 @@ def test_flow_kernels_on_the_host(lib, k, mesh_fn):
     assert lib.fh_reconstruct_trace(k, nc, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.facet_cell), ip(hm.facet_local),
                                     cd(1.0), dp(Qs_), dp(ps_), dp(gK), dp(lout)) == 0
     assert rel(lout.T, o.reconstruct_trace(Q, p)) < 1e-11
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+@pytest.mark.parametrize("mesh_fn", MESHES[:2])
+def test_gamma_rows_and_reconstruction_rhs_on_the_host(lib, k, mesh_fn):
+    """`k_gamma_cell` + `k_facet_sum` (the constraint rows of the monolithic operator, `hdg_imex.py:342-351`) against
+    the oracle's assembled monolithic matrix, and `k_recon_rhs` (`hdg_imex.py:204-207`) against the oracle's
+    quadrature restatement"""
+    from oracle.timesteppers import IMEXOracle
+
+    mesh = mesh_fn()
+    ts = IMEXOracle(mesh, k, 0.1)
+    hm, o = HostMesh(mesh), ts.o
+    nc, nf, nq1 = mesh.nc, mesh.nf, o.nQ1
+    rng = np.random.default_rng(10 + k)
+    Q, B = rng.standard_normal((nc, 2, nq1)), rng.standard_normal((nc, 2, nq1))
+    p, lam = rng.standard_normal((nc, o.np_)), rng.standard_normal((nf, k + 1))
+    Qs_, Bs_, ps_, ls_ = soa_Q(Q), soa_Q(B), np.ascontiguousarray(p.T), np.ascontiguousarray(lam.T)
+
+    Rp, gK, Rl = np.zeros((o.np_, nc)), np.zeros((3 * (k + 1), nc)), np.zeros((k + 1, nf))
+    assert lib.fh_gamma(k, nc, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ip(hm.facet_cell), ip(hm.facet_local),
+                        cd(1.0), dp(Qs_), dp(ps_), dp(ls_), dp(Rp), dp(gK), dp(Rl)) == 0
+    Kmat, (offp, offl, N) = o.assemble_monolithic()
+    y = Kmat @ np.concatenate([Q.ravel(), p.ravel(), lam.ravel()])
+    assert rel(Rp.T, y[offp:offl].reshape(nc, o.np_)) < 1e-11
+    assert rel(Rl.T, y[offl:].reshape(nf, k + 1)) < 1e-11
+
+    nbr, nbr_e = np.zeros((3, nc), np.int32), np.zeros((3, nc), np.int32)
+    assert lib.fh_build_nbr(nc, nf, ip(hm.cell_facet), ip(hm.facet_cell), ip(hm.facet_local), ip(nbr), ip(nbr_e)) == 0
+    Rp2, Rl2 = np.zeros((o.np_, nc)), np.zeros((k + 1, nf))
+    assert lib.fh_recon_rhs(k, nc, nf, dp(hm.xy), ip(nbr), ip(nbr_e), ip(hm.cell_facet), ip(hm.cell_flip), dp(Qs_),
+                            dp(Bs_), dp(Rp2), dp(Rl2)) == 0
+    Rp_o, Rl_o = ts.reconstruction_rhs(Q, B)
+    assert rel(Rp2.T, Rp_o) < 1e-11
+    if np.abs(Rl_o).max() > 0:
+        assert rel(Rl2.T, Rl_o) < 1e-11
+    else:
+        assert np.abs(Rl2).max() == 0.0

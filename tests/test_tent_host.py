@@ -132,7 +132,7 @@ class HostTentative:
         return out
 
     # -- run_tentative_aug -----------------------------------------------------------------------------------
-    def solve(self, Qstar, adt, upwind, b, rtol, use_cellblock, maxit=400):
+    def solve(self, Qstar, adt, upwind, b, rtol, use_cellblock, maxit=400, x0=None):
         nq, nmu = 2 * self.nq1 * self.nc, self.nm * self.nf
         inv_aalpha = 1.0 / (adt * self.alpha)
         self.cellblock = None
@@ -155,8 +155,9 @@ class HostTentative:
             out_mu = self.sweep(inv_aalpha, nyx, mu, 0.0, 0.0, 0, 1)              # N in_x - X mu
             return np.concatenate([out_x.ravel(), out_mu.ravel()])
 
-        # BiCGStab on the augmented system, zero initial guess: r0 = (b, 0)
-        r = np.concatenate([b.ravel(), np.zeros(nmu)])
+        # BiCGStab on the augmented system; r0 = (b - A x0, 0) with mu0 = a alpha N x0 (zero guess: r0 = (b, 0))
+        r0x = b if x0 is None else b - self.fimpl(upwind, Qstar, x0, 1.0, -adt)
+        r = np.concatenate([r0x.ravel(), np.zeros(nmu)])
         bb = float(b.ravel() @ b.ravel())
         rhat, p, y = r.copy(), r.copy(), np.zeros(nq + nmu)
         rho, its = float(rhat @ r), 0
@@ -178,7 +179,8 @@ class HostTentative:
         yx, ymu = split(y)
         in_x = self.scaled_x(yx)
         mu, _ = self.precond_x(inv_aalpha, in_x, ymu)
-        return self.xhat(in_x, mu), its
+        dx = self.xhat(in_x, mu)
+        return (dx if x0 is None else x0 + dx), its
 
 
 def _problem(k, nx, flux, cfl=0.32):

@@ -26,8 +26,10 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-@pytest.mark.parametrize("flux", ["upwind", "centered"])
-@pytest.mark.parametrize("k,nx", [(1, 8), (2, 8), (3, 4)])
+# (k = 3 with the central flux is left out: at this CFL number the solver *without* the cell blocks needs more than
+# 600 iterations in the host port of tests/test_tent_host.py -- 122 with them -- so there is no baseline to compare)
+@pytest.mark.parametrize("k,nx,flux", [(1, 8, "upwind"), (1, 8, "centered"), (2, 8, "upwind"), (2, 8, "centered"),
+                                       (3, 4, "upwind")])
 def test_cellblock_preconditioner_keeps_the_solution_and_cuts_iterations(k, nx, flux):
     require_degree(k)
     mesh, dt, nt = UnitSquareMesh(nx, perturb=0.1), 0.32 / nx, 3

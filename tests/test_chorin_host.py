@@ -78,7 +78,7 @@ class HostChorin:
         return Qt + dt * u, phi, (its_t, its_p)                                        # :150, :189
 
 
-@pytest.mark.parametrize("k,nx,flux", [(1, 6, "upwind"), (2, 4, "upwind"), (2, 4, "centered")])
+@pytest.mark.parametrize("k,nx,flux", [(1, 6, "upwind"), (2, 4, "upwind"), (2, 4, "centered"), (3, 3, "centered")])
 def test_two_chorin_steps_from_device_kernels(libs, k, nx, flux):
     mesh, dt = UnitSquareMesh(nx, perturb=0.1), 0.02
     orc = ChorinOracle(mesh, k, dt, flux=flux)

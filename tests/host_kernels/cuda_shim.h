@@ -23,3 +23,9 @@ static inline void __syncthreads() {}
 static inline double __shfl_down_sync(unsigned, double v, int) { return 0.0 * v; }
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
+static inline void __threadfence() {}
+static inline int atomicAdd(int* p, int v) {
+  int old = *p;
+  *p += v;
+  return old;
+}

@@ -109,6 +109,7 @@ struct hdg_engine {
   double *tent_xh = nullptr, *tent_y = nullptr;  // [2*NQ1][nc]; [n_aug]
   // experimental cell-block advection preconditioner (hdg_advblock.cuh); off unless hdg_set_tuning("tent_cellblock", 1)
   int tune_cellblock = 0;
+  int tune_flex = 0;          // experimental flexible solution update of the tentative BiCGStab ("tent_flex")
   double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*) (FP64 work copy)
   float *adv_blk32 = nullptr; // [NQ1*NQ1][nc]  the same rounded to FP32: what k_advblock_apply reads
   double *adv_in = nullptr;   // [2*NQ1][nc]    C in_x
@@ -656,7 +657,10 @@ static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const 
 // On entry r0 (the initial residual) sits in bi[0]; the solution update is accumulated in y.
 template <class Op>
 static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, std::vector<uint64_t> key, double* y,
-                         const double* part_ref, double rtol, int maxit, int* iters) {
+                         const double* part_ref, double rtol, int maxit, int* iters,
+                         const double* flex_xh = nullptr, double* flex_x = nullptr, size_t flex_nx = 0) {
+  // flex_x != nullptr (experimental, "tent_flex"): op leaves [Phat^-1 in]_x in flex_xh and the solution flex_x is
+  // accumulated from these preconditioned directions (k_bi_s_flex / k_bi_xr_flex); y is not used then
   const int G = h->grid;
   double *r = h->bi[0], *rhat = h->bi[1], *p = h->bi[2], *v = h->bi[3], *sv = h->bi[4], *t = h->bi[5];
   double* P = h->partial;
@@ -678,16 +682,26 @@ static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, std::vecto
   key.push_back((uint64_t)own.own2);
   key.push_back((uint64_t)(h->comm && h->comm->p2p.enabled));
   key.push_back((uint64_t)chunk);
+  key.push_back(key_of(flex_xh));
+  key.push_back(key_of(flex_x));
+  key.push_back((uint64_t)flex_nx);
   auto body = [&]() {
     for (int i = 0; i < chunk; ++i) {
       op(p, v);
       LAUNCH(h, k_dot2, G, BLOCK, n, own, rhat, v, (const double*)nullptr, p_rv, (double*)nullptr);
       allreduce_slots(h, p_rv, 1);
-      LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
+      if (flex_x)
+        LAUNCH(h, k_bi_s_flex, G, BLOCK, n, r, v, sv, p_rv, h->bscal, flex_nx, flex_xh, flex_x);
+      else
+        LAUNCH(h, k_bi_s, G, BLOCK, n, r, v, sv, p_rv, h->bscal);
       op(sv, t);
       LAUNCH(h, k_dot2, G, BLOCK, n, own, t, sv, (const double*)t, p_ts, p_tt);
       allreduce_slots(h, p_ts, 2);
-      LAUNCH(h, k_bi_xr, G, BLOCK, n, own, p, sv, t, rhat, y, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
+      if (flex_x)
+        LAUNCH(h, k_bi_xr_flex, G, BLOCK, n, own, sv, t, rhat, r, p_ts, p_tt, p_rho, p_rr, h->bscal, flex_nx, flex_xh,
+               flex_x);
+      else
+        LAUNCH(h, k_bi_xr, G, BLOCK, n, own, p, sv, t, rhat, y, r, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
       allreduce_slots(h, p_rho, 2);
       LAUNCH(h, k_bi_p, G, BLOCK, n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, h->bscal);
     }
@@ -960,8 +974,12 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
                                (uint64_t)h->tent_sweeps, (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax),
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
                                key_of(h->adv_blk32), key_of(h->adv_in)};
-  int brc = bicgstab_loop(h, n, own, op, key, y, part_bb, rtol, maxit, iters);
-  if (brc == HDG_ECUDA) return brc;
+  // experimental ("tent_flex"): accumulate x from the preconditioned directions op leaves in tent_xh; x holds the
+  // initial guess (or zero) on entry, so no recovery step follows
+  const bool flex = h->tune_flex != 0;
+  int brc = bicgstab_loop(h, n, own, op, key, y, part_bb, rtol, maxit, iters, flex ? h->tent_xh : (const double*)nullptr,
+                          flex ? x : (double*)nullptr, flex ? nx : 0);
+  if (brc == HDG_ECUDA || flex) return brc;
   // x += [Phat^-1 y]_x
   const double* yx = scaled_x(y);
   double* mu = precond_x(yx, y + nx);
@@ -1795,6 +1813,14 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
   if (!strcmp(name, "sweep_minblocks")) {
     h->tune_sweep = value;
     // the variant is baked into the captured BiCGStab graph
+    if (h->g_bicg.exec) {
+      cudaGraphExecDestroy(h->g_bicg.exec);
+      h->g_bicg.exec = nullptr;
+    }
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_flex")) {
+    h->tune_flex = value != 0;
     if (h->g_bicg.exec) {
       cudaGraphExecDestroy(h->g_bicg.exec);
       h->g_bicg.exec = nullptr;

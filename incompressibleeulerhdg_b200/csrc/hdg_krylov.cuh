@@ -454,6 +454,48 @@ __global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, OwnMask own, const do
   a1 = block_reduce(a1);
   if (threadIdx.x == 0) p_rr[blockIdx.x] = a1;
 }
+// Flexible variants (experimental, hdg_set_tuning "tent_flex"): the solution is accumulated from the *preconditioned*
+// directions instead of being recovered from the accumulated Krylov vector at the end.  xh = [Phat^-1 .]_x is what the
+// operator application leaves behind for its argument (the first nx entries of the augmented vectors are the velocity
+// part).  The recursive residual then stays the residual of the accumulated x even if the preconditioner is not an
+// exactly linear operator (FP32 storage inside it; tests/experiments/tent_fp32_sweeps.py).
+//   k_bi_s_flex :  s = r - alpha v ;  x += alpha xh(p)
+//   k_bi_xr_flex:  x += omega xh(s);  r = s - omega t ;  partials <rhat,r>, <r,r>
+__global__ void __launch_bounds__(BLOCK) k_bi_s_flex(size_t n, const double* __restrict__ r,
+                                                     const double* __restrict__ v, double* __restrict__ sv,
+                                                     const double* __restrict__ p_rv, const BiScalars* __restrict__ s,
+                                                     size_t nx, const double* __restrict__ xh, double* __restrict__ x) {
+  if (s->done) return;
+  double alpha = s->rho / reduce_partials(p_rv, gridDim.x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    sv[i] = fma(-alpha, v[i], r[i]);
+    if (i < nx) x[i] = fma(alpha, xh[i], x[i]);
+  }
+}
+__global__ void __launch_bounds__(BLOCK) k_bi_xr_flex(size_t n, OwnMask own, const double* __restrict__ sv,
+                                                      const double* __restrict__ t, const double* __restrict__ rhat,
+                                                      double* __restrict__ r, const double* __restrict__ p_ts,
+                                                      const double* __restrict__ p_tt, double* __restrict__ p_rho,
+                                                      double* __restrict__ p_rr, const BiScalars* __restrict__ s,
+                                                      size_t nx, const double* __restrict__ xh, double* __restrict__ x) {
+  if (s->done) return;
+  double tt = reduce_partials(p_tt, gridDim.x);
+  double omega = tt > 0.0 ? reduce_partials(p_ts, gridDim.x) / tt : 0.0;
+  double a0 = 0.0, a1 = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nx) x[i] = fma(omega, xh[i], x[i]);
+    double ri = fma(-omega, t[i], sv[i]);
+    r[i] = ri;
+    if (is_owned(own, i)) {
+      a0 = fma(rhat[i], ri, a0);
+      a1 = fma(ri, ri, a1);
+    }
+  }
+  a0 = block_reduce(a0);
+  if (threadIdx.x == 0) p_rho[blockIdx.x] = a0;
+  a1 = block_reduce(a1);
+  if (threadIdx.x == 0) p_rr[blockIdx.x] = a1;
+}
 // beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v); bookkeeping (last block publishes)
 __global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restrict__ r, const double* __restrict__ v,
                                                 double* __restrict__ p, const double* __restrict__ p_rv,

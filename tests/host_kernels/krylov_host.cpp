@@ -101,6 +101,16 @@ int kh_bi_xr(size_t n, const double* p, const double* sv, const double* t, const
   k_bi_xr(n, ALL, p, sv, t, rhat, x, r, p_rv, p_ts, p_tt, p_rho, p_rr, &g_bi);
   return 0;
 }
+int kh_bi_s_flex(size_t n, const double* r, const double* v, double* sv, const double* p_rv, size_t nx, const double* xh,
+                 double* x) {
+  k_bi_s_flex(n, r, v, sv, p_rv, &g_bi, nx, xh, x);
+  return 0;
+}
+int kh_bi_xr_flex(size_t n, const double* sv, const double* t, const double* rhat, double* r, const double* p_ts,
+                  const double* p_tt, double* p_rho, double* p_rr, size_t nx, const double* xh, double* x) {
+  k_bi_xr_flex(n, ALL, sv, t, rhat, r, p_ts, p_tt, p_rho, p_rr, &g_bi, nx, xh, x);
+  return 0;
+}
 int kh_bi_p(size_t n, const double* r, const double* v, double* p, const double* p_rv, const double* p_ts,
             const double* p_tt, const double* p_rho, const double* p_rr) {
   k_bi_p(n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, &g_bi);

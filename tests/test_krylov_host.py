@@ -110,8 +110,10 @@ def test_trace_cg_kernels_on_the_host(libs, k, nx):
     assert np.array_equal(s_, a.T) and np.array_equal(back, a)
 
 
-def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit):
-    """bicgstab_loop with the engine's BiCGStab kernels; returns the accumulated update y and the iteration count"""
+def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit, flex=None):
+    """bicgstab_loop with the engine's BiCGStab kernels; returns the accumulated update y and the iteration count.
+    flex = (xh, x, nx) selects the flexible variant ("tent_flex"): `op` leaves [Phat^-1 in]_x in the array xh and
+    the solution x (velocity part, nx entries) is accumulated from these directions instead of y."""
     r = np.ascontiguousarray(r0.copy())
     rhat, p, v, sv, t, y = (np.zeros(n) for _ in range(6))
     p_rv, p_ts, p_tt, p_rho, p_rr, p_bb = (np.zeros(1) for _ in range(6))
@@ -125,10 +127,18 @@ def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit):
             break
         v[:] = op(p)
         lk.kh_dot2(sz(n), dp(rhat), dp(v), None, dp(p_rv), None)
-        lk.kh_bi_s(sz(n), dp(r), dp(v), dp(sv), dp(p_rv))
+        if flex is None:
+            lk.kh_bi_s(sz(n), dp(r), dp(v), dp(sv), dp(p_rv))
+        else:
+            lk.kh_bi_s_flex(sz(n), dp(r), dp(v), dp(sv), dp(p_rv), sz(flex[2]), dp(flex[0]), dp(flex[1]))
         t[:] = op(sv)
         lk.kh_dot2(sz(n), dp(t), dp(sv), dp(t), dp(p_ts), dp(p_tt))
-        lk.kh_bi_xr(sz(n), dp(p), dp(sv), dp(t), dp(rhat), dp(y), dp(r), dp(p_rv), dp(p_ts), dp(p_tt), dp(p_rho), dp(p_rr))
+        if flex is None:
+            lk.kh_bi_xr(sz(n), dp(p), dp(sv), dp(t), dp(rhat), dp(y), dp(r), dp(p_rv), dp(p_ts), dp(p_tt), dp(p_rho),
+                        dp(p_rr))
+        else:
+            lk.kh_bi_xr_flex(sz(n), dp(sv), dp(t), dp(rhat), dp(r), dp(p_ts), dp(p_tt), dp(p_rho), dp(p_rr), sz(flex[2]),
+                             dp(flex[0]), dp(flex[1]))
         lk.kh_bi_p(sz(n), dp(r), dp(v), dp(p), dp(p_rv), dp(p_ts), dp(p_tt), dp(p_rho), dp(p_rr))
     return y, it.value, done.value
 
@@ -153,10 +163,13 @@ def test_bicgstab_kernels_on_the_host(libs, k, nx):
         return (np.ascontiguousarray(vec[:nq].reshape(2 * ht.nq1, ht.nc)),
                 np.ascontiguousarray(vec[nq:].reshape(ht.nm, ht.nf)))
 
+    tent_xh = np.zeros((2 * ht.nq1, ht.nc))  # what the operator application leaves behind: [Phat^-1 in]_x
+
     def op(vec):  # A_aug Phat^-1 (run_tentative_aug)
         vx, vmu = split(vec)
         mu, nyx = ht.precond_x(inv_aalpha, vx, vmu)
         xh = ht.xhat(vx, mu)
+        tent_xh[:] = xh
         out_x = ht.fimpl(True, Qstar, xh, 1.0, -adt, Z=vx, alpha=0.0)
         out_mu = ht.sweep(inv_aalpha, nyx, mu, 0.0, 0.0, 0, 1)
         return np.concatenate([out_x.ravel(), out_mu.ravel()])
@@ -170,3 +183,9 @@ def test_bicgstab_kernels_on_the_host(libs, k, nx):
     assert np.abs(aos(x, o.nQ1) - x_ref).max() < 1e-9 * np.abs(x_ref).max()
     _, its_np = ht.solve(Qstar, adt, True, bs, 1e-12, False)
     assert abs(its - its_np) <= 2, (its, its_np)
+    # flexible variant ("tent_flex"): x accumulated from the preconditioned directions, no recovery step
+    xf = np.zeros((2 * ht.nq1, ht.nc))
+    _, its_f, done = bicgstab_kernels(lk, op, nq + nmu, r0, float(bs.ravel() @ bs.ravel()), 1e-12, 400,
+                                      flex=(tent_xh, xf, nq))
+    assert done == 1 and abs(its_f - its) <= 2
+    assert np.abs(aos(xf, o.nQ1) - x_ref).max() < 1e-9 * np.abs(x_ref).max()

@@ -1,5 +1,5 @@
-"""Experimental knob ``tent_cellblock`` (csrc/hdg_advblock.cuh): the cell-block advection preconditioner of the
-tentative-velocity solve.  Written after the round's GPU budget was spent, so it has never run on a GPU: the
+"""Experimental knobs of the tentative-velocity solve: ``tent_cellblock`` (csrc/hdg_advblock.cuh, the cell-block
+advection preconditioner) and ``tent_flex`` (flexible solution update of BiCGStab, csrc/hdg_krylov.cuh).  Written after the round's GPU budget was spent, so it has never run on a GPU: the
 device arithmetic is checked on the CPU (tests/test_advblock_host.py), the solver integration is not.  The knob
 is off by default and this file only runs with HDG_EXPERIMENTAL=1 -- the first thing to do with it on a B200:
 
@@ -46,3 +46,26 @@ def test_cellblock_preconditioner_keeps_the_solution_and_cuts_iterations(k, nx, 
     assert rel(runs[1][0], Qo) < 1e-10 and rel(runs[1][1], po) < 1e-10
     assert rel(runs[1][0], runs[0][0]) < 1e-10
     assert runs[1][2] < 0.8 * runs[0][2]
+
+
+@pytest.mark.parametrize("knobs", [("tent_flex",), ("tent_flex", "tent_cellblock")])
+def test_flexible_bicgstab_update_keeps_the_solution(knobs):
+    """``tent_flex``: the tentative velocity is accumulated from the preconditioned directions (k_bi_s_flex /
+    k_bi_xr_flex, checked on the CPU in tests/test_krylov_host.py) instead of being recovered from the accumulated
+    Krylov vector; same solution, about the same iteration count, with and without a warm start"""
+    k, nx = 2, 8
+    require_degree(k)
+    mesh, dt, nt = UnitSquareMesh(nx, perturb=0.1), 0.32 / nx, 3
+    Qo, po = ChorinOracle(mesh, k, dt).solve(TaylorGreenOracle("exponential", 0.5), nt * dt)
+    for warm in (False, True):
+        its = {}
+        for on in (0, 1):
+            ts = TS.IncompressibleEulerHDGImplicit(mesh, k, dt, krylov_rtol=1e-13, warm_start=warm)
+            for name in knobs:
+                ts.engine.set_tuning(name, on)
+            prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+            Q, p = ts.solve(*prob.initial_condition(), None, prob.f_rhs(), nt * dt)
+            its[on] = ts.niter_tentative.value
+            assert rel(Q.to_host(), Qo) < 1e-10 and rel(p.to_host(), po) < 1e-10, (knobs, warm, on)
+        print(f"{knobs} warm_start={warm}: BiCGStab iterations per solve {its[0]:.1f} -> {its[1]:.1f}")
+        assert its[1] <= its[0] + 3

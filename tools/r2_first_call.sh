@@ -3,7 +3,7 @@
 #   gpurun --timeout 1100 -- bash tools/r2_first_call.sh
 # 1. the full GPU parity suite of the default build (includes the tests written after the last GPU call)
 # 2. the experimental cell-block advection preconditioner: parity + iteration counts
-# 3. bench A/B: default | cell blocks | cell blocks with 6 / 4 / 3 Schur sweeps   (one JSON line each)
+# 3. bench A/B: default | cell blocks | cell blocks with 6 / 4 / 3 Schur sweeps | + flexible update (one JSON line each)
 # 4. ncu launch list of the best candidate (share of every kernel in a step)
 # Afterwards (separate calls, one kernel each): tools/gpu_profile.sh for k_tent_sweep, k_advblock_apply, k_fimpl.
 mkdir -p gpurun_out
@@ -13,7 +13,8 @@ HDG_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_cellblock_gpu.py -
     > gpurun_out/pytest_cellblock_${T}.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_cellblock_${T}.log
 B="bench.py --steps 5 --warmup 6 --e2e-steps 2"
 timeout 240 python $B > gpurun_out/bench_${T}_default.json 2> gpurun_out/bench_${T}_default.err
-for tune in tent_cellblock=1 tent_cellblock=1,tent_sweeps=6 tent_cellblock=1,tent_sweeps=4 tent_cellblock=1,tent_sweeps=3; do
+for tune in tent_cellblock=1 tent_cellblock=1,tent_sweeps=6 tent_cellblock=1,tent_sweeps=4 tent_cellblock=1,tent_sweeps=3 \
+            tent_cellblock=1,tent_sweeps=4,tent_flex=1; do
   name=$(echo $tune | tr ',=' '__')
   HDG_TUNING=$tune timeout 200 python $B --no-cpu-baseline > gpurun_out/bench_${T}_${name}.json 2> gpurun_out/bench_${T}_${name}.err
 done

@@ -1,8 +1,9 @@
 #!/bin/bash
 # First GPU call of round 2: everything round 1 left unmeasured, in one box (about 12 minutes).
-#   gpurun --timeout 1100 -- bash tools/r2_first_call.sh
+#   gpurun --timeout 1500 -- bash tools/r2_first_call.sh
 # 1. the full GPU parity suite of the default build (includes the tests written after the last GPU call)
-# 2. the experimental cell-block advection preconditioner: parity + iteration counts
+# 2. the experimental cell-block advection preconditioner and flexible update: their own
+#    tests, then the whole suite with the knobs on
 # 3. bench A/B: default | cell blocks | cell blocks with 6 / 4 / 3 Schur sweeps | + flexible update (one JSON line each)
 # 4. ncu launch list of the best candidate (share of every kernel in a step)
 # Afterwards (separate calls, one kernel each): tools/gpu_profile.sh for k_tent_sweep, k_advblock_apply, k_fimpl.
@@ -11,6 +12,9 @@ T=r2a
 timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${T}.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_${T}.log
 HDG_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_cellblock_gpu.py -m gpu -q -s \
     > gpurun_out/pytest_cellblock_${T}.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_cellblock_${T}.log
+# the whole parity suite once more with the experimental knobs on (every timestepper test then runs through them)
+HDG_TUNING=tent_cellblock=1,tent_sweeps=4,tent_flex=1 timeout 400 python -m pytest tests -m gpu -q \
+    > gpurun_out/pytest_gpu_${T}_knobs.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_${T}_knobs.log
 B="bench.py --steps 5 --warmup 6 --e2e-steps 2"
 timeout 240 python $B > gpurun_out/bench_${T}_default.json 2> gpurun_out/bench_${T}_default.err
 for tune in tent_cellblock=1 tent_cellblock=1,tent_sweeps=6 tent_cellblock=1,tent_sweeps=4 tent_cellblock=1,tent_sweeps=3 \

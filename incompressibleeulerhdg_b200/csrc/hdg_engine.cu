@@ -110,6 +110,8 @@ struct hdg_engine {
   // experimental cell-block advection preconditioner (hdg_advblock.cuh); off unless hdg_set_tuning("tent_cellblock", 1)
   int tune_cellblock = 0;
   int tune_flex = 0;          // experimental flexible solution update of the tentative BiCGStab ("tent_flex")
+  int tune_fp32 = 0;          // experimental FP32-stored Schur sweep vectors ("tent_fp32"; needs tent_flex)
+  float *tent_f32[3] = {nullptr, nullptr, nullptr};  // facet work [NM][nf] in FP32: mu, mu2, d
   double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*) (FP64 work copy)
   float *adv_blk32 = nullptr; // [NQ1*NQ1][nc]  the same rounded to FP32: what k_advblock_apply reads
   double *adv_in = nullptr;   // [2*NQ1][nc]    C in_x
@@ -781,6 +783,24 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
       LAUNCH(h, (k_tent_sweep<K, 5>), _g, 128, __VA_ARGS__);                                     \
   } while (0)
 
+#define LAUNCH_SWEEP32(h, K, ...)                                                                \
+  do {                                                                                           \
+    const int _g = cdiv((h)->nf, 128);                                                           \
+    if ((h)->tune_sweep >= 8)                                                                    \
+      LAUNCH(h, (k_tent_sweep32<K, 8>), _g, 128, __VA_ARGS__);                                   \
+    else if ((h)->tune_sweep >= 6)                                                               \
+      LAUNCH(h, (k_tent_sweep32<K, 6>), _g, 128, __VA_ARGS__);                                   \
+    else                                                                                         \
+      LAUNCH(h, (k_tent_sweep32<K, 5>), _g, 128, __VA_ARGS__);                                   \
+  } while (0)
+
+// FP32-stored sweep vectors are used when asked for ("tent_fp32"), only together with the flexible update, and only
+// where no FP64 halo exchange sits between the sweeps (one GPU, or local sweeps)
+static inline bool tent_fp32_active(const hdg_engine* h) {
+  const bool multi = h->comm && h->comm->nranks > 1;
+  return h->tune_fp32 != 0 && h->tune_flex != 0 && (!multi || h->tent_local_sweeps);
+}
+
 template <int K>
 static int tent_setup(hdg_engine* h) {
   constexpr int NM = TentDims<K>::NM;
@@ -839,6 +859,20 @@ template <int K>
 static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* t) {
   std::vector<ChebCoef> cc;
   cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
+  if (tent_fp32_active(h)) {
+    // iterate, correction and intermediate outputs in FP32 (k_tent_sweep32); the last sweep writes the multiplier in
+    // FP64 into tent_f[2], which is what the consumers read in either mode
+    float *x = h->tent_f32[0], *x2 = h->tent_f32[1];
+    for (int j = 0; j < h->tent_sweeps; ++j) {
+      const bool last = j == h->tent_sweeps - 1;
+      LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha, t, (const float*)x,
+                     h->tent_f32[2], last ? (float*)nullptr : x2, last ? h->tent_f[2] : (double*)nullptr, cc[j].cd,
+                     cc[j].cr, j == 0 ? 1 : 0);
+      std::swap(x, x2);
+    }
+    halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, h->tent_f[2]);
+    return h->tent_f[2];
+  }
   double *x = h->tent_f[2], *x2 = h->tent_f[3];
   for (int j = 0; j < h->tent_sweeps; ++j) {
     // With local sweeps every rank iterates on its own facets plus the ghost layer without refreshing
@@ -923,6 +957,8 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     lc.x[1] = h->bi[5];
     LAUNCH(h, k_lincomb, G, BLOCK, nx, lc, r);
   }
+  if (tent_fp32_active(h) && !h->tent_f32[0])
+    for (int i = 0; i < 3; ++i) CUDA_TRY(h, dmalloc(&h->tent_f32[i], nmu));
   // experimental: compose the preconditioner with the inverse cell-diagonal blocks C of I - a F0(Q*)
   // (hdg_advblock.cuh): Phat^-1 -> Phat^-1 diag(C, I).  Built once per solve (Q*, a change from solve to solve).
   const bool cellblock = h->tune_cellblock != 0;
@@ -973,7 +1009,8 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   std::vector<uint64_t> key = {2ull, key_of(Qstar), key_of(adt), (uint64_t)upwind, key_of(h->alpha),
                                (uint64_t)h->tent_sweeps, (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax),
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
-                               key_of(h->adv_blk32), key_of(h->adv_in)};
+                               key_of(h->adv_blk32), key_of(h->adv_in), (uint64_t)tent_fp32_active(h),
+                               key_of(h->tent_f32[0]), key_of(h->tent_f32[1]), key_of(h->tent_f32[2])};
   // experimental ("tent_flex"): accumulate x from the preconditioned directions op leaves in tent_xh; x holds the
   // initial guess (or zero) on entry, so no recovery step follows
   const bool flex = h->tune_flex != 0;
@@ -1278,7 +1315,8 @@ int hdg_destroy(hdg_handle h) {
                   h->wQ, h->wP, h->wL, h->wQ2, h->wP2, h->wL2, h->stage, h->cell_nbr, h->cell_nbr_e, h->bdm_fm,
                   h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
                   h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
-                  h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in};
+                  h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in, h->tent_f32[0], h->tent_f32[1],
+                  h->tent_f32[2]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg})
@@ -1813,6 +1851,14 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
   if (!strcmp(name, "sweep_minblocks")) {
     h->tune_sweep = value;
     // the variant is baked into the captured BiCGStab graph
+    if (h->g_bicg.exec) {
+      cudaGraphExecDestroy(h->g_bicg.exec);
+      h->g_bicg.exec = nullptr;
+    }
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_fp32")) {
+    h->tune_fp32 = value != 0;
     if (h->g_bicg.exec) {
       cudaGraphExecDestroy(h->g_bicg.exec);
       h->g_bicg.exec = nullptr;

@@ -243,6 +243,86 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
   }
 }
 
+// FP32-*stored* variant of the Chebyshev / facet-block-Jacobi sweep (mode 0 of k_tent_sweep; experimental,
+// hdg_set_tuning "tent_fp32", only together with "tent_flex"): the iterate x, the correction d and the output are
+// float arrays, the arithmetic stays FP64, the right-hand side stays FP64.  172 instead of 236 bytes per facet.  With
+// rounded vectors the preconditioner is no longer an exactly linear operator, which only the flexible solution update
+// of BiCGStab tolerates (tests/experiments/tent_fp32_sweeps.py).  The last sweep of a solve writes the multiplier in
+// FP64 (xout64) for k_tent_xhat and the residual row of the operator.
+template <int K, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* __restrict__ facet_local,
+                                                      const double* __restrict__ tc, const int* __restrict__ tcol,
+                                                      const int* __restrict__ tbits, double inv_aalpha,
+                                                      const double* __restrict__ rhs, const float* __restrict__ x,
+                                                      float* __restrict__ d, float* __restrict__ xout32,
+                                                      double* __restrict__ xout64, double cd, double cr, int zero) {
+  constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    const int bits = tbits[f];
+    int e[2], col[2][2];
+    double c[2][3], v[2][2][NM], own[NM], b[NM], dprev[NM];
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      e[s] = facet_local[(size_t)s * nf + f];
+      HDG_UNROLL
+      for (int j = 0; j < 3; ++j) c[s][j] = tc[(size_t)(3 * s + j) * nf + f];
+      HDG_UNROLL
+      for (int jj = 0; jj < 2; ++jj) col[s][jj] = tcol[(size_t)(2 * s + jj) * nf + f];
+    }
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      own[j] = zero ? 0.0 : (double)x[(size_t)j * nf + f];
+      b[j] = rhs[(size_t)j * nf + f];
+      dprev[j] = (cd != 0.0) ? (double)d[(size_t)j * nf + f] : 0.0;
+    }
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s)
+      HDG_UNROLL
+      for (int jj = 0; jj < 2; ++jj)
+        HDG_UNROLL
+        for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0 : (double)x[(size_t)l * nf + col[s][jj]];
+    double acc[NM], D[NMH];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) acc[j] = 0.0;
+    HDG_UNROLL
+    for (int i = 0; i < NMH; ++i) D[i] = 0.0;
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) D[tri(j, j)] = inv_aalpha;
+    HDG_UNROLL
+    for (int s = 0; s < 2; ++s) {
+      if (e[s] < 0) continue;
+      const int fl0 = (bits >> (3 * s)) & 1;
+      const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
+      switch (e[s]) {
+        case 0: tent_side<K, 0>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+        case 1: tent_side<K, 1>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+        default: tent_side<K, 2>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+      }
+    }
+    double r[NM];
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      double w = acc[j];
+      if (!zero) {
+        HDG_UNROLL
+        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], w);
+      }
+      r[j] = b[j] - w;
+    }
+    cholesky<NM>(D);
+    chol_solve<NM>(D, r);
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) {
+      const double di = fma(cd, dprev[j], cr * r[j]);
+      d[(size_t)j * nf + f] = (float)di;
+      if (xout64)
+        xout64[(size_t)j * nf + f] = own[j] + di;
+      else
+        xout32[(size_t)j * nf + f] = (float)(own[j] + di);
+    }
+  }
+}
+
 // xh = y - M^-1 N^T mu   (mode 0)   or   xh += y - M^-1 N^T mu   (mode 1, final recovery)
 template <int K>
 __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy, const int* __restrict__ flip,

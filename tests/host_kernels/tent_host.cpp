@@ -45,6 +45,13 @@ int th_sweep(int k, int nf, const int* facet_local, const double* tc, const int*
   BY_K(k, (k_tent_sweep<K, 5>(nf, facet_local, tc, tcol, tbits, inv_aalpha, rhs, rhs2, x, d, xout, cd, cr, zero, mode)))
 }
 
+// FP32-stored sweep (mode 0): exactly one of xout32 / xout64 is given
+int th_sweep32(int k, int nf, const int* facet_local, const double* tc, const int* tcol, const int* tbits,
+               double inv_aalpha, const double* rhs, const float* x, float* d, float* xout32, double* xout64, double cd,
+               double cr, int zero) {
+  BY_K(k, (k_tent_sweep32<K, 5>(nf, facet_local, tc, tcol, tbits, inv_aalpha, rhs, x, d, xout32, xout64, cd, cr, zero)))
+}
+
 int th_xhat(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, const double* Y,
             const double* mu, double* Xh, int mode) {
   BY_K(k, k_tent_xhat<K>(xy, flip, cell_facet, nc, nf, Y, mu, Xh, mode))

@@ -189,3 +189,71 @@ def test_bicgstab_kernels_on_the_host(libs, k, nx):
                                       flex=(tent_xh, xf, nq))
     assert done == 1 and abs(its_f - its) <= 2
     assert np.abs(aos(xf, o.nQ1) - x_ref).max() < 1e-9 * np.abs(x_ref).max()
+
+
+def test_fp32_stored_sweeps_need_and_work_with_the_flexible_update(libs):
+    """``tent_fp32`` (k_tent_sweep32: iterate and correction of the Chebyshev sweeps stored in FP32): with the present
+    recovery x = [Phat^-1 y]_x the attainable accuracy drops to ~1e-8, with the flexible update it is back at
+    round-off -- which is why the engine only uses the FP32 sweeps together with ``tent_flex``"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    k, nx = 2, 4
+    mesh, o, Q0, Qs, adt = _problem(k, nx, "upwind")
+    lk, lt = libs["krylov"], libs["tent"]
+    FP = ctypes.POINTER(ctypes.c_float)
+
+    class HostTentative32(HostTentative):
+        def schur_solve(self, inv_aalpha, t):  # tent_schur_solve, FP32 branch
+            a, b_ = self.lmax / 8.0, 1.1 * self.lmax
+            theta, delta = 0.5 * (b_ + a), 0.5 * (b_ - a)
+            sigma = theta / delta
+            rho, coefs = 1.0 / sigma, [(0.0, 1.0 / theta)]
+            for _ in range(1, self.sweeps):
+                rho_new = 1.0 / (2.0 * sigma - rho)
+                coefs.append((rho_new * rho, 2.0 * rho_new / delta))
+                rho = rho_new
+            x, x2, d = (np.zeros((self.nm, self.nf), np.float32) for _ in range(3))
+            out64 = np.zeros((self.nm, self.nf))
+            for j, (cdv, crv) in enumerate(coefs):
+                last = j == len(coefs) - 1
+                assert lt.th_sweep32(self.k, self.nf, ip(self.facet_local), dp(self.tc), ip(self.tcol), ip(self.tbits),
+                                     cd(inv_aalpha), dp(t), x.ctypes.data_as(FP), d.ctypes.data_as(FP),
+                                     None if last else x2.ctypes.data_as(FP), dp(out64) if last else None, cd(cdv),
+                                     cd(crv), int(j == 0)) == 0
+                x, x2 = x2, x
+            return out64
+
+    b = Q0 + 0.01 * np.random.default_rng(11).standard_normal(Q0.shape)
+    M = sp.diags(np.repeat(o.detJ, o.nQ))
+    x_ref = spla.spsolve((M - adt * o.f_impl_matrix(Qs)).tocsc(), M @ b.ravel()).reshape(b.shape)
+    ht = HostTentative32(lt, mesh, k)
+    nq, nmu = 2 * ht.nq1 * ht.nc, ht.nm * ht.nf
+    inv_aalpha = 1.0 / (adt * ht.alpha)
+    Qstar, bs = soa(Qs), soa(b)
+    tent_xh = np.zeros((2 * ht.nq1, ht.nc))
+
+    def split(vec):
+        return (np.ascontiguousarray(vec[:nq].reshape(2 * ht.nq1, ht.nc)),
+                np.ascontiguousarray(vec[nq:].reshape(ht.nm, ht.nf)))
+
+    def op(vec):
+        vx, vmu = split(vec)
+        mu, nyx = ht.precond_x(inv_aalpha, vx, vmu)
+        tent_xh[:] = ht.xhat(vx, mu)
+        out_x = ht.fimpl(True, Qstar, tent_xh, 1.0, -adt, Z=vx, alpha=0.0)
+        out_mu = ht.sweep(inv_aalpha, nyx, mu, 0.0, 0.0, 0, 1)
+        return np.concatenate([out_x.ravel(), out_mu.ravel()])
+
+    r0, bb = np.concatenate([bs.ravel(), np.zeros(nmu)]), float(bs.ravel() @ bs.ravel())
+    y, its, done = bicgstab_kernels(lk, op, nq + nmu, r0, bb, 1e-12, 400)
+    yx, ymu = split(y)
+    mu, _ = ht.precond_x(inv_aalpha, yx, ymu)
+    err_recovered = np.abs(aos(ht.xhat(yx, mu), o.nQ1) - x_ref).max() / np.abs(x_ref).max()
+    xf = np.zeros((2 * ht.nq1, ht.nc))
+    _, its_f, done_f = bicgstab_kernels(lk, op, nq + nmu, r0, bb, 1e-12, 400, flex=(tent_xh, xf, nq))
+    err_flex = np.abs(aos(xf, o.nQ1) - x_ref).max() / np.abs(x_ref).max()
+    print(f"FP32-stored sweeps: iterations {its} / {its_f}, error against the direct solve: recovered {err_recovered:.1e}, "
+          f"flexible {err_flex:.1e}")
+    assert done == 1 and done_f == 1
+    assert err_flex < 1e-10 < err_recovered

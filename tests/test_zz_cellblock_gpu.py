@@ -48,11 +48,13 @@ def test_cellblock_preconditioner_keeps_the_solution_and_cuts_iterations(k, nx, 
     assert runs[1][2] < 0.8 * runs[0][2]
 
 
-@pytest.mark.parametrize("knobs", [("tent_flex",), ("tent_flex", "tent_cellblock")])
+@pytest.mark.parametrize("knobs", [("tent_flex",), ("tent_flex", "tent_cellblock"), ("tent_flex", "tent_fp32"),
+                                   ("tent_flex", "tent_fp32", "tent_cellblock")])
 def test_flexible_bicgstab_update_keeps_the_solution(knobs):
     """``tent_flex``: the tentative velocity is accumulated from the preconditioned directions (k_bi_s_flex /
     k_bi_xr_flex, checked on the CPU in tests/test_krylov_host.py) instead of being recovered from the accumulated
-    Krylov vector; same solution, about the same iteration count, with and without a warm start"""
+    Krylov vector; same solution, about the same iteration count, with and without a warm start.  ``tent_fp32`` on top
+    of it stores the vectors of the Chebyshev sweeps in FP32 (k_tent_sweep32)"""
     k, nx = 2, 8
     require_degree(k)
     mesh, dt, nt = UnitSquareMesh(nx, perturb=0.1), 0.32 / nx, 3

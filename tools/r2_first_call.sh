@@ -13,12 +13,12 @@ timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_${T}.log
 HDG_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_zz_cellblock_gpu.py -m gpu -q -s \
     > gpurun_out/pytest_cellblock_${T}.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_cellblock_${T}.log
 # the whole parity suite once more with the experimental knobs on (every timestepper test then runs through them)
-HDG_TUNING=tent_cellblock=1,tent_sweeps=4,tent_flex=1 timeout 400 python -m pytest tests -m gpu -q \
+HDG_TUNING=tent_cellblock=1,tent_sweeps=4,tent_flex=1,tent_fp32=1 timeout 400 python -m pytest tests -m gpu -q \
     > gpurun_out/pytest_gpu_${T}_knobs.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu_${T}_knobs.log
 B="bench.py --steps 5 --warmup 6 --e2e-steps 2"
 timeout 240 python $B > gpurun_out/bench_${T}_default.json 2> gpurun_out/bench_${T}_default.err
 for tune in tent_cellblock=1 tent_cellblock=1,tent_sweeps=6 tent_cellblock=1,tent_sweeps=4 tent_cellblock=1,tent_sweeps=3 \
-            tent_cellblock=1,tent_sweeps=4,tent_flex=1; do
+            tent_cellblock=1,tent_sweeps=4,tent_flex=1 tent_cellblock=1,tent_sweeps=4,tent_flex=1,tent_fp32=1; do
   name=$(echo $tune | tr ',=' '__')
   HDG_TUNING=$tune timeout 200 python $B --no-cpu-baseline > gpurun_out/bench_${T}_${name}.json 2> gpurun_out/bench_${T}_${name}.err
 done

@@ -1,5 +1,9 @@
-// B200-native HDG solve engine: condensed mixed-Poisson path (K1-K5) and the C-ABI of
-// include/hdg_b200.h.  sm_100a only; there is no CPU fallback.
+// B200-native HDG solve engine: engine state, host orchestration of the solvers (streams, CUDA graphs, multi-GPU
+// exchanges) and the C-ABI of include/hdg_b200.h.  sm_100a only; there is no CPU fallback.
+// The kernels live in the headers next to this file -- hdg_local.cuh (per-cell algebra), hdg_poisson.cuh (condensation,
+// gather, forward / back-substitution), hdg_krylov.cuh (CG / BiCGStab vector kernels), hdg_mg.cuh (multigrid),
+// hdg_flow.cuh (velocity side), hdg_tent.cuh + hdg_advblock.cuh (tentative-velocity preconditioner), hdg_tracer.cuh,
+// hdg_comm.cuh (NCCL / peer-memory transport) -- so that tests/host_kernels can also execute their arithmetic on the CPU.
 //
 // Data layout in HBM (everything FP64, SoA = dof major / entity minor so that thread-per-entity
 // kernels are perfectly coalesced):

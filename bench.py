@@ -144,6 +144,12 @@ def cpu_chorin_sample(nx_sample, degree, nsteps, target_cells, cores=None):
     }, sec_per_step
 
 
+def cpu_baseline_sample(args, target_cells):
+    """the CPU baseline of the own arm's line: the oracle port on a bounded sample"""
+    base, _ = cpu_chorin_sample(args.cpu_nx, args.degree, 1, target_cells)
+    return base
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -216,6 +222,7 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; this program prints ONE line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from incompressibleeulerhdg_b200.functions import Function
     from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
     from incompressibleeulerhdg_b200.model_problems import TaylorGreen
     from incompressibleeulerhdg_b200.timesteppers import IncompressibleEulerHDGImplicit
@@ -223,18 +230,23 @@ def run_ours(args):
     nx, k = args.nx, args.degree
     dt = 0.32 / nx
     nxm, nym, height = mesh_shape(args, world)
+    t_setup = time.perf_counter()
     mesh = UnitSquareMesh(nxm, nym, perturb=0.1)
     if height != 1.0:  # weak scaling: [0,1] x [0,world]; the Taylor-Green field stays a no-flow solution there
         mesh.cell_xy[..., 1] *= height
     # torch.distributed is initialised => the timestepper partitions the mesh over the ranks
     ts = IncompressibleEulerHDGImplicit(mesh, k, dt, flux="upwind", use_projection_method=True, device=local,
-                                        krylov_rtol=args.rtol)
+                                        krylov_rtol=args.rtol, warm_start=True, warm_order=args.warm_order)
     eng = ts.engine
     work_units = float(world) if args.scaling == "weak" else 1.0  # 2 nx^2-cell timesteps per global step
     prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
     Q0, p0 = prob.initial_condition()
     f_rhs = prob.f_rhs()
     ts.initialise(Q0, p0)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    mem_gb = torch.cuda.mem_get_info(local)
+    mem_used_gb = (mem_gb[1] - mem_gb[0]) / 2**30
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,161 +261,267 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def l2(f):
+        return float(np.sqrt(eng.l2_inner_dev(f.space.kind, f.data, f.data)))
+
+    def errors_and_checksums(t_now):
+        """L2 errors against model_problem.solution(t) (`driver.py:365-380`) and rank-reduced checksums of the fields:
+        the 1- and N-GPU runs of the same config must print the same numbers (to solver tolerance)"""
+        Qe, pe = prob.solution(t_now)
+        dQ, dp_ = Function(ts._V_Q), Function(ts._V_p)
+        eng.lincomb_dev(dQ.data, [(1.0, ts.Q.data), (-1.0, Qe.data)])
+        eng.lincomb_dev(dp_.data, [(1.0, ts.p.data), (-1.0, pe.data)])
+        return {"t": t_now, "l2_error_velocity": l2(dQ), "l2_error_pressure": l2(dp_),
+                "l2_norm_velocity": l2(ts.Q), "l2_norm_pressure": l2(ts.p),
+                "l2_inner_velocity_exact": float(eng.l2_inner_dev(0, ts.Q.data, Qe.data))}
+
+    def timed_steps(nsteps, step_no, step_fn=None):
+        """(ms max over ranks, launches, iteration summary) of `nsteps` steps bracketed by barrier + synchronize"""
+        step_fn = step_fn or (lambda kk: ts.step(kk, f_rhs))
+        h0 = len(ts.iteration_history)
+        l0 = eng.launch_count
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(nsteps):
+            step_fn(step_no)
+            step_no += 1
+        ev1.record()
+        barrier()
+        hist = ts.iteration_history[h0:]
+        its = {"tentative_per_solve": float(np.mean([a for a, _ in hist])), "trace_cg_per_solve": float(np.mean([b for _, b in hist])),
+               "per_step_tentative_pressure": hist}
+        return max_over_ranks(ev0.elapsed_time(ev1)), eng.launch_count - l0, its, step_no
+
     step_no = 0
-    # ---- device-resident arm -------------------------------------------------------------------
+    # ---- device-resident arm (the headline `value`) ----------------------------------------------
     for _ in range(args.warmup):
         ts.step(step_no, f_rhs)
         step_no += 1
     eng.reset_timers()
-    l0 = eng.launch_count
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kc0 = eng.kernel_counts()
+    st0 = eng.tentative_stats()
     with ClockSampler(local) as clocks:
-        ev0.record()
-        for _ in range(args.steps):
-            ts.step(step_no, f_rhs)
-            step_no += 1
-        ev1.record()
-        barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = eng.launch_count - l0
+        ms, launches, its_main, step_no = timed_steps(args.steps, step_no)
+    kc1 = eng.kernel_counts()
+    st1 = eng.tentative_stats()
     timers = eng.timers()
-    its_p, its_t = ts.niter_pressure.value, ts.niter_tentative.value
     value = work_units * args.steps / (ms / 1e3)
+    check_main = errors_and_checksums(step_no * dt)
+    per_step_launches = {kname: (kc1[kname] - kc0.get(kname, 0)) / args.steps for kname in kc1 if kc1[kname] != kc0.get(kname, 0)}
 
-    # ---- end-to-end arm: forcing from pinned host memory each step, (Q, p) back to the host ----
-    from incompressibleeulerhdg_b200.functions import Function
-
+    # ---- end-to-end arm: the same number of steps driven with HOST buffers.  Per step the forcing field comes from
+    # pinned host memory (H2D) and the new velocity and pressure go back to pinned host memory (D2H); the transfers run
+    # on the engine's copy stream (hdg_upload_begin / hdg_download_begin) and overlap the solver kernels: the upload
+    # of step n + 1 and the download of step n - 1 are in flight while step n computes.
     sQ, sp_, _ = eng.shapes()
     f_dev = Function(ts._V_Q)
-    ts._V_Q.interpolate(f_rhs(0.0), out=f_dev)
-    f_host = torch.from_numpy(eng.download(0, f_dev.data)).pin_memory()
-    Q_host = torch.empty(sQ, dtype=torch.float64).pin_memory()
-    p_host = torch.empty(sp_, dtype=torch.float64).pin_memory()
+    ts._V_Q.interpolate(f_rhs(step_no * dt), out=f_dev)
+    f_host = [torch.from_numpy(eng.download(0, f_dev.data)).pin_memory() for _ in range(2)]
+    Q_host = [torch.empty(sQ, dtype=torch.float64).pin_memory() for _ in range(2)]
+    p_host = [torch.empty(sp_, dtype=torch.float64).pin_memory() for _ in range(2)]
+    e2e_state = {"n": 0}
+    eng.upload_begin(0, f_host[0].numpy(), slot=0)
 
     def e2e_step(kstep):
-        scale = float(np.exp(-0.5 * dt))  # host-side update of the forcing values for the next step
-        eng.upload(0, f_host.numpy(), out=f_dev.data)
+        n = e2e_state["n"]
+        slot = n % 2
+        eng.upload_end(0, f_dev.data, slot=slot)              # forcing of this step (started one step ago)
+        # the forcing of the next step starts travelling now (its values are the caller's business: updating 42 M
+        # doubles on the host is not part of the path, so the two host buffers keep the forcing of the first step)
+        eng.upload_begin(0, f_host[1 - slot].numpy(), slot=1 - slot)
         ts.step(kstep, f_rhs, f_field=f_dev)
-        eng.download(0, ts.Q.data, out=Q_host.numpy())
-        eng.download(1, ts.p.data, out=p_host.numpy())
-        return scale
+        eng.download_begin(0, ts.Q.data, Q_host[slot].numpy(), slot=slot)
+        eng.download_begin(1, ts.p.data, p_host[slot].numpy(), slot=slot)
+        e2e_state["n"] = n + 1
 
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = args.steps if args.e2e_steps <= 0 else min(args.steps, args.e2e_steps)
     e2e_step(step_no)
     step_no += 1
-    barrier()
+    eng.copy_wait()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step(step_no)
-        step_no += 1
-    barrier()
+    e2e_ms, _, its_e2e, step_no = timed_steps(e2e_steps, step_no, e2e_step)
+    eng.copy_wait()  # the last step's results have arrived on the host
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = work_units * e2e_steps / e2e_s
+    e2e_probe = float(Q_host[(e2e_state["n"] - 1) % 2].abs().max())  # the result was really read on the host
 
-    # ---- roofline of the dominant trace-solve kernel: back-to-back launches between two CUDA events on
-    # the engine stream (the in-loop samples below also contain the host enqueue gap after the
-    # per-iteration convergence check, so they under-report the kernel)
+    # ---- cold start: the reference's behaviour (zero / Q^n initial guesses), a few steps of the same run ----------
+    cold = None
+    if args.cold_steps > 0:
+        ts.warm_start = False
+        eng.set_initial_guess(False)
+        cms, _, its_cold, step_no = timed_steps(args.cold_steps, step_no)
+        cold = {"value": work_units * args.cold_steps / (cms / 1e3), "unit": UNIT, "steps": args.cold_steps,
+                "ms_per_step": cms / args.cold_steps, "iterations": its_cold}
+    check_end = errors_and_checksums(step_no * dt)
+
+    # ---- kernel probes: back-to-back launches between two CUDA events on the engine stream ------------------------
+    def b2b(fn, nrep, nwarm=3):
+        for _ in range(nwarm):
+            fn()
+        barrier()
+        sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sa.record()
+        for _ in range(nrep):
+            fn()
+        sb.record()
+        torch.cuda.synchronize()
+        return sa.elapsed_time(sb) / nrep
+
     xs, ys = eng.empty(2).normal_(), eng.empty(2)
-    barrier()  # the e2e phase leaves the ranks skewed; the exchange inside the SpMV would wait for the slowest
-    for _ in range(3):
-        eng.trace_spmv_dev(xs, ys)
-    barrier()
-    n_spmv = 20
-    sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sa.record()
-    for _ in range(n_spmv):
-        eng.trace_spmv_dev(xs, ys)
-    sb.record()
-    torch.cuda.synchronize()
-    spmv_b2b_ms = sa.elapsed_time(sb) / n_spmv
-    # the matrix-free advection operator of the tentative solve, timed the same way
+    spmv_b2b_ms = b2b(lambda: eng.trace_spmv_dev(xs, ys), 20)
     Xf, Yf = eng.empty(0).normal_(), eng.empty(0)
-    for _ in range(2):
-        eng.fimpl_apply_dev(ts._Q_star.data, Xf, Yf, c0=1.0, c1=-dt)
-    barrier()
-    n_fimpl = 10
-    sa.record()
-    for _ in range(n_fimpl):
-        eng.fimpl_apply_dev(ts._Q_star.data, Xf, Yf, c0=1.0, c1=-dt)
-    sb.record()
-    torch.cuda.synchronize()
-    fimpl_b2b_ms = sa.elapsed_time(sb) / n_fimpl
-    del Xf, Yf
-    # the kernel with the largest share of the step (profiles/launches_r1k.md: 39 %): one Chebyshev / facet-block-
-    # Jacobi sweep on the facet Schur complement of the tentative-velocity preconditioner, timed the same way
+    fimpl_b2b_ms = b2b(lambda: eng.fimpl_apply_dev(ts._Q_star.data, Xf, Yf, c0=1.0, c1=-dt), 10, 2)
+    # forward elimination and back-substitution of the condensed mixed-Poisson solve (k_forward, k_back)
+    Rp, lam = eng.empty(1).normal_(), eng.empty(2).normal_()
+    Pf = eng.empty(1)
+    fwd_ms = b2b(lambda: eng.forward_eliminate_dev(None, Rp, None, ys), 10, 2)
+    back_ms = b2b(lambda: eng.back_substitute_dev(None, Rp, lam, Yf, Pf), 10, 2)
+    del Xf, Yf, Rp, lam, Pf
     n_sweep, sweep_b2b_ms, sweep_err = 20, None, None
     try:
         sweep_b2b_ms = eng.tent_sweep_probe(dt, n_sweep)
     except Exception as exc:  # a measurement aid must not cost the bench line
         sweep_err = f"{type(exc).__name__}: {exc}"
     fp64_peak = eng.measure_fp64_peak()  # TFLOP/s, 8 independent DFMA chains per thread
+    # condensation + assembly (K1-K3): re-run the set-up three times, event timers of k_condense / k_assemble
+    t_before = eng.timers()
+    for _ in range(3):
+        eng.setup_poisson()
+    t_after = eng.timers()
+    condense_ms = (t_after["condense"][0] - t_before["condense"][0]) / 3
+    assemble_ms = (t_after["assemble"][0] - t_before["assemble"][0]) / 3
+    # ---- a large time step: the reference's default dt = 0.04 (src/driver.py:80-86), CFL = dt nx (41 at nx = 1024) --
+    high = None
+    if args.high_cfl_steps > 0:
+        ts.warm_start = False
+        eng.set_initial_guess(False)
+        ts._dt = args.high_cfl_dt
+        ts.tentative_maxit = args.high_cfl_maxit
+        ts.initialise(Q0, p0)
+        stA = eng.tentative_stats()
+        high = {"dt": args.high_cfl_dt, "cfl": args.high_cfl_dt * nx, "steps": args.high_cfl_steps, "unit": UNIT,
+                "tentative_maxit": args.high_cfl_maxit}
+        try:
+            hms, _, its_high, _ = timed_steps(args.high_cfl_steps, 0)
+            high.update({"converged": True, "ms_per_step": hms / args.high_cfl_steps,
+                         "value": work_units * args.high_cfl_steps / (hms / 1e3), "iterations": its_high,
+                         "check": errors_and_checksums(args.high_cfl_steps * args.high_cfl_dt)})
+        except Exception as exc:  # a solve that does not converge must not cost the bench line
+            high.update({"converged": False, "error": f"{type(exc).__name__}: {exc}"})
+        stB = eng.tentative_stats()
+        high["tentative_solver"] = {kk: stB[kk] - stA[kk] for kk in stB}
+        ts._dt = dt
+
     if world > 1:
         barrier()
 
     if rank == 0:
         peak, peak_src = load_peaks()
         b = k + 1
-        nf_loc = eng.nf  # facets this rank's SpMV runs over (owned + ghost)
+        nf_loc, nc_loc = eng.nf, eng.nc  # entities this rank's kernels run over (owned + ghost)
+        nq1, npp, nl = (k + 2) * (k + 3) // 2, (k + 1) * (k + 2) // 2, 3 * (k + 1)
+        na = 2 * nq1 + npp
+        ms_step = ms / args.steps
+
+        def hbm(name, launch_ms, nbytes, note=None, **extra):
+            d = {"kernel": name, "bound": "hbm", "achieved": nbytes / launch_ms / 1e6, "peak": peak, "unit": "GB/s",
+                 "frac": nbytes / launch_ms / 1e6 / peak, "peak_source": peak_src,
+                 "algorithmic_bytes_per_launch": int(nbytes), "launch_ms": launch_ms}
+            if note:
+                d["note"] = note
+            d.update(extra)
+            return d
+
+        kernels = {}
         nblocks = 5 * nf_loc
         spmv_bytes = nblocks * b * b * 8 + nblocks * 4 + 2 * b * nf_loc * 8
-        spmv_ms, spmv_n = timers["spmv_sampled"]
-        ach = spmv_bytes / spmv_b2b_ms / 1e6
-        roofline = {
-            "kernel": f"k_cg_spmv<{b}> (blocked-ELL trace SpMV of the CG; with N > 1 the launch includes this "
-                      "rank's NCCL facet-halo exchange)",
-            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at
-            # nx=1024, k=2 on one GPU (profiles/ncu_r1b_cg_spmv_raw.csv.gz): 1.279 GB + 74.4 MB
-            "traffic": 1353474384 if (world == 1 and nx == 1024 and k == 2) else None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": spmv_bytes,
-            "launch_ms": spmv_b2b_ms, "launches_timed": n_spmv,
-            "in_loop_sampled_ms": spmv_ms / max(spmv_n, 1), "in_loop_samples": int(spmv_n),
-        }
-        # second-hottest kernel family (tentative velocity): k_fimpl is FP64-issue bound, not HBM bound
-        dfma_per_cell = {1: 7 * 48 + 3 * 220, 2: 16 * 80 + 3 * 350, 3: 36 * 120 + 3 * 735, 4: 64 * 168 + 3 * 1176}[k]
-        t = fimpl_b2b_ms
-        other = {"k_fimpl": {
-            "launch_ms": t, "bound": "fp64", "dfma_per_cell": dfma_per_cell,
-            "achieved_tflops": 2.0 * dfma_per_cell * eng.nc / t / 1e9, "peak_tflops_measured": fp64_peak,
-            "frac": 2.0 * dfma_per_cell * eng.nc / t / 1e9 / fp64_peak, "launches_timed": n_fimpl}}
-        # per facet: geometry 6 doubles + 7 ints, and rhs, x, d (read), d, xout (written) of NM = k + 2 doubles each;
-        # the 4 neighbour facets' x are re-reads of the same vector (L2)
+        kernels["k_cg_spmv"] = hbm(f"k_cg_spmv<{b}> (blocked-ELL trace SpMV of the CG; with N > 1 the launch includes this "
+                                   "rank's facet-halo exchange)", spmv_b2b_ms, spmv_bytes, launches_timed=20,
+                                   traffic=1353474384 if (world == 1 and nx == 1024 and k == 2) else None,
+                                   traffic_source="ncu --set full, profiles/ncu_r1b_cg_spmv_raw.csv.gz")
         nm = k + 2
-        sweep_bytes = (6 * 8 + 7 * 4 + 5 * nm * 8) * nf_loc
+        f32 = bool(getattr(eng, "tuning", {}).get("tent_fp32", 1)) and (world == 1)
+        # per facet: geometry 6 doubles + 7 ints, rhs (double) and x, d (read), d, xout (written) of NM entries each:
+        # FP32-stored iterate / correction (default on one GPU) or FP64; the 4 neighbour facets' x are L2 re-reads
+        sweep_bytes = (6 * 8 + 7 * 4 + nm * 8 + 4 * nm * (4 if f32 else 8)) * nf_loc
+        sweep_name = "k_tent_sweep32" if f32 else "k_tent_sweep"
         if sweep_b2b_ms:
-            sw = sweep_bytes / sweep_b2b_ms / 1e6
-            other["k_tent_sweep"] = {
-                "launch_ms": sweep_b2b_ms, "bound": "hbm", "algorithmic_bytes_per_launch": sweep_bytes,
-                "achieved": sw, "peak": peak, "unit": "GB/s", "frac": sw / peak, "launches_timed": n_sweep,
-                "share_of_step": "39 % of the device time of a step in profiles/launches_r1k.md"}
+            kernels[sweep_name] = hbm(f"{sweep_name}<{k}> (Chebyshev / facet-block-Jacobi sweep on the facet Schur complement "
+                                      "of the tentative-velocity preconditioner)", sweep_b2b_ms, sweep_bytes,
+                                      note="latency-limited (ncu r1h: DRAM traffic = algorithmic bytes)", launches_timed=n_sweep)
         else:
-            other["k_tent_sweep"] = {"error": sweep_err}
+            kernels[sweep_name] = {"error": sweep_err}
+        dfma_per_cell = {1: 7 * 48 + 3 * 220, 2: 16 * 80 + 3 * 350, 3: 36 * 120 + 3 * 735, 4: 64 * 168 + 3 * 1176}[k]
+        tf = 2.0 * dfma_per_cell * nc_loc / fimpl_b2b_ms / 1e9
+        kernels["k_fimpl"] = {"kernel": f"k_fimpl<{k},upwind> (matrix-free advection + flux + penalty operator)",
+                              "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                              "peak_source": "self-measured FP64 FMA rate (hdg_measure_fp64_peak; MEASURED_PEAKS.json has no "
+                                             "FP64 entry)", "dfma_per_cell": dfma_per_cell, "launch_ms": fimpl_b2b_ms,
+                              "launches_timed": 10,
+                              "hbm_frac": (4 * 2 * nq1 * 8) * nc_loc / fimpl_b2b_ms / 1e6 / peak}
+        # condensation metric of BASELINE.json ("condensation % of roofline"): DESIGN.md 4 / SURVEY.md 8d bytes per cell
+        kernels["k_condense"] = hbm(f"k_condense<{k}> (local operator + Schur complement S_K, closed form)", condense_ms,
+                                    (6 + nl * nl) * 8 * nc_loc, launches_timed=3,
+                                    generic_route_flops_per_cell={1: 6030, 2: 28097, 3: 92586, 4: 246582}[k])
+        kernels["k_assemble"] = hbm(f"k_assemble<{k}> (deterministic gather of S_K into the blocked-ELL trace matrix)",
+                                    assemble_ms, (2 * 3 * b * b + 6 * b * b) * 8 * nf_loc, launches_timed=3)
+        kernels["k_forward"] = hbm(f"k_forward<{k}> + k_trace_rhs (forward elimination, recompute variant)", fwd_ms,
+                                   (6 + npp + nl) * 8 * nc_loc + (2 * nl // 3 + nl // 3) * 8 * nf_loc, launches_timed=10)
+        kernels["k_back"] = hbm(f"k_back<{k}> (back-substitution, recompute variant)", back_ms,
+                                (6 + npp + nl + na) * 8 * nc_loc, launches_timed=10)
+        # share of the step: launches per step (counted by the engine) x back-to-back launch time
+        counts = {"k_cg_spmv": per_step_launches.get("k_cg_spmv", 0.0),
+                  sweep_name: per_step_launches.get("k_tent_sweep32", 0.0) + per_step_launches.get("k_tent_sweep", 0.0),
+                  "k_fimpl": per_step_launches.get("k_fimpl", 0.0), "k_forward": per_step_launches.get("k_forward", 0.0),
+                  "k_back": per_step_launches.get("k_back", 0.0)}
+        for name, cnt in counts.items():
+            if "launch_ms" in kernels.get(name, {}):
+                kernels[name]["launches_per_step"] = cnt
+                kernels[name]["share_of_step"] = cnt * kernels[name]["launch_ms"] / ms_step
+        dominant = max((n_ for n_ in counts if "share_of_step" in kernels.get(n_, {})),
+                       key=lambda n_: kernels[n_]["share_of_step"])
+        roofline = dict(kernels[dominant])
+        roofline.setdefault("traffic", None)
+        roofline["selected_as"] = "largest share of the timed step among the probed kernels"
+        other = {n_: v for n_, v in kernels.items() if n_ != dominant}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu, _ = cpu_chorin_sample(args.cpu_nx, k, 1, mesh.nc)
+            cpu = cpu_baseline_sample(args, mesh.nc)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {**workload_config(args, world), "tuning": dict(getattr(eng, "tuning", {}))},
+            "config": {**workload_config(args, world), "tuning": dict(getattr(eng, "tuning", {})),
+                       "initial_guess": f"time-extrapolated (degree {args.warm_order}); cold-start figure under cold_start"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.prod(sQ)) * 8,
-                    "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps},
+                    "d2h_bytes_per_step": (int(np.prod(sQ)) + int(np.prod(sp_))) * 8, "steps": e2e_steps,
+                    "device_ms_per_step": e2e_ms / e2e_steps, "iterations": {kk: v for kk, v in its_e2e.items() if kk != "per_step_tentative_pressure"},
+                    "copies": "pinned host buffers, engine copy stream, overlapped with the solver (hdg_upload_begin / "
+                              "hdg_download_begin)", "host_result_absmax": e2e_probe},
             "gpu_launches": int(launches),
+            "gpu_launches_per_step_by_kernel": {kk: v for kk, v in sorted(per_step_launches.items(), key=lambda kv: -kv[1])[:24]},
             "cuda_graph_replays": int(eng.graph_replays),
             "warm_start_restarts": int(eng.guess_restarts),
             "roofline": roofline,
             "other_kernels": other,
             "cpu_baseline": cpu,
-            "iterations": {"trace_cg_per_solve": its_p, "tentative_bicgstab_per_solve": its_t,
-                           "per_step_tentative_pressure": ts.iteration_history},
+            "cold_start": cold,
+            "high_cfl": high,
+            "check": {"after_timed_region": check_main, "at_end": check_end},
+            "iterations": {"trace_cg_per_solve": its_main["trace_cg_per_solve"],
+                           "tentative_bicgstab_per_solve": its_main["tentative_per_solve"],
+                           "per_step_tentative_pressure": ts.iteration_history[:args.warmup + args.steps],
+                           "tentative_solver": {kk: st1[kk] - st0[kk] for kk in st1}},
             "comm": {**eng.comm_stats(), "transport": ("nvlink-p2p" if getattr(eng, "p2p", False) else "nccl")
                      if world > 1 else "none", "p2p_timeouts": eng.p2p_status()},
             "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
                                       ("bdm_projection", "tentative_velocity_solve", "forward_elimination",
                                        "trace_solve", "back_substitution")},
+            "setup": {"seconds": setup_s, "device_memory_gb": mem_used_gb},
         }
         print(json.dumps(line))
     if world > 1:
@@ -422,7 +540,13 @@ def main():
     ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--cpu-nx", type=int, default=16, help="mesh size of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = the same as --steps)")
+    ap.add_argument("--warm-order", type=int, default=3, help="degree of the time extrapolation of the initial guesses")
+    ap.add_argument("--cold-steps", type=int, default=2, help="extra steps with the reference's cold starts (0 = skip)")
+    ap.add_argument("--high-cfl-steps", type=int, default=1,
+                    help="extra steps at the reference's default dt (src/driver.py:80-86), reported under high_cfl")
+    ap.add_argument("--high-cfl-dt", type=float, default=0.04)
+    ap.add_argument("--high-cfl-maxit", type=int, default=3000, help="iteration budget of one tentative solve there")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the named nx x nx mesh partitioned over the GPUs (BASELINE.json configs[2]); "

@@ -95,6 +95,17 @@ int hdg_get_trace_matrix(hdg_handle h, double* val_host, int32_t* col_host);
  * be NULL (= zero).  Writes the solution (Q, p, l); *iters receives the Krylov iteration count
  * that the reference reads at hdg_imex.py:265-271.  shift != 0 additionally applies
  * _shift_pressure (hdg_imex.py:471-478).  Host buffers, AoS layout; synchronous. */
+/* Pipelined host transfers (the host-buffer route a PETSc Vec / numpy caller takes, `hdg_imex.py:257-272`, without
+ * stalling the solver): the copy runs on an engine-owned copy stream and overlaps the kernels of the compute stream.
+ * `slot` (0 or 1) selects one of two staging buffers per direction.  hdg_upload_begin starts host -> device and
+ * returns; hdg_upload_end orders the compute stream behind it and converts AoS -> SoA into dev_soa.
+ * hdg_download_begin converts SoA -> AoS on the compute stream, starts device -> host and returns; hdg_copy_wait blocks
+ * until all started transfers have completed.  Host buffers should be pinned. */
+int hdg_upload_begin(hdg_handle h, int kind, const double* host_aos, int slot);
+int hdg_upload_end(hdg_handle h, int kind, int slot, double* dev_soa);
+int hdg_download_begin(hdg_handle h, int kind, const double* dev_soa, double* host_aos, int slot);
+int hdg_copy_wait(hdg_handle h);
+
 int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l,
                            double* Q, double* p, double* l, double rtol, int maxit, int shift,
                            int* iters);
@@ -166,6 +177,11 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
  * advection-free operator whose facet Schur complement is inverted by `sweeps` Chebyshev /
  * facet-block-Jacobi sweeps (mesh-independent iteration counts; see csrc/hdg_tent.cuh). */
 int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps);
+/* Counters of the tentative-velocity solver since hdg_create: out6 = {solves, BiCGStab iterations, FGMRES iterations,
+ * fallbacks from BiCGStab to the restarted flexible GMRES (taken when BiCGStab stagnates, e.g. at the reference's
+ * default dt = 0.04, src/driver.py:80-86, where it solves with GMRES+ILU / LU, hdg_imex.py:224-228,
+ * hdg_implicit.py:126-129), failed true-residual verifications, FGMRES restart cycles}. */
+int hdg_tentative_stats(hdg_handle h, int64_t* out6);
 /* multi-GPU only.  local_sweeps == 0 (default): the ghost facets are refreshed before every Chebyshev
  * sweep of the facet Schur preconditioner, which reproduces the single-GPU iteration exactly.
  * local_sweeps != 0: the sweeps run without halo exchanges in between (restricted overlapping Schwarz
@@ -306,6 +322,9 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value);
 int hdg_graph_replays(hdg_handle h, int64_t* replays);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */
 int64_t hdg_launch_count(hdg_handle h);
+/* The same per kernel: "name=launches\n" lines (names without template arguments) written into buf (at most len
+ * bytes, NUL-terminated); returns the number of bytes the complete text needs. */
+int64_t hdg_kernel_counts(hdg_handle h, char* buf, int64_t len);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
-// Cell-block advection preconditioner of the tentative-velocity solve (experimental, off by default:
-// hdg_set_tuning("tent_cellblock", 1)).
+// Cell-block advection preconditioner of the tentative-velocity solve (default since round 2;
+// hdg_set_tuning("tent_cellblock", 0) switches it off).
 //
 // The facet-multiplier preconditioner of hdg_tent.cuh removes the stiff normal-jump penalty but leaves the
 // advection operator  I - a F0,  F0 = M^-1 f_impl(.;Q*) with alpha = 0  (hdg_imex.py:313-331), untouched;
@@ -104,9 +104,10 @@ __device__ __forceinline__ void advblock_build_cell(const double* __restrict__ x
 // FP64, which halves the bytes of the only HBM-bound kernel of this preconditioner.  Rounding the *entries* of C
 // only replaces C by a slightly different fixed matrix -- the preconditioner stays an exactly linear operator, so
 // right-preconditioned BiCGStab and the converged solution are unaffected (unlike FP32 *vectors*).
+// sK (optional): sK[cell] = tr(C_K) / N, the cell-wise scalar of the scaled Schur complement (hdg_tent.cuh)
 template <int N>
 __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* __restrict__ blk,
-                                                     float* __restrict__ blk32) {
+                                                     float* __restrict__ blk32, double* __restrict__ sK = nullptr) {
   double A[N * N];
   if constexpr (N <= 10) {
     HDG_UNROLL
@@ -131,6 +132,12 @@ __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* _
       blk[(size_t)i * nc + cell] = A[i];
       blk32[(size_t)i * nc + cell] = (float)A[i];
     }
+    if (sK) {
+      double tr = 0.0;
+      HDG_UNROLL
+      for (int i = 0; i < N; ++i) tr += A[i * N + i];
+      sK[cell] = tr / N;
+    }
   } else {
     for (int i = 0; i < N * N; ++i) A[i] = blk[(size_t)i * nc + cell];
     for (int p = 0; p < N; ++p) {
@@ -147,6 +154,11 @@ __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* _
     for (int i = 0; i < N * N; ++i) {
       blk[(size_t)i * nc + cell] = A[i];
       blk32[(size_t)i * nc + cell] = (float)A[i];
+    }
+    if (sK) {
+      double tr = 0.0;
+      for (int i = 0; i < N; ++i) tr += A[i * N + i];
+      sK[cell] = tr / N;
     }
   }
 }
@@ -186,9 +198,10 @@ __global__ void __launch_bounds__(128) k_advblock_build(const double* __restrict
 }
 
 template <int K>
-__global__ void __launch_bounds__(64) k_advblock_invert(int nc, double* __restrict__ blk, float* __restrict__ blk32) {
+__global__ void __launch_bounds__(64) k_advblock_invert(int nc, double* __restrict__ blk, float* __restrict__ blk32,
+                                                        double* __restrict__ sK) {
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x)
-    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32);
+    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32, sK);
 }
 
 template <int K>

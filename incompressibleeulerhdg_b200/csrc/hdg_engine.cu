@@ -22,7 +22,10 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hdg_b200.h"
@@ -51,6 +54,7 @@ struct GraphCache {
   cudaGraphExec_t exec = nullptr;
   std::vector<uint64_t> key;
   int64_t nlaunch = 0;  // kernels inside the graph (for hdg_launch_count)
+  std::vector<std::pair<const char*, int64_t>> by_kernel;  // ... per kernel (for hdg_kernel_counts)
 };
 
 struct hdg_engine {
@@ -96,8 +100,8 @@ struct hdg_engine {
   size_t bi_len = 0;
   // penalty-robust tentative-velocity solver (hdg_tent.cuh)
   int tent_mode = 1;          // 0 plain BiCGStab, 1 facet-multiplier formulation
-  int tent_sweeps = 8;        // Chebyshev sweeps on the facet Schur complement (8: fewest ms per solve in
-                              // the nx=512 probe, profiles/probe_params_r1e.jsonl)
+  int tent_sweeps = 4;        // Chebyshev sweeps on the facet Schur complement (4 with the cell blocks: fewest ms per
+                              // step at nx=1024, profiles/r2/bench_r2a_knob_ab.jsonl; 8 was the optimum without them)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
   int tune_sweep = 5;         // register-allocation variant of k_tent_sweep (hdg_set_tuning)
   int tune_tracer = 1;        // 1 = tracer advection from the compile-time tables, 0 = runtime tables
@@ -111,14 +115,31 @@ struct hdg_engine {
   double *tent_cm = nullptr;  // [3*NM][nc]
   double *tent_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // facet work [NM][nf]: t, nyx, mu, mu2, d
   double *tent_xh = nullptr, *tent_y = nullptr;  // [2*NQ1][nc]; [n_aug]
-  // experimental cell-block advection preconditioner (hdg_advblock.cuh); off unless hdg_set_tuning("tent_cellblock", 1)
-  int tune_cellblock = 0;
-  int tune_flex = 0;          // experimental flexible solution update of the tentative BiCGStab ("tent_flex")
-  int tune_fp32 = 0;          // experimental FP32-stored Schur sweep vectors ("tent_fp32"; needs tent_flex)
+  // cell-block advection preconditioner (hdg_advblock.cuh), flexible solution update and FP32-stored Schur sweep
+  // vectors: defaults since the round-2 A/B on a B200 (7.55 -> 9.88 timesteps/s at nx=1024, k=2, same results;
+  // profiles/r2/bench_r2a_knob_ab.jsonl); hdg_set_tuning("tent_cellblock" | "tent_flex" | "tent_fp32", 0) switches off
+  int tune_cellblock = 1;
+  int tune_flex = 1;          // flexible solution update of the tentative BiCGStab ("tent_flex")
+  int tune_fp32 = 1;          // FP32-stored Schur sweep vectors ("tent_fp32"; needs tent_flex)
   float *tent_f32[3] = {nullptr, nullptr, nullptr};  // facet work [NM][nf] in FP32: mu, mu2, d
   double *adv_blk = nullptr;  // [NQ1*NQ1][nc]  inverse cell-diagonal blocks of I - a F0(Q*) (FP64 work copy)
   float *adv_blk32 = nullptr; // [NQ1*NQ1][nc]  the same rounded to FP32: what k_advblock_apply reads
   double *adv_in = nullptr;   // [2*NQ1][nc]    C in_x
+  int tune_scaledx = 1;       // scaled facet Schur complement (k_tent_scale_tc, hdg_tent.cuh; "tent_scaledx"; needs the cell blocks)
+  double *adv_sK = nullptr;   // [nc]  tr(C_K) / NQ1
+  double *tent_cs = nullptr;  // [6][nf]  tc scaled by s_K of the cell on that side
+  double *tent_z = nullptr;   // [2*NQ1][nc]  xh + M^-1 N^T mu (velocity row of the augmented operator, scaled variant)
+  // robust path of the tentative solve: restarted flexible GMRES (run_fgmres), taken when BiCGStab stagnates
+  int tune_krylov = 0;        // 0 = BiCGStab, FGMRES as the fallback; 1 = BiCGStab only; 2 = FGMRES only ("tent_krylov")
+  int tune_gmres_m = 0;       // restart length ("tent_gmres_m"); 0 = automatic: what fits into 2 GB, between 30 and 200
+  int tune_bicg_cap = 150;    // BiCGStab iterations before the fallback ("tent_bicg_cap")
+  int tune_verify = 1;        // check the true residual b - A x after BiCGStab reports convergence ("tent_verify")
+  double bicg_failed_adt = -1.0;  // a dt for which BiCGStab has failed: later solves go straight to FGMRES
+  double *gm_V = nullptr, *gm_Z = nullptr, *gm_part = nullptr, *gm_red = nullptr, *gm_coef = nullptr;
+  double *gm_host = nullptr;  // pinned [m + 4]
+  int gm_m = 0;
+  size_t gm_n = 0, gm_nx = 0;
+  int64_t tent_stats[6] = {0, 0, 0, 0, 0, 0};  // solves, BiCGStab its, FGMRES its, fallbacks, failed verifications, FGMRES cycles
   // work vectors
   double *gK = nullptr;                                      // [NL][nc]
   double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
@@ -133,8 +154,16 @@ struct hdg_engine {
   size_t stage_bytes = 0;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // asynchronous host <-> device transfers on an engine-owned copy stream (hdg_upload_begin / hdg_download_begin):
+  // two staging slots per direction, ordered with the compute stream through events
+  cudaStream_t cstream = nullptr;
+  double* cstage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [direction 0 = h2d, 1 = d2h][slot]
+  size_t cstage_bytes[2][2] = {{0, 0}, {0, 0}};
+  cudaEvent_t cev_ready[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // staging slot filled
+  cudaEvent_t cev_done[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // staging slot consumed
   // bookkeeping
   int64_t launches = 0;
+  std::unordered_map<const char*, int64_t> kcount;  // launches per kernel, keyed by the LAUNCH macro's string literal
   std::string err;
   struct Timer {
     double ms = 0;
@@ -166,6 +195,7 @@ static std::string g_create_err;
   do {                                                           \
     kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);    \
     (h)->launches++;                                             \
+    (h)->kcount[#kernel]++;                                      \
   } while (0)
 
 static inline int cdiv(int64_t a, int b) { return (int)((a + b - 1) / b); }
@@ -403,6 +433,7 @@ static int run_graphed(hdg_engine* h, GraphCache& gc, const std::vector<uint64_t
     int rc = graph_launch(h, gc.exec);
     if (rc) return rc;
     h->launches += gc.nlaunch;
+    for (const auto& kv : gc.by_kernel) h->kcount[kv.first] += kv.second;
     h->graph_replays++;
     return HDG_OK;
   }
@@ -411,6 +442,7 @@ static int run_graphed(hdg_engine* h, GraphCache& gc, const std::vector<uint64_t
     gc.exec = nullptr;
   }
   const int64_t l0 = h->launches;
+  const std::unordered_map<const char*, int64_t> k0 = h->kcount;
   cudaStream_t user = h->stream;
   if (cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
     cudaGetLastError();
@@ -445,6 +477,12 @@ static int run_graphed(hdg_engine* h, GraphCache& gc, const std::vector<uint64_t
   }
   gc.key = key;
   gc.nlaunch = h->launches - l0;
+  gc.by_kernel.clear();
+  for (const auto& kv : h->kcount) {
+    auto it = k0.find(kv.first);
+    const int64_t d = kv.second - (it == k0.end() ? 0 : it->second);
+    if (d > 0) gc.by_kernel.emplace_back(kv.first, d);
+  }
   return graph_launch(h, gc.exec);
 }
 
@@ -853,14 +891,28 @@ static int tent_setup(hdg_engine* h) {
     }
     h->tent_f[2] = x;
     h->tent_f[3] = x2;
-    h->tent_lmax = lam;
+    // element-wise bound: valid for every positive cell weighting of X (scaled Schur complement, k_tent_scale_tc)
+    LAUNCH(h, k_tent_elem_bound<K>, cdiv(h->nc, 64), 64, h->cell_xy, h->nc, h->tent_cm);
+    std::vector<double> le(nc);
+    CUDA_TRY(h, cudaMemcpyAsync(le.data(), h->tent_cm, nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    double lelem = 0.0;
+    for (double v : le) lelem = std::max(lelem, v);
+    if (h->comm && h->comm->nranks > 1) {  // the same Chebyshev interval on every rank
+      CUDA_TRY(h, cudaMemcpyAsync(h->tent_cm, &lelem, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      NCCL_DO(h, g_nccl.AllReduce(h->tent_cm, h->tent_cm, 1, ncclDouble, ncclMax, h->comm->nccl, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(&lelem, h->tent_cm, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    // cheb_coefs puts the upper end of the interval at 1.1 lmax; the power iterations converge from below (3 % margin)
+    h->tent_lmax = std::max(lam, 1.03 * lelem / 1.1);
   }
   return HDG_OK;
 }
 
 // mu = Cheb_d(X)^-1 t ; returns the buffer that holds mu
 template <int K>
-static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* t) {
+static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* t, const double* tc) {
   std::vector<ChebCoef> cc;
   cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
   if (tent_fp32_active(h)) {
@@ -869,7 +921,7 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
     float *x = h->tent_f32[0], *x2 = h->tent_f32[1];
     for (int j = 0; j < h->tent_sweeps; ++j) {
       const bool last = j == h->tent_sweeps - 1;
-      LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha, t, (const float*)x,
+      LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, tc, h->tent_col, h->tent_bits, inv_aalpha, t, (const float*)x,
                      h->tent_f32[2], last ? (float*)nullptr : x2, last ? h->tent_f[2] : (double*)nullptr, cc[j].cd,
                      cc[j].cr, j == 0 ? 1 : 0);
       std::swap(x, x2);
@@ -884,7 +936,7 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
     // matrix (condition ~7 after block-Jacobi), its inverse decays geometrically across the overlap, so
     // the preconditioner is perturbed only at the partition cuts -- and it stays a fixed linear operator.
     if (j > 0 && !h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, x);
-    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, tc, h->tent_col, h->tent_bits,
            inv_aalpha, t, (const double*)nullptr, (const double*)x, h->tent_f[4], x2, cc[j].cd, cc[j].cr,
            j == 0 ? 1 : 0, 0);
     std::swap(x, x2);
@@ -909,11 +961,23 @@ static int run_sweep_probe(hdg_engine* h, double adt, int nrep, double* ms_per_l
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const int warm = 3;
+  const bool f32 = tent_fp32_active(h);  // the variant the solver runs: FP32-stored iterate / correction (default) or FP64
+  if (f32) {
+    for (int i = 0; i < 3; ++i) {
+      if (!h->tent_f32[i]) CUDA_TRY(h, dmalloc(&h->tent_f32[i], n));
+      CUDA_TRY(h, cudaMemsetAsync(h->tent_f32[i], 0, n * sizeof(float), h->stream));
+    }
+  }
   for (int i = 0; i < warm + nrep; ++i) {
     if (i == warm) cudaEventRecord(e0, h->stream);
-    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha,
-                 (const double*)h->tent_f[0], (const double*)nullptr, (const double*)h->tent_f[2], h->tent_f[4],
-                 h->tent_f[3], 0.3, 0.7, 0, 0);
+    if (f32)
+      LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha,
+                     (const double*)h->tent_f[0], (const float*)h->tent_f32[0], h->tent_f32[2], h->tent_f32[1],
+                     (double*)nullptr, 0.3, 0.7, 0);
+    else
+      LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits, inv_aalpha,
+                   (const double*)h->tent_f[0], (const double*)nullptr, (const double*)h->tent_f[2], h->tent_f[4],
+                   h->tent_f[3], 0.3, 0.7, 0, 0);
   }
   cudaEventRecord(e1, h->stream);
   cudaError_t err = cudaEventSynchronize(e1);
@@ -925,6 +989,164 @@ static int run_sweep_probe(hdg_engine* h, double adt, int nrep, double* ms_per_l
   CUDA_TRY(h, cudaGetLastError());
   *ms_per_launch = (double)ms / nrep;
   return HDG_OK;
+}
+
+// Restarted flexible GMRES on the augmented tentative-velocity system (kernels k_gm_* in hdg_krylov.cuh): the robust
+// path behind BiCGStab.  op(v, out, xh) applies A_aug Phat^-1 and leaves [Phat^-1 v]_x in xh; the solution is updated
+// from these stored directions, so the preconditioner may be any (even nonlinear, FP32-rounded) map.  Every cycle starts
+// from the true primal residual b - A x (resid), which is also the convergence test -- the reference's criterion
+// ||b - A x|| <= rtol ||b|| (hdg_imex.py:224-228, PETSc's default for its GMRES).  Host-driven: one stream
+// synchronisation per iteration for the Hessenberg column (the path is for hard systems, where an iteration is
+// milliseconds of device work).
+template <class Op, class Resid>
+static int run_fgmres(hdg_engine* h, size_t n, size_t nx, OwnMask own, const double* part_bb, Op op, Resid resid,
+                      double* x, double rtol, int maxit, int* iters) {
+  const int G = h->grid;
+  int m = h->tune_gmres_m;
+  if (m <= 0) m = (int)std::min<size_t>(200, std::max<size_t>(30, ((size_t)2 << 30) / ((n + nx) * sizeof(double))));
+  m = std::max(2, m);
+  if (h->gm_m < m || h->gm_n != n || h->gm_nx != nx) {
+    for (double** pbuf : {&h->gm_V, &h->gm_Z, &h->gm_part, &h->gm_coef}) {
+      if (*pbuf) cudaFree(*pbuf);
+      *pbuf = nullptr;
+    }
+    h->gm_m = 0;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+    // basis + directions may take at most 60 % of what is free
+    const size_t per_vec = (n + nx) * sizeof(double);
+    const int m_fit = (int)std::min<size_t>((size_t)m, (size_t)(0.6 * (double)free_b) / per_vec > 1 ? (size_t)(0.6 * (double)free_b) / per_vec - 1 : 0);
+    if (m_fit < 2) FAIL(h, HDG_ECUDA, "run_fgmres: not enough device memory for a Krylov basis");
+    m = m_fit;
+    CUDA_TRY(h, dmalloc(&h->gm_V, (size_t)(m + 1) * n));
+    CUDA_TRY(h, dmalloc(&h->gm_Z, (size_t)m * nx));
+    CUDA_TRY(h, dmalloc(&h->gm_part, (size_t)(m + 3) * G));
+    CUDA_TRY(h, dmalloc(&h->gm_coef, (size_t)(m + 3)));
+    if (h->gm_host) cudaFreeHost(h->gm_host);
+    CUDA_TRY(h, cudaMallocHost((void**)&h->gm_host, (size_t)(2 * m + 16) * sizeof(double)));
+    if (h->gm_red) cudaFree(h->gm_red);
+    CUDA_TRY(h, dmalloc(&h->gm_red, (size_t)(m + 8)));
+    h->gm_m = m;
+    h->gm_n = n;
+    h->gm_nx = nx;
+  }
+  m = std::min(m, h->gm_m);
+  double *V = h->gm_V, *Z = h->gm_Z, *part = h->gm_part, *red = h->gm_red, *host = h->gm_host;
+  Comm* c = h->comm;
+  const bool multi = c && c->nranks > 1;
+  const int S_WW = m + 1, S_NRM = m + 2;
+  // sums of the partials of slots [0, nslots) -> red (device), summed over the ranks
+  auto finish = [&](int first, int nslots) {
+    LAUNCH(h, k_part_finish, nslots, BLOCK, (const double*)(part + (size_t)first * G), G, red + first);
+    if (multi) NCCL_DO(h, g_nccl.AllReduce(red + first, red + first, (size_t)nslots, ncclDouble, ncclSum, c->nccl, h->stream));
+  };
+  std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+  int its = 0;
+  // ||b||^2 (partial sums left by the caller, already summed over the ranks)
+  LAUNCH(h, k_part_finish, 1, BLOCK, part_bb, G, red + m + 4);
+  CUDA_TRY(h, cudaMemcpyAsync(host + 1, red + m + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const double bb = host[1];
+  int rc = HDG_ENOCONV;
+  double prev_rr = -1.0;
+  bool prev_est_conv = false;
+  while (true) {
+    h->tent_stats[5]++;
+    // v_0 = (b - A x, 0) / beta
+    double rr = 0.0;
+    int r0 = resid(V, &rr);
+    if (r0) return r0;
+    if (!std::isfinite(rr)) FAIL(h, HDG_ENOCONV, "run_fgmres: the residual is not finite");
+    const double beta = std::sqrt(rr);
+    if (rr <= rtol * rtol * bb) {
+      rc = HDG_OK;
+      break;
+    }
+    // round-off floor of the true residual (eps times the penalty stiffness a alpha / h^2, which can exceed rtol): the
+    // recurrence of the previous cycle met rtol, the true residual is within 100 rtol and no longer decreases
+    if (prev_est_conv && rr >= 0.25 * prev_rr && rr <= 1e4 * rtol * rtol * bb) {
+      rc = HDG_OK;
+      break;
+    }
+    prev_rr = rr;
+    prev_est_conv = false;
+    if (its >= maxit) break;
+    CUDA_TRY(h, cudaMemsetAsync(V + nx, 0, (n - nx) * sizeof(double), h->stream));
+    // resid left ||r||^2 in red[0]
+    LAUNCH(h, k_gm_scale, G, BLOCK, nx, V, (const double*)red, 0);
+    std::fill(g.begin(), g.end(), 0.0);
+    g[0] = beta;
+    int jj = 0;
+    for (int j = 0; j < m; ++j) {
+      double* w = V + (size_t)(j + 1) * n;
+      op(V + (size_t)j * n, w, Z + (size_t)j * nx);
+      double nrm2 = 0.0, ww = 0.0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int i0 = 0; i0 <= j; i0 += GM_CHUNK) {
+          const int cnt = std::min(GM_CHUNK, j + 1 - i0);
+          LAUNCH(h, k_gm_dots, G, BLOCK, n, own, (const double*)w, (const double*)V, n, i0, cnt, i0 == 0 ? S_WW : -1, part);
+        }
+        finish(0, j + 1);
+        finish(S_WW, 1);
+        for (int i0 = 0; i0 <= j; i0 += GM_CHUNK) {
+          const int cnt = std::min(GM_CHUNK, j + 1 - i0);
+          LAUNCH(h, k_gm_axpy, G, BLOCK, n, own, w, (const double*)V, n, i0, cnt, (const double*)red,
+                 i0 + cnt == j + 1 ? S_NRM : -1, part);
+        }
+        finish(S_NRM, 1);
+        CUDA_TRY(h, cudaMemcpyAsync(host + 2, red, (size_t)(m + 3) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->comm_rc) return h->comm_rc;
+        for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = (pass == 0 ? 0.0 : H[(size_t)i * m + j]) + host[2 + i];
+        ww = host[2 + S_WW];
+        nrm2 = host[2 + S_NRM];
+        // classical Gram-Schmidt, repeated once when more than half of the vector was cancelled (DGKS criterion)
+        if (pass == 0 && nrm2 >= 0.5 * ww) break;
+      }
+      ++its;
+      const double hn = std::sqrt(std::max(nrm2, 0.0));
+      H[(size_t)(j + 1) * m + j] = hn;
+      // Givens rotations on the new column
+      for (int i = 0; i < j; ++i) {
+        const double a0 = H[(size_t)i * m + j], a1 = H[(size_t)(i + 1) * m + j];
+        H[(size_t)i * m + j] = cs[i] * a0 + sn[i] * a1;
+        H[(size_t)(i + 1) * m + j] = -sn[i] * a0 + cs[i] * a1;
+      }
+      {
+        const double a0 = H[(size_t)j * m + j], a1 = H[(size_t)(j + 1) * m + j];
+        const double d = std::hypot(a0, a1);
+        cs[j] = d > 0.0 ? a0 / d : 1.0;
+        sn[j] = d > 0.0 ? a1 / d : 0.0;
+        H[(size_t)j * m + j] = d;
+        H[(size_t)(j + 1) * m + j] = 0.0;
+        g[j + 1] = -sn[j] * g[j];
+        g[j] = cs[j] * g[j];
+      }
+      jj = j + 1;
+      const double est = std::fabs(g[j + 1]);
+      if (!std::isfinite(est)) FAIL(h, HDG_ENOCONV, "run_fgmres: breakdown (non-finite Hessenberg entry)");
+      if (est * est <= rtol * rtol * bb) {
+        prev_est_conv = true;
+        break;
+      }
+      if (its >= maxit || hn <= 1e-300) break;
+      if (j + 1 < m) LAUNCH(h, k_gm_scale, G, BLOCK, n, w, (const double*)red, S_NRM);
+    }
+    // y = H^-1 g (upper triangular), x += Z y
+    for (int i = jj - 1; i >= 0; --i) {
+      double v = g[i];
+      for (int l = i + 1; l < jj; ++l) v -= H[(size_t)i * m + l] * y[l];
+      y[i] = v / H[(size_t)i * m + i];
+    }
+    for (int i = 0; i < jj; ++i) host[2 + i] = y[i];
+    CUDA_TRY(h, cudaMemcpyAsync(h->gm_coef, host + 2, (size_t)jj * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int j0 = 0; j0 < jj; j0 += GM_CHUNK)
+      LAUNCH(h, k_gm_update, G, BLOCK, nx, x, (const double*)Z, nx, j0, std::min(GM_CHUNK, jj - j0),
+             (const double*)h->gm_coef);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // host + 2 is rewritten by the next cycle
+  }
+  if (iters) *iters = its;
+  return rc;
 }
 
 template <int K>
@@ -975,8 +1197,19 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
       LAUNCH(h, (k_advblock_build<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
     else
       LAUNCH(h, (k_advblock_build<K, false>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
-    LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk, h->adv_blk32);
+    if (!h->adv_sK) CUDA_TRY(h, dmalloc(&h->adv_sK, (size_t)h->nc));
+    LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk, h->adv_blk32, h->adv_sK);
   }
+  // scaled facet Schur complement (hdg_tent.cuh): the sweeps run on tc * s_K, xhat subtracts s_K M^-1 N^T mu
+  const bool scaledx = cellblock && h->tune_scaledx != 0;
+  if (scaledx) {
+    if (!h->tent_cs) CUDA_TRY(h, dmalloc(&h->tent_cs, 6 * (size_t)h->nf));
+    if (!h->tent_z) CUDA_TRY(h, dmalloc(&h->tent_z, nx));
+    halo_exchange(h, PLAN_CELLS, 1, h->adv_sK);
+    LAUNCH(h, k_tent_scale_tc, cdiv(h->nf, 256), 256, h->nf, h->facet_cell, h->tent_c, h->adv_sK, h->tent_cs);
+  }
+  const double* tcx = scaledx ? h->tent_cs : h->tent_c;
+  const double* sKx = scaledx ? h->adv_sK : (const double*)nullptr;
   // x part of the vector the multiplier preconditioner sees: C in_x (cell-local, so it is applied before the
   // ghost refresh inside precond_x) or in_x itself
   auto scaled_x = [&](const double* in) -> const double* {
@@ -993,39 +1226,106 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     LAUNCH(h, k_tent_moments<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->nc, in, h->tent_cm);
     LAUNCH(h, k_tent_trhs<K>, fgrid, 256, h->tent_cm, h->facet_cell, h->facet_local, h->nc, h->nf, in_mu, h->tent_f[0],
            h->tent_f[1]);
-    return tent_schur_solve<K>(h, inv_aalpha, h->tent_f[0]);
+    return tent_schur_solve<K>(h, inv_aalpha, h->tent_f[0], tcx);
   };
-  auto op = [&](const double* vin, double* out) {
+  // out = A_aug Phat^-1 vin; xh receives [Phat^-1 vin]_x (length nx)
+  auto op = [&](const double* vin, double* out, double* xh) {
     const double* in = scaled_x(vin);
     double* mu = precond_x(in, vin + nx);
-    LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, in, mu, h->tent_xh, 0);
+    LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, in, mu, xh, 0, sKx,
+           scaledx ? h->tent_z : (double*)nullptr);
     {
       ScopedTimer tf(h, T_FIMPL);
-      launch_fimpl<K>(h, upwind, Qstar, h->tent_xh, 1.0, -adt, out, in, 0.0);  // out_x = in_x - a F0(xhat)
+      // out_x = (I - a F0) xh + M^-1 N^T mu = z - a F0(xh),  z = xh + M^-1 N^T mu (= in_x without the scaling)
+      launch_fimpl<K>(h, upwind, Qstar, xh, 1.0, -adt, out, scaledx ? (const double*)h->tent_z : in, 0.0);
     }
     // out_mu = N in_x - X mu
-    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, h->tent_c, h->tent_col, h->tent_bits,
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, tcx, h->tent_col, h->tent_bits,
            inv_aalpha, (const double*)h->tent_f[1], (const double*)nullptr, (const double*)mu, (double*)nullptr,
            out + nx, 0.0, 0.0, 0, 1);
   };
-  double* y = h->tent_y;
-  CUDA_TRY(h, cudaMemsetAsync(y, 0, n * sizeof(double), h->stream));
   std::vector<uint64_t> key = {2ull, key_of(Qstar), key_of(adt), (uint64_t)upwind, key_of(h->alpha),
                                (uint64_t)h->tent_sweeps, (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax),
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
                                key_of(h->adv_blk32), key_of(h->adv_in), (uint64_t)tent_fp32_active(h),
-                               key_of(h->tent_f32[0]), key_of(h->tent_f32[1]), key_of(h->tent_f32[2])};
-  // experimental ("tent_flex"): accumulate x from the preconditioned directions op leaves in tent_xh; x holds the
-  // initial guess (or zero) on entry, so no recovery step follows
+                               key_of(h->tent_f32[0]), key_of(h->tent_f32[1]), key_of(h->tent_f32[2]),
+                               (uint64_t)scaledx, key_of(tcx), key_of(sKx), key_of(h->tent_z)};
+  // true residual of the primal system:  out_r (length nx, may be null) = b - A x ; returns ||.||^2 over the owned cells
+  // in *rr (host).  The augmented residual the Krylov loops monitor bounds it only up to the penalty stiffness.
+  auto true_residual = [&](double* out_r, double* rr) -> int {
+    halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, x);
+    launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
+    LAUNCH(h, k_resid_norm, G, BLOCK, nx, mask_cells(h, 2 * Dims<K>::NQ1), b, (const double*)h->bi[5], out_r, h->partial);
+    allreduce_slots(h, h->partial, 1);
+    LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)h->partial, G, h->gm_red);
+    CUDA_TRY(h, cudaMemcpyAsync(h->gm_host, h->gm_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *rr = h->gm_host[0];
+    return HDG_OK;
+  };
+  if (!h->gm_red) {
+    CUDA_TRY(h, dmalloc(&h->gm_red, 8));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->gm_host, 8 * sizeof(double)));
+  }
+  h->tent_stats[0]++;
+  if (iters) *iters = 0;
+  // ||b||^2 for the host-side tests
+  LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)part_bb, G, h->gm_red);
+  CUDA_TRY(h, cudaMemcpyAsync(h->gm_host + 1, h->gm_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   const bool flex = h->tune_flex != 0;
-  int brc = bicgstab_loop(h, n, own, op, key, y, part_bb, rtol, maxit, iters, flex ? h->tent_xh : (const double*)nullptr,
-                          flex ? x : (double*)nullptr, flex ? nx : 0);
-  if (brc == HDG_ECUDA || flex) return brc;
-  // x += [Phat^-1 y]_x
-  const double* yx = scaled_x(y);
-  double* mu = precond_x(yx, y + nx);
-  LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, yx, mu, x, 1);
-  return brc;
+  bool converged = false;
+  int its_total = 0;
+  const bool try_bicg = h->tune_krylov != 2 && h->bicg_failed_adt != adt;
+  if (try_bicg) {
+    double* y = h->tent_y;
+    if (!flex) CUDA_TRY(h, cudaMemsetAsync(y, 0, n * sizeof(double), h->stream));
+    auto op2 = [&](const double* vin, double* out) { op(vin, out, h->tent_xh); };
+    const int cap = h->tune_krylov == 1 ? maxit : std::min(maxit, h->tune_bicg_cap);
+    int its_b = 0;
+    // flexible update (default): x is accumulated from the preconditioned directions op leaves in tent_xh; x holds the
+    // initial guess (or zero) on entry, so no recovery step follows
+    int brc = bicgstab_loop(h, n, own, op2, key, y, part_bb, rtol, cap, &its_b, flex ? h->tent_xh : (const double*)nullptr,
+                            flex ? x : (double*)nullptr, flex ? nx : 0);
+    if (brc == HDG_ECUDA) return brc;
+    its_total += its_b;
+    h->tent_stats[1] += its_b;
+    if (!flex) {  // x += [Phat^-1 y]_x
+      const double* yx = scaled_x(y);
+      double* mu = precond_x(yx, y + nx);
+      LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, yx, mu, x, 1, sKx);
+    }
+    converged = brc == HDG_OK;
+    if (converged && h->tune_verify && h->tune_krylov != 1) {
+      double rr = 0.0;
+      int vrc = true_residual(nullptr, &rr);
+      if (vrc) return vrc;
+      const double bb = h->gm_host[1];
+      // the recurrence residual of the augmented system met rtol; accept a true primal residual within 10 rtol
+      if (!(rr <= 100.0 * rtol * rtol * bb)) {
+        converged = false;
+        h->tent_stats[4]++;
+        if (!std::isfinite(rr) || rr > bb) CUDA_TRY(h, cudaMemsetAsync(x, 0, nx * sizeof(double), h->stream));
+      }
+    } else if (!converged && h->tune_krylov != 1) {
+      double rr = 0.0;
+      int vrc = true_residual(nullptr, &rr);
+      if (vrc) return vrc;
+      if (!std::isfinite(rr) || rr > h->gm_host[1]) CUDA_TRY(h, cudaMemsetAsync(x, 0, nx * sizeof(double), h->stream));
+    }
+    if (!converged && h->tune_krylov != 1) {
+      h->tent_stats[3]++;
+      h->bicg_failed_adt = adt;
+    }
+  }
+  int rc_final = converged ? HDG_OK : HDG_ENOCONV;
+  if (!converged && h->tune_krylov != 1 && its_total < maxit) {
+    int its_g = 0;
+    rc_final = run_fgmres(h, n, nx, own, (const double*)part_bb, op, true_residual, x, rtol, maxit - its_total, &its_g);
+    its_total += its_g;
+    h->tent_stats[2] += its_g;
+  }
+  if (iters) *iters = its_total;
+  return rc_final;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1320,7 +1620,7 @@ int hdg_destroy(hdg_handle h) {
                   h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
                   h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
                   h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in, h->tent_f32[0], h->tent_f32[1],
-                  h->tent_f32[2]};
+                  h->tent_f32[2], h->adv_sK, h->tent_cs, h->tent_z, h->gm_V, h->gm_Z, h->gm_part, h->gm_red, h->gm_coef};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg})
@@ -1345,6 +1645,14 @@ int hdg_destroy(hdg_handle h) {
   if (h->scal_host) cudaFreeHost(h->scal_host);
   if (h->bscal_host) cudaFreeHost(h->bscal_host);
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->gm_host) cudaFreeHost(h->gm_host);
+  for (int d = 0; d < 2; ++d)
+    for (int sl = 0; sl < 2; ++sl) {
+      if (h->cstage[d][sl]) cudaFree(h->cstage[d][sl]);
+      if (h->cev_ready[d][sl]) cudaEventDestroy(h->cev_ready[d][sl]);
+      if (h->cev_done[d][sl]) cudaEventDestroy(h->cev_done[d][sl]);
+    }
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   for (int i = 0; i < T_COUNT; ++i) flush_timer(h, i);
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1789,6 +2097,82 @@ int hdg_download(hdg_handle h, int kind, const double* dev_soa, double* host_aos
   return HDG_OK;
 }
 
+// ---- pipelined host transfers ----------------------------------------------------------------------------------
+// The copies run on the engine's copy stream and overlap the solver kernels of the compute stream; `slot` (0 / 1)
+// selects one of two staging buffers per direction, so that the transfer of step n + 1 can be in flight while
+// step n computes.  Host buffers must be pinned for the overlap to happen (pageable memory still works, serialised).
+static int copy_slot(hdg_engine* h, int dir, int slot, size_t bytes) {
+  if (!h->cstream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+  if (!h->cev_ready[dir][slot]) {
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->cev_ready[dir][slot], cudaEventDisableTiming));
+    CUDA_TRY(h, cudaEventCreateWithFlags(&h->cev_done[dir][slot], cudaEventDisableTiming));
+  }
+  if (h->cstage_bytes[dir][slot] < bytes) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->cstream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->cstage[dir][slot]) cudaFree(h->cstage[dir][slot]);
+    h->cstage[dir][slot] = nullptr;
+    h->cstage_bytes[dir][slot] = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->cstage[dir][slot], bytes));
+    h->cstage_bytes[dir][slot] = bytes;
+  }
+  return HDG_OK;
+}
+
+// start the host -> device copy of an AoS field into staging slot `slot` (returns at once)
+int hdg_upload_begin(hdg_handle h, int kind, const double* host_aos, int slot) {
+  if (!h || !host_aos || slot < 0 || slot > 1) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  if (field_len(h, kind, n, ent, ndof)) FAIL(h, HDG_EINVAL, "hdg_upload_begin: bad kind");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = copy_slot(h, 0, slot, n * sizeof(double));
+  if (rc) return rc;
+  // the previous user of the slot (a conversion kernel on the compute stream) must be through
+  CUDA_TRY(h, cudaStreamWaitEvent(h->cstream, h->cev_done[0][slot], 0));
+  CUDA_TRY(h, cudaMemcpyAsync(h->cstage[0][slot], host_aos, n * sizeof(double), cudaMemcpyHostToDevice, h->cstream));
+  CUDA_TRY(h, cudaEventRecord(h->cev_ready[0][slot], h->cstream));
+  return HDG_OK;
+}
+
+// make the compute stream wait for that copy and convert the staging slot into the SoA device field
+int hdg_upload_end(hdg_handle h, int kind, int slot, double* dev_soa) {
+  if (!h || !dev_soa || slot < 0 || slot > 1 || !h->cstage[0][slot]) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  if (field_len(h, kind, n, ent, ndof)) FAIL(h, HDG_EINVAL, "hdg_upload_end: bad kind");
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->cev_ready[0][slot], 0));
+  LAUNCH(h, k_aos_to_soa, h->grid, BLOCK, (const double*)h->cstage[0][slot], dev_soa, ent, ndof);
+  CUDA_TRY(h, cudaEventRecord(h->cev_done[0][slot], h->stream));
+  return HDG_OK;
+}
+
+// convert an SoA device field into staging slot `slot` on the compute stream and start its device -> host copy on
+// the copy stream (returns at once; the field may be overwritten by later work on the compute stream)
+int hdg_download_begin(hdg_handle h, int kind, const double* dev_soa, double* host_aos, int slot) {
+  if (!h || !dev_soa || !host_aos || slot < 0 || slot > 1) return HDG_EINVAL;
+  int64_t n;
+  int ent, ndof;
+  if (field_len(h, kind, n, ent, ndof)) FAIL(h, HDG_EINVAL, "hdg_download_begin: bad kind");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int rc = copy_slot(h, 1, slot, n * sizeof(double));
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->cev_done[1][slot], 0));  // the slot's previous copy has left
+  LAUNCH(h, k_soa_to_aos, h->grid, BLOCK, dev_soa, h->cstage[1][slot], ent, ndof);
+  CUDA_TRY(h, cudaEventRecord(h->cev_ready[1][slot], h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->cstream, h->cev_ready[1][slot], 0));
+  CUDA_TRY(h, cudaMemcpyAsync(host_aos, h->cstage[1][slot], n * sizeof(double), cudaMemcpyDeviceToHost, h->cstream));
+  CUDA_TRY(h, cudaEventRecord(h->cev_done[1][slot], h->cstream));
+  return HDG_OK;
+}
+
+// block the host until every transfer started with hdg_upload_begin / hdg_download_begin has completed
+int hdg_copy_wait(hdg_handle h) {
+  if (!h) return HDG_EINVAL;
+  if (h->cstream) CUDA_TRY(h, cudaStreamSynchronize(h->cstream));
+  return HDG_OK;
+}
+
 int hdg_poisson_apply_host(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
                            double* p, double* l, double rtol, int maxit, int shift, int* iters) {
   if (!h || !Q || !p || !l) return HDG_EINVAL;
@@ -1843,6 +2227,27 @@ int hdg_reset_timers(hdg_handle h) {
 
 int64_t hdg_launch_count(hdg_handle h) { return h ? h->launches : 0; }
 
+// "kernel=launches\n" lines, kernel names without template arguments; returns the number of bytes needed
+int64_t hdg_kernel_counts(hdg_handle h, char* buf, int64_t len) {
+  if (!h) return 0;
+  std::map<std::string, int64_t> merged;
+  for (const auto& kv : h->kcount) {
+    std::string name(kv.first);
+    size_t a = name.find_first_not_of("( ");
+    name = name.substr(a == std::string::npos ? 0 : a);
+    size_t b = name.find_first_of("<) ");
+    merged[name.substr(0, b)] += kv.second;
+  }
+  std::string out;
+  for (const auto& kv : merged) out += kv.first + "=" + std::to_string(kv.second) + "\n";
+  if (buf && len > 0) {
+    const size_t ncopy = std::min<size_t>(out.size(), (size_t)len - 1);
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
+
 // ---- velocity side ------------------------------------------------------------------------------
 int hdg_set_penalty(hdg_handle h, double alpha) {
   if (!h || !(alpha >= 0)) return HDG_EINVAL;
@@ -1883,6 +2288,31 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
       cudaGraphExecDestroy(h->g_bicg.exec);
       h->g_bicg.exec = nullptr;
     }
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_scaledx")) {
+    h->tune_scaledx = value != 0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_krylov")) {
+    if (value < 0 || value > 2) return HDG_EINVAL;
+    h->tune_krylov = value;
+    h->bicg_failed_adt = -1.0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_gmres_m")) {
+    if (value < 0 || value == 1 || value > 1000) return HDG_EINVAL;
+    h->tune_gmres_m = value;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_bicg_cap")) {
+    if (value < 1) return HDG_EINVAL;
+    h->tune_bicg_cap = value;
+    h->bicg_failed_adt = -1.0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_verify")) {
+    h->tune_verify = value != 0;
     return HDG_OK;
   }
   if (!strcmp(name, "tracer_tables")) {
@@ -1931,6 +2361,12 @@ int hdg_set_initial_guess(hdg_handle h, int on) {
   return HDG_OK;
 }
 
+int hdg_tentative_stats(hdg_handle h, int64_t* out6) {
+  if (!h || !out6) return HDG_EINVAL;
+  for (int i = 0; i < 6; ++i) out6[i] = h->tent_stats[i];
+  return HDG_OK;
+}
+
 int hdg_set_tentative_comm(hdg_handle h, int local_sweeps) {
   if (!h) return HDG_EINVAL;
   h->tent_local_sweeps = local_sweeps != 0;
@@ -1938,9 +2374,9 @@ int hdg_set_tentative_comm(hdg_handle h, int local_sweeps) {
 }
 
 int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps) {
-  if (!h || mode < 0 || mode > 1 || sweeps < 1 || sweeps > 64) return HDG_EINVAL;
+  if (!h || mode < 0 || mode > 1 || sweeps > 64) return HDG_EINVAL;
   h->tent_mode = mode;
-  h->tent_sweeps = sweeps;
+  if (sweeps > 0) h->tent_sweeps = sweeps;  // <= 0: keep the current number of sweeps
   return HDG_OK;
 }
 

@@ -541,3 +541,99 @@ __global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Restarted flexible GMRES for the tentative-velocity system: the robust path, taken when BiCGStab stagnates or breaks
+// down (large CFL numbers: the reference's default dt = 0.04, src/driver.py:80-86, is CFL 10 - 40 on the benchmark
+// meshes; it hands the system to GMRES+ILU, hdg_imex.py:224-228, or a direct LU, hdg_implicit.py:126-129).
+// Classical Gram-Schmidt in chunks of GM_CHUNK basis vectors per pass over w; all reductions two-stage with a fixed
+// tree, finished per slot by k_part_finish (hdg_comm.cuh).  The small Hessenberg least-squares problem lives on the host.
+// ------------------------------------------------------------------------------------------------
+constexpr int GM_CHUNK = 8;
+
+// part[(i0 + c) G + block] = sum_owned w V_{i0+c},  c < cnt <= GM_CHUNK;  ww_slot >= 0: part[ww_slot G + block] = sum w w
+__global__ void __launch_bounds__(BLOCK) k_gm_dots(size_t n, OwnMask own, const double* __restrict__ w,
+                                                   const double* __restrict__ V, size_t ldv, int i0, int cnt,
+                                                   int ww_slot, double* __restrict__ part) {
+  double acc[GM_CHUNK], ww = 0.0;
+  HDG_UNROLL
+  for (int c = 0; c < GM_CHUNK; ++c) acc[c] = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (!is_owned(own, i)) continue;
+    const double wi = w[i];
+    ww = fma(wi, wi, ww);
+    HDG_UNROLL
+    for (int c = 0; c < GM_CHUNK; ++c)
+      if (c < cnt) acc[c] = fma(wi, V[(size_t)(i0 + c) * ldv + i], acc[c]);
+  }
+  HDG_UNROLL
+  for (int c = 0; c < GM_CHUNK; ++c) {
+    if (c < cnt) {  // cnt is uniform over the grid: every thread reaches the barriers of block_reduce
+      double s = block_reduce(acc[c]);
+      if (threadIdx.x == 0) part[(size_t)(i0 + c) * gridDim.x + blockIdx.x] = s;
+    }
+  }
+  if (ww_slot >= 0) {
+    ww = block_reduce(ww);
+    if (threadIdx.x == 0) part[(size_t)ww_slot * gridDim.x + blockIdx.x] = ww;
+  }
+}
+
+// w -= sum_{c < cnt} coef[i0 + c] V_{i0+c};  norm_slot >= 0: part[norm_slot G + block] = sum_owned w_new^2
+__global__ void __launch_bounds__(BLOCK) k_gm_axpy(size_t n, OwnMask own, double* __restrict__ w,
+                                                   const double* __restrict__ V, size_t ldv, int i0, int cnt,
+                                                   const double* __restrict__ coef, int norm_slot,
+                                                   double* __restrict__ part) {
+  double h[GM_CHUNK];
+  HDG_UNROLL
+  for (int c = 0; c < GM_CHUNK; ++c) h[c] = c < cnt ? coef[i0 + c] : 0.0;
+  double nn = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    HDG_UNROLL
+    for (int c = 0; c < GM_CHUNK; ++c)
+      if (c < cnt) wi = fma(-h[c], V[(size_t)(i0 + c) * ldv + i], wi);
+    w[i] = wi;
+    if (is_owned(own, i)) nn = fma(wi, wi, nn);
+  }
+  if (norm_slot >= 0) {
+    nn = block_reduce(nn);
+    if (threadIdx.x == 0) part[(size_t)norm_slot * gridDim.x + blockIdx.x] = nn;
+  }
+}
+
+// w *= 1 / sqrt(red[slot])   (red: finished sums, k_part_finish)
+__global__ void __launch_bounds__(BLOCK) k_gm_scale(size_t n, double* __restrict__ w, const double* __restrict__ red,
+                                                    int slot) {
+  const double s = 1.0 / sqrt(red[slot]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i] *= s;
+}
+
+// x += sum_{c < cnt} y[j0 + c] Z_{j0+c}   (solution update from the stored preconditioned directions)
+__global__ void __launch_bounds__(BLOCK) k_gm_update(size_t n, double* __restrict__ x, const double* __restrict__ Z,
+                                                     size_t ldz, int j0, int cnt, const double* __restrict__ y) {
+  double c_[GM_CHUNK];
+  HDG_UNROLL
+  for (int c = 0; c < GM_CHUNK; ++c) c_[c] = c < cnt ? y[j0 + c] : 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double xi = x[i];
+    HDG_UNROLL
+    for (int c = 0; c < GM_CHUNK; ++c)
+      if (c < cnt) xi = fma(c_[c], Z[(size_t)(j0 + c) * ldz + i], xi);
+    x[i] = xi;
+  }
+}
+
+// r = b - t (r may be null: norm only); part[block] = sum_owned (b - t)^2
+__global__ void __launch_bounds__(BLOCK) k_resid_norm(size_t n, OwnMask own, const double* __restrict__ b,
+                                                      const double* __restrict__ t, double* __restrict__ r,
+                                                      double* __restrict__ part) {
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = b[i] - t[i];
+    if (r) r[i] = v;
+    if (is_owned(own, i)) s = fma(v, v, s);
+  }
+  s = block_reduce(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}

@@ -323,16 +323,22 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
   }
 }
 
-// xh = y - M^-1 N^T mu   (mode 0)   or   xh += y - M^-1 N^T mu   (mode 1, final recovery)
+// xh = y - s_K M^-1 N^T mu   (mode 0)   or   xh += y - s_K M^-1 N^T mu   (mode 1, final recovery);
+// sK (optional) = the per-cell scalar of the scaled Schur complement (k_tent_scale_tc), 1 if null.
+// Zout (optional, mode 0) = xh + M^-1 N^T mu = y + (1 - s_K) M^-1 N^T mu: what the velocity row of the augmented
+// operator adds to -a F0(xh)  (with s_K = 1 this is y itself and the caller passes y instead).
 template <int K>
 __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy, const int* __restrict__ flip,
                                                    const int* __restrict__ cell_facet, int nc, int nf,
                                                    const double* __restrict__ Y, const double* __restrict__ mu,
-                                                   double* __restrict__ Xh, int mode) {
+                                                   double* __restrict__ Xh, int mode,
+                                                   const double* __restrict__ sK = nullptr,
+                                                   double* __restrict__ Zout = nullptr) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NM = TentDims<K>::NM;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     Geo g = make_geo(xy, nc, cell);
+    const double sk = sK ? sK[cell] : 1.0;
     double a0[NQ1], a1[NQ1];
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i) a0[i] = a1[i] = 0.0;
@@ -357,7 +363,12 @@ __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i) {
       size_t i0 = (size_t)i * nc + cell, i1 = (size_t)(NQ1 + i) * nc + cell;
-      double v0 = Y[i0] - a0[i], v1 = Y[i1] - a1[i];
+      const double y0 = Y[i0], y1 = Y[i1];
+      double v0 = fma(-sk, a0[i], y0), v1 = fma(-sk, a1[i], y1);
+      if (Zout) {
+        Zout[i0] = v0 + a0[i];
+        Zout[i1] = v1 + a1[i];
+      }
       if (mode == 1) {
         v0 += Xh[i0];
         v1 += Xh[i1];
@@ -365,5 +376,88 @@ __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy
       Xh[i0] = v0;
       Xh[i1] = v1;
     }
+  }
+}
+
+// Scaled facet Schur complement.  With the cell-block advection preconditioner C = blockdiag(I - a F0)^-1
+// (hdg_advblock.cuh) the exact Schur complement of the block preconditioner [[C^-1, M^-1 N^T], [N, -1/(a alpha)]] is
+// 1/(a alpha) + N C M^-1 N^T, which is no longer a table times a geometric scalar.  Replacing C by its cell-wise mean
+// diagonal  s_K = tr(C_K) / NQ1  inside the Schur complement and in the back-substitution keeps the structure of X --
+// the same sweep kernel runs on rescaled coefficients tcs = tc * s_K -- and still carries the bulk of the effect: in a
+// dense model of the augmented system (k = 2, 72 cells) FGMRES needs 62 / 110 / 302 / 640 applications at CFL
+// 0.32 / 1 / 4 / 10, against 74 / 182 / 724 / > 1500 with the unscaled X and 46 / 77 / 196 / 361 with the exact
+// combined operator.  The operator row  out_mu = N xh - mu / (a alpha)  stays exact, because xh is formed with the
+// same s_K (k_tent_xhat) and the residual sweep runs on the same tcs.
+__global__ void k_tent_scale_tc(int nf, const int* __restrict__ facet_cell, const double* __restrict__ tc,
+                                const double* __restrict__ sK, double* __restrict__ tcs) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
+    for (int s = 0; s < 2; ++s) {
+      const int cell = facet_cell[(size_t)s * nf + f];
+      const double w = cell >= 0 ? sK[cell] : 0.0;
+      for (int j = 0; j < 3; ++j) tcs[(size_t)(3 * s + j) * nf + f] = w * tc[(size_t)(3 * s + j) * nf + f];
+    }
+  }
+}
+
+// lam[cell] = lambda_max( blockdiag(G_K)^-1 G_K )  of the element matrix G_K = N_K M_K^-1 N_K^T (3 x 3 blocks of
+// NM x NM, block (e, e') = (n_e . n_e') / detJ GG(e, e')), by power iteration.  For any positive cell weights w_K the
+// facet-block-Jacobi preconditioned  1/(a alpha) + sum_K w_K P_K^T G_K P_K  has its spectrum below max_K lam[K]
+// (element-wise bound), so this is the upper end of the Chebyshev interval that is safe for the scaled Schur
+// complement of every solve.  Geometry only, once per engine.
+template <int K>
+__global__ void __launch_bounds__(64) k_tent_elem_bound(const double* __restrict__ xy, int nc, double* __restrict__ lam) {
+  using T = RefTables<K>;
+  constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double c[3][3];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e)
+      HDG_UNROLL
+      for (int e2 = 0; e2 < 3; ++e2) c[e][e2] = (g.n[e][0] * g.n[e2][0] + g.n[e][1] * g.n[e2][1]) * g.idetJ;
+    double D[3][NMH];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j)
+        HDG_UNROLL
+        for (int l = 0; l <= j; ++l) D[e][tri(j, l)] = c[e][e] * T::GG(e, e, j, l);
+      cholesky<NM>(D[e]);
+    }
+    double x[3][NM];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e)
+      HDG_UNROLL
+      for (int j = 0; j < NM; ++j) x[e][j] = 1.0 + 0.37 * (e * NM + j) - 0.11 * (e * NM + j) * (e * NM + j);
+    double lmax = 0.0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int it = 0; it < 60; ++it) {
+      double y[3][NM], nx2 = 0.0, ny2 = 0.0;
+      HDG_UNROLL
+      for (int e = 0; e < 3; ++e) {
+        HDG_UNROLL
+        for (int j = 0; j < NM; ++j) {
+          double v = 0.0;
+          HDG_UNROLL
+          for (int e2 = 0; e2 < 3; ++e2)
+            HDG_UNROLL
+            for (int l = 0; l < NM; ++l) v = fma(c[e][e2] * T::GG(e, e2, j, l), x[e2][l], v);
+          y[e][j] = v;
+          nx2 = fma(x[e][j], x[e][j], nx2);
+        }
+        chol_solve<NM>(D[e], y[e]);
+        HDG_UNROLL
+        for (int j = 0; j < NM; ++j) ny2 = fma(y[e][j], y[e][j], ny2);
+      }
+      lmax = sqrt(ny2 / nx2);
+      const double inv = rsqrt(ny2);
+      HDG_UNROLL
+      for (int e = 0; e < 3; ++e)
+        HDG_UNROLL
+        for (int j = 0; j < NM; ++j) x[e][j] = y[e][j] * inv;
+    }
+    lam[cell] = lmax;
   }
 }

@@ -59,6 +59,7 @@ SIGNATURES = {
     "hdg_back_substitute_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hdg_set_penalty": (C.c_int, [_vp, C.c_double]),
     "hdg_set_tentative_solver": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "hdg_tentative_stats": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_set_tentative_comm": (C.c_int, [_vp, C.c_int]),
     "hdg_project_bdm_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_fimpl_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
@@ -103,6 +104,11 @@ SIGNATURES = {
     "hdg_graph_replays": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_guess_restarts": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_launch_count": (C.c_int64, [_vp]),
+    "hdg_kernel_counts": (C.c_int64, [_vp, C.c_char_p, C.c_int64]),
+    "hdg_upload_begin": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
+    "hdg_upload_end": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "hdg_download_begin": (C.c_int, [_vp, C.c_int, _vp, _dp, C.c_int]),
+    "hdg_copy_wait": (C.c_int, [_vp]),
 }
 
 
@@ -358,6 +364,34 @@ class HDGEngine:
         self._check(self.lib.hdg_download(self._h, kind, _dev(dev), _ptr(out)))
         return out
 
+    # pipelined transfers on the engine's copy stream (host arrays must stay alive, and should be pinned, until copy_wait)
+    def upload_begin(self, kind: int, host_aos, slot: int = 0):
+        assert host_aos.dtype == np.float64 and host_aos.flags.c_contiguous
+        self._check(self.lib.hdg_upload_begin(self._h, int(kind), _ptr(host_aos), int(slot)))
+
+    def upload_end(self, kind: int, out, slot: int = 0):
+        self._check(self.lib.hdg_upload_end(self._h, int(kind), int(slot), _dev(out)))
+        return out
+
+    def download_begin(self, kind: int, dev, out, slot: int = 0):
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == int(np.prod(self.shapes()[kind]))
+        self._check(self.lib.hdg_download_begin(self._h, int(kind), _dev(dev), _ptr(out), int(slot)))
+
+    def copy_wait(self):
+        self._check(self.lib.hdg_copy_wait(self._h))
+
+    def kernel_counts(self) -> dict:
+        """launches per engine kernel since the engine was created (names without template arguments)"""
+        need = self.lib.hdg_kernel_counts(self._h, None, 0)
+        buf = C.create_string_buffer(int(need) + 64)
+        self.lib.hdg_kernel_counts(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, _, cnt = line.partition("=")
+            if name:
+                out[name] = int(cnt)
+        return out
+
     # -- condensed mixed-Poisson path ----------------------------------------------------------------
     def setup_poisson(self, keep_local: bool = False):
         self._check(self.lib.hdg_setup_poisson(self._h, int(keep_local)))
@@ -476,9 +510,17 @@ class HDGEngine:
     def set_penalty(self, alpha: float):
         self._check(self.lib.hdg_set_penalty(self._h, float(alpha)))
 
-    def set_tentative_solver(self, mode: int = 1, sweeps: int = 8):
-        """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps"""
+    def set_tentative_solver(self, mode: int = 1, sweeps: int = 0):
+        """0 = plain BiCGStab, 1 = facet-multiplier formulation with Chebyshev Schur sweeps (sweeps = 0 keeps the
+        engine's current number, 4 by default)"""
         self._check(self.lib.hdg_set_tentative_solver(self._h, int(mode), int(sweeps)))
+
+    def tentative_stats(self):
+        """counters of the tentative-velocity solver since the engine was created (`hdg_tentative_stats`)"""
+        out = (C.c_int64 * 6)()
+        self._check(self.lib.hdg_tentative_stats(self._h, out))
+        keys = ("solves", "bicgstab_iterations", "fgmres_iterations", "fallbacks", "failed_verifications", "fgmres_cycles")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def set_tentative_comm(self, local_sweeps: bool = False):
         """multi-GPU: skip (True) or perform (False) the halo exchanges between Schur sweeps"""
@@ -490,7 +532,7 @@ class HDGEngine:
     def fimpl_apply_dev(self, Qstar, X, Y, c0=0.0, c1=1.0, upwind=True):
         self._check(self.lib.hdg_fimpl_apply_dev(self._h, _dev(Qstar), _dev(X), float(c0), float(c1), int(upwind), _dev(Y)))
 
-    def tentative_solve_dev(self, Qstar, adt, rhs, x, upwind=True, rtol=1e-10, maxit=1000, zero_guess=True,
+    def tentative_solve_dev(self, Qstar, adt, rhs, x, upwind=True, rtol=1e-10, maxit=20000, zero_guess=True,
                             check=True):
         its = C.c_int(0)
         rc = self.lib.hdg_tentative_solve_dev(self._h, _dev(Qstar), float(adt), int(upwind), _dev(rhs), _dev(x),

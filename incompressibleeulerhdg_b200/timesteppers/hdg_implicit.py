@@ -27,10 +27,14 @@ from .common import IncompressibleEuler
 
 __all__ = ["IncompressibleEulerHDGImplicit"]
 
+# value at t_n of the degree-m polynomial through the m + 1 previous values (newest first)
+_EXTRAPOLATION = {0: (1.0,), 1: (2.0, -1.0), 2: (3.0, -3.0, 1.0), 3: (4.0, -6.0, 4.0, -1.0),
+                  4: (5.0, -10.0, 10.0, -5.0, 1.0)}
+
 
 class IncompressibleEulerHDGImplicit(IncompressibleEuler):
     def __init__(self, mesh, degree, dt, flux="upwind", use_projection_method=True, callbacks=None, device=0,
-                 krylov_rtol=1e-12, progress=False, preconditioner="gtmg", warm_start=True):
+                 krylov_rtol=1e-12, progress=False, preconditioner="gtmg", warm_start=False, warm_order=3):
         super().__init__(mesh, degree, dt, label="HDG Implicit", device=device, preconditioner=preconditioner)
         self.flux = flux
         assert self.flux in ["upwind", "centered"]
@@ -39,12 +43,18 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self.alpha = 1  # penalty parameter (:41)
         self.engine.set_penalty(self.alpha)
         self.krylov_rtol = krylov_rtol
-        # warm_start: both Krylov solves start from time-extrapolated guesses instead of Q^n / zero:
-        # tentative velocity Q^n + 2 d^{n-1} - d^{n-2} with d = Q~ - Q (linear extrapolation of the
-        # increment), trace 3 lambda^{n-1} - 3 lambda^{n-2} + lambda^{n-3} (quadratic).  The
-        # tolerances refer to the right-hand side norms, so the converged fields are the same; only the
-        # iteration counts drop.  (The reference solves both systems directly, hdg_implicit.py:129,146.)
+        # BiCGStab iterations + FGMRES iterations of the fallback (engine knobs tent_bicg_cap, tent_krylov): large
+        # time steps (the reference default dt = 0.04, src/driver.py:80-86) need hundreds to thousands
+        self.tentative_maxit = 20000
+        # warm_start (off by default: the reference solves both systems from scratch, hdg_implicit.py:129,146):
+        # both Krylov solves start from time-extrapolated guesses instead of Q^n / zero: tentative velocity
+        # Q^n + sum_j c_j d^{n-j} with d = Q~ - Q and the c_j of polynomial extrapolation of degree
+        # warm_order (as far as the history reaches), trace 3 lambda^{n-1} - 3 lambda^{n-2} + lambda^{n-3}.
+        # The tolerances refer to the right-hand side norms, so the converged fields are the same; only the
+        # iteration counts drop.
         self.warm_start = warm_start
+        self.warm_order = int(warm_order)
+        assert 0 <= self.warm_order <= 4
         self.progress = progress
         self.niter_tentative = Averager()
         self.niter_pressure = Averager()
@@ -57,7 +67,7 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
     def tentative_velocity_solve(self, Q_star, rhs, Q_tentative, zero_guess):
         return self.engine.tentative_solve_dev(Q_star.data, self._dt, rhs.data, Q_tentative.data,
                                                upwind=(self.flux == "upwind"), rtol=self.krylov_rtol,
-                                               zero_guess=zero_guess)
+                                               zero_guess=zero_guess, maxit=self.tentative_maxit)
 
     @PerformanceLog("pressure_solve")
     def pressure_solve(self, Rp, u, phi, lmbda):
@@ -76,8 +86,8 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self._lmbda = self._V_trace.zeros()
         self._lmbda_prev = self._V_trace.zeros()
         self._lmbda_prev2 = self._V_trace.zeros()
-        self._dQt = self._V_Q.zeros()  # Q~ - Q of the previous step
-        self._dQt_prev = self._V_Q.zeros()  # ... and of the one before
+        # Q~ - Q of the previous steps, newest first (history of the extrapolated tentative-velocity guess)
+        self._dQt_hist = [self._V_Q.zeros() for _ in range(self.warm_order + 1)] if self.warm_start else []
         self._nsteps = 0
         self.iteration_history = []  # (tentative its, pressure its) per step
         self.engine.set_initial_guess(bool(self.warm_start) and self.use_projection_method)
@@ -108,11 +118,12 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
             if self.use_projection_method:
                 if self.warm_start:
                     n = self._nsteps
-                    if n >= 2:
-                        eng.lincomb_dev(self._Q_tentative.data, [(1.0, Q.data), (2.0, self._dQt.data),
-                                                                  (-1.0, self._dQt_prev.data)])
-                    else:
-                        eng.lincomb_dev(self._Q_tentative.data, [(1.0, Q.data), (1.0, self._dQt.data)])
+                    # polynomial extrapolation of the increment through its last m + 1 values: binomial weights
+                    m = min(self.warm_order, n - 1)
+                    terms = [(1.0, Q.data)]
+                    if n >= 1:
+                        terms += [(_EXTRAPOLATION[m][j], self._dQt_hist[j].data) for j in range(m + 1)]
+                    eng.lincomb_dev(self._Q_tentative.data, terms)
                     # the guess goes into the oldest trace buffer, which then becomes the current one
                     l1, l2, l3 = self._lmbda, self._lmbda_prev, self._lmbda_prev2
                     if n >= 3:
@@ -127,9 +138,9 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
                 its = self.tentative_velocity_solve(self._Q_star, self._rhs, self._Q_tentative, zero_guess=False)  # :129
                 its_t = its
                 self.niter_tentative.update(its)
-                if self.warm_start:  # d^{n-2} <- d^{n-1}, d^{n-1} <- Q~ - Q
-                    self._dQt, self._dQt_prev = self._dQt_prev, self._dQt
-                    eng.lincomb_dev(self._dQt.data, [(1.0, self._Q_tentative.data), (-1.0, Q.data)])
+                if self.warm_start:  # shift the history, newest increment Q~ - Q first
+                    self._dQt_hist.insert(0, self._dQt_hist.pop())
+                    eng.lincomb_dev(self._dQt_hist[0].data, [(1.0, self._Q_tentative.data), (-1.0, Q.data)])
                 eng.weak_divergence_dev(self._Q_tentative.data, self._Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
                 its = self.pressure_solve(self._Rp, self._u, self._phi, self._lmbda)  # :146
                 self.niter_pressure.update(its)

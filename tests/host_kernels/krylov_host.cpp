@@ -120,4 +120,27 @@ int kh_bi_state(int* iters, int* done) {
   *iters = g_bi.iters; *done = g_bi.done;
   return 0;
 }
+
+// ---- restarted flexible GMRES (run_fgmres, csrc/hdg_engine.cu) ------------------------------------------------------
+int kh_gm_dots(long n, const double* w, const double* V, long ldv, int i0, int cnt, int ww_slot, double* part) {
+  k_gm_dots((size_t)n, ALL, w, V, (size_t)ldv, i0, cnt, ww_slot, part);
+  return 0;
+}
+int kh_gm_axpy(long n, double* w, const double* V, long ldv, int i0, int cnt, const double* coef, int norm_slot,
+               double* part) {
+  k_gm_axpy((size_t)n, ALL, w, V, (size_t)ldv, i0, cnt, coef, norm_slot, part);
+  return 0;
+}
+int kh_gm_scale(long n, double* w, const double* red, int slot) {
+  k_gm_scale((size_t)n, w, red, slot);
+  return 0;
+}
+int kh_gm_update(long n, double* x, const double* Z, long ldz, int j0, int cnt, const double* y) {
+  k_gm_update((size_t)n, x, Z, (size_t)ldz, j0, cnt, y);
+  return 0;
+}
+int kh_resid_norm(long n, const double* b, const double* t, double* r, double* part) {
+  k_resid_norm((size_t)n, ALL, b, t, r, part);
+  return 0;
+}
 }

@@ -66,6 +66,30 @@ int th_advblock(int k, int upwind, int nc, const double* xy, const int* nbr, con
   })
 }
 
+// as th_advblock, also returning sK[cell] = tr(C_K) / NQ1 (scaled Schur complement)
+int th_advblock_sk(int k, int upwind, int nc, const double* xy, const int* nbr, const double* Qstar, double adt,
+                   double* blk, float* blk32, double* sK) {
+  BY_K(k, for (int cell = 0; cell < nc; ++cell) {
+    if (upwind) advblock_build_cell<K, true>(xy, nbr, nc, cell, Qstar, adt, blk);
+    else advblock_build_cell<K, false>(xy, nbr, nc, cell, Qstar, adt, blk);
+    advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32, sK);
+  })
+}
+
+int th_scale_tc(int nf, const int* facet_cell, const double* tc, const double* sK, double* tcs) {
+  k_tent_scale_tc(nf, facet_cell, tc, sK, tcs);
+  return 0;
+}
+
+int th_xhat_scaled(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, const double* Y,
+                   const double* mu, double* Xh, int mode, const double* sK, double* Zout) {
+  BY_K(k, k_tent_xhat<K>(xy, flip, cell_facet, nc, nf, Y, mu, Xh, mode, sK, Zout))
+}
+
+int th_elem_bound(int k, int nc, const double* xy, double* lam) {
+  BY_K(k, k_tent_elem_bound<K>(xy, nc, lam))
+}
+
 int th_advblock_apply(int k, int nc, const float* blk32, const double* X, double* Y) {
   BY_K(k, for (int cell = 0; cell < nc; ++cell) advblock_apply_cell<K>(nc, cell, blk32, X, Y))
 }

@@ -11,9 +11,9 @@ own arm (default)   device-resident timestepping through the Python timestepper 
                     `value` = timesteps/s with all inputs in HBM; `e2e` = the same step driven with
                     HOST buffers: per step the forcing comes from pinned host memory (H2D) and the
                     new velocity/pressure go back to the host (D2H), all inside the timed region.
-reference arm       the CPU restatement of the reference path (oracle/, numpy+scipy sparse direct
-                    solvers; the reference itself needs Firedrake/PETSc which cannot be installed
-                    here) on a bounded sample, scaled to the same unit.
+reference arm       the compiled CPU restatement of the reference path (oracle/cpu_ref, C++/OpenMP on all host
+                    cores; the reference itself needs Firedrake/PETSc, which cannot be installed here) on a
+                    bounded sample (nx = 256, 1/16 of the cells), scaled to the same unit.
 
 Prints ONE JSON line (see the task contract for the keys).
 """
@@ -95,59 +95,59 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's Chorin step on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(job):
-    """one core's share: `nsteps` Chorin steps of the oracle on its own nx_sample mesh; returns (s/step, cells)"""
-    nx_sample, degree, nsteps = job
-    os.environ["OMP_NUM_THREADS"] = "1"
-    try:
-        from threadpoolctl import threadpool_limits
+class CpuChorin:
+    """The compiled CPU restatement (oracle/cpu_ref/hdg_cpu_ref.cpp: C++/OpenMP, all host cores) stepping the same
+    workload -- Chorin k=2, dt = 0.32/nx, Taylor-Green, rtol as the GPU arm -- on an nx_sample x nx_sample mesh.  The
+    result is scaled linearly in the number of cells to the target mesh (generous to the CPU: the iteration counts of its
+    Krylov solvers do not drop on finer meshes).  Timer labels are the reference's (src/auxilliary/logging.py:11-31)."""
 
-        threadpool_limits(1)
-    except Exception:
-        pass
-    from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
-    from oracle.timesteppers import ChorinOracle, TaylorGreenOracle
+    def __init__(self, nx_sample, degree, rtol, target_cells):
+        from incompressibleeulerhdg_b200.mesh import UnitSquareMesh
+        from oracle.cpu_ref import ChorinCpuRef
+        from oracle.timesteppers import TaylorGreenOracle
 
-    mesh = UnitSquareMesh(nx_sample, perturb=0.1)
-    dt = 0.32 / nx_sample
-    ts = ChorinOracle(mesh, degree, dt)
-    prob = TaylorGreenOracle("exponential", 0.5)
-    Q, p = ts.initial_state(prob)
-    times = []
-    for k in range(nsteps):
+        self.nx, self.k, self.target_cells = nx_sample, degree, target_cells
+        self.mesh = UnitSquareMesh(nx_sample, perturb=0.1)
+        self.dt = 0.32 / nx_sample
         t0 = time.perf_counter()
-        Q, p = ts.step(Q, p, prob.f_rhs(k * dt))
-        times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), mesh.nc
+        self.ref = ChorinCpuRef(self.mesh, degree, self.dt, rtol=rtol, maxit=2000)
+        self.prob = TaylorGreenOracle("exponential", 0.5)
+        self.Q, self.p = self.ref.initial_state(self.prob)
+        self.setup_s = time.perf_counter() - t0
+        self.nstep = 0
+        self.factor = target_cells / self.mesh.nc
 
+    def step(self):
+        """one timestep including the interpolation of the forcing (hdg_implicit.py:100); returns seconds"""
+        t0 = time.perf_counter()
+        f = self.ref.forcing(self.prob.f_rhs(self.nstep * self.dt))
+        self.ref.step(self.Q, self.p, f)
+        self.nstep += 1
+        return time.perf_counter() - t0
 
-def cpu_chorin_sample(nx_sample, degree, nsteps, target_cells, cores=None):
-    """The CPU restatement on all host cores: every core steps its own nx_sample mesh concurrently (the
-    best case of a mesh-partitioned MPI run: no halo exchange, no load imbalance), and the aggregate
-    cell-steps/s is scaled linearly to the target mesh (generous: sparse direct solvers grow faster)."""
-    import multiprocessing as mp
-
-    cores = max(1, min(os.cpu_count() or 1, 64) if cores is None else cores)
-    if cores == 1:
-        res = [_cpu_worker((nx_sample, degree, nsteps))]
-    else:
-        with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_cpu_worker, [(nx_sample, degree, nsteps)] * cores)
-    sec_per_step = float(np.mean([r[0] for r in res]))
-    cells = res[0][1]
-    cell_steps_per_s = sum(r[1] / r[0] for r in res)
-    return {
-        "value": cell_steps_per_s / target_cells, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{nsteps} Chorin step(s) of oracle/timesteppers.py (numpy + scipy splu) on nx={nx_sample} k={degree} "
-                  f"({cells} cells) on each of {cores} cores concurrently ({sec_per_step:.2f} s/step per core), "
-                  f"aggregate cell-steps/s scaled linearly to {target_cells} cells",
-    }, sec_per_step
+    def describe(self, sec_per_step, nsteps):
+        its = self.ref.iterations[-nsteps:]
+        tm = self.ref.timers()
+        n = max(1, tm["timestep"]["calls"])
+        return {
+            "value": 1.0 / (sec_per_step * self.factor), "unit": UNIT, "cores": self.ref.threads, "kind": "port",
+            "sample": f"{nsteps} Chorin step(s) of oracle/cpu_ref/hdg_cpu_ref.cpp (C++/OpenMP, {self.ref.threads} threads; "
+                      f"BiCGStab + facet-multiplier preconditioner, two-level CG on the condensed trace system, rtol as the "
+                      f"GPU arm) on nx={self.nx} k={self.k} ({self.mesh.nc} cells, dt=0.32/nx): {sec_per_step:.2f} s/step, "
+                      f"scaled linearly in cells (x{self.factor:g}) to {self.target_cells} cells",
+            "sample_seconds_per_step": sec_per_step, "extrapolation_factor": self.factor, "setup_seconds": self.setup_s,
+            "iterations_tentative_pressure": [list(i) for i in its],
+            "seconds_per_step_by_label": {lab: v["seconds"] / n for lab, v in tm.items()},
+            "checked_against": "oracle/ (numpy, pinned to the reference's forms) to 1e-10: tests/test_cpu_ref.py",
+        }
 
 
 def cpu_baseline_sample(args, target_cells):
-    """the CPU baseline of the own arm's line: the oracle port on a bounded sample"""
-    base, _ = cpu_chorin_sample(args.cpu_nx, args.degree, 1, target_cells)
-    return base
+    """the CPU baseline of the own arm's line: one warm-up step and `--cpu-steps` timed steps of the compiled CPU port"""
+    cpu = CpuChorin(args.cpu_nx, args.degree, args.rtol, target_cells)
+    cpu.step()
+    secs = [cpu.step() for _ in range(max(1, args.cpu_steps))]
+    return cpu.describe(float(np.mean(secs)), len(secs))
 
 
 def run_reference(args):
@@ -156,15 +156,12 @@ def run_reference(args):
         return
     nxm, nym, _ = mesh_shape(args, max(1, args.gpus))
     target_cells = 2 * nxm * nym
-    t_all = []
-    base = None
-    for s in range(args.warmup + args.steps):
-        b, sec = cpu_chorin_sample(args.cpu_nx, args.degree, 1, target_cells)
-        if s >= args.warmup:
-            t_all.append(1.0 / b["value"])
-            base = b
-    val = 1.0 / float(np.mean(t_all))
-    base["value"] = val
+    cpu = CpuChorin(args.cpu_nx, args.degree, args.rtol, target_cells)
+    for _ in range(args.warmup):
+        cpu.step()
+    secs = [cpu.step() for _ in range(args.steps)]
+    base = cpu.describe(float(np.mean(secs)), len(secs))
+    val = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": args.scaling,
@@ -173,8 +170,10 @@ def run_reference(args):
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "Firedrake/PETSc (the reference's own code path) is not installable in this image; this arm times "
-                "the CPU restatement under oracle/",
+        "timed_region_s": float(np.sum(secs)),
+        "note": "Firedrake/PETSc (the reference's own code path) is not installable in this image; this arm times the "
+                "compiled CPU restatement under oracle/cpu_ref on all host cores, each step = one timestep of the same "
+                "workload on a mesh with 1/extrapolation_factor of the cells",
     }
     print(json.dumps(line))
 
@@ -539,7 +538,9 @@ def main():
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--rtol", type=float, default=1e-12)
-    ap.add_argument("--cpu-nx", type=int, default=16, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--cpu-nx", type=int, default=256,
+                    help="mesh size of the bounded CPU sample (256: 1/16 of the cells of the nx = 1024 workload)")
+    ap.add_argument("--cpu-steps", type=int, default=1, help="timed steps of the cpu_baseline leg of the own arm")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = the same as --steps)")
     ap.add_argument("--warm-order", type=int, default=3, help="degree of the time extrapolation of the initial guesses")
     ap.add_argument("--cold-steps", type=int, default=2, help="extra steps with the reference's cold starts (0 = skip)")

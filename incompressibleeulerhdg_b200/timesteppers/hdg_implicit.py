@@ -45,7 +45,7 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         self.krylov_rtol = krylov_rtol
         # BiCGStab iterations + FGMRES iterations of the fallback (engine knobs tent_bicg_cap, tent_krylov): large
         # time steps (the reference default dt = 0.04, src/driver.py:80-86) need hundreds to thousands
-        self.tentative_maxit = 20000
+        self.tentative_maxit = 5000
         # warm_start (off by default: the reference solves both systems from scratch, hdg_implicit.py:129,146):
         # both Krylov solves start from time-extrapolated guesses instead of Q^n / zero: tentative velocity
         # Q^n + sum_j c_j d^{n-j} with d = Q~ - Q and the c_j of polynomial extrapolation of degree

@@ -46,7 +46,9 @@ enum {
   HDG_ENOGPU = 3,   /* no CUDA device: the engine has no CPU fallback */
   HDG_ESTATE = 4,   /* call order violated (e.g. apply before setup) */
   HDG_ENCCL = 5,    /* NCCL error */
-  HDG_ENOCONV = 6   /* Krylov solver hit maxit (results are still written) */
+  HDG_ENOCONV = 6,  /* Krylov solver hit maxit (results are still written) */
+  HDG_ECOMM = 7     /* peer-memory transport: a halo exchange or all-reduce timed out (fatal for the handle: ghost data
+                       and reductions after that point are invalid; sticky until hdg_p2p_enable is called again) */
 };
 
 /* ---- life cycle ------------------------------------------------------------------------------ */

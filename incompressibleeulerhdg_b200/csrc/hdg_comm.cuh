@@ -87,7 +87,10 @@ constexpr int HDG_RED_MAX = 8;         // doubles per all-reduce
 // boxes, waits for theirs and sums in rank order (bitwise identical on all ranks).  Slabs and boxes are
 // double-buffered by a per-pair / per-reduction counter, which is sufficient because peer sets are
 // symmetric and each side can only be one exchange ahead of the other (its next push needs the
-// peer's previous one).  Spins are bounded: on a timeout the kernel sets `error` and proceeds.
+// peer's previous one).  Spins are bounded (spin_cycles, two minutes by default, HDG_P2P_TIMEOUT_S): a timeout is
+// FATAL -- the kernel sets the sticky `error`, does not unpack and does not advance its counters, every later
+// transport kernel returns at once, and the host turns the flag into HDG_ECOMM at the next scalar readback of a
+// Krylov loop and at the end of every C-ABI call that communicated (p2p_poll in hdg_engine.cu).
 struct P2PHeader {
   unsigned long long halo_flag[HDG_MAX_RANKS];  // halo_flag[q]: number of pushes received from rank q
   unsigned long long red_flag[HDG_MAX_RANKS];   // red_flag[q]: number of reductions rank q contributed to
@@ -96,11 +99,14 @@ struct P2PHeader {
   // CUDA graph of a Krylov iteration can be replayed: every kernel derives "this exchange" from them
   unsigned long long pair_cnt[HDG_MAX_RANKS];   // completed exchanges with rank q
   unsigned long long red_cnt;                   // completed all-reduces
-  int error;                                    // set by a kernel whose bounded spin ran out
+  int error;                                    // sticky: set by a kernel whose bounded spin ran out
   unsigned int ticket;                          // last-block detection of the push kernel
   unsigned int ticket2;                         // ... and of the wait/unpack kernel
-  int pad[13];
+  int pad0;
+  long long spin_cycles;                        // bound of one spin in SM clock cycles
+  int pad[10];
 };
+static_assert(sizeof(P2PHeader) % 8 == 0, "the mailbox slabs behind the header hold doubles");
 
 struct P2P {
   bool enabled = false;
@@ -114,7 +120,8 @@ __host__ __device__ inline double* p2p_slab(char* base, size_t slab, int nranks,
   return reinterpret_cast<double*>(base + sizeof(P2PHeader)) + ((size_t)parity * nranks + sender) * slab;
 }
 
-struct P2PPeers {  // kernel argument: the peers of one exchange
+static_assert(HDG_MAX_RANKS <= 256, "k_p2p_wait_unpack / k_p2p_allreduce index peers by threadIdx.x");
+struct P2PPeers {  // kernel argument: the peers of one exchange (at most HDG_MAX_RANKS - 1, checked by hdg_set_halo_plan)
   int npeers;
   int rank[HDG_MAX_RANKS];
   int send_ptr[HDG_MAX_RANKS + 1];
@@ -122,13 +129,17 @@ struct P2PPeers {  // kernel argument: the peers of one exchange
   char* peer_base[HDG_MAX_RANKS];
 };
 
-constexpr long long HDG_SPIN_CYCLES = 4000000000ll;  // ~2 s at 1.9 GHz
+constexpr long long HDG_SPIN_CYCLES = 230000000000ll;  // default bound: ~2 minutes at 1.9 GHz
 
-__device__ __forceinline__ void p2p_wait(volatile unsigned long long* flag, unsigned long long want, int* error) {
+__device__ __forceinline__ bool p2p_failed(const P2PHeader* own) { return *(volatile const int*)&own->error != 0; }
+
+__device__ __forceinline__ void p2p_wait(volatile unsigned long long* flag, unsigned long long want, P2PHeader* own) {
   const long long t0 = clock64();
+  const long long bound = own->spin_cycles > 0 ? own->spin_cycles : HDG_SPIN_CYCLES;
   while (*flag < want) {
-    if (clock64() - t0 > HDG_SPIN_CYCLES) {
-      *error = 1;
+    if (p2p_failed(own)) break;  // another waiter already gave up
+    if (clock64() - t0 > bound) {
+      *(volatile int*)&own->error = 1;
       break;
     }
   }
@@ -143,6 +154,7 @@ struct Comm {
   double* red = nullptr;  // device [16] reduction scratch
   int64_t exchanges = 0, allreduces = 0;
   P2P p2p;
+  int* p2p_err_host = nullptr;  // pinned copy of P2PHeader::error (p2p_poll)
 };
 
 // sendbuf[i*ndof + d] = field[d*n_local + send_idx[i]]
@@ -170,6 +182,7 @@ __global__ void k_halo_unpack(int total, int ndof, int n_local, int n_owned, con
 __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int nranks, size_t slab, int ndof,
                                                   int n_local, const int* __restrict__ send_idx,
                                                   const double* __restrict__ field, char* own_base) {
+  if (p2p_failed(p2p_header(own_base))) return;  // fatal state: the host reports HDG_ECOMM
   const int total = pp.send_ptr[pp.npeers];
   const size_t n = (size_t)total * ndof;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
@@ -204,11 +217,13 @@ __global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks
                                                          int n_owned, char* own_base, double* __restrict__ field) {
   P2PHeader* own = p2p_header(own_base);
   __shared__ unsigned long long cnt[HDG_MAX_RANKS];
+  if (p2p_failed(own)) return;
   if (threadIdx.x < pp.npeers) {
     cnt[threadIdx.x] = own->pair_cnt[pp.rank[threadIdx.x]] + 1ull;  // this exchange
-    p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], cnt[threadIdx.x], &own->error);
+    p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], cnt[threadIdx.x], own);
   }
   __syncthreads();
+  if (p2p_failed(own)) return;  // timed out: no stale slab is unpacked, pair_cnt does not advance
   __threadfence_system();
   const int total = pp.recv_ptr[pp.npeers];
   const size_t n = (size_t)total * ndof;
@@ -243,6 +258,7 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, i
                                                        int G, int nslots) {
   __shared__ double mine[HDG_RED_MAX];
   __shared__ double total[HDG_RED_MAX];
+  if (p2p_failed(p2p_header(all.base[myrank]))) return;
   const unsigned long long count = p2p_header(all.base[myrank])->red_cnt + 1ull;  // this reduction
   for (int s = 0; s < nslots; ++s) {
     const double* p = part + (size_t)s * G;
@@ -263,8 +279,9 @@ __global__ void __launch_bounds__(256) k_p2p_allreduce(P2PAll all, int myrank, i
   }
   __syncthreads();
   P2PHeader* own = p2p_header(all.base[myrank]);
-  if (threadIdx.x < nranks) p2p_wait(&own->red_flag[threadIdx.x], count, &own->error);
+  if (threadIdx.x < nranks) p2p_wait(&own->red_flag[threadIdx.x], count, own);
   __syncthreads();
+  if (p2p_failed(own)) return;  // timed out: the partial sums stay local, red_cnt does not advance
   __threadfence_system();
   if (threadIdx.x < nslots) {
     double v = 0.0;

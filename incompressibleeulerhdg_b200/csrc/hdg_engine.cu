@@ -133,6 +133,7 @@ struct hdg_engine {
   int tune_krylov = 0;        // 0 = BiCGStab, FGMRES as the fallback; 1 = BiCGStab only; 2 = FGMRES only ("tent_krylov")
   int tune_gmres_m = 0;       // restart length ("tent_gmres_m"); 0 = automatic: what fits into 2 GB, between 30 and 200
   int tune_bicg_cap = 150;    // BiCGStab iterations before the fallback ("tent_bicg_cap")
+  double tent_tolscale = 1.0; // tolerance of the augmented recurrence relative to rtol (run_tentative_aug, accept)
   int tune_trace = 0;         // HDG_TENT_TRACE=1: residual norms of the tentative solves on stderr
   int tune_verify = 1;        // check the true residual b - A x after BiCGStab reports convergence ("tent_verify")
   double bicg_failed_adt = -1.0;  // a dt for which BiCGStab has failed: later solves go straight to FGMRES
@@ -380,6 +381,32 @@ static void allreduce_slots(hdg_engine* h, double* part, int nslots) {
   c->allreduces++;
 }
 
+// Peer-memory transport failures are fatal: p2p_poll_async enqueues a copy of the sticky P2PHeader::error next to a
+// scalar readback that is synchronised anyway, p2p_poll_result turns it into HDG_ECOMM (sticky comm_rc), and p2p_poll
+// does both at the end of a C-ABI call that communicated.
+static void p2p_poll_async(hdg_engine* h) {
+  Comm* c = h->comm;
+  if (!c || !c->p2p.enabled || !c->p2p_err_host) return;
+  cudaMemcpyAsync(c->p2p_err_host, &p2p_header(c->p2p.base)->error, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+}
+static int p2p_poll_result(hdg_engine* h) {
+  Comm* c = h->comm;
+  if (c && c->p2p_err_host && *c->p2p_err_host && !h->comm_rc) {
+    h->comm_rc = HDG_ECOMM;
+    h->err = "peer-memory transport: a halo exchange or all-reduce timed out waiting for rank data (rank " +
+             std::to_string(c->rank) + " of " + std::to_string(c->nranks) +
+             "); ghost data and reductions after that point are invalid";
+  }
+  return h->comm_rc;
+}
+static int p2p_poll(hdg_engine* h) {
+  Comm* c = h->comm;
+  if (!c || !c->p2p.enabled || !c->p2p_err_host) return h->comm_rc;
+  p2p_poll_async(h);
+  cudaStreamSynchronize(h->stream);
+  return p2p_poll_result(h);
+}
+
 static inline bool all_owned(const hdg_engine* h) { return h->nc_own == h->nc && h->nf_own == h->nf; }
 static OwnMask mask_cells(const hdg_engine* h, int ndof) {
   return OwnMask{all_owned(h) ? 1 : 0, (unsigned long long)ndof * h->nc, h->nc, h->nc_own, 1, 1};
@@ -398,6 +425,17 @@ static OwnMask mask_aug(const hdg_engine* h, int ndof_cell, int ndof_facet) {
 // (Krylov scalars, exchange counters), so the replay is exact.  Graphs are used on a single GPU and with
 // the peer-memory transport; with the NCCL transport the body is launched kernel by kernel.
 // ------------------------------------------------------------------------------------------------
+// Drop every cached graph: called by whatever frees or replaces a resource that a captured iteration body bakes into
+// its kernel arguments (multigrid levels and their Chebyshev bounds, halo plans, transport, tuning knobs) -- cudaMalloc
+// tends to hand back the same addresses, so the pointer keys alone would not notice.
+static void invalidate_graphs(hdg_engine* h) {
+  for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg}) {
+    if (gc->exec) cudaGraphExecDestroy(gc->exec);
+    gc->exec = nullptr;
+    gc->key.clear();
+  }
+}
+
 static inline uint64_t key_of(const void* p) { return (uint64_t)(uintptr_t)p; }
 static inline uint64_t key_of(double v) {
   uint64_t u;
@@ -700,10 +738,16 @@ static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const 
 
 // generic driver: op(in, out) applies the (preconditioned) operator to a vector of length n.
 // On entry r0 (the initial residual) sits in bi[0]; the solution update is accumulated in y.
-template <class Op>
+// `accept` (optional) is asked when the recurrence residual has met the tolerance: it returns 0 to accept, a factor in
+// (0, 1) by which the tolerance is tightened before the iteration continues (k_bi_resume), or a negative value to give up
+struct NoAccept {
+  double operator()() const { return 0.0; }
+};
+template <class Op, class Accept = NoAccept>
 static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, std::vector<uint64_t> key, double* y,
                          const double* part_ref, double rtol, int maxit, int* iters,
-                         const double* flex_xh = nullptr, double* flex_x = nullptr, size_t flex_nx = 0) {
+                         const double* flex_xh = nullptr, double* flex_x = nullptr, size_t flex_nx = 0,
+                         Accept accept = Accept()) {
   // flex_x != nullptr (experimental, "tent_flex"): op leaves [Phat^-1 in]_x in flex_xh and the solution flex_x is
   // accumulated from these preconditioned directions (k_bi_s_flex / k_bi_xr_flex); y is not used then
   const int G = h->grid;
@@ -759,7 +803,22 @@ static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, std::vecto
     if (grc) return grc;
     launched += m;
     CUDA_TRY(h, cudaMemcpyAsync(h->bscal_host, h->bscal, sizeof(BiScalars), cudaMemcpyDeviceToHost, h->stream));
+    p2p_poll_async(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (p2p_poll_result(h)) return h->comm_rc;
+    if (h->bscal_host->done == 1 && h->bscal_host->iters < maxit) {
+      const double factor = accept();
+      if (h->comm_rc) return h->comm_rc;
+      if (factor > 0.0 && factor < 1.0) {
+        LAUNCH(h, k_bi_resume, G, BLOCK, n, (const double*)r, (const double*)v, p, (const double*)p_rv,
+               (const double*)p_ts, (const double*)p_tt, h->bscal, factor);
+        continue;
+      }
+      if (factor < 0.0) {
+        if (iters) *iters = h->bscal_host->iters;
+        return HDG_ENOCONV;
+      }
+    }
     if (h->bscal_host->done || launched >= maxit) finished = true;
   }
   if (iters) *iters = h->bscal_host->iters;
@@ -1001,7 +1060,7 @@ static int run_sweep_probe(hdg_engine* h, double adt, int nrep, double* ms_per_l
 // milliseconds of device work).
 template <class Op, class Resid>
 static int run_fgmres(hdg_engine* h, size_t n, size_t nx, OwnMask own, const double* part_bb, Op op, Resid resid,
-                      double* x, double rtol, int maxit, int* iters) {
+                      double* x, double rtol, int maxit, int* iters, const double* est_rtol = nullptr) {
   const int G = h->grid;
   int m = h->tune_gmres_m;
   if (m <= 0) m = (int)std::min<size_t>(200, std::max<size_t>(30, ((size_t)2 << 30) / ((n + nx) * sizeof(double))));
@@ -1127,7 +1186,9 @@ static int run_fgmres(hdg_engine* h, size_t n, size_t nx, OwnMask own, const dou
       jj = j + 1;
       const double est = std::fabs(g[j + 1]);
       if (!std::isfinite(est)) FAIL(h, HDG_ENOCONV, "run_fgmres: breakdown (non-finite Hessenberg entry)");
-      if (est * est <= rtol * rtol * bb) {
+      // est_rtol (optional, may be changed by `resid` between the cycles): tolerance of the recurrence estimate
+      const double et = est_rtol ? *est_rtol : rtol;
+      if (est * est <= et * et * bb) {
         prev_est_conv = true;
         break;
       }
@@ -1257,9 +1318,11 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   auto true_residual = [&](double* out_r, double* rr) -> int {
     halo_exchange(h, PLAN_CELLS, 2 * Dims<K>::NQ1, x);
     launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->bi[5]);
-    LAUNCH(h, k_resid_norm, G, BLOCK, nx, mask_cells(h, 2 * Dims<K>::NQ1), b, (const double*)h->bi[5], out_r, h->partial);
-    allreduce_slots(h, h->partial, 1);
-    LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)h->partial, G, h->gm_red);
+    // slots 6, 7 of the partial sums: 0-5 belong to a BiCGStab run that may be resumed (k_bi_resume)
+    double* part6 = h->partial + 6 * (size_t)G;
+    LAUNCH(h, k_resid_norm, G, BLOCK, nx, mask_cells(h, 2 * Dims<K>::NQ1), b, (const double*)h->bi[5], out_r, part6);
+    allreduce_slots(h, part6, 1);
+    LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)part6, G, h->gm_red);
     CUDA_TRY(h, cudaMemcpyAsync(h->gm_host, h->gm_red, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *rr = h->gm_host[0];
@@ -1276,10 +1339,11 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     if (vrc) return vrc;
     CUDA_TRY(h, cudaMemsetAsync(scratch + nx, 0, nmu * sizeof(double), h->stream));
     op(scratch, scratch_out, xh_out);
+    double* part6 = h->partial + 6 * (size_t)G;
     LAUNCH(h, k_dot2, G, BLOCK, nx, mask_cells(h, 2 * Dims<K>::NQ1), (const double*)xh_out, (const double*)xh_out,
-           (const double*)x, h->partial, h->partial + G);
-    allreduce_slots(h, h->partial, 2);
-    LAUNCH(h, k_part_finish, 2, BLOCK, (const double*)h->partial, G, h->gm_red + 2);
+           (const double*)x, part6, part6 + G);
+    allreduce_slots(h, part6, 2);
+    LAUNCH(h, k_part_finish, 2, BLOCK, (const double*)part6, G, h->gm_red + 2);
     CUDA_TRY(h, cudaMemcpyAsync(h->gm_host + 2, h->gm_red + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *zz = h->gm_host[2];
@@ -1310,8 +1374,34 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     int its_b = 0;
     // flexible update (default): x is accumulated from the preconditioned directions op leaves in tent_xh; x holds the
     // initial guess (or zero) on entry, so no recovery step follows
-    int brc = bicgstab_loop(h, n, own, op2, key, y, part_bb, rtol, cap, &its_b, flex ? h->tent_xh : (const double*)nullptr,
-                            flex ? x : (double*)nullptr, flex ? nx : 0);
+    // Acceptance (flexible update only: x is current at every iteration).  The recurrence residual is that of the
+    // augmented system, whose multiplier row is weighted differently from the primal error (measured at nx = 1024:
+    // recurrence 8e-13 ||b||, preconditioned primal residual 4e-11 ||x||).  When the preconditioned primal residual is
+    // not yet within rtol ||x||, the iteration continues with the tolerance tightened by the measured ratio; the ratio is
+    // remembered (tent_tolscale), so that later solves start with the tolerance that is expected to pass.
+    bool verified = false;
+    int tightened = 0;
+    auto accept = [&]() -> double {
+      if (!flex || !h->tune_verify || h->tune_krylov == 1) return 0.0;
+      double rr = 0.0, zz = 0.0, xx = 0.0;
+      if (prec_residual(h->bi[4], h->bi[5], h->tent_xh, &rr, &zz, &xx)) return -1.0;
+      const double bb = h->gm_host[1];
+      if (zz <= rtol * rtol * xx || rr <= rtol * rtol * bb) {
+        verified = true;
+        return 0.0;
+      }
+      if (!std::isfinite(zz) || tightened >= 4) return -1.0;
+      ++tightened;
+      const double ratio = std::sqrt(zz / std::max(xx, 1e-300)) / rtol;  // > 1
+      const double f = std::max(1e-4, 0.5 / ratio);
+      h->tent_tolscale = std::max(1e-6, h->tent_tolscale * f);
+      return f;
+    };
+    int brc = bicgstab_loop(h, n, own, op2, key, y, part_bb, flex && h->tune_verify ? rtol * h->tent_tolscale : rtol, cap,
+                            &its_b, flex ? h->tent_xh : (const double*)nullptr, flex ? x : (double*)nullptr,
+                            flex ? nx : 0, accept);
+    // let the tolerance relax again slowly, so that one hard solve does not tax all later ones
+    if (verified && tightened == 0) h->tent_tolscale = std::min(1.0, h->tent_tolscale * 1.25);
     if (brc == HDG_ECUDA) return brc;
     if (h->tune_trace)
       fprintf(stderr, "[hdg tent] BiCGStab rc=%d iterations=%d  recurrence ||r||/ref=%.3e\n", brc, its_b,
@@ -1324,7 +1414,9 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
       LAUNCH(h, k_tent_xhat<K>, cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, yx, mu, x, 1, sKx);
     }
     converged = brc == HDG_OK;
-    if (converged && h->tune_verify && h->tune_krylov != 1) {
+    if (converged && verified) {
+      // accepted inside the loop
+    } else if (converged && h->tune_verify && h->tune_krylov != 1) {
       double rr = 0.0, zz = 0.0, xx = 0.0;
       int vrc = prec_residual(h->bi[3], h->bi[4], h->tent_xh, &rr, &zz, &xx);
       if (vrc) return vrc;
@@ -1352,14 +1444,26 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     int its_g = 0;
     // cycle start: v_0 = (b - A x, 0); accepted when the preconditioned residual meets rtol (see prec_residual).  The
     // second basis slot and the first direction slot are free at that point and serve as scratch.
+    double est_tol = rtol * h->tent_tolscale;
+    int cycles = 0;
     auto cycle_residual = [&](double* V, double* rr, bool* accept) -> int {
       double zz = 0.0, xx = 0.0;
       int vrc = prec_residual(V, V + n, h->gm_Z, rr, &zz, &xx);
       if (vrc) return vrc;
       *accept = zz <= rtol * rtol * xx;
+      // the cycles end on the recurrence estimate of the augmented residual: tighten it by the measured ratio when the
+      // preconditioned primal residual is not there yet (as for BiCGStab above)
+      if (!*accept && cycles++ > 0 && std::isfinite(zz) && xx > 0.0) {
+        const double ratio = std::sqrt(zz / xx) / rtol;
+        if (ratio < 1e3) {
+          h->tent_tolscale = std::max(1e-6, h->tent_tolscale * std::max(1e-3, 0.5 / ratio));
+          est_tol = rtol * h->tent_tolscale;
+        }
+      }
       return HDG_OK;  // ||r||^2 is still in gm_red[0] (true_residual), which run_fgmres scales v_0 with
     };
-    rc_final = run_fgmres(h, n, nx, own, (const double*)part_bb, op, cycle_residual, x, rtol, maxit - its_total, &its_g);
+    rc_final = run_fgmres(h, n, nx, own, (const double*)part_bb, op, cycle_residual, x, rtol, maxit - its_total, &its_g,
+                          &est_tol);
     its_total += its_g;
     h->tent_stats[2] += its_g;
   }
@@ -1377,6 +1481,7 @@ static void free_csr(DevCsr& m) {
   m = DevCsr();
 }
 static void mg_free(hdg_engine* h) {
+  invalidate_graphs(h);  // level arrays and smoother bounds are baked into the captured V-cycle
   MgState* mg = h->mg;
   if (!mg) return;
   for (auto& l : mg->L) {
@@ -1542,7 +1647,9 @@ static int run_pcg_mg(hdg_engine* h, double rtol, int maxit, const double* guess
   static const bool cg_trace = getenv("HDG_CG_TRACE") != nullptr;  // per-iteration scalars on stderr (diagnostics)
   while (true) {
     CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    p2p_poll_async(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (p2p_poll_result(h)) return h->comm_rc;
     if (cg_trace) {
       std::vector<double> pq(G);
       cudaMemcpy(pq.data(), part_pq, G * sizeof(double), cudaMemcpyDeviceToHost);
@@ -2019,7 +2126,9 @@ static int run_cg(hdg_engine* h, double rtol, int maxit, const double* guess, in
     if (grc) return grc;
     launched += n;
     CUDA_TRY(h, cudaMemcpyAsync(h->scal_host, h->scal, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    p2p_poll_async(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (p2p_poll_result(h)) return h->comm_rc;
     if (h->scal_host->done || launched >= maxit) finished = true;
   }
   if (iters) *iters = h->scal_host->iters;
@@ -2085,7 +2194,7 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
     LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
   }
   CUDA_TRY(h, cudaGetLastError());
-  if (h->comm_rc) return h->comm_rc;
+  if (p2p_poll(h)) return h->comm_rc;
   if (cg_rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "trace CG did not converge within maxit");
   return HDG_OK;
 }
@@ -2296,6 +2405,8 @@ int hdg_set_penalty(hdg_handle h, double alpha) {
 
 int hdg_set_tuning(hdg_handle h, const char* name, int value) {
   if (!h || !name) return HDG_EINVAL;
+  cudaStreamSynchronize(h->stream);
+  invalidate_graphs(h);  // most knobs change the body or the arguments of a captured iteration
   if (!strcmp(name, "sweep_minblocks")) {
     h->tune_sweep = value;
     // the variant is baked into the captured BiCGStab graph
@@ -2463,7 +2574,7 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
       DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
     }
   }
-  if (h->comm_rc) return h->comm_rc;
+  if (p2p_poll(h)) return h->comm_rc;
   if (rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "tentative-velocity BiCGStab did not converge within maxit");
   return rc;
 }
@@ -2563,7 +2674,7 @@ int hdg_gamma_apply_dev(hdg_handle h, const double* Q, const double* p, const do
     LAUNCH(h, k_facet_sum<K>, h->grid, BLOCK, h->gK, h->facet_cell, h->facet_local, h->nc, h->nf, Rl);
   });
   CUDA_TRY(h, cudaGetLastError());
-  return h->comm_rc;
+  return p2p_poll(h);
 }
 
 int hdg_dot_dev(hdg_handle h, int kind, const double* x, const double* y, double* result) {
@@ -2581,7 +2692,7 @@ int hdg_dot_dev(hdg_handle h, int kind, const double* x, const double* y, double
   double s = 0.0;
   for (double v : part) s += v;
   *result = s;
-  return h->comm_rc;
+  return p2p_poll(h);
 }
 
 int hdg_l2_inner_dev(hdg_handle h, int kind, const double* x, const double* y, double* result) {
@@ -2730,6 +2841,18 @@ int hdg_p2p_alloc(hdg_handle h, int64_t slab_doubles, void* handle64) {
   const size_t bytes = sizeof(P2PHeader) + 2 * (size_t)c->nranks * (size_t)slab_doubles * sizeof(double);
   CUDA_TRY(h, cudaMalloc((void**)&c->p2p.base, bytes));
   CUDA_TRY(h, cudaMemset(c->p2p.base, 0, bytes));
+  {
+    // bound of one spin: two minutes unless HDG_P2P_TIMEOUT_S says otherwise (ranks reach their first exchange after
+    // rank-variable host work: mesh partitioning, multigrid set-up, graph instantiation, a profiler)
+    double secs = 120.0;
+    if (const char* e = getenv("HDG_P2P_TIMEOUT_S")) secs = std::max(0.001, atof(e));
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    const long long cycles = (long long)(secs * 1e3 * (double)khz);
+    CUDA_TRY(h, cudaMemcpy(&p2p_header(c->p2p.base)->spin_cycles, &cycles, sizeof(cycles), cudaMemcpyHostToDevice));
+    if (!c->p2p_err_host) CUDA_TRY(h, cudaMallocHost((void**)&c->p2p_err_host, sizeof(int)));
+    *c->p2p_err_host = 0;
+  }
   c->p2p.slab = (size_t)slab_doubles;
   c->p2p.peer_base[c->rank] = c->p2p.base;
   cudaIpcMemHandle_t hd;
@@ -2764,7 +2887,16 @@ int hdg_p2p_enable(hdg_handle h, int on) {
       if (!c->p2p.peer_base[q]) FAIL(h, HDG_ESTATE, "hdg_p2p_enable: peers are not attached");
   }
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  invalidate_graphs(h);  // the captured bodies contain either the NCCL or the peer-memory exchange
   c->p2p.enabled = on != 0;
+  if (on && c->p2p.base && c->p2p_err_host && *c->p2p_err_host) {
+    // re-arming after a fatal timeout: the caller has re-synchronised the ranks; clear the sticky state (the exchange
+    // counters of both sides of every pair must be equal again, which only a collective restart guarantees)
+    const int zero[3] = {0, 0, 0};
+    CUDA_TRY(h, cudaMemcpy(&p2p_header(c->p2p.base)->error, zero, sizeof(zero), cudaMemcpyHostToDevice));
+    *c->p2p_err_host = 0;
+    if (h->comm_rc == HDG_ECOMM) h->comm_rc = 0;
+  }
   return HDG_OK;
 }
 
@@ -2776,6 +2908,7 @@ int hdg_p2p_status(hdg_handle h, int* error) {
   CUDA_TRY(h, cudaMemcpyAsync(error, &p2p_header(h->comm->p2p.base)->error, sizeof(int), cudaMemcpyDeviceToHost,
                               h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (*error && !h->comm_rc) p2p_poll(h);  // make the failure sticky for every later call as well
   return HDG_OK;
 }
 
@@ -2798,7 +2931,14 @@ int hdg_set_halo_plan(hdg_handle h, int kind, int n_owned, int n_local, int npee
   if (npeers > 0 && (!peer_rank || !send_ptr || !recv_off || !recv_cnt)) return HDG_EINVAL;
   if ((kind == PLAN_CELLS && n_local != h->nc) || (kind == PLAN_FACETS && n_local != h->nf))
     FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: n_local does not match the engine's mesh");
+  // the peers of one exchange travel to the kernels in fixed-size arrays (P2PPeers)
+  if (npeers > HDG_MAX_RANKS - 1) FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: more peers than HDG_MAX_RANKS - 1");
+  for (int j = 1; j < npeers; ++j)
+    if (peer_rank[j] <= peer_rank[j - 1]) FAIL(h, HDG_EINVAL, "hdg_set_halo_plan: peer ranks must be strictly increasing");
   CUDA_TRY(h, cudaSetDevice(h->device));
+  // captured graphs bake in send_idx and the peer table of this plan
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  invalidate_graphs(h);
   HaloPlanDev& pl = h->comm->plans[kind];
   if (pl.send_idx) cudaFree(pl.send_idx);
   pl = HaloPlanDev();
@@ -2836,17 +2976,18 @@ int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   halo_exchange(h, kind, ndof, field);
   CUDA_TRY(h, cudaGetLastError());
-  return h->comm_rc;
+  return p2p_poll(h);
 }
 
 int hdg_allreduce_sum_dev(hdg_handle h, double* values, int n) {
   if (!h || !values || n < 1 || n > 16) return HDG_EINVAL;
   if (!h->comm || h->comm->nranks == 1) return HDG_OK;
   NCCL_DO(h, g_nccl.AllReduce(values, values, (size_t)n, ncclDouble, ncclSum, h->comm->nccl, h->stream));
-  return h->comm_rc;
+  return p2p_poll(h);
 }
 
 int hdg_mg_set_distribution(hdg_handle h, int repl_level, const int32_t* gather_counts, const int32_t* gather_gid) {
+  if (h) invalidate_graphs(h);
   if (!h || !gather_counts || !gather_gid) return HDG_EINVAL;
   if (!h->mg) FAIL(h, HDG_ESTATE, "hdg_mg_set_distribution: call hdg_mg_setup first");
   if (!h->comm) FAIL(h, HDG_ESTATE, "hdg_mg_set_distribution: call hdg_comm_init first");
@@ -3045,7 +3186,7 @@ static int run_project_cg(hdg_engine* h, const double* Q, double* Qcg, double rt
   halo_exchange(h, PLAN_CG, 2, t->x);
   LAUNCH(h, k_cgp_tocell<K>, cgrid, 128, nc, ncg, t->cellmap, t->x, Qcg);
   CUDA_TRY(h, cudaGetLastError());
-  if (h->comm_rc) return h->comm_rc;
+  if (p2p_poll(h)) return h->comm_rc;
   if (iters) *iters = it;
   if (!done) FAIL(h, HDG_ENOCONV, "CG velocity projection did not converge");
   return HDG_OK;

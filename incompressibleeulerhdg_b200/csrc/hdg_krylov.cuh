@@ -23,6 +23,7 @@ struct CgScalars {
 struct BiScalars {
   double rho, rr0, rr, tol2;
   int iters, done, maxit, ticket;
+  double rho_prev;  // rho of the iteration before the last one (k_bi_resume rebuilds the direction p from it)
 };
 
 
@@ -532,10 +533,52 @@ __global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restri
     int ticket = atomicAdd(&s->ticket, 1);
     if (ticket == (int)gridDim.x - 1) {
       s->ticket = 0;
+      s->rho_prev = rho_old;
       s->rho = rho_new;
       s->rr = rr;
       s->iters = it + 1;
       s->done = conv ? 1 : (stop ? 2 : 0);
+      __threadfence();
+    }
+  }
+}
+
+// Continue a BiCGStab run that stopped as converged (done == 1) with the tolerance tightened by `factor` (< 1): the
+// direction update k_bi_p skipped at the converged iteration is done now -- the partial sums of that iteration are
+// still in place -- and the done flag is cleared.  Used when the acceptance test of the caller (the preconditioned
+// primal residual of the tentative-velocity system) asks for more than the recurrence residual delivered.
+__global__ void __launch_bounds__(BLOCK) k_bi_resume(size_t n, const double* __restrict__ r, const double* __restrict__ v,
+                                                     double* __restrict__ p, const double* __restrict__ p_rv,
+                                                     const double* __restrict__ p_ts, const double* __restrict__ p_tt,
+                                                     BiScalars* s, double factor) {
+  __shared__ int done_in, it, maxit;
+  __shared__ double rho_prev, rho;
+  if (threadIdx.x == 0) {
+    done_in = s->done;
+    it = s->iters;
+    maxit = s->maxit;
+    rho_prev = s->rho_prev;
+    rho = s->rho;
+  }
+  __syncthreads();
+  if (done_in != 1 || it >= maxit) return;
+  double alpha = rho_prev / reduce_partials(p_rv, gridDim.x);
+  double tt = reduce_partials(p_tt, gridDim.x);
+  double omega = tt > 0.0 ? reduce_partials(p_ts, gridDim.x) / tt : 0.0;
+  const bool ok = omega != 0.0 && rho != 0.0 && rho_prev != 0.0;
+  if (ok) {
+    double beta = (rho / rho_prev) * (alpha / omega);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    int ticket = atomicAdd(&s->ticket, 1);
+    if (ticket == (int)gridDim.x - 1) {
+      s->ticket = 0;
+      s->tol2 *= factor * factor;
+      s->done = ok ? 0 : 2;
       __threadfence();
     }
   }

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhdg_b200
 TIMER_LABELS = ("setup_poisson", "forward_elimination", "trace_solve", "back_substitution", "bdm_projection",
                 "tentative_velocity_solve", "h2d", "d2h", "spmv_sampled", "fimpl_sampled", "condense", "assemble")
 
-HDG_OK, HDG_EINVAL, HDG_ECUDA, HDG_ENOGPU, HDG_ESTATE, HDG_ENCCL, HDG_ENOCONV = range(7)
+HDG_OK, HDG_EINVAL, HDG_ECUDA, HDG_ENOGPU, HDG_ESTATE, HDG_ENCCL, HDG_ENOCONV, HDG_ECOMM = range(8)
 
 _lib = None
 
@@ -243,7 +243,7 @@ class HDGEngine:
             self.set_halo_plan(0, pt.cells)
             self.set_halo_plan(1, pt.facets)
             if os.environ.get("HDG_P2P", "1") != "0":
-                self.p2p_setup()
+                self.p2p_setup_or_nccl()
 
     # -- multi-GPU ----------------------------------------------------------------------------------
     @property
@@ -269,6 +269,57 @@ class HDGEngine:
         self._check(self.lib.hdg_set_halo_plan(self._h, int(kind), int(plan.n_owned), int(plan.n_local), int(peers.size),
                                                p(peers), p(sptr), p(sidx), p(roff), p(rcnt)))
 
+    def p2p_setup_or_nccl(self):
+        """peer-memory transport when every rank can use it (one NVSwitch box, <= 8 ranks, peer access and CUDA IPC
+        available), decided collectively; otherwise the NCCL send/recv path stays in place"""
+        import warnings
+
+        import torch
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return  # a caller-supplied communicator without a process group: NCCL transport only
+        ok = self.nranks <= 8
+        if ok:
+            try:
+                ok = all(torch.cuda.can_device_access_peer(self.device, d) for d in range(torch.cuda.device_count())
+                         if d != self.device) or torch.cuda.device_count() == 1
+            except Exception:
+                ok = False
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            if self.rank == 0:
+                warnings.warn("hdg_b200: peer-memory transport unavailable on some rank; using NCCL send/recv")
+            return
+        err = None
+        try:
+            self.p2p_setup()
+        except Exception as exc:  # e.g. cudaIpcOpenMemHandle refused (MIG, containers without IPC)
+            err = exc
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, err is None)
+        if not all(flags):
+            if self.p2p:
+                self.p2p_enable(False)
+                self.p2p = False
+            if self.rank == 0:
+                warnings.warn(f"hdg_b200: peer-memory transport could not be set up ({err}); using NCCL send/recv")
+
+    def _collective_barrier(self):
+        """ranks arrive at their first device-side exchange after rank-variable host work (scipy hierarchy / space
+        construction): line them up so that no bounded spin of the peer-memory transport starts minutes early"""
+        if self.part is None or self.part.nranks == 1:
+            return
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.synchronize()
+                dist.barrier()
+        except ImportError:
+            pass
+
     def p2p_setup(self, slab_doubles: int | None = None):
         """switch halo exchanges and all-reduces to the NVLink peer-memory transport: allocate this
         rank's mailbox, gather the CUDA IPC handles over torch.distributed, map the peers"""
@@ -292,8 +343,8 @@ class HDGEngine:
         dist.all_gather_object(handles, buf.raw)
         blob = C.create_string_buffer(b"".join(handles), 64 * self.nranks)
         self._check(self.lib.hdg_p2p_attach(self._h, blob))
-        dist.barrier()  # nobody pushes before everybody has mapped everybody
         self.p2p = True
+        dist.barrier()  # nobody pushes before everybody has mapped everybody
 
     def p2p_enable(self, on: bool = True):
         self._check(self.lib.hdg_p2p_enable(self._h, int(bool(on))))
@@ -479,6 +530,7 @@ class HDGEngine:
         Tt = conv(H.Tt if dist else H.T.T)
         lmax = np.ascontiguousarray(H.lmax, dtype=np.float64)
         pinv = np.ascontiguousarray(H.pinv, dtype=np.float64)
+        self._collective_barrier()  # hdg_mg_setup runs power iterations with halo exchanges and all-reduces
         self._check(self.lib.hdg_mg_setup(self._h, nl, A, P, R, C.byref(T), C.byref(Tt), _ptr(lmax), _ptr(pinv),
                                           int(smooth_fine), int(smooth_coarse), float(cheb_ratio)))
         if dist:
@@ -608,6 +660,7 @@ class HDGEngine:
         tab_cell, tab_facet = cgspace.tracer_tables(self.k, nq_facet)
         cellmap = np.ascontiguousarray(sp.cellmap.T, dtype=np.int32)  # SoA [nloc][nc]
         dinv = np.ascontiguousarray(1.0 / sp.diag)
+        self._collective_barrier()
         self._check(self.lib.hdg_tracer_setup(
             self._h, sp.ndof, sp.ndof if n_owned is None else n_owned, cellmap.ctypes.data_as(_ip),
             sp.inc_ptr.ctypes.data_as(_ip), sp.inc_idx.ctypes.data_as(_ip), _ptr(sp.W), _ptr(dinv), tab_cell.shape[0],

@@ -124,6 +124,19 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
                           double* Q, double* p, double* l, double rtol, int maxit, int shift,
                           int* iters);
 
+/* The same solve with the back-substitution FUSED with the caller's update (north_star item 5: "back-substitution
+ * fused with the Richardson/projection update"; replaces SCPC.apply followed by the assignments of
+ * src/timesteppers/hdg_imex.py:580-587 / hdg_implicit.py:150,188-190).  With (u, phi, lam) the solution after
+ * _shift_pressure (hdg_imex.py:471-478), the kernel k_back_update computes in registers, without writing u or phi:
+ *     Q_acc <- cq Q_acc + cb Q_base + cu u      (Chorin: cq = 0, cb = 1, Q_base = tentative velocity, cu = dt;
+ *                                                IMEX Richardson stage: cq = 1, cb = 1, cu = a_ii dt)
+ *     p_acc <- cp p_acc + phi                   (Chorin: cp = 0; IMEX: cp = 1)
+ *     l     <- lam
+ * Q_base may be NULL when cb == 0.  Device SoA buffers as for hdg_poisson_apply_dev. */
+int hdg_poisson_apply_update_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double cq,
+                                 double* Q_acc, double cb, const double* Q_base, double cu, double cp, double* p_acc,
+                                 double* l, double rtol, int maxit, int* iters);
+
 /* ---- multigrid preconditioner for the trace solve (GTMGPC replacement, hdg_imex.py:138-169) ---- */
 typedef struct {
   int32_t nrows, ncols;

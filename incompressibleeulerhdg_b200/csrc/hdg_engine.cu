@@ -2137,9 +2137,11 @@ static int run_cg(hdg_engine* h, double rtol, int maxit, const double* guess, in
 
 extern "C" {
 
-int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
-                          double* p, double* l, double rtol, int maxit, int shift, int* iters) {
-  if (!h || !Q || !p || !l) return HDG_EINVAL;
+// upd == nullptr: (Q, p, l) receive the solution.  upd != nullptr (hdg_poisson_apply_update_dev): the back-substitution
+// applies the caller's update in registers (k_back_update) and the pressure shift follows from its partial sums.
+static int poisson_apply_impl(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
+                              double* p, double* l, double rtol, int maxit, int shift, int* iters, BackUpdate* upd) {
+  if (!h || !l || (!upd && (!Q || !p))) return HDG_EINVAL;
   if (!h->poisson_ready) FAIL(h, HDG_ESTATE, "hdg_poisson_apply: call hdg_setup_poisson first");
   CUDA_TRY(h, cudaSetDevice(h->device));
   int rc = hdg_forward_eliminate_dev(h, rhs_Q, rhs_p, rhs_l, h->cg_r);
@@ -2186,17 +2188,54 @@ int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p
   } else {
     CUDA_TRY(h, cudaMemcpyAsync(l, h->cg_x, (size_t)b * h->nf * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
-  rc = hdg_back_substitute_dev(h, rhs_Q, rhs_p, l, Q, p);
-  if (rc) return rc;
-  if (shift) {
-    LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, h->nc_own, p, h->partial);
+  if (upd) {
+    ScopedTimer t(h, T_BACK);
+    halo_exchange(h, PLAN_FACETS, h->k + 1, l);
+    upd->partial = h->partial;
+    upd->nc_own = h->nc_own;
+    const BackUpdate U = *upd;
+    // grid-stride over G blocks of 128 threads: the partial sums of int phi dx land in h->partial[0..G)
+    DISPATCH_K(h, {
+      LAUNCH(h, k_back_update<K>, h->grid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
+             rhs_p, (const double*)l, U);
+    });
     allreduce_slots(h, h->partial, 1);
-    LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
+    LAUNCH(h, k_shift_n, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, (const double*)h->partial, h->grid, U.pacc, l);
+  } else {
+    rc = hdg_back_substitute_dev(h, rhs_Q, rhs_p, l, Q, p);
+    if (rc) return rc;
+    if (shift) {
+      LAUNCH(h, k_pmean_partial, h->grid, BLOCK, h->cell_xy, h->nc, h->nc_own, p, h->partial);
+      allreduce_slots(h, h->partial, 1);
+      LAUNCH(h, k_shift, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, h->partial, p, l);
+    }
   }
   CUDA_TRY(h, cudaGetLastError());
   if (p2p_poll(h)) return h->comm_rc;
   if (cg_rc == HDG_ENOCONV) FAIL(h, HDG_ENOCONV, "trace CG did not converge within maxit");
   return HDG_OK;
+}
+
+int hdg_poisson_apply_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double* Q,
+                          double* p, double* l, double rtol, int maxit, int shift, int* iters) {
+  return poisson_apply_impl(h, rhs_Q, rhs_p, rhs_l, Q, p, l, rtol, maxit, shift, iters, nullptr);
+}
+
+int hdg_poisson_apply_update_dev(hdg_handle h, const double* rhs_Q, const double* rhs_p, const double* rhs_l, double cq,
+                                 double* Q_acc, double cb, const double* Q_base, double cu, double cp, double* p_acc,
+                                 double* l, double rtol, int maxit, int* iters) {
+  if (!h || !Q_acc || !p_acc || !l || (cb != 0.0 && !Q_base)) return HDG_EINVAL;
+  BackUpdate U;
+  U.cq = cq;
+  U.cb = cb;
+  U.cu = cu;
+  U.cp = cp;
+  U.Qbase = Q_base;
+  U.Qacc = Q_acc;
+  U.pacc = p_acc;
+  U.partial = nullptr;
+  U.nc_own = 0;
+  return poisson_apply_impl(h, rhs_Q, rhs_p, rhs_l, nullptr, nullptr, l, rtol, maxit, 1, iters, &U);
 }
 
 int hdg_field_size(hdg_handle h, int kind, int64_t* n) {

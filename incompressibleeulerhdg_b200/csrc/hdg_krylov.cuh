@@ -325,6 +325,18 @@ __global__ void __launch_bounds__(BLOCK) k_pmean_partial(const double* __restric
   acc = block_reduce(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
+// pressure shift after the fused back-substitution (k_back_update, hdg_poisson.cuh): `partial` holds the partial sums of
+// sum_K detJ phi_0 of THIS solve's phi, which was accumulated into p (p <- cp p + phi), so removing the mean of phi
+// from p is the same subtraction on mode 0; lam (the trace of this solve) is shifted like in k_shift
+__global__ void __launch_bounds__(BLOCK) k_shift_n(int nc, int nf, double inv_volume, const double* __restrict__ partial,
+                                                   int npartial, double* __restrict__ p, double* __restrict__ lam) {
+  double integral = reduce_partials(partial, npartial) * 0.70710678118654752440;
+  double shift = integral * inv_volume;
+  double ps = shift * 0.70710678118654752440;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) p[i] -= ps;
+  if (lam)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) lam[i] -= shift;
+}
 __global__ void __launch_bounds__(BLOCK) k_shift(int nc, int nf, double inv_volume, const double* __restrict__ partial,
                                                  double* __restrict__ p, double* __restrict__ lam) {
   double integral = reduce_partials(partial, gridDim.x) * 0.70710678118654752440;

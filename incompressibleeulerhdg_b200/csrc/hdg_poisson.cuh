@@ -269,3 +269,86 @@ __global__ void __launch_bounds__(128) k_back(const double* __restrict__ xy, con
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K5 fused with the update of the caller (north_star item 5; a6 + a7): back-substitution whose result never goes to
+// memory as (u, phi) -- the Richardson / projection update of the timesteppers is applied in registers:
+//     Qacc <- cq Qacc + cb Qbase + cu u        (Chorin  Q = Q~ + dt u, hdg_implicit.py:150:      cq = 0, cb = 1, cu = dt;
+//                                               IMEX    Q_i += Q~ + a dt u, hdg_imex.py:580-587: cq = 1, cb = 1, cu = a dt)
+//     pacc <- cp pacc + phi                    (Chorin  p = phi, hdg_implicit.py:188;  IMEX  p_i += phi: cp = 1)
+// together with the partial sums of  int_K phi dx = detJ phi_0 / sqrt(2)  over the owned cells, which the pressure shift
+// (_shift_pressure, hdg_imex.py:471-478; hdg_implicit.py:189-190) needs: k_shift then only touches mode 0 of pacc.
+// Saves writing u, phi and re-reading u, phi, Q~ (and the pressure pass of k_pmean_partial) per solve.
+// Launched with a grid-stride grid of G blocks of 128 threads; partial has G entries.
+// ------------------------------------------------------------------------------------------------
+struct BackUpdate {
+  double cq, cb, cu, cp;
+  const double* Qbase;  // may be null when cb == 0
+  double* Qacc;
+  double* pacc;
+  double* partial;
+  int nc_own;
+};
+
+__device__ __forceinline__ double block_reduce128(double v) {  // fixed tree, 128 threads; result valid in thread 0
+  __shared__ double sm128[4];
+  HDG_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm128[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (sm128[0] + sm128[1]) + (sm128[2] + sm128[3]);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_back_update(const double* __restrict__ xy, const int* __restrict__ flip,
+                                                     const int* __restrict__ cell_facet, int nc, int nf, double tau,
+                                                     const double* __restrict__ Ru, const double* __restrict__ Rp,
+                                                     const double* __restrict__ lamg, BackUpdate U) {
+  using D = Dims<K>;
+  constexpr int NQ1 = D::NQ1, NP = D::NP, NL1 = D::NL1;
+  double acc = 0.0;
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
+    Geo g = make_geo(xy, nc, cell);
+    double L[D::NH];
+    build_H<K>(g, tau, L);
+    cholesky<NP>(L);
+    double u[2][NQ1], phi[NP], lam[3][NL1];
+    HDG_UNROLL
+    for (int e = 0; e < 3; ++e) {
+      int f = cell_facet[(size_t)e * nc + cell];
+      int fl = flip[(size_t)e * nc + cell];
+      HDG_UNROLL
+      for (int m = 0; m < NL1; ++m) lam[e][m] = flip_sign(fl, m) * lamg[(size_t)m * nf + f];
+    }
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) u[c][i] = Ru ? Ru[(size_t)(c * NQ1 + i) * nc + cell] : 0.0;
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) phi[a] = Rp ? Rp[(size_t)a * nc + cell] : 0.0;
+    local_solve<K, true>(g, tau, L, lam, u, phi);
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) {
+        const size_t idx = (size_t)(c * NQ1 + i) * nc + cell;
+        double v = U.cu * u[c][i];
+        if (U.cb != 0.0) v = fma(U.cb, U.Qbase[idx], v);
+        if (U.cq != 0.0) v = fma(U.cq, U.Qacc[idx], v);
+        U.Qacc[idx] = v;
+      }
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) {
+      const size_t idx = (size_t)a * nc + cell;
+      double v = phi[a];
+      if (U.cp != 0.0) v = fma(U.cp, U.pacc[idx], v);
+      U.pacc[idx] = v;
+    }
+    if (cell < U.nc_own) acc = fma(g.detJ, phi[0], acc);
+  }
+#ifdef __CUDA_ARCH__
+  acc = block_reduce128(acc);
+#endif
+  if (threadIdx.x == 0) U.partial[blockIdx.x] = acc;
+}
+

@@ -49,6 +49,8 @@ SIGNATURES = {
                                          C.POINTER(C.c_int)]),
     "hdg_poisson_apply_dev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_int, C.c_int,
                                         C.POINTER(C.c_int)]),
+    "hdg_poisson_apply_update_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, _vp, C.c_double, _vp, C.c_double,
+                                               C.c_double, _vp, _vp, C.c_double, C.c_int, C.POINTER(C.c_int)]),
     "hdg_set_initial_guess": (C.c_int, [_vp, C.c_int]),
     "hdg_mg_setup": (C.c_int, [_vp, C.c_int, C.POINTER(hdg_csr), C.POINTER(hdg_csr), C.POINTER(hdg_csr),
                                C.POINTER(hdg_csr), C.POINTER(hdg_csr), _dp, _dp, C.c_int, C.c_int, C.c_double]),
@@ -483,6 +485,19 @@ class HDGEngine:
         its = C.c_int(0)
         rc = self.lib.hdg_poisson_apply_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(rhs_l), _dev(Q), _dev(p), _dev(l),
                                             float(rtol), int(maxit), int(bool(shift)), C.byref(its))
+        self._check(rc, allow=() if check else (HDG_ENOCONV,))
+        self.last_iterations = its.value
+        return its.value
+
+    def poisson_apply_update_dev(self, rhs_Q, rhs_p, rhs_l, Q_acc, p_acc, l, cq=0.0, cb=1.0, Q_base=None, cu=1.0,
+                                 cp=0.0, rtol=1e-12, maxit=10000, check=True):
+        """condensed solve whose back-substitution applies the caller's update in registers (k_back_update):
+        Q_acc <- cq Q_acc + cb Q_base + cu u,  p_acc <- cp p_acc + phi,  l <- lam  with (u, phi, lam) the solution after
+        the pressure shift; returns the trace-solve iteration count"""
+        its = C.c_int(0)
+        rc = self.lib.hdg_poisson_apply_update_dev(self._h, _dev(rhs_Q), _dev(rhs_p), _dev(rhs_l), float(cq), _dev(Q_acc),
+                                                   float(cb), _dev(Q_base), float(cu), float(cp), _dev(p_acc), _dev(l),
+                                                   float(rtol), int(maxit), C.byref(its))
         self._check(rc, allow=() if check else (HDG_ENOCONV,))
         self.last_iterations = its.value
         return its.value

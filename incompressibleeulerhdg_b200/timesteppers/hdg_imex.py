@@ -188,6 +188,18 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                                          rtol=self.krylov_rtol, maxit=100000, shift=False)
         raise KeyError(key)
 
+    @PerformanceLog("pressure_solve")
+    def pressure_solve_update(self, i):
+        """stage-i pressure correction (`hdg_imex.py:257-272`) fused with `_shift_pressure(update)` (:579) and the
+        Richardson update  Q_i += Q~ + a dt u,  p_i += phi  (:580-593); the update trace stays in ``self._update.l``"""
+        eng = self.engine
+        adt = self._a_impl[i, i] * self._dt
+        st = self._stage_state[i]
+        eng.weak_divergence_dev(self._Q_tentative[i].data, self._work_p.data, scale=-1.0 / adt, mode=1)  # :177-179
+        return eng.poisson_apply_update_dev(None, self._work_p.data, None, st.Q.data, st.p.data, self._update.l.data,
+                                            cq=1.0, cb=1.0, Q_base=self._Q_tentative[i].data, cu=adt, cp=1.0,
+                                            rtol=self.krylov_rtol, maxit=100000)
+
     @PerformanceLog("tentative_velocity_solve")
     def tentative_velocity_solve(self, key):
         """Compute the tentative velocity (`hdg_imex.py:274-281`, forms :232-255)"""
@@ -251,14 +263,11 @@ class IncompressibleEulerHDGIMEX(IncompressibleEuler):
                         for _ in range(self.n_richardson):  # :570
                             its = self.tentative_velocity_solve(f"stage_{i:d}")
                             self.niter_tentative.update(its)
-                            its = self.pressure_solve(f"stage_{i:d}")
+                            # :575-593 in one call: pressure solve, _shift_pressure(update) (:579) and the velocity /
+                            # pressure updates (:580-593) inside the back-substitution kernel
+                            its = self.pressure_solve_update(i)
                             self.niter_pressure.update(its)
-                            self._shift_pressure(self._update)  # :579
-                            up = self._update
-                            eng.lincomb_dev(st.Q.data, [(1.0, st.Q.data), (1.0, self._Q_tentative[i].data),
-                                                        (adt, up.Q.data)])  # :580-587
-                            eng.lincomb_dev(st.p.data, [(1.0, st.p.data), (1.0, up.p.data)])  # :588-593
-                            eng.lincomb_dev(st.l.data, [(1.0, st.l.data), (1.0, up.l.data)])  # :594-599
+                            eng.lincomb_dev(st.l.data, [(1.0, st.l.data), (1.0, self._update.l.data)])  # :594-599
                     else:
                         with PerformanceLog("unsplit_solve"):  # :601-620
                             self._monolithic.solve(self._Qstar[i - 1], adt, self._rho[i], st.Q, st.p, st.l,

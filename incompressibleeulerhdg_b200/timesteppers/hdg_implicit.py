@@ -74,6 +74,12 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
         return self.engine.poisson_apply_dev(None, Rp.data, None, u.data, phi.data, lmbda.data, rtol=self.krylov_rtol,
                                              maxit=2000 if self.preconditioner == "gtmg" else 100000, shift=True)
 
+    @PerformanceLog("pressure_solve")
+    def pressure_solve_update(self, Rp, Q, Q_tentative, p, lmbda):
+        return self.engine.poisson_apply_update_dev(None, Rp.data, None, Q.data, p.data, lmbda.data, cq=0.0, cb=1.0,
+                                                    Q_base=Q_tentative.data, cu=self._dt, cp=0.0, rtol=self.krylov_rtol,
+                                                    maxit=2000 if self.preconditioner == "gtmg" else 100000)
+
     def initialise(self, Q_initial, p_initial):
         """interpolate the initial conditions and allocate the per-step work fields (:82-84)"""
         self.Q = self._V_Q.interpolate(Q_initial)
@@ -142,10 +148,11 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
                     self._dQt_hist.insert(0, self._dQt_hist.pop())
                     eng.lincomb_dev(self._dQt_hist[0].data, [(1.0, self._Q_tentative.data), (-1.0, Q.data)])
                 eng.weak_divergence_dev(self._Q_tentative.data, self._Rp.data, scale=-1.0 / self._dt, mode=0)  # :145
-                its = self.pressure_solve(self._Rp, self._u, self._phi, self._lmbda)  # :146
+                # :146 + :150 + :188-190 in one call: the back-substitution writes Q = Q~ + dt u and p = phi - mean
+                # directly (hdg_poisson_apply_update_dev), u and phi never go to memory
+                its = self.pressure_solve_update(self._Rp, Q, self._Q_tentative, p, self._lmbda)
                 self.niter_pressure.update(its)
                 self.iteration_history.append((its_t, its))
-                eng.lincomb_dev(Q.data, [(1.0, self._Q_tentative.data), (self._dt, self._u.data)])  # :150
                 self._nsteps += 1
             else:
                 with PerformanceLog("unsplit_solve"):
@@ -153,8 +160,9 @@ class IncompressibleEulerHDGImplicit(IncompressibleEuler):
                     its = self._monolithic.solve(self._Q_star, self._dt, self._rhs, Q, self._phi, self._lmbda,
                                                  rtol=self.krylov_rtol, upwind=(self.flux == "upwind"))  # :185
                     self.niter_pressure.update(its)
-            p.assign(self._phi)  # :189-190
-            eng.shift_pressure_dev(p.data, None)
+            if not self.use_projection_method:
+                p.assign(self._phi)  # :189-190
+                eng.shift_pressure_dev(p.data, None)
             if self.q_tracer is not None:  # :192-193  q <- q + dt M^-1 adv(q, P_CG Q^k), explicit Euler
                 with PerformanceLog("tracer_advection"):
                     self._tracer_advection(self.q_tracer, self._u_cg, self._q_new, c0=1.0, acc=self.q_tracer,

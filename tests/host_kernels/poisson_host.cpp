@@ -32,4 +32,12 @@ int ph_back(int k, int nc, int nf, const double* xy, const int* flip, const int*
             const double* Ru, const double* Rp, const double* lam, double* uo, double* po) {
   BY_K(k, k_back<K>(xy, flip, cell_facet, nc, nf, tau, Ru, Rp, lam, uo, po))
 }
+
+// back-substitution fused with the caller's update (k_back_update); partial[0] = sum over the owned cells of detJ phi_0
+int ph_back_update(int k, int nc, int nc_own, int nf, const double* xy, const int* flip, const int* cell_facet, double tau,
+                   const double* Ru, const double* Rp, const double* lam, double cq, double cb, double cu, double cp,
+                   const double* Qbase, double* Qacc, double* pacc, double* partial) {
+  BackUpdate U{cq, cb, cu, cp, Qbase, Qacc, pacc, partial, nc_own};
+  BY_K(k, k_back_update<K>(xy, flip, cell_facet, nc, nf, tau, Ru, Rp, lam, U))
+}
 }

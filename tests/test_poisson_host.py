@@ -111,3 +111,15 @@ def test_forward_and_back_kernels_match_the_oracle(lib, k):
     xl = np.linalg.solve(A, (Rloc - np.einsum("nal,nl->na", Bk, lam.ravel()[o.trace_dofs()]))[:, :, None])[:, :, 0]
     assert rel(uo.reshape(2, o.nQ1, nc).transpose(2, 0, 1), xl[:, :o.nQ].reshape(nc, 2, o.nQ1)) < 1e-11
     assert rel(po.T, xl[:, o.nQ:]) < 1e-11
+    # the same fused with the update of the caller (k_back_update): Qacc <- cq Qacc + cb Qbase + cu u, pacc <- cp pacc + phi,
+    # partial sum of detJ phi_0 over the owned cells (the pressure shift of hdg_imex.py:471-478 follows from it)
+    Qb, Qa, pa = rng.standard_normal(uo.shape), rng.standard_normal(uo.shape), rng.standard_normal(po.shape)
+    for cq, cb, cu, cp in ((0.0, 1.0, 0.37, 0.0), (1.0, 1.0, 0.05, 1.0), (0.0, 0.0, 1.0, 0.0)):
+        Qacc, pacc, part = Qa.copy(), pa.copy(), np.zeros(1)
+        nc_own = nc - 2
+        assert lib.ph_back_update(k, nc, nc_own, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ctypes.c_double(TAU),
+                                  dp(Ru_s), dp(Rp_s), dp(lam_s), ctypes.c_double(cq), ctypes.c_double(cb),
+                                  ctypes.c_double(cu), ctypes.c_double(cp), dp(Qb), dp(Qacc), dp(pacc), dp(part)) == 0
+        assert rel(Qacc, cq * Qa + cb * Qb + cu * uo) < 1e-12
+        assert rel(pacc, cp * pa + po) < 1e-12
+        assert abs(part[0] - np.sum(o.detJ[:nc_own] * po[0, :nc_own])) < 1e-12 * np.abs(po).max()

@@ -300,10 +300,12 @@ def run_ours(args):
     eng.reset_timers()
     kc0 = eng.kernel_counts()
     st0 = eng.tentative_stats()
+    mx0 = eng.mixed_stats()
     with ClockSampler(local) as clocks:
         ms, launches, its_main, step_no = timed_steps(args.steps, step_no)
     kc1 = eng.kernel_counts()
     st1 = eng.tentative_stats()
+    mx1 = eng.mixed_stats()
     timers = eng.timers()
     value = work_units * args.steps / (ms / 1e3)
     check_main = errors_and_checksums(step_no * dt)
@@ -413,7 +415,15 @@ def run_ours(args):
         high["tentative_solver"] = {kk: stB[kk] - stA[kk] for kk in stB}
         ts._dt = dt
 
+    comm_probe = None
     if world > 1:
+        barrier()
+        # one facet / cell halo exchange and one 2-slot all-reduce in isolation (back-to-back on the engine stream)
+        fx, ar = eng.comm_probe(1, k + 2, nred=2, nrep=200)
+        cx, _ = eng.comm_probe(0, (k + 2) * (k + 3), nred=0, nrep=200)
+        comm_probe = {"facet_halo_us": max_over_ranks(fx), "cell_halo_us": max_over_ranks(cx),
+                      "allreduce_2_slots_us": max_over_ranks(ar),
+                      "what": "device time per call, 200 back-to-back calls between two events, max over ranks"}
         barrier()
 
     if rank == 0:
@@ -493,6 +503,12 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "precision_note": ("tentative-velocity solve = FP64 iterative refinement whose inner BiCGStab iterations run "
+                               "in FP32 (HDG_TUNING=tent_mixed=1); everything else FP64"
+                               if getattr(eng, "tuning", {}).get("tent_mixed") else
+                               "FP64 throughout; only inside the right preconditioner of the tentative-velocity BiCGStab "
+                               "are the Chebyshev sweep iterates and the inverse cell blocks STORED in FP32 (flexible "
+                               "solution update; accepted on the FP64 preconditioned residual <= rtol ||x||)"),
             "config": {**workload_config(args, world), "tuning": dict(getattr(eng, "tuning", {})),
                        "initial_guess": f"time-extrapolated (degree {args.warm_order}); cold-start figure under cold_start"},
             "clocks": clocks.summary(),
@@ -514,9 +530,10 @@ def run_ours(args):
             "iterations": {"trace_cg_per_solve": its_main["trace_cg_per_solve"],
                            "tentative_bicgstab_per_solve": its_main["tentative_per_solve"],
                            "per_step_tentative_pressure": ts.iteration_history[:args.warmup + args.steps],
-                           "tentative_solver": {kk: st1[kk] - st0[kk] for kk in st1}},
+                           "tentative_solver": {kk: st1[kk] - st0[kk] for kk in st1},
+                           "tentative_mixed_precision": {kk: mx1[kk] - mx0[kk] for kk in mx1}},
             "comm": {**eng.comm_stats(), "transport": ("nvlink-p2p" if getattr(eng, "p2p", False) else "nccl")
-                     if world > 1 else "none", "p2p_timeouts": eng.p2p_status()},
+                     if world > 1 else "none", "p2p_timeouts": eng.p2p_status(), "probe": comm_probe},
             "breakdown_ms_per_step": {lab: timers[lab][0] / args.steps for lab in
                                       ("bdm_projection", "tentative_velocity_solve", "forward_elimination",
                                        "trace_solve", "back_substitution")},

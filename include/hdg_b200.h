@@ -197,6 +197,10 @@ int hdg_set_tentative_solver(hdg_handle h, int mode, int sweeps);
  * default dt = 0.04, src/driver.py:80-86, where it solves with GMRES+ILU / LU, hdg_imex.py:224-228,
  * hdg_implicit.py:126-129), failed true-residual verifications, FGMRES restart cycles}. */
 int hdg_tentative_stats(hdg_handle h, int64_t* out6);
+/* Counters of the mixed-precision tentative-velocity solver (FP64 iterative refinement around an FP32 BiCGStab, the
+ * default; hdg_set_tuning("tent_mixed", 0) selects the all-FP64 solver): out4 = {solves, outer refinement steps,
+ * inner FP32 iterations, hand-overs to the FP64 solver}. */
+int hdg_mixed_stats(hdg_handle h, int64_t* out4);
 /* multi-GPU only.  local_sweeps == 0 (default): the ghost facets are refreshed before every Chebyshev
  * sweep of the facet Schur preconditioner, which reproduces the single-GPU iteration exactly.
  * local_sweeps != 0: the sweeps run without halo exchanges in between (restricted overlapping Schwarz
@@ -295,6 +299,10 @@ int hdg_p2p_status(hdg_handle h, int* error);
 int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field);
 /* in-place sum over ranks of n <= 16 device doubles */
 int hdg_allreduce_sum_dev(hdg_handle h, double* values, int n);
+/* Measurement aid: device time (microseconds) of one halo exchange of an [ndof][n_local] field of plan `kind` and of one
+ * all-reduce of `nred` partial-sum slots, each averaged over `nrep` back-to-back calls on the engine stream.  Collective:
+ * every rank calls it with the same arguments.  Zeros on a single rank. */
+int hdg_comm_probe(hdg_handle h, int kind, int ndof, int nred, int nrep, double* us_exchange, double* us_allreduce);
 /* multigrid levels l < repl_level are row-distributed (their CSR blocks passed to hdg_mg_setup hold
  * the owned rows with local column numbering and need halo plan 2+l); levels >= repl_level are
  * replicated.  gather_counts[q] / gather_gid: rows of level repl_level owned by rank q and their

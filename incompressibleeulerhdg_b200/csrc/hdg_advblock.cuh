@@ -165,21 +165,22 @@ __device__ __forceinline__ void advblock_invert_cell(int nc, int cell, double* _
 
 // Y_c = C_K X_c for both velocity components of one cell (X, Y: SoA velocity fields [2 NQ1][nc]; Y must not alias X);
 // blk is the FP32-stored inverse, the arithmetic is FP64
-template <int K>
+// (S = double; with S = float -- the mixed-precision solver -- vectors and arithmetic are FP32 like the stored block)
+template <int K, typename S = double>
 __device__ __forceinline__ void advblock_apply_cell(int nc, int cell, const float* __restrict__ blk,
-                                                    const double* __restrict__ X, double* __restrict__ Y) {
+                                                    const S* __restrict__ X, S* __restrict__ Y) {
   constexpr int NQ1 = Dims<K>::NQ1;
-  double x[2][NQ1];
+  S x[2][NQ1];
   HDG_UNROLL
   for (int c = 0; c < 2; ++c)
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i) x[c][i] = X[(size_t)(c * NQ1 + i) * nc + cell];
   HDG_UNROLL
   for (int i = 0; i < NQ1; ++i) {
-    double y0 = 0.0, y1 = 0.0;
+    S y0 = 0, y1 = 0;
     HDG_UNROLL
     for (int j = 0; j < NQ1; ++j) {
-      const double a = (double)blk[(size_t)(i * NQ1 + j) * nc + cell];
+      const S a = (S)blk[(size_t)(i * NQ1 + j) * nc + cell];
       y0 = fma(a, x[0][j], y0);
       y1 = fma(a, x[1][j], y1);
     }
@@ -204,9 +205,9 @@ __global__ void __launch_bounds__(64) k_advblock_invert(int nc, double* __restri
     advblock_invert_cell<Dims<K>::NQ1>(nc, cell, blk, blk32, sK);
 }
 
-template <int K>
+template <int K, typename S = double>
 __global__ void __launch_bounds__(128) k_advblock_apply(int nc, const float* __restrict__ blk,
-                                                        const double* __restrict__ X, double* __restrict__ Y) {
+                                                        const S* __restrict__ X, S* __restrict__ Y) {
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x)
     advblock_apply_cell<K>(nc, cell, blk, X, Y);
 }

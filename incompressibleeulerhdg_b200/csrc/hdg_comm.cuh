@@ -158,8 +158,10 @@ struct Comm {
 };
 
 // sendbuf[i*ndof + d] = field[d*n_local + send_idx[i]]
+// (T = element type of the field: double, or float for the vectors of the mixed-precision tentative solver)
+template <typename T>
 __global__ void k_halo_pack(int total, int ndof, int n_local, const int* __restrict__ send_idx,
-                            const double* __restrict__ field, double* __restrict__ buf) {
+                            const T* __restrict__ field, T* __restrict__ buf) {
   size_t n = (size_t)total * ndof;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int d = (int)(t / total);
@@ -168,8 +170,9 @@ __global__ void k_halo_pack(int total, int ndof, int n_local, const int* __restr
   }
 }
 // field[d*n_local + n_owned + g] = recvbuf[g*ndof + d]
-__global__ void k_halo_unpack(int total, int ndof, int n_local, int n_owned, const double* __restrict__ buf,
-                              double* __restrict__ field) {
+template <typename T>
+__global__ void k_halo_unpack(int total, int ndof, int n_local, int n_owned, const T* __restrict__ buf,
+                              T* __restrict__ field) {
   size_t n = (size_t)total * ndof;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int d = (int)(t / total);
@@ -179,9 +182,10 @@ __global__ void k_halo_unpack(int total, int ndof, int n_local, int n_owned, con
 }
 
 // push: slab[(i - send_ptr[j]) * ndof + d] on peer j = field[d*n_local + send_idx[i]], then signal
+template <typename T>
 __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int nranks, size_t slab, int ndof,
                                                   int n_local, const int* __restrict__ send_idx,
-                                                  const double* __restrict__ field, char* own_base) {
+                                                  const T* __restrict__ field, char* own_base) {
   if (p2p_failed(p2p_header(own_base))) return;  // fatal state: the host reports HDG_ECOMM
   const int total = pp.send_ptr[pp.npeers];
   const size_t n = (size_t)total * ndof;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int n
     int j = 0;
     while (i >= pp.send_ptr[j + 1]) ++j;
     const unsigned long long cnt = p2p_header(own_base)->pair_cnt[pp.rank[j]] + 1ull;  // this exchange
-    double* dst = p2p_slab(pp.peer_base[j], slab, nranks, (int)(cnt & 1ull), myrank);
+    T* dst = reinterpret_cast<T*>(p2p_slab(pp.peer_base[j], slab, nranks, (int)(cnt & 1ull), myrank));
     dst[(size_t)(i - pp.send_ptr[j]) * ndof + d] = field[(size_t)d * n_local + send_idx[i]];
   }
   // the last CTA to finish publishes the data: all remote stores of this grid precede the flags
@@ -213,8 +217,9 @@ __global__ void __launch_bounds__(256) k_p2p_push(P2PPeers pp, int myrank, int n
 }
 
 // wait for every peer's push of this exchange, then field[d*n_local + n_owned + g] = slab_q[(g - recv_ptr[q])*ndof + d]
+template <typename T>
 __global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks, size_t slab, int ndof, int n_local,
-                                                         int n_owned, char* own_base, double* __restrict__ field) {
+                                                         int n_owned, char* own_base, T* __restrict__ field) {
   P2PHeader* own = p2p_header(own_base);
   __shared__ unsigned long long cnt[HDG_MAX_RANKS];
   if (p2p_failed(own)) return;
@@ -232,10 +237,79 @@ __global__ void __launch_bounds__(256) k_p2p_wait_unpack(P2PPeers pp, int nranks
     int g = (int)(t - (size_t)d * total);
     int j = 0;
     while (g >= pp.recv_ptr[j + 1]) ++j;
-    const double* src = p2p_slab(own_base, slab, nranks, (int)(cnt[j] & 1ull), pp.rank[j]);
+    const T* src = reinterpret_cast<const T*>(p2p_slab(own_base, slab, nranks, (int)(cnt[j] & 1ull), pp.rank[j]));
     field[(size_t)d * n_local + n_owned + g] = __ldcv(&src[(size_t)(g - pp.recv_ptr[j]) * ndof + d]);
   }
   // the last CTA to finish closes the exchange: every CTA has read the counters by then
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int tk = atomicAdd(&own->ticket2, 1u);
+    if (tk == gridDim.x - 1) {
+      own->ticket2 = 0;
+      for (int j = 0; j < pp.npeers; ++j) own->pair_cnt[pp.rank[j]] = cnt[j];
+      __threadfence();
+    }
+  }
+}
+
+// push + wait + unpack of one halo exchange in ONE kernel (half the launches of the pair above and no stream-order gap
+// between them): every CTA first stores its share of the owned entries into the peers' slabs; the last CTA to finish
+// raises the peers' flags; then every CTA waits for this rank's flags and copies its share of the slabs into the ghost
+// entries; the last CTA to finish advances the exchange counters.  No CTA waits before it has pushed, and the flags of
+// a rank depend on its own pushes only, so two ranks cannot wait for each other -- provided all CTAs of the grid are
+// resident (the launch caps the grid at the number of SMs).
+template <typename T>
+__global__ void __launch_bounds__(256) k_p2p_exchange(P2PPeers pp, int myrank, int nranks, size_t slab, int ndof,
+                                                      int n_local, int n_owned, const int* __restrict__ send_idx,
+                                                      T* __restrict__ field, char* own_base) {
+  P2PHeader* own = p2p_header(own_base);
+  __shared__ unsigned long long cnt[HDG_MAX_RANKS];
+  if (p2p_failed(own)) return;
+  if (threadIdx.x < pp.npeers) cnt[threadIdx.x] = own->pair_cnt[pp.rank[threadIdx.x]] + 1ull;  // this exchange
+  __syncthreads();
+  {
+    const int total = pp.send_ptr[pp.npeers];
+    const size_t n = (size_t)total * ndof;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+      int d = (int)(t / total);
+      int i = (int)(t - (size_t)d * total);
+      int j = 0;
+      while (i >= pp.send_ptr[j + 1]) ++j;
+      T* dst = reinterpret_cast<T*>(p2p_slab(pp.peer_base[j], slab, nranks, (int)(cnt[j] & 1ull), myrank));
+      dst[(size_t)(i - pp.send_ptr[j]) * ndof + d] = field[(size_t)d * n_local + send_idx[i]];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tk = atomicAdd(&own->ticket, 1u);
+    if (tk == gridDim.x - 1) {
+      own->ticket = 0;
+      __threadfence_system();
+      for (int j = 0; j < pp.npeers; ++j) {
+        volatile unsigned long long* f = &p2p_header(pp.peer_base[j])->halo_flag[myrank];
+        *f = cnt[j];
+      }
+      __threadfence_system();
+    }
+  }
+  if (threadIdx.x < pp.npeers) p2p_wait(&own->halo_flag[pp.rank[threadIdx.x]], cnt[threadIdx.x], own);
+  __syncthreads();
+  if (p2p_failed(own)) return;
+  __threadfence_system();
+  {
+    const int total = pp.recv_ptr[pp.npeers];
+    const size_t n = (size_t)total * ndof;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+      int d = (int)(t / total);
+      int g = (int)(t - (size_t)d * total);
+      int j = 0;
+      while (g >= pp.recv_ptr[j + 1]) ++j;
+      const T* src = reinterpret_cast<const T*>(p2p_slab(own_base, slab, nranks, (int)(cnt[j] & 1ull), pp.rank[j]));
+      field[(size_t)d * n_local + n_owned + g] = __ldcv(&src[(size_t)(g - pp.recv_ptr[j]) * ndof + d]);
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();

@@ -133,6 +133,23 @@ struct hdg_engine {
   int tune_krylov = 0;        // 0 = BiCGStab, FGMRES as the fallback; 1 = BiCGStab only; 2 = FGMRES only ("tent_krylov")
   int tune_gmres_m = 0;       // restart length ("tent_gmres_m"); 0 = automatic: what fits into 2 GB, between 30 and 200
   int tune_bicg_cap = 150;    // BiCGStab iterations before the fallback ("tent_bicg_cap")
+  // mixed-precision tentative solve (run_tentative_mixed; "tent_mixed", default on): FP32 inner BiCGStab on the
+  // augmented correction equation inside an FP64 iterative refinement
+  int tune_mixed = 0;         // off by default: measured on a B200 at nx = 1024 (profiles/r2/bench_r2e_mixed_ab.jsonl,
+                              // launches_r2f_mixed.md) the FP32-stored kernels are latency bound like their FP64
+                              // versions (4.3 vs 5.0 ms per iteration) while the refinement restarts cost 20-30 % more
+                              // iterations: 8.1-8.7 vs 8.0-9.0 timesteps/s, no gain
+  int tune_p2p_fused = 1;     // halo exchange as one kernel (k_p2p_exchange) instead of push + wait/unpack ("p2p_fused")
+  double mixed_failed_adt = -1.0;  // a dt for which the refinement stagnated: later solves use the FP64 solver
+  int tune_inner_tol = 50;    // inner tolerance 10^-(value/10) of the recurrence residual ("tent_inner_tol")
+  int tune_inner_cap = 60;    // inner iterations per outer step ("tent_inner_cap")
+  float *mxb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [n_aug] r, rhat, p, v, s, t
+  float *mx_adv = nullptr, *mx_cm = nullptr, *mx_t = nullptr, *mx_nyx = nullptr, *mx_mu = nullptr, *mx_xh = nullptr,
+        *mx_z = nullptr, *mx_qstar = nullptr, *mx_dx = nullptr;
+  double *mx_r64 = nullptr, *mx_w64 = nullptr;  // [2*NQ1][nc] residual and operator output of the outer iteration
+  size_t mx_n = 0;
+  GraphCache g_bicg32;
+  int64_t mixed_stats[4] = {0, 0, 0, 0};  // solves, outer steps, inner iterations, fallbacks to the FP64 solver
   double tent_tolscale = 1.0; // tolerance of the augmented recurrence relative to rtol (run_tentative_aug, accept)
   int tune_trace = 0;         // HDG_TENT_TRACE=1: residual norms of the tentative solves on stderr
   int tune_verify = 1;        // check the true residual b - A x after BiCGStab reports convergence ("tent_verify")
@@ -146,6 +163,8 @@ struct hdg_engine {
   double *gK = nullptr;                                      // [NL][nc]
   double *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [b][nf]
   double *partial = nullptr;                                 // [8][grid]
+  double *back_partial = nullptr;                            // [cdiv(nc,128)] partial sums of k_back_update
+  int back_partial_len = 0;
   CgScalars* scal = nullptr;                                 // device
   CgScalars* scal_host = nullptr;                            // pinned
   BiScalars* bscal = nullptr;
@@ -289,8 +308,10 @@ static bool comm_grow(double** buf, size_t* cap, size_t need) {
   return true;
 }
 
-// refresh the ghost entries of an SoA field [ndof][n_local] of entity kind `kind`
-static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfield) {
+// refresh the ghost entries of an SoA field [ndof][n_local] of entity kind `kind` (T = double, or float for the vectors
+// of the mixed-precision tentative solver)
+template <typename T>
+static void halo_exchange_t(hdg_engine* h, int kind, int ndof, const T* cfield) {
   Comm* c = h->comm;
   if (!c || c->nranks == 1 || !cfield) return;
   HaloPlanDev& pl = c->plans[kind];
@@ -301,7 +322,7 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
     }
     return;
   }
-  double* field = const_cast<double*>(cfield);  // only the ghost entries are written
+  T* field = const_cast<T*>(cfield);  // only the ghost entries are written
   if (c->p2p.enabled) {
     // push over NVLink peer memory: pack kernel stores into the peers' mailbox slabs and raises their
     // flags; the unpack kernel waits on the local flags (hdg_comm.cuh)
@@ -319,6 +340,7 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
     }
     pp.send_ptr[pp.npeers] = pl.total_send;
     pp.recv_ptr[pp.npeers] = pl.total_recv;
+    need = (need * sizeof(T) + sizeof(double) - 1) / sizeof(double);  // slab capacity is counted in doubles
     if (need > c->p2p.slab) {
       if (!h->comm_rc) {
         h->comm_rc = HDG_EINVAL;
@@ -327,10 +349,16 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
       }
       return;
     }
-    if (pp.npeers > 0) {
+    if (pp.npeers > 0 && h->tune_p2p_fused) {
+      // one kernel per exchange; all its CTAs must be resident (they wait for the peers after pushing)
+      const int64_t work = (int64_t)std::max(pl.total_send, pl.total_recv) * ndof;
+      const int ge = std::max(1, std::min(h->num_sms, cdiv(work, 256)));
+      LAUNCH(h, k_p2p_exchange, ge, 256, pp, c->rank, c->nranks, c->p2p.slab, ndof, pl.n_local, pl.n_owned,
+             (const int*)pl.send_idx, field, c->p2p.base);
+    } else if (pp.npeers > 0) {
       const int gs = std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_send * ndof, 256)));
       LAUNCH(h, k_p2p_push, gs, 256, pp, c->rank, c->nranks, c->p2p.slab, ndof, pl.n_local, (const int*)pl.send_idx,
-             (const double*)field, c->p2p.base);
+             (const T*)field, c->p2p.base);
       const int gr = std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_recv * ndof, 256)));
       LAUNCH(h, k_p2p_wait_unpack, gr, 256, pp, c->nranks, c->p2p.slab, ndof, pl.n_local, pl.n_owned, c->p2p.base,
              field);
@@ -338,30 +366,39 @@ static void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfiel
     c->exchanges++;
     return;
   }
-  if (!comm_grow(&c->sendbuf, &c->send_cap, (size_t)pl.total_send * ndof) ||
+  if (!comm_grow(&c->sendbuf, &c->send_cap, (size_t)pl.total_send * ndof) ||  // counted in doubles: enough for any T
       !comm_grow(&c->recvbuf, &c->recv_cap, (size_t)pl.total_recv * ndof)) {
     h->comm_rc = HDG_ECUDA;
     h->err = "halo exchange: out of device memory for the staging buffers";
     return;
   }
+  T* sendbuf = reinterpret_cast<T*>(c->sendbuf);
+  T* recvbuf = reinterpret_cast<T*>(c->recvbuf);
+  const ncclDataType_t nct = sizeof(T) == sizeof(double) ? ncclDouble : ncclFloat;
   if (pl.total_send > 0)
     LAUNCH(h, k_halo_pack, std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_send * ndof, 256))), 256,
-           pl.total_send, ndof, pl.n_local, pl.send_idx, (const double*)field, c->sendbuf);
+           pl.total_send, ndof, pl.n_local, (const int*)pl.send_idx, (const T*)field, sendbuf);
   NCCL_DO(h, g_nccl.GroupStart());
   for (size_t j = 0; j < pl.peers.size(); ++j) {
     int ns = pl.send_ptr[j + 1] - pl.send_ptr[j];
     if (ns > 0)
-      NCCL_DO(h, g_nccl.Send(c->sendbuf + (size_t)pl.send_ptr[j] * ndof, (size_t)ns * ndof, ncclDouble, pl.peers[j],
-                             c->nccl, h->stream));
+      NCCL_DO(h, g_nccl.Send(sendbuf + (size_t)pl.send_ptr[j] * ndof, (size_t)ns * ndof, nct, pl.peers[j], c->nccl,
+                             h->stream));
     if (pl.recv_cnt[j] > 0)
-      NCCL_DO(h, g_nccl.Recv(c->recvbuf + (size_t)(pl.recv_off[j] - pl.n_owned) * ndof, (size_t)pl.recv_cnt[j] * ndof,
-                             ncclDouble, pl.peers[j], c->nccl, h->stream));
+      NCCL_DO(h, g_nccl.Recv(recvbuf + (size_t)(pl.recv_off[j] - pl.n_owned) * ndof, (size_t)pl.recv_cnt[j] * ndof, nct,
+                             pl.peers[j], c->nccl, h->stream));
   }
   NCCL_DO(h, g_nccl.GroupEnd());
   if (pl.total_recv > 0)
     LAUNCH(h, k_halo_unpack, std::max(1, std::min(h->grid, cdiv((int64_t)pl.total_recv * ndof, 256))), 256,
-           pl.total_recv, ndof, pl.n_local, pl.n_owned, (const double*)c->recvbuf, field);
+           pl.total_recv, ndof, pl.n_local, pl.n_owned, (const T*)recvbuf, field);
   c->exchanges++;
+}
+static inline void halo_exchange(hdg_engine* h, int kind, int ndof, const double* cfield) {
+  halo_exchange_t<double>(h, kind, ndof, cfield);
+}
+static inline void halo_exchange(hdg_engine* h, int kind, int ndof, const float* cfield) {
+  halo_exchange_t<float>(h, kind, ndof, cfield);
 }
 
 // sum the partial-sum slots part[0..nslots)[G] over all ranks (in place; consumers stay unchanged)
@@ -429,7 +466,7 @@ static OwnMask mask_aug(const hdg_engine* h, int ndof_cell, int ndof_facet) {
 // its kernel arguments (multigrid levels and their Chebyshev bounds, halo plans, transport, tuning knobs) -- cudaMalloc
 // tends to hand back the same addresses, so the pointer keys alone would not notice.
 static void invalidate_graphs(hdg_engine* h) {
-  for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg}) {
+  for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg, &h->g_bicg32}) {
     if (gc->exec) cudaGraphExecDestroy(gc->exec);
     gc->exec = nullptr;
     gc->key.clear();
@@ -1472,6 +1509,238 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
 }
 
 // ------------------------------------------------------------------------------------------------
+// Mixed-precision tentative-velocity solve: FP64 iterative refinement around an FP32 BiCGStab.
+//
+//   repeat:  r = b - A x                      FP64 (k_fimpl<double>): the only place where cancellation matters
+//            accept when || [Phat^-1 (r, 0)]_x || <= rtol ||x||   (the criterion of run_tentative_aug; the
+//                                             preconditioner is applied in FP32 to r / ||r||, which is exact enough
+//                                             for a norm)
+//            solve  A_aug d = (r, 0) / ||r||  FP32 BiCGStab, flexible update, to the inner tolerance
+//            x += ||r|| d_x                   FP64
+//
+// Every vector of the inner solver is stored in float, its bandwidth-bound kernels compute in FP64 registers and
+// round on store, the operator kernel k_fimpl<float> (FP64-issue bound in double) computes in FP32.  The facet Schur
+// sweeps were FP32-stored already.  The inner solve works on the *correction* equation with a unit right-hand side,
+// so FP32's 7 digits are spent on the correction, not on the solution; the accuracy of the result is set by the FP64
+// residual and the acceptance test alone.  Needs the default composition of the preconditioner (cell blocks, scaled
+// Schur complement); anything else, a stagnating refinement or a failing inner solver falls back to run_tentative_aug.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+static int mixed_alloc(hdg_engine* h) {
+  constexpr int NM = TentDims<K>::NM, NQ1 = Dims<K>::NQ1;
+  const size_t nx = 2 * (size_t)NQ1 * h->nc, nmu = (size_t)NM * h->nf, n = nx + nmu;
+  if (h->mx_n == n) return HDG_OK;
+  for (int i = 0; i < 6; ++i) CUDA_TRY(h, dmalloc(&h->mxb[i], n));
+  CUDA_TRY(h, dmalloc(&h->mx_adv, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_cm, 3 * (size_t)NM * h->nc));
+  CUDA_TRY(h, dmalloc(&h->mx_t, nmu));
+  CUDA_TRY(h, dmalloc(&h->mx_nyx, nmu));
+  CUDA_TRY(h, dmalloc(&h->mx_mu, nmu));
+  CUDA_TRY(h, dmalloc(&h->mx_xh, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_z, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_qstar, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_dx, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_r64, nx));
+  CUDA_TRY(h, dmalloc(&h->mx_w64, nx));
+  for (int i = 0; i < 3; ++i)
+    if (!h->tent_f32[i]) CUDA_TRY(h, dmalloc(&h->tent_f32[i], nmu));
+  h->mx_n = n;
+  return HDG_OK;
+}
+
+template <int K>
+static int run_tentative_mixed(hdg_engine* h, const double* Qstar, double adt, bool upwind, const double* b, double* x,
+                               double rtol, int maxit, bool zero_guess, int* iters, bool* handled) {
+  constexpr int NM = TentDims<K>::NM, NQ1 = Dims<K>::NQ1;
+  *handled = false;
+  const int G = h->grid;
+  const size_t nx = 2 * (size_t)NQ1 * h->nc, nmu = (size_t)NM * h->nf, n = nx + nmu;
+  int rc = tent_setup<K>(h);
+  if (rc) return rc;
+  rc = mixed_alloc<K>(h);
+  if (rc) return rc;
+  const double inv_aalpha = 1.0 / (adt * h->alpha);
+  const int cgrid = cdiv(h->nc, 128), fgrid = cdiv(h->nf, 256);
+  const OwnMask own = mask_aug(h, 2 * NQ1, NM), own_x = mask_cells(h, 2 * NQ1);
+  const bool multi = h->comm && h->comm->nranks > 1;
+  if (!h->gm_red) {
+    CUDA_TRY(h, dmalloc(&h->gm_red, 8));
+    CUDA_TRY(h, cudaMallocHost((void**)&h->gm_host, 8 * sizeof(double)));
+  }
+  // ---- preconditioner data of this solve (FP64 kernels, as in run_tentative_aug) ----------------------------------
+  if (!h->adv_blk) CUDA_TRY(h, dmalloc(&h->adv_blk, (size_t)NQ1 * NQ1 * h->nc));
+  if (!h->adv_blk32) CUDA_TRY(h, dmalloc(&h->adv_blk32, (size_t)NQ1 * NQ1 * h->nc));
+  if (!h->adv_sK) CUDA_TRY(h, dmalloc(&h->adv_sK, (size_t)h->nc));
+  if (!h->tent_cs) CUDA_TRY(h, dmalloc(&h->tent_cs, 6 * (size_t)h->nf));
+  if (upwind)
+    LAUNCH(h, (k_advblock_build<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
+  else
+    LAUNCH(h, (k_advblock_build<K, false>), cgrid, 128, h->cell_xy, h->cell_nbr, h->nc, Qstar, adt, h->adv_blk);
+  LAUNCH(h, k_advblock_invert<K>, cdiv(h->nc, 64), 64, h->nc, h->adv_blk, h->adv_blk32, h->adv_sK);
+  halo_exchange(h, PLAN_CELLS, 1, (const double*)h->adv_sK);
+  LAUNCH(h, k_tent_scale_tc, cdiv(h->nf, 256), 256, h->nf, h->facet_cell, h->tent_c, h->adv_sK, h->tent_cs);
+  LAUNCH(h, k_mx_to_float, G, BLOCK, nx, Qstar, 1.0, h->mx_qstar);
+  const double* tcx = h->tent_cs;
+  const double* sKx = h->adv_sK;
+  std::vector<ChebCoef> cc;
+  cheb_coefs(h->tent_lmax, 8.0, h->tent_sweeps, cc);
+  float *r = h->mxb[0], *rhat = h->mxb[1], *p = h->mxb[2], *v = h->mxb[3], *sv = h->mxb[4], *t = h->mxb[5];
+  // out = A_aug Phat^-1 vin in FP32 storage; xh = [Phat^-1 vin]_x
+  auto op = [&](const float* vin, float* out, float* xh) {
+    LAUNCH(h, (k_advblock_apply<K, float>), cgrid, 128, h->nc, (const float*)h->adv_blk32, vin, h->mx_adv);
+    halo_exchange(h, PLAN_CELLS, 2 * NQ1, (const float*)h->mx_adv);
+    if (h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, NM, vin + nx);
+    LAUNCH(h, (k_tent_moments<K, float>), cgrid, 128, h->cell_xy, h->cell_flip, h->nc, (const float*)h->mx_adv, h->mx_cm);
+    LAUNCH(h, (k_tent_trhs<K, float>), fgrid, 256, (const float*)h->mx_cm, h->facet_cell, h->facet_local, h->nc, h->nf,
+           vin + nx, h->mx_t, h->mx_nyx);
+    float *sx = h->tent_f32[0], *sx2 = h->tent_f32[1];
+    for (int j = 0; j < h->tent_sweeps; ++j) {
+      const bool last = j == h->tent_sweeps - 1;
+      if (j > 0 && multi && !h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, NM, (const float*)sx);
+      LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, tcx, h->tent_col, h->tent_bits, inv_aalpha, (const float*)h->mx_t,
+                     (const float*)sx, h->tent_f32[2], last ? (float*)nullptr : sx2, last ? h->mx_mu : (float*)nullptr,
+                     cc[j].cd, cc[j].cr, j == 0 ? 1 : 0);
+      std::swap(sx, sx2);
+    }
+    halo_exchange(h, PLAN_FACETS, NM, (const float*)h->mx_mu);
+    LAUNCH(h, (k_tent_xhat<K, float>), cgrid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf,
+           (const float*)h->mx_adv, (const float*)h->mx_mu, xh, 0, sKx, h->mx_z);
+    {
+      ScopedTimer tf(h, T_FIMPL);
+      if (upwind)
+        LAUNCH(h, (k_fimpl<K, true, float>), cgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, 0.0,
+               (const float*)h->mx_qstar, (const float*)xh, (const float*)h->mx_z, 1.0f, (float)(-adt), out);
+      else
+        LAUNCH(h, (k_fimpl<K, false, float>), cgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, 0.0,
+               (const float*)h->mx_qstar, (const float*)xh, (const float*)h->mx_z, 1.0f, (float)(-adt), out);
+    }
+    LAUNCH_SWEEP(h, K, h->nf, h->facet_local, tcx, h->tent_col, h->tent_bits, inv_aalpha, (const float*)h->mx_nyx,
+                 (const float*)nullptr, (const float*)h->mx_mu, (float*)nullptr, out + nx, 0.0, 0.0, 0, 1);
+  };
+  double* P = h->partial;
+  double *p_rv = P, *p_ts = P + G, *p_tt = P + 2 * (size_t)G, *p_rho = P + 3 * (size_t)G, *p_rr = P + 4 * (size_t)G;
+  double* part6 = P + 6 * (size_t)G;
+  const int chunk = 4;
+  std::vector<uint64_t> key = {7ull, key_of(Qstar), key_of(adt), (uint64_t)upwind, (uint64_t)h->tent_sweeps,
+                               (uint64_t)h->tent_local_sweeps, key_of(h->tent_lmax), key_of(h->mxb[0]), key_of(h->mx_dx),
+                               key_of(h->mx_qstar), key_of(h->adv_blk32), key_of(h->tent_cs), (uint64_t)n,
+                               (uint64_t)own.all, (uint64_t)own.own1, (uint64_t)own.own2, (uint64_t)h->tune_sweep,
+                               (uint64_t)(h->comm && h->comm->p2p.enabled), (uint64_t)chunk};
+  auto body = [&]() {
+    for (int i = 0; i < chunk; ++i) {
+      op(p, v, h->mx_xh);
+      LAUNCH(h, k_dot2, G, BLOCK, n, own, (const float*)rhat, (const float*)v, (const float*)nullptr, p_rv,
+             (double*)nullptr);
+      allreduce_slots(h, p_rv, 1);
+      LAUNCH(h, k_bi_s_flex, G, BLOCK, n, (const float*)r, (const float*)v, sv, (const double*)p_rv,
+             (const BiScalars*)h->bscal, nx, (const float*)h->mx_xh, h->mx_dx);
+      op(sv, t, h->mx_xh);
+      LAUNCH(h, k_dot2, G, BLOCK, n, own, (const float*)t, (const float*)sv, (const float*)t, p_ts, p_tt);
+      allreduce_slots(h, p_ts, 2);
+      LAUNCH(h, k_bi_xr_flex, G, BLOCK, n, own, (const float*)sv, (const float*)t, (const float*)rhat, r,
+             (const double*)p_ts, (const double*)p_tt, p_rho, p_rr, (const BiScalars*)h->bscal, nx,
+             (const float*)h->mx_xh, h->mx_dx);
+      allreduce_slots(h, p_rho, 2);
+      LAUNCH(h, k_bi_p, G, BLOCK, n, (const float*)r, (const float*)v, p, (const double*)p_rv, (const double*)p_ts,
+             (const double*)p_tt, (const double*)p_rho, (const double*)p_rr, h->bscal);
+    }
+  };
+  const double inner_rtol = std::pow(10.0, -0.1 * h->tune_inner_tol);
+  h->mixed_stats[0]++;
+  h->tent_stats[0]++;
+  int its_total = 0;
+  double rr_prev = -1.0, ratio = -1.0;  // ratio = || [Phat^-1 (r,0)]_x || / ||r||, measured at the first outer step
+  bool converged = false;
+  if (zero_guess) CUDA_TRY(h, cudaMemsetAsync(x, 0, nx * sizeof(double), h->stream));
+  const int max_outer = 12;
+  for (int outer = 0; outer < max_outer && its_total < maxit; ++outer) {
+    h->mixed_stats[1]++;
+    // ---- FP64 residual ----------------------------------------------------------------------------------------------
+    if (zero_guess && outer == 0) {
+      LAUNCH(h, k_resid_norm, G, BLOCK, nx, own_x, b, (const double*)x, h->mx_r64, part6);  // x == 0: r = b
+    } else {
+      halo_exchange(h, PLAN_CELLS, 2 * NQ1, (const double*)x);
+      launch_fimpl<K>(h, upwind, Qstar, x, 1.0, -adt, h->mx_w64);
+      LAUNCH(h, k_resid_norm, G, BLOCK, nx, own_x, b, (const double*)h->mx_w64, h->mx_r64, part6);
+    }
+    LAUNCH(h, k_dot2, G, BLOCK, nx, own_x, (const double*)x, (const double*)x, (const double*)nullptr, part6 + G,
+           (double*)nullptr);
+    allreduce_slots(h, part6, 2);
+    LAUNCH(h, k_part_finish, 2, BLOCK, (const double*)part6, G, h->gm_red);
+    CUDA_TRY(h, cudaMemcpyAsync(h->gm_host, h->gm_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    p2p_poll_async(h);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (p2p_poll_result(h)) return h->comm_rc;
+    const double rr = h->gm_host[0], xx = h->gm_host[1];
+    if (!std::isfinite(rr)) break;
+    if (rr == 0.0) {
+      converged = true;
+      break;
+    }
+    if (rr_prev > 0.0 && rr > 0.25 * rr_prev) break;  // the refinement stagnates: hand over to the FP64 solver
+    rr_prev = rr;
+    const double rnorm = std::sqrt(rr);
+    // ---- (r, 0) / ||r|| in FP32 ---------------------------------------------------------------------------------
+    LAUNCH(h, k_mx_to_float, G, BLOCK, nx, (const double*)h->mx_r64, 1.0 / rnorm, r);
+    CUDA_TRY(h, cudaMemsetAsync(r + nx, 0, nmu * sizeof(float), h->stream));
+    // ---- acceptance: measured at the first step, afterwards only when the estimate says it may pass ---------------
+    if (xx > 0.0 && (ratio < 0.0 || ratio * rnorm <= 3.0 * rtol * std::sqrt(xx))) {
+      op(r, t, h->mx_xh);
+      LAUNCH(h, k_dot2, G, BLOCK, nx, own_x, (const float*)h->mx_xh, (const float*)h->mx_xh, (const float*)nullptr, part6,
+             (double*)nullptr);
+      allreduce_slots(h, part6, 1);
+      LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)part6, G, h->gm_red + 2);
+      CUDA_TRY(h, cudaMemcpyAsync(h->gm_host + 2, h->gm_red + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      ratio = std::sqrt(h->gm_host[2]);
+      if (h->tune_trace)
+        fprintf(stderr, "[hdg tent/mixed] outer %d  ||b-Ax||=%.3e  ||Phat^-1(b-Ax)||/||x||=%.3e  inner its so far %d\n",
+                outer, rnorm, ratio * rnorm / std::sqrt(xx), its_total);
+      if (ratio * rnorm <= rtol * std::sqrt(xx)) {
+        converged = true;
+        break;
+      }
+    } else if (h->tune_trace) {
+      fprintf(stderr, "[hdg tent/mixed] outer %d  ||b-Ax||=%.3e  (estimate %.3e)\n", outer, rnorm,
+              ratio > 0.0 && xx > 0.0 ? ratio * rnorm / std::sqrt(xx) : -1.0);
+    }
+    // ---- FP32 BiCGStab on the correction equation -----------------------------------------------------------------
+    CUDA_TRY(h, cudaMemsetAsync(h->mx_dx, 0, nx * sizeof(float), h->stream));
+    LAUNCH(h, k_bi_init, G, BLOCK, n, own, (const float*)r, (const float*)nullptr, r, rhat, p, p_rr);
+    allreduce_slots(h, p_rr, 1);
+    const int cap = std::min(h->tune_inner_cap, maxit - its_total);
+    LAUNCH(h, k_bi_start, 1, BLOCK, h->bscal, (const double*)p_rr, (const double*)nullptr, G, inner_rtol, cap);
+    int launched = 0;
+    while (true) {
+      int grc = run_graphed(h, h->g_bicg32, key, body);
+      if (grc) return grc;
+      launched += chunk;
+      CUDA_TRY(h, cudaMemcpyAsync(h->bscal_host, h->bscal, sizeof(BiScalars), cudaMemcpyDeviceToHost, h->stream));
+      p2p_poll_async(h);
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      if (p2p_poll_result(h)) return h->comm_rc;
+      if (h->bscal_host->done || launched >= cap) break;
+    }
+    its_total += h->bscal_host->iters;
+    h->mixed_stats[2] += h->bscal_host->iters;
+    h->tent_stats[1] += h->bscal_host->iters;
+    if (h->tune_trace)
+      fprintf(stderr, "[hdg tent/mixed]   inner BiCGStab done=%d iterations=%d  recurrence %.3e\n", h->bscal_host->done,
+              h->bscal_host->iters, std::sqrt(h->bscal_host->rr / std::max(h->bscal_host->rr0, 1e-300)));
+    if (!std::isfinite(h->bscal_host->rr) || h->bscal_host->iters == 0) break;
+    LAUNCH(h, k_mx_axpy, G, BLOCK, nx, x, rnorm, (const float*)h->mx_dx);
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  if (iters) *iters = its_total;
+  if (converged) {
+    *handled = true;
+    return HDG_OK;
+  }
+  h->mixed_stats[3]++;
+  return HDG_OK;  // not handled: the caller continues with the FP64 solver from the current x
+}
+
+// ------------------------------------------------------------------------------------------------
 // multigrid-preconditioned CG (host orchestration)
 // ------------------------------------------------------------------------------------------------
 static void free_csr(DevCsr& m) {
@@ -1766,10 +2035,12 @@ int hdg_destroy(hdg_handle h) {
                   h->bi[0], h->bi[1], h->bi[2], h->bi[3], h->bi[4], h->bi[5], h->bscal, h->tent_c, h->tent_col,
                   h->tent_bits, h->tent_cm, h->tent_f[0], h->tent_f[1], h->tent_f[2], h->tent_f[3], h->tent_f[4],
                   h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in, h->tent_f32[0], h->tent_f32[1],
-                  h->tent_f32[2], h->adv_sK, h->tent_cs, h->tent_z, h->gm_V, h->gm_Z, h->gm_part, h->gm_red, h->gm_coef};
+                  h->tent_f32[2], h->adv_sK, h->tent_cs, h->tent_z, h->gm_V, h->gm_Z, h->gm_part, h->gm_red, h->gm_coef,
+                  h->mxb[0], h->mxb[1], h->mxb[2], h->mxb[3], h->mxb[4], h->mxb[5], h->mx_adv, h->mx_cm, h->mx_t,
+                  h->mx_nyx, h->mx_mu, h->mx_xh, h->mx_z, h->mx_qstar, h->mx_dx, h->mx_r64, h->mx_w64, h->back_partial};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg})
+  for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg, &h->g_bicg32})
     if (gc->exec) cudaGraphExecDestroy(gc->exec);
   if (h->g_in) cudaEventDestroy(h->g_in);
   if (h->g_out) cudaEventDestroy(h->g_out);
@@ -2191,14 +2462,28 @@ static int poisson_apply_impl(hdg_handle h, const double* rhs_Q, const double* r
   if (upd) {
     ScopedTimer t(h, T_BACK);
     halo_exchange(h, PLAN_FACETS, h->k + 1, l);
-    upd->partial = h->partial;
+    // one cell per thread like k_back (a grid-stride launch of G blocks measured 2.3 x slower, profiles/r2/
+    // launches_r2f_mixed.md); its per-block partial sums of int phi dx are finished into slot 0 of h->partial
+    const int nblk = cdiv(h->nc, 128);
+    if (h->back_partial_len < nblk) {
+      if (h->back_partial) cudaFree(h->back_partial);
+      h->back_partial = nullptr;
+      CUDA_TRY(h, dmalloc(&h->back_partial, (size_t)nblk));
+      h->back_partial_len = nblk;
+    }
+    upd->partial = h->back_partial;
     upd->nc_own = h->nc_own;
     const BackUpdate U = *upd;
-    // grid-stride over G blocks of 128 threads: the partial sums of int phi dx land in h->partial[0..G)
     DISPATCH_K(h, {
-      LAUNCH(h, k_back_update<K>, h->grid, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
+      LAUNCH(h, k_back_update<K>, nblk, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
              rhs_p, (const double*)l, U);
     });
+    if (!h->gm_red) {
+      CUDA_TRY(h, dmalloc(&h->gm_red, 8));
+      CUDA_TRY(h, cudaMallocHost((void**)&h->gm_host, 8 * sizeof(double)));
+    }
+    LAUNCH(h, k_part_finish, 1, BLOCK, (const double*)h->back_partial, nblk, h->gm_red + 4);
+    LAUNCH(h, k_part_spread, 1, BLOCK, h->partial, h->grid, (const double*)(h->gm_red + 4));
     allreduce_slots(h, h->partial, 1);
     LAUNCH(h, k_shift_n, h->grid, BLOCK, h->nc, h->nf, 1.0 / h->volume, (const double*)h->partial, h->grid, U.pacc, l);
   } else {
@@ -2500,6 +2785,25 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     h->bicg_failed_adt = -1.0;
     return HDG_OK;
   }
+  if (!strcmp(name, "p2p_fused")) {
+    h->tune_p2p_fused = value != 0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_mixed")) {
+    h->tune_mixed = value != 0;
+    h->mixed_failed_adt = -1.0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_inner_tol")) {
+    if (value < 10 || value > 80) return HDG_EINVAL;
+    h->tune_inner_tol = value;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "tent_inner_cap")) {
+    if (value < 1) return HDG_EINVAL;
+    h->tune_inner_cap = value;
+    return HDG_OK;
+  }
   if (!strcmp(name, "tent_trace")) {
     h->tune_trace = value != 0;
     return HDG_OK;
@@ -2560,6 +2864,12 @@ int hdg_tentative_stats(hdg_handle h, int64_t* out6) {
   return HDG_OK;
 }
 
+int hdg_mixed_stats(hdg_handle h, int64_t* out4) {
+  if (!h || !out4) return HDG_EINVAL;
+  for (int i = 0; i < 4; ++i) out4[i] = h->mixed_stats[i];
+  return HDG_OK;
+}
+
 int hdg_set_tentative_comm(hdg_handle h, int local_sweeps) {
   if (!h) return HDG_EINVAL;
   h->tent_local_sweeps = local_sweeps != 0;
@@ -2608,7 +2918,23 @@ int hdg_tentative_solve_dev(hdg_handle h, const double* Qstar, double adt, int u
   {
     ScopedTimer t(h, T_TENT);
     if (h->tent_mode == 1 && h->alpha > 0.0 && adt > 0.0) {
-      DISPATCH_K(h, rc = run_tentative_aug<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
+      bool handled = false;
+      int its_mixed = 0;
+      rc = HDG_OK;
+      const bool mixed = h->tune_mixed && h->tune_cellblock && h->tune_scaledx && h->tune_flex && h->tune_krylov == 0 &&
+                         h->mixed_failed_adt != adt;
+      if (mixed) {
+        DISPATCH_K(h, rc = run_tentative_mixed<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0,
+                                                  &its_mixed, &handled));
+        if (iters) *iters = its_mixed;
+        if (!rc && !handled) h->mixed_failed_adt = adt;  // e.g. a large time step: later solves skip the attempt
+      }
+      if (!rc && !handled) {
+        int its64 = 0;
+        DISPATCH_K(h, rc = run_tentative_aug<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, std::max(1, maxit - its_mixed),
+                                                zero_guess != 0 && !mixed, &its64));
+        if (iters) *iters = its_mixed + its64;
+      }
     } else {
       DISPATCH_K(h, rc = run_bicgstab<K>(h, Qstar, adt, upwind != 0, rhs, x, rtol, maxit, zero_guess != 0, iters));
     }
@@ -3015,6 +3341,44 @@ int hdg_halo_exchange_dev(hdg_handle h, int kind, int ndof, double* field) {
   CUDA_TRY(h, cudaSetDevice(h->device));
   halo_exchange(h, kind, ndof, field);
   CUDA_TRY(h, cudaGetLastError());
+  return p2p_poll(h);
+}
+
+// nrep halo exchanges (and, with nred > 0, nrep all-reduces of nred slots) back to back on the engine stream between two
+// events: the device time of one exchange / one all-reduce in isolation (every rank must call it with the same arguments)
+int hdg_comm_probe(hdg_handle h, int kind, int ndof, int nred, int nrep, double* us_exchange, double* us_allreduce) {
+  if (!h || !us_exchange || !us_allreduce || nrep < 1 || ndof < 1 || nred < 0 || nred > HDG_RED_MAX) return HDG_EINVAL;
+  *us_exchange = *us_allreduce = 0.0;
+  Comm* c = h->comm;
+  if (!c || c->nranks == 1) return HDG_OK;
+  if (kind < 0 || kind >= HDG_MAX_PLANS || !c->plans[kind].set) FAIL(h, HDG_ESTATE, "hdg_comm_probe: no such halo plan");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  double* field = nullptr;
+  CUDA_TRY(h, dmalloc(&field, (size_t)ndof * c->plans[kind].n_local));
+  CUDA_TRY(h, cudaMemsetAsync(field, 0, (size_t)ndof * c->plans[kind].n_local * sizeof(double), h->stream));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  for (int i = 0; i < 5; ++i) halo_exchange(h, kind, ndof, (const double*)field);
+  cudaEventRecord(e0, h->stream);
+  for (int i = 0; i < nrep; ++i) halo_exchange(h, kind, ndof, (const double*)field);
+  cudaEventRecord(e1, h->stream);
+  for (int i = 0; i < nrep && nred > 0; ++i) allreduce_slots(h, h->partial, nred);
+  cudaEventRecord(e2, h->stream);
+  cudaError_t err = cudaEventSynchronize(e2);
+  float ms01 = 0, ms12 = 0;
+  if (err == cudaSuccess) {
+    cudaEventElapsedTime(&ms01, e0, e1);
+    cudaEventElapsedTime(&ms12, e1, e2);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaFree(field);
+  CUDA_TRY(h, err);
+  *us_exchange = 1e3 * ms01 / nrep;
+  *us_allreduce = nred > 0 ? 1e3 * ms12 / nrep : 0.0;
   return p2p_poll(h);
 }
 

@@ -30,9 +30,8 @@ __global__ void k_build_nbr(const int* __restrict__ cell_facet, const int* __res
   }
 }
 
-template <int K>
-__device__ __forceinline__ void load_Q(const double* __restrict__ Q, int nc, int cell,
-                                       double (&q)[2][Dims<K>::NQ1]) {
+template <int K, typename P, typename R>  // P: storage type of the field, R: register type (both deduced)
+__device__ __forceinline__ void load_Q(const P* __restrict__ Q, int nc, int cell, R (&q)[2][Dims<K>::NQ1]) {
   constexpr int NQ1 = Dims<K>::NQ1;
   HDG_UNROLL
   for (int c = 0; c < 2; ++c)
@@ -128,18 +127,18 @@ __global__ void __launch_bounds__(128) k_bdm_lift(const double* __restrict__ xy,
 // ------------------------------------------------------------------------------------------------
 // traces of a velocity field on local facet E at the NQF Gauss points (cell-local parametrisation)
 // ------------------------------------------------------------------------------------------------
-template <int K, int E>
-__device__ __forceinline__ void trace_at_points(const double (&x)[2][Dims<K>::NQ1], bool reversed,
-                                                double (&out)[RefTables<K>::NQF][2]) {
+template <int K, int E, typename R>
+__device__ __forceinline__ void trace_at_points(const R (&x)[2][Dims<K>::NQ1], bool reversed,
+                                                R (&out)[RefTables<K>::NQF][2]) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) {
-    double v0 = 0.0, v1 = 0.0;
+    R v0 = 0, v1 = 0;
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i) {
-      v0 = fma(T::PHIF(E, q, i), x[0][i], v0);
-      v1 = fma(T::PHIF(E, q, i), x[1][i], v1);
+      v0 = fma((R)T::PHIF(E, q, i), x[0][i], v0);
+      v1 = fma((R)T::PHIF(E, q, i), x[1][i], v1);
     }
     out[q][0] = v0;
     out[q][1] = v1;
@@ -149,7 +148,7 @@ __device__ __forceinline__ void trace_at_points(const double (&x)[2][Dims<K>::NQ
     for (int q = 0; q < NQF / 2; ++q) {
       HDG_UNROLL
       for (int c = 0; c < 2; ++c) {
-        double t = out[q][c];
+        R t = out[q][c];
         out[q][c] = out[NQF - 1 - q][c];
         out[NQF - 1 - q][c] = t;
       }
@@ -157,10 +156,10 @@ __device__ __forceinline__ void trace_at_points(const double (&x)[2][Dims<K>::NQ
   }
 }
 
-template <int K>
-__device__ __forceinline__ void nbr_trace(const double* __restrict__ X, int nc, int nbr, int e2,
-                                          double (&out)[RefTables<K>::NQF][2]) {
-  double xn[2][Dims<K>::NQ1];
+template <int K, typename P, typename R>
+__device__ __forceinline__ void nbr_trace(const P* __restrict__ X, int nc, int nbr, int e2,
+                                          R (&out)[RefTables<K>::NQF][2]) {
+  R xn[2][Dims<K>::NQ1];
   load_Q<K>(X, nc, nbr, xn);
   switch (e2) {
     case 0: trace_at_points<K, 0>(xn, true, out); break;
@@ -175,43 +174,45 @@ __device__ __forceinline__ void nbr_trace(const double* __restrict__ X, int nc, 
 //   - int_K w_c (Q*.grad) x_c
 //   + int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr).w - alpha/h_F ((x_K - x_nbr).n)(w.n)
 //   - int_{dK bnd} alpha/h_F (x.n)(w.n)
+// R = arithmetic and storage type of the fields: double on every FP64 path; float inside the mixed-precision
+// tentative-velocity solver (hdg_engine.cu, run_tentative_mixed), where the operator only acts on corrections.
 // ------------------------------------------------------------------------------------------------
-template <int K, bool UPWIND, int E>
+template <int K, bool UPWIND, int E, typename P, typename R>
 __device__ __forceinline__ void fimpl_facet(const Geo& g, double alpha, int nc, int nbr, int nbr_e,
-                                            const double* __restrict__ X, const double (&x)[2][Dims<K>::NQ1],
-                                            const double (&Qh)[2][Dims<K>::NQ1], double (&acc)[2][Dims<K>::NQ1]) {
+                                            const P* __restrict__ X, const R (&x)[2][Dims<K>::NQ1],
+                                            const R (&Qh)[2][Dims<K>::NQ1], R (&acc)[2][Dims<K>::NQ1]) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
-  const double nx = g.n[E][0], ny = g.n[E][1];
-  const double scale = g.le[E] * g.idetJ;
-  const double hf = alpha / g.le[E];
-  double xo[NQF][2];
+  const R nx = (R)g.n[E][0], ny = (R)g.n[E][1];
+  const R scale = (R)(g.le[E] * g.idetJ);
+  const R hf = (R)(alpha / g.le[E]);
+  R xo[NQF][2];
   trace_at_points<K, E>(x, false, xo);
-  double vec[NQF][2];
+  R vec[NQF][2];
   if (nbr >= 0) {
-    double xnb[NQF][2];
+    R xnb[NQF][2];
     nbr_trace<K>(X, nc, nbr, nbr_e, xnb);
     // n . Q* through the pulled-back field: Q* = J Qh  =>  n.Q*_i = (J^T n)_d Qh[d][i]
     double J00 = g.Ji[1][1] * g.detJ, J01 = -g.Ji[0][1] * g.detJ, J10 = -g.Ji[1][0] * g.detJ,
            J11 = g.Ji[0][0] * g.detJ;
-    double m0 = nx * J00 + ny * J10, m1 = nx * J01 + ny * J11;
+    const R m0 = (R)(g.n[E][0] * J00 + g.n[E][1] * J10), m1 = (R)(g.n[E][0] * J01 + g.n[E][1] * J11);
     HDG_UNROLL
     for (int q = 0; q < NQF; ++q) {
-      double s = 0.0;
+      R s = 0;
       HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i) s = fma(T::PHIF(E, q, i), m0 * Qh[0][i] + m1 * Qh[1][i], s);
-      double j0 = xo[q][0] - xnb[q][0], j1 = xo[q][1] - xnb[q][1];
-      double coef = 0.5 * s - (UPWIND ? fabs(s) : 0.0);
-      double pen = hf * (j0 * nx + j1 * ny);
-      double w = T::WF(q) * scale;
+      for (int i = 0; i < NQ1; ++i) s = fma((R)T::PHIF(E, q, i), m0 * Qh[0][i] + m1 * Qh[1][i], s);
+      R j0 = xo[q][0] - xnb[q][0], j1 = xo[q][1] - xnb[q][1];
+      R coef = (R)0.5 * s - (UPWIND ? fabs(s) : (R)0);
+      R pen = hf * (j0 * nx + j1 * ny);
+      R w = (R)T::WF(q) * scale;
       vec[q][0] = w * (coef * j0 - pen * nx);
       vec[q][1] = w * (coef * j1 - pen * ny);
     }
   } else {
     HDG_UNROLL
     for (int q = 0; q < NQF; ++q) {
-      double pen = hf * (xo[q][0] * nx + xo[q][1] * ny);
-      double w = T::WF(q) * scale;
+      R pen = hf * (xo[q][0] * nx + xo[q][1] * ny);
+      R w = (R)T::WF(q) * scale;
       vec[q][0] = -w * pen * nx;
       vec[q][1] = -w * pen * ny;
     }
@@ -220,59 +221,59 @@ __device__ __forceinline__ void fimpl_facet(const Geo& g, double alpha, int nc, 
   for (int q = 0; q < NQF; ++q)
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i) {
-      acc[0][i] = fma(T::PHIF(E, q, i), vec[q][0], acc[0][i]);
-      acc[1][i] = fma(T::PHIF(E, q, i), vec[q][1], acc[1][i]);
+      acc[0][i] = fma((R)T::PHIF(E, q, i), vec[q][0], acc[0][i]);
+      acc[1][i] = fma((R)T::PHIF(E, q, i), vec[q][1], acc[1][i]);
     }
 }
 
-template <int K, bool UPWIND>
+template <int K, bool UPWIND, typename R = double>
 __global__ void __launch_bounds__(128, (K <= 2 ? 3 : 1)) k_fimpl(const double* __restrict__ xy, const int* __restrict__ nbr,
                                                const int* __restrict__ nbr_e, int nc, double alpha,
-                                               const double* __restrict__ Qstar, const double* __restrict__ X,
-                                               const double* __restrict__ Z, double c0, double c1,
-                                               double* __restrict__ Y) {
+                                               const R* __restrict__ Qstar, const R* __restrict__ X,
+                                               const R* __restrict__ Z, R c0, R c1, R* __restrict__ Y) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
     Geo g = make_geo(xy, nc, cell);
-    double x[2][NQ1], Qh[2][NQ1], acc[2][NQ1];
+    R x[2][NQ1], Qh[2][NQ1], acc[2][NQ1];
     load_Q<K>(X, nc, cell, x);
     {
-      double qs[2][NQ1];
+      R qs[2][NQ1];
       load_Q<K>(Qstar, nc, cell, qs);
+      const R j00 = (R)g.Ji[0][0], j01 = (R)g.Ji[0][1], j10 = (R)g.Ji[1][0], j11 = (R)g.Ji[1][1];
       HDG_UNROLL
       for (int i = 0; i < NQ1; ++i) {
-        Qh[0][i] = g.Ji[0][0] * qs[0][i] + g.Ji[0][1] * qs[1][i];
-        Qh[1][i] = g.Ji[1][0] * qs[0][i] + g.Ji[1][1] * qs[1][i];
+        Qh[0][i] = j00 * qs[0][i] + j01 * qs[1][i];
+        Qh[1][i] = j10 * qs[0][i] + j11 * qs[1][i];
       }
     }
     HDG_UNROLL
     for (int c = 0; c < 2; ++c)
       HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i) acc[c][i] = 0.0;
+      for (int i = 0; i < NQ1; ++i) acc[c][i] = 0;
     // volume term: -(1/detJ) int_K w_c (Q*.grad x_c) = -sum_q WQ[q] phi_i(q) (Qh . grad^ x_c)(q)
     HDG_UNROLL
     for (int q = 0; q < NQ; ++q) {
-      double a0 = 0.0, a1 = 0.0, g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+      R a0 = 0, a1 = 0, g00 = 0, g01 = 0, g10 = 0, g11 = 0;
       HDG_UNROLL
       for (int i = 0; i < NQ1; ++i) {
-        a0 = fma(T::PHI(q, i), Qh[0][i], a0);
-        a1 = fma(T::PHI(q, i), Qh[1][i], a1);
+        a0 = fma((R)T::PHI(q, i), Qh[0][i], a0);
+        a1 = fma((R)T::PHI(q, i), Qh[1][i], a1);
         if (T::DPHI(0, q, i) != 0.0) {
-          g00 = fma(T::DPHI(0, q, i), x[0][i], g00);
-          g10 = fma(T::DPHI(0, q, i), x[1][i], g10);
+          g00 = fma((R)T::DPHI(0, q, i), x[0][i], g00);
+          g10 = fma((R)T::DPHI(0, q, i), x[1][i], g10);
         }
         if (T::DPHI(1, q, i) != 0.0) {
-          g01 = fma(T::DPHI(1, q, i), x[0][i], g01);
-          g11 = fma(T::DPHI(1, q, i), x[1][i], g11);
+          g01 = fma((R)T::DPHI(1, q, i), x[0][i], g01);
+          g11 = fma((R)T::DPHI(1, q, i), x[1][i], g11);
         }
       }
-      double w = -T::WQ(q);
-      double v0 = w * (a0 * g00 + a1 * g01), v1 = w * (a0 * g10 + a1 * g11);
+      R w = -(R)T::WQ(q);
+      R v0 = w * (a0 * g00 + a1 * g01), v1 = w * (a0 * g10 + a1 * g11);
       HDG_UNROLL
       for (int i = 0; i < NQ1; ++i) {
-        acc[0][i] = fma(T::PHI(q, i), v0, acc[0][i]);
-        acc[1][i] = fma(T::PHI(q, i), v1, acc[1][i]);
+        acc[0][i] = fma((R)T::PHI(q, i), v0, acc[0][i]);
+        acc[1][i] = fma((R)T::PHI(q, i), v1, acc[1][i]);
       }
     }
     fimpl_facet<K, UPWIND, 0>(g, alpha, nc, nbr[cell], nbr_e[cell], X, x, Qh, acc);

@@ -380,15 +380,16 @@ __global__ void k_int_transpose(const int* __restrict__ aos, int* __restrict__ s
 // hdg_imex.py:233-247 / hdg_implicit.py:103-129; the reference uses GMRES+ILU resp. direct LU).
 // Five kernels per iteration, reductions deterministic as in the CG.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, OwnMask own, const double* __restrict__ a,
-                                                const double* __restrict__ b, const double* __restrict__ c,
+template <typename S = double>  // S: storage type of the vectors (float in the mixed-precision solver); sums in FP64
+__global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, OwnMask own, const S* __restrict__ a,
+                                                const S* __restrict__ b, const S* __restrict__ c,
                                                 double* __restrict__ p_ab, double* __restrict__ p_cc) {
   // partial <a,b> and (optionally) <c,c> over the owned entries
   double s0 = 0.0, s1 = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     if (!is_owned(own, i)) continue;
-    s0 = fma(a[i], b[i], s0);
-    if (c) s1 = fma(c[i], c[i], s1);
+    s0 = fma((double)a[i], (double)b[i], s0);
+    if (c) s1 = fma((double)c[i], (double)c[i], s1);
   }
   s0 = block_reduce(s0);
   if (threadIdx.x == 0) p_ab[blockIdx.x] = s0;
@@ -399,16 +400,17 @@ __global__ void __launch_bounds__(BLOCK) k_dot2(size_t n, OwnMask own, const dou
 }
 
 // r = b - t (t = A x0, or r = b if t == nullptr; b may alias r); rhat = r; p = r; partial <r,r>
-__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, OwnMask own, const double* b, const double* __restrict__ t,
-                                                   double* r, double* __restrict__ rhat,
-                                                   double* __restrict__ p, double* __restrict__ part) {
+template <typename S = double>
+__global__ void __launch_bounds__(BLOCK) k_bi_init(size_t n, OwnMask own, const S* b, const S* __restrict__ t,
+                                                   S* r, S* __restrict__ rhat,
+                                                   S* __restrict__ p, double* __restrict__ part) {
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    double v = t ? b[i] - t[i] : b[i];
+    S v = t ? b[i] - t[i] : b[i];
     r[i] = v;
     rhat[i] = v;
     p[i] = v;
-    if (is_owned(own, i)) s = fma(v, v, s);
+    if (is_owned(own, i)) s = fma((double)v, (double)v, s);
   }
   s = block_reduce(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
@@ -474,33 +476,36 @@ __global__ void __launch_bounds__(BLOCK) k_bi_xr(size_t n, OwnMask own, const do
 // exactly linear operator (FP32 storage inside it; tests/experiments/tent_fp32_sweeps.py).
 //   k_bi_s_flex :  s = r - alpha v ;  x += alpha xh(p)
 //   k_bi_xr_flex:  x += omega xh(s);  r = s - omega t ;  partials <rhat,r>, <r,r>
-__global__ void __launch_bounds__(BLOCK) k_bi_s_flex(size_t n, const double* __restrict__ r,
-                                                     const double* __restrict__ v, double* __restrict__ sv,
+template <typename S = double>
+__global__ void __launch_bounds__(BLOCK) k_bi_s_flex(size_t n, const S* __restrict__ r,
+                                                     const S* __restrict__ v, S* __restrict__ sv,
                                                      const double* __restrict__ p_rv, const BiScalars* __restrict__ s,
-                                                     size_t nx, const double* __restrict__ xh, double* __restrict__ x) {
+                                                     size_t nx, const S* __restrict__ xh, S* __restrict__ x) {
   if (s->done) return;
   double alpha = s->rho / reduce_partials(p_rv, gridDim.x);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    sv[i] = fma(-alpha, v[i], r[i]);
-    if (i < nx) x[i] = fma(alpha, xh[i], x[i]);
+    sv[i] = (S)fma(-alpha, (double)v[i], (double)r[i]);
+    if (i < nx) x[i] = (S)fma(alpha, (double)xh[i], (double)x[i]);
   }
 }
-__global__ void __launch_bounds__(BLOCK) k_bi_xr_flex(size_t n, OwnMask own, const double* __restrict__ sv,
-                                                      const double* __restrict__ t, const double* __restrict__ rhat,
-                                                      double* __restrict__ r, const double* __restrict__ p_ts,
+template <typename S = double>
+__global__ void __launch_bounds__(BLOCK) k_bi_xr_flex(size_t n, OwnMask own, const S* __restrict__ sv,
+                                                      const S* __restrict__ t, const S* __restrict__ rhat,
+                                                      S* __restrict__ r, const double* __restrict__ p_ts,
                                                       const double* __restrict__ p_tt, double* __restrict__ p_rho,
                                                       double* __restrict__ p_rr, const BiScalars* __restrict__ s,
-                                                      size_t nx, const double* __restrict__ xh, double* __restrict__ x) {
+                                                      size_t nx, const S* __restrict__ xh, S* __restrict__ x) {
   if (s->done) return;
   double tt = reduce_partials(p_tt, gridDim.x);
   double omega = tt > 0.0 ? reduce_partials(p_ts, gridDim.x) / tt : 0.0;
   double a0 = 0.0, a1 = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    if (i < nx) x[i] = fma(omega, xh[i], x[i]);
-    double ri = fma(-omega, t[i], sv[i]);
-    r[i] = ri;
+    if (i < nx) x[i] = (S)fma(omega, (double)xh[i], (double)x[i]);
+    const S rs = (S)fma(-omega, (double)t[i], (double)sv[i]);
+    r[i] = rs;
+    const double ri = rs;  // the stored (rounded) residual is the one the recurrence continues with
     if (is_owned(own, i)) {
-      a0 = fma(rhat[i], ri, a0);
+      a0 = fma((double)rhat[i], ri, a0);
       a1 = fma(ri, ri, a1);
     }
   }
@@ -510,8 +515,9 @@ __global__ void __launch_bounds__(BLOCK) k_bi_xr_flex(size_t n, OwnMask own, con
   if (threadIdx.x == 0) p_rr[blockIdx.x] = a1;
 }
 // beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v); bookkeeping (last block publishes)
-__global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restrict__ r, const double* __restrict__ v,
-                                                double* __restrict__ p, const double* __restrict__ p_rv,
+template <typename S = double>
+__global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const S* __restrict__ r, const S* __restrict__ v,
+                                                S* __restrict__ p, const double* __restrict__ p_rv,
                                                 const double* __restrict__ p_ts, const double* __restrict__ p_tt,
                                                 const double* __restrict__ p_rho, const double* __restrict__ p_rr,
                                                 BiScalars* s) {
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__(BLOCK) k_bi_p(size_t n, const double* __restri
   if (!stop) {
     double beta = (rho_new / rho_old) * (alpha / omega);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-      p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+      p[i] = (S)fma(beta, fma(-omega, (double)v[i], (double)p[i]), (double)r[i]);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -692,3 +698,20 @@ __global__ void __launch_bounds__(BLOCK) k_resid_norm(size_t n, OwnMask own, con
   s = block_reduce(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
+
+// ------------------------------------------------------------------------------------------------
+// conversions of the mixed-precision tentative-velocity solver (run_tentative_mixed, hdg_engine.cu)
+// ------------------------------------------------------------------------------------------------
+// out = (float)(scale * in)
+__global__ void __launch_bounds__(BLOCK) k_mx_to_float(size_t n, const double* __restrict__ in, double scale,
+                                                       float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (float)(scale * in[i]);
+}
+// x += scale * dx   (the FP32 correction of one outer step, accumulated in FP64)
+__global__ void __launch_bounds__(BLOCK) k_mx_axpy(size_t n, double* __restrict__ x, double scale,
+                                                   const float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = fma(scale, (double)dx[i], x[i]);
+}
+

@@ -59,10 +59,11 @@ __global__ void k_tent_setup(const double* __restrict__ xy, const int* __restric
 }
 
 // cm[(e NM + j) nc + cell] = sigma int_0^1 (y . n_e) l_j ds  in the global facet orientation
-template <int K>
+// S (here and below) = storage type of the solver vectors: double, or float inside the mixed-precision solver
+// (run_tentative_mixed in hdg_engine.cu); the arithmetic of these bandwidth-bound kernels stays FP64
+template <int K, typename S = double>
 __global__ void __launch_bounds__(128) k_tent_moments(const double* __restrict__ xy, const int* __restrict__ flip,
-                                                      int nc, const double* __restrict__ Y,
-                                                      double* __restrict__ cm) {
+                                                      int nc, const S* __restrict__ Y, S* __restrict__ cm) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NM = TentDims<K>::NM;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
@@ -86,17 +87,16 @@ __global__ void __launch_bounds__(128) k_tent_moments(const double* __restrict__
           if (T::BF(e, j, i) != 0.0) m[j] = fma(T::BF(e, j, i), yn, m[j]);
       }
       HDG_UNROLL
-      for (int j = 0; j < NM; ++j) cm[(size_t)(e * NM + j) * nc + cell] = flip_sign(fl, j) * m[j];
+      for (int j = 0; j < NM; ++j) cm[(size_t)(e * NM + j) * nc + cell] = (S)(flip_sign(fl, j) * m[j]);
     }
   }
 }
 
 // t = N y_x - y_mu  (y_mu may be null); optionally also sum = N y_x
-template <int K>
-__global__ void __launch_bounds__(256) k_tent_trhs(const double* __restrict__ cm, const int* __restrict__ facet_cell,
+template <int K, typename S = double>
+__global__ void __launch_bounds__(256) k_tent_trhs(const S* __restrict__ cm, const int* __restrict__ facet_cell,
                                                    const int* __restrict__ facet_local, int nc, int nf,
-                                                   const double* __restrict__ ymu, double* __restrict__ t,
-                                                   double* __restrict__ nyx) {
+                                                   const S* __restrict__ ymu, S* __restrict__ t, S* __restrict__ nyx) {
   constexpr int NM = TentDims<K>::NM;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     int c0 = facet_cell[f], c1 = facet_cell[(size_t)nf + f];
@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(256) k_tent_trhs(const double* __restrict__ cm
     for (int j = 0; j < NM; ++j) {
       double v = cm[(size_t)(e0 * NM + j) * nc + c0];
       if (c1 >= 0) v += cm[(size_t)(e1 * NM + j) * nc + c1];
-      if (nyx) nyx[(size_t)j * nf + f] = v;
+      if (nyx) nyx[(size_t)j * nf + f] = (S)v;
       if (ymu) v -= ymu[(size_t)j * nf + f];
-      t[(size_t)j * nf + f] = v;
+      t[(size_t)j * nf + f] = (S)v;
     }
   }
 }
@@ -154,13 +154,13 @@ __device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const dou
 // MINB = resident CTAs per SM the register allocation is tuned for (5: 96 registers at
 // k = 2; 6: 80 registers; 8: 64 registers with a 120-byte spill) -- selected at run time by
 // hdg_set_tuning("sweep_minblocks") so that the variants can be compared on the same box.
-template <int K, int MINB>
+template <int K, int MINB, typename S = double>
 __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __restrict__ facet_local,
                                                     const double* __restrict__ tc, const int* __restrict__ tcol,
                                                     const int* __restrict__ tbits, double inv_aalpha,
-                                                    const double* __restrict__ rhs, const double* __restrict__ rhs2,
-                                                    const double* __restrict__ x, double* __restrict__ d,
-                                                    double* __restrict__ xout, double cd, double cr, int zero,
+                                                    const S* __restrict__ rhs, const S* __restrict__ rhs2,
+                                                    const S* __restrict__ x, S* __restrict__ d,
+                                                    S* __restrict__ xout, double cd, double cr, int zero,
                                                     int mode) {
   constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
@@ -224,21 +224,21 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
     }
     if (mode == 1) {
       HDG_UNROLL
-      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = r[j];
+      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = (S)r[j];
       continue;
     }
     cholesky<NM>(D);
     chol_solve<NM>(D, r);
     if (mode == 2) {
       HDG_UNROLL
-      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = r[j];
+      for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = (S)r[j];
       continue;
     }
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
       double di = fma(cd, dprev[j], cr * r[j]);
-      d[(size_t)j * nf + f] = di;
-      xout[(size_t)j * nf + f] = own[j] + di;
+      d[(size_t)j * nf + f] = (S)di;
+      xout[(size_t)j * nf + f] = (S)(own[j] + di);
     }
   }
 }
@@ -249,13 +249,14 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
 // rounded vectors the preconditioner is no longer an exactly linear operator, which only the flexible solution update
 // of BiCGStab tolerates (tests/experiments/tent_fp32_sweeps.py).  The last sweep of a solve writes the multiplier in
 // FP64 (xout64) for k_tent_xhat and the residual row of the operator.
-template <int K, int MINB>
+// S = storage type of the right-hand side and of the final multiplier (double; float in the mixed-precision solver)
+template <int K, int MINB, typename S = double>
 __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* __restrict__ facet_local,
                                                       const double* __restrict__ tc, const int* __restrict__ tcol,
                                                       const int* __restrict__ tbits, double inv_aalpha,
-                                                      const double* __restrict__ rhs, const float* __restrict__ x,
+                                                      const S* __restrict__ rhs, const float* __restrict__ x,
                                                       float* __restrict__ d, float* __restrict__ xout32,
-                                                      double* __restrict__ xout64, double cd, double cr, int zero) {
+                                                      S* __restrict__ xout64, double cd, double cr, int zero) {
   constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const int bits = tbits[f];
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
       const double di = fma(cd, dprev[j], cr * r[j]);
       d[(size_t)j * nf + f] = (float)di;
       if (xout64)
-        xout64[(size_t)j * nf + f] = own[j] + di;
+        xout64[(size_t)j * nf + f] = (S)(own[j] + di);
       else
         xout32[(size_t)j * nf + f] = (float)(own[j] + di);
     }
@@ -327,13 +328,13 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
 // sK (optional) = the per-cell scalar of the scaled Schur complement (k_tent_scale_tc), 1 if null.
 // Zout (optional, mode 0) = xh + M^-1 N^T mu = y + (1 - s_K) M^-1 N^T mu: what the velocity row of the augmented
 // operator adds to -a F0(xh)  (with s_K = 1 this is y itself and the caller passes y instead).
-template <int K>
+template <int K, typename S = double>
 __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy, const int* __restrict__ flip,
                                                    const int* __restrict__ cell_facet, int nc, int nf,
-                                                   const double* __restrict__ Y, const double* __restrict__ mu,
-                                                   double* __restrict__ Xh, int mode,
+                                                   const S* __restrict__ Y, const S* __restrict__ mu,
+                                                   S* __restrict__ Xh, int mode,
                                                    const double* __restrict__ sK = nullptr,
-                                                   double* __restrict__ Zout = nullptr) {
+                                                   S* __restrict__ Zout = nullptr) {
   using T = RefTables<K>;
   constexpr int NQ1 = Dims<K>::NQ1, NM = TentDims<K>::NM;
   for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < nc; cell += gridDim.x * blockDim.x) {
@@ -366,15 +367,15 @@ __global__ void __launch_bounds__(128) k_tent_xhat(const double* __restrict__ xy
       const double y0 = Y[i0], y1 = Y[i1];
       double v0 = fma(-sk, a0[i], y0), v1 = fma(-sk, a1[i], y1);
       if (Zout) {
-        Zout[i0] = v0 + a0[i];
-        Zout[i1] = v1 + a1[i];
+        Zout[i0] = (S)(v0 + a0[i]);
+        Zout[i1] = (S)(v1 + a1[i]);
       }
       if (mode == 1) {
         v0 += Xh[i0];
         v1 += Xh[i1];
       }
-      Xh[i0] = v0;
-      Xh[i1] = v1;
+      Xh[i0] = (S)v0;
+      Xh[i1] = (S)v1;
     }
   }
 }

@@ -62,6 +62,7 @@ SIGNATURES = {
     "hdg_set_penalty": (C.c_int, [_vp, C.c_double]),
     "hdg_set_tentative_solver": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hdg_tentative_stats": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "hdg_mixed_stats": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_set_tentative_comm": (C.c_int, [_vp, C.c_int]),
     "hdg_project_bdm_dev": (C.c_int, [_vp, _vp, _vp]),
     "hdg_fimpl_apply_dev": (C.c_int, [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp]),
@@ -90,6 +91,7 @@ SIGNATURES = {
     "hdg_p2p_status": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "hdg_halo_exchange_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hdg_allreduce_sum_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "hdg_comm_probe": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "hdg_mg_set_distribution": (C.c_int, [_vp, C.c_int, _ip, _ip]),
     "hdg_comm_stats": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64)]),
@@ -588,6 +590,18 @@ class HDGEngine:
         self._check(self.lib.hdg_tentative_stats(self._h, out))
         keys = ("solves", "bicgstab_iterations", "fgmres_iterations", "fallbacks", "failed_verifications", "fgmres_cycles")
         return dict(zip(keys, [int(v) for v in out]))
+
+    def comm_probe(self, kind: int, ndof: int, nred: int = 2, nrep: int = 200):
+        """(microseconds per halo exchange, per all-reduce) in isolation; collective (`hdg_comm_probe`)"""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._check(self.lib.hdg_comm_probe(self._h, int(kind), int(ndof), int(nred), int(nrep), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def mixed_stats(self):
+        """counters of the mixed-precision tentative solver (`hdg_mixed_stats`)"""
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.hdg_mixed_stats(self._h, out))
+        return dict(zip(("solves", "outer_steps", "inner_fp32_iterations", "handed_to_fp64"), [int(v) for v in out]))
 
     def set_tentative_comm(self, local_sweeps: bool = False):
         """multi-GPU: skip (True) or perform (False) the halo exchanges between Schur sweeps"""

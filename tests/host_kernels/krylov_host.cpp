@@ -85,7 +85,7 @@ int kh_dot2(size_t n, const double* a, const double* b, const double* c, double*
   return 0;
 }
 int kh_bi_init(size_t n, const double* b, double* r, double* rhat, double* p, double* part) {
-  k_bi_init(n, ALL, b, nullptr, r, rhat, p, part);
+  k_bi_init(n, ALL, b, (const double*)nullptr, r, rhat, p, part);
   return 0;
 }
 int kh_bi_start(const double* part, const double* part_ref, double rtol, int maxit) {

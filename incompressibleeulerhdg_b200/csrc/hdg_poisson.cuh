@@ -327,24 +327,32 @@ __global__ void __launch_bounds__(128) k_back_update(const double* __restrict__ 
     HDG_UNROLL
     for (int a = 0; a < NP; ++a) phi[a] = Rp ? Rp[(size_t)a * nc + cell] : 0.0;
     local_solve<K, true>(g, tau, L, lam, u, phi);
+    if (cell < U.nc_own) acc = fma(g.detJ, phi[0], acc);
+    // all loads of the update first, then all stores: the pointers come out of a struct, so the compiler must assume
+    // that a store to Qacc / pacc may change what a later load of Qbase returns and would serialise 2 NQ1 round trips
+    const double* __restrict__ qb = U.Qbase;
+    double* __restrict__ qa = U.Qacc;
+    double* __restrict__ pa = U.pacc;
     HDG_UNROLL
     for (int c = 0; c < 2; ++c)
       HDG_UNROLL
       for (int i = 0; i < NQ1; ++i) {
         const size_t idx = (size_t)(c * NQ1 + i) * nc + cell;
         double v = U.cu * u[c][i];
-        if (U.cb != 0.0) v = fma(U.cb, U.Qbase[idx], v);
-        if (U.cq != 0.0) v = fma(U.cq, U.Qacc[idx], v);
-        U.Qacc[idx] = v;
+        if (U.cb != 0.0) v = fma(U.cb, qb[idx], v);
+        if (U.cq != 0.0) v = fma(U.cq, qa[idx], v);
+        u[c][i] = v;
       }
-    HDG_UNROLL
-    for (int a = 0; a < NP; ++a) {
-      const size_t idx = (size_t)a * nc + cell;
-      double v = phi[a];
-      if (U.cp != 0.0) v = fma(U.cp, U.pacc[idx], v);
-      U.pacc[idx] = v;
+    if (U.cp != 0.0) {
+      HDG_UNROLL
+      for (int a = 0; a < NP; ++a) phi[a] = fma(U.cp, pa[(size_t)a * nc + cell], phi[a]);
     }
-    if (cell < U.nc_own) acc = fma(g.detJ, phi[0], acc);
+    HDG_UNROLL
+    for (int c = 0; c < 2; ++c)
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) qa[(size_t)(c * NQ1 + i) * nc + cell] = u[c][i];
+    HDG_UNROLL
+    for (int a = 0; a < NP; ++a) pa[(size_t)a * nc + cell] = phi[a];
   }
 #ifdef __CUDA_ARCH__
   acc = block_reduce128(acc);

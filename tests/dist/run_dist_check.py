@@ -89,7 +89,7 @@ def timestepper_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name, loc
 
 def tracer_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name):
     """passive tracer on the partitioned mesh vs the single-GPU run (CG-dof halo plan, owned-only dots).
-    Opt-in (HDG_DIST_TRACER=1): the multi-GPU tracer path has host-side tests only so far."""
+    (HDG_DIST_TRACER=0 skips it)"""
     from incompressibleeulerhdg_b200.functions import Expression
 
     q0 = Expression(lambda x, y: np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y), 0)
@@ -111,30 +111,51 @@ def tracer_case(rank, world, local, mesh, k, cls, kwargs, dt, nt, name):
                               "p2p_timeouts": ts.engine.p2p_status()})
 
 
+def only(name):
+    """HDG_DIST_ONLY=<substring>: run just the matching cases (debugging aid)"""
+    pat = os.environ.get("HDG_DIST_ONLY")
+    return pat is None or pat in name
+
+
 def main():
+    import faulthandler
+
+    # a rank that is stuck prints its Python stack (HDG_DIST_DUMP_S seconds after start, default 400)
+    faulthandler.dump_traceback_later(float(os.environ.get("HDG_DIST_DUMP_S", "400")), exit=False)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
     m16 = UnitSquareMesh(16, perturb=0.1)
-    poisson_case(rank, world, local, m16, 2, "jacobi", 0, "poisson_k2_jacobi")
-    poisson_case(rank, world, local, m16, 2, "gtmg", 100000, "poisson_k2_gtmg_replicated")
-    poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels")
-    poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels_nccl", p2p=False)
-    poisson_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "gtmg", 60, "poisson_k1_gtmg_distributed")
-    poisson_case(rank, world, local, UnitDiskMesh(3), 3, "jacobi", 0, "poisson_k3_disk_jacobi")
-    timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2")
-    timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2,
-                     "chorin_k2_local_sweeps", local_sweeps=True)
-    timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGImplicit",
-                     {"use_projection_method": False}, 0.02, 1, "fully_implicit_k1")
-    timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
-                     {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1")
-    if os.environ.get("HDG_DIST_TRACER", "0") == "1":
-        os.environ["HDG_TRACER_MULTI"] = "1"
-        tracer_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2_tracer")
-        tracer_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
-                    {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1_tracer")
+    if only("poisson_k2_jacobi"):
+        poisson_case(rank, world, local, m16, 2, "jacobi", 0, "poisson_k2_jacobi")
+    if only("poisson_k2_gtmg_replicated"):
+        poisson_case(rank, world, local, m16, 2, "gtmg", 100000, "poisson_k2_gtmg_replicated")
+    if only("poisson_k2_gtmg_distributed_levels"):
+        poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels")
+    if only("poisson_k2_gtmg_distributed_levels_nccl"):
+        poisson_case(rank, world, local, m16, 2, "gtmg", 100, "poisson_k2_gtmg_distributed_levels_nccl", p2p=False)
+    if only("poisson_k1_gtmg_distributed"):
+        poisson_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "gtmg", 60, "poisson_k1_gtmg_distributed")
+    if only("poisson_k3_disk_jacobi"):
+        poisson_case(rank, world, local, UnitDiskMesh(3), 3, "jacobi", 0, "poisson_k3_disk_jacobi")
+    if only("chorin_k2"):
+        timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2")
+    if only("chorin_k2_local_sweeps"):
+        timestepper_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2,
+                         "chorin_k2_local_sweeps", local_sweeps=True)
+    if only("fully_implicit_k1"):
+        timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGImplicit",
+                         {"use_projection_method": False}, 0.02, 1, "fully_implicit_k1")
+    if only("imex_ssp2_k1"):
+        timestepper_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
+                         {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1")
+    if os.environ.get("HDG_DIST_TRACER", "1") == "1":
+        if only("chorin_k2_tracer"):
+            tracer_case(rank, world, local, m16, 2, "IncompressibleEulerHDGImplicit", {}, 0.01, 2, "chorin_k2_tracer")
+        if only("imex_ssp2_k1_tracer"):
+            tracer_case(rank, world, local, UnitSquareMesh(12, perturb=0.1), 1, "IncompressibleEulerHDGIMEXSSP2_332",
+                        {"n_richardson": 2}, 0.01, 1, "imex_ssp2_k1_tracer")
     dist.barrier()
     dist.destroy_process_group()
     if failures:

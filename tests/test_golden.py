@@ -276,3 +276,36 @@ def test_shear_flow_pressure_uses_the_reference_fourier_coefficients():
               / (1 + n[:, None] ** 2)).sum(axis=0)
     _, p0 = prob.initial_condition()
     assert np.abs(p0(x, y) - g["delta"] * np.cos(x) * series).max() < 1e-13
+
+
+# ---- mid-size golden (tests/golden/golden_midsize_v1.npz, made once by tests/golden/make_golden_midsize.py) ----------
+GOLD_M = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_midsize_v1.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfl032", "cfl32"])
+def test_engine_chorin_midsize_golden(name):
+    """BASELINE.json configs[2] reduced to nx = 32 (2048 cells), k = 2, two Chorin steps, at the bench's CFL and at ten
+    times it: the engine against the oracle's committed sparse-direct result, 1e-10"""
+    from incompressibleeulerhdg_b200 import timesteppers as TS
+    from incompressibleeulerhdg_b200.model_problems import TaylorGreen
+
+    require_degree(2)
+    dt = float(GOLD_M[f"chorin_k2_nx32_{name}/dt"])
+    m = UnitSquareMesh(32, perturb=0.1)
+    ts = TS.IncompressibleEulerHDGImplicit(m, 2, dt, krylov_rtol=1e-13)
+    prob = TaylorGreen(ts._V_Q, ts._V_p, "exponential", 0.5)
+    Q, p = ts.solve(*prob.initial_condition(), None, prob.f_rhs(), 2 * dt)
+    assert rel(Q.to_host(), GOLD_M[f"chorin_k2_nx32_{name}/Q"]) < 1e-10
+    assert rel(p.to_host(), GOLD_M[f"chorin_k2_nx32_{name}/p"]) < 1e-10
+
+
+def test_cpu_baseline_midsize_golden():
+    """the compiled CPU baseline of bench.py (oracle/cpu_ref) against the same committed vectors"""
+    from oracle.cpu_ref import ChorinCpuRef
+    from oracle.timesteppers import TaylorGreenOracle
+
+    dt = float(GOLD_M["chorin_k2_nx32_cfl032/dt"])
+    c = ChorinCpuRef(UnitSquareMesh(32, perturb=0.1), 2, dt, rtol=1e-13)
+    Q, p = c.solve(TaylorGreenOracle("exponential", 0.5), 2 * dt)
+    assert rel(Q, GOLD_M["chorin_k2_nx32_cfl032/Q"]) < 1e-10 and rel(p, GOLD_M["chorin_k2_nx32_cfl032/p"]) < 1e-10

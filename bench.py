@@ -451,7 +451,7 @@ def run_ours(args):
                                    traffic=1353474384 if (world == 1 and nx == 1024 and k == 2) else None,
                                    traffic_source="ncu --set full, profiles/ncu_r1b_cg_spmv_raw.csv.gz")
         nm = k + 2
-        f32 = bool(getattr(eng, "tuning", {}).get("tent_fp32", 1)) and (world == 1)
+        f32 = bool(getattr(eng, "tuning", {}).get("tent_fp32", 1))
         # per facet: geometry 6 doubles + 7 ints, rhs (double) and x, d (read), d, xout (written) of NM entries each:
         # FP32-stored iterate / correction (default on one GPU) or FP64; the 4 neighbour facets' x are L2 re-reads
         sweep_bytes = (6 * 8 + 7 * 4 + nm * 8 + 4 * nm * (4 if f32 else 8)) * nf_loc

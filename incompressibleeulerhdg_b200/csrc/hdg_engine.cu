@@ -933,12 +933,9 @@ static int run_bicgstab(hdg_engine* h, const double* Qstar, double adt, bool upw
       LAUNCH(h, (k_tent_sweep32<K, 5>), _g, 128, __VA_ARGS__);                                   \
   } while (0)
 
-// FP32-stored sweep vectors are used when asked for ("tent_fp32"), only together with the flexible update, and only
-// where no FP64 halo exchange sits between the sweeps (one GPU, or local sweeps)
-static inline bool tent_fp32_active(const hdg_engine* h) {
-  const bool multi = h->comm && h->comm->nranks > 1;
-  return h->tune_fp32 != 0 && h->tune_flex != 0 && (!multi || h->tent_local_sweeps);
-}
+// FP32-stored sweep vectors are used when asked for ("tent_fp32"), only together with the flexible update (on several
+// GPUs the ghost facets of the float iterate are refreshed between the sweeps by the typed halo exchange)
+static inline bool tent_fp32_active(const hdg_engine* h) { return h->tune_fp32 != 0 && h->tune_flex != 0; }
 
 template <int K>
 static int tent_setup(hdg_engine* h) {
@@ -1018,6 +1015,7 @@ static double* tent_schur_solve(hdg_engine* h, double inv_aalpha, const double* 
     float *x = h->tent_f32[0], *x2 = h->tent_f32[1];
     for (int j = 0; j < h->tent_sweeps; ++j) {
       const bool last = j == h->tent_sweeps - 1;
+      if (j > 0 && !h->tent_local_sweeps) halo_exchange(h, PLAN_FACETS, TentDims<K>::NM, (const float*)x);
       LAUNCH_SWEEP32(h, K, h->nf, h->facet_local, tc, h->tent_col, h->tent_bits, inv_aalpha, t, (const float*)x,
                      h->tent_f32[2], last ? (float*)nullptr : x2, last ? h->tent_f[2] : (double*)nullptr, cc[j].cd,
                      cc[j].cr, j == 0 ? 1 : 0);

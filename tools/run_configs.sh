@@ -13,7 +13,11 @@ run() {  # name, args...
   echo "rc=$?" >> "gpurun_out/config_${name}.log"
 }
 run 0_implicit_k1_nx16 --nx 16 --degree 1 --timestepper imex_implicit --dt 0.1 --tfinal 1.0 --kappa 0.5
-run 1_implicit_k2_nx256 --nx 256 --degree 2 --timestepper implicit --dt 0.04 --tfinal $(python -c "print(0.04*${steps})")
+# configs[1]: the driver's default dt = 0.04 is CFL 10 at nx = 256, where the FGMRES of the fully implicit stage stalls
+# (profiles/r2/config_1_implicit_k2_nx256_dt0.04.log: 300 iterations per step, relative residual ~1e-1; the stepper
+# now raises); the same config at CFL 0.32 and 1.3
+run 1_implicit_k2_nx256_cfl032 --nx 256 --degree 2 --timestepper implicit --dt 0.00125 --tfinal $(python -c "print(0.00125*${steps})")
+run 1_implicit_k2_nx256_cfl13 --nx 256 --degree 2 --timestepper implicit --dt 0.005 --tfinal $(python -c "print(0.005*${steps})")
 run 3_imex_ssp2_k3_nx512 --nx 512 --degree 3 --timestepper imex_ssp2_332 --use_projection_method --richardson 2 \
     --dt 0.0005 --tfinal $(python -c "print(0.0005*${steps})")
 echo done

@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(256) k_tent_trhs(const S* __restrict__ cm, con
 // the switch over the local facet index, so that the divergent part is arithmetic only and the ~22
 // independent loads of a facet are in flight together (the kernel is latency bound: ncu r1h shows 50 %
 // long-scoreboard stalls at 52 % occupancy with DRAM traffic already at the algorithmic minimum).
-template <int K, int E>
+template <int K, int E, typename V>  // V: register type of the neighbour values (float in k_tent_sweep32)
 __device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const double (&c)[3],
-                                          const double (&v)[2][TentDims<K>::NM], bool offdiag,
+                                          const V (&v)[2][TentDims<K>::NM], bool offdiag,
                                           double (&acc)[TentDims<K>::NM], double (&D)[TentDims<K>::NMH]) {
   using T = RefTables<K>;
   constexpr int NM = TentDims<K>::NM;
@@ -140,7 +140,7 @@ __device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const dou
       double sum = 0.0;
       HDG_UNROLL
       for (int l = 0; l < NM; ++l)
-        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), flip_sign(fl[jj - 1], l) * v[jj - 1][l], sum);
+        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), flip_sign(fl[jj - 1], l) * (double)v[jj - 1][l], sum);
       acc[j] = fma(c[jj] * flip_sign(fl0, j), sum, acc[j]);
     }
   }
@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const int bits = tbits[f];
     int e[2], col[2][2];
-    double c[2][3], v[2][2][NM], own[NM], b[NM], dprev[NM];
+    // the FP32-stored values stay float in registers until they are used (the kernel is latency bound at 31 %
+    // occupancy, ncu r2i: every register saved while the ~22 loads are in flight buys resident warps)
+    double c[2][3], b[NM];
+    float v[2][2][NM], own[NM], dprev[NM];
     HDG_UNROLL
     for (int s = 0; s < 2; ++s) {
       e[s] = facet_local[(size_t)s * nf + f];
@@ -272,16 +275,16 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
     }
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
-      own[j] = zero ? 0.0 : (double)x[(size_t)j * nf + f];
+      own[j] = zero ? 0.0f : x[(size_t)j * nf + f];
       b[j] = rhs[(size_t)j * nf + f];
-      dprev[j] = (cd != 0.0) ? (double)d[(size_t)j * nf + f] : 0.0;
+      dprev[j] = (cd != 0.0) ? d[(size_t)j * nf + f] : 0.0f;
     }
     HDG_UNROLL
     for (int s = 0; s < 2; ++s)
       HDG_UNROLL
       for (int jj = 0; jj < 2; ++jj)
         HDG_UNROLL
-        for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0 : (double)x[(size_t)l * nf + col[s][jj]];
+        for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0f : x[(size_t)l * nf + col[s][jj]];
     double acc[NM], D[NMH];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) acc[j] = 0.0;
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
       double w = acc[j];
       if (!zero) {
         HDG_UNROLL
-        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], w);
+        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], (double)own[l], w);
       }
       r[j] = b[j] - w;
     }
@@ -314,12 +317,12 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
     chol_solve<NM>(D, r);
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
-      const double di = fma(cd, dprev[j], cr * r[j]);
+      const double di = fma(cd, (double)dprev[j], cr * r[j]);
       d[(size_t)j * nf + f] = (float)di;
       if (xout64)
-        xout64[(size_t)j * nf + f] = (S)(own[j] + di);
+        xout64[(size_t)j * nf + f] = (S)((double)own[j] + di);
       else
-        xout32[(size_t)j * nf + f] = (float)(own[j] + di);
+        xout32[(size_t)j * nf + f] = (float)((double)own[j] + di);
     }
   }
 }

@@ -117,6 +117,7 @@ class MonolithicStage:
         m = self.restart
         self.last_inner = (0, 0)
         total = 0
+        beta_prev = None
         bnorm = np.sqrt(eng.dot_dev(0, rho.data, rho.data))
         if bnorm == 0.0:
             bnorm = 1.0
@@ -129,6 +130,12 @@ class MonolithicStage:
             beta = np.sqrt(self._dot(V[0], V[0]))
             self.last_relative_residual = beta / bnorm
             if beta <= rtol * bnorm:
+                break
+            # round-off floor of the true residual: within 1000 rtol and no longer decreasing from cycle to cycle
+            if beta_prev is not None and beta > 0.5 * beta_prev and beta <= 1e3 * rtol * bnorm:
+                break
+            beta_prev = beta
+            if total >= self.maxit and beta <= max(1e3 * rtol, 1e-9) * bnorm:
                 break
             if total >= self.maxit:
                 # never hand back an unconverged stage silently (BASELINE configs[1] at the driver's default

@@ -1,0 +1,26 @@
+#!/bin/bash
+# GPU call 10 of round 2 (2 GPUs): the complete 1-vs-2 GPU check (stack dump if a rank is stuck), strong-scaled bench
+# with FP32-stored sweeps on both ranks
+mkdir -p gpurun_out
+T=r2j
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543"
+HDG_DIST_DUMP_S=150 HDG_P2P_TIMEOUT_S=30 timeout 330 $TR tests/dist/run_dist_check.py > gpurun_out/dist_check_${T}_2gpu.jsonl 2> gpurun_out/dist_check_${T}_2gpu.err
+echo "dist check rc=$?"; grep -c '"ok": true' gpurun_out/dist_check_${T}_2gpu.jsonl; grep '"ok": false' gpurun_out/dist_check_${T}_2gpu.jsonl | cut -c1-300
+grep -v "site-packages" gpurun_out/dist_check_${T}_2gpu.err | grep -A25 "most recent call first\|HDGError" | head -90
+B="bench.py --gpus 2 --steps 8 --warmup 6 --no-cpu-baseline --cold-steps 0 --high-cfl-steps 0"
+timeout 300 $TR $B > gpurun_out/bench_${T}_2gpu.json 2> gpurun_out/bench_${T}_2gpu.err; echo "bench2 rc=$?"
+python - <<'PY'
+import glob, json
+for f in sorted(glob.glob("gpurun_out/bench_r2j_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("bench_r2j_")[1][:-5], round(d["value"],3), "steps/s | e2e", round(d["e2e"]["value"],3), "| tent ms", round(d["breakdown_ms_per_step"]["tentative_velocity_solve"],2),
+              "its", round(d["iterations"]["tentative_bicgstab_per_solve"],2), "cg", round(d["iterations"]["trace_cg_per_solve"],2), "| trace ms", round(d["breakdown_ms_per_step"]["trace_solve"],2), "back", round(d["breakdown_ms_per_step"]["back_substitution"],3))
+        print("   check", d["check"]["after_timed_region"])
+        print("   comm", d["comm"])
+        print("   roof", d["roofline"]["kernel"][:20], d["roofline"]["launch_ms"], d["gpu_launches_per_step_by_kernel"])
+    except Exception as e:
+        print(f, "unreadable:", e)
+        print(open(f.replace(".json",".err")).read()[-1500:])
+PY
+echo done

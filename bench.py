@@ -459,7 +459,12 @@ def run_ours(args):
         if sweep_b2b_ms:
             kernels[sweep_name] = hbm(f"{sweep_name}<{k}> (Chebyshev / facet-block-Jacobi sweep on the facet Schur complement "
                                       "of the tentative-velocity preconditioner)", sweep_b2b_ms, sweep_bytes,
-                                      note="latency-limited (ncu r1h: DRAM traffic = algorithmic bytes)", launches_timed=n_sweep)
+                                      note="latency-limited: 31 % theoretical occupancy (96 registers), 0.7 eligible of 4.4 "
+                                           "active warps per scheduler, DRAM traffic = algorithmic bytes "
+                                           "(profiles/r2/ncu_r2l_tent_sweep32_summary.txt)", launches_timed=n_sweep,
+                                      traffic=(440709120 + 88334592) if (f32 and world == 1 and nx == 1024 and k == 2) else None,
+                                      traffic_source="ncu --set full of one launch inside a step, "
+                                                     "profiles/r2/ncu_r2l_tent_sweep32_raw.csv.gz")
         else:
             kernels[sweep_name] = {"error": sweep_err}
         dfma_per_cell = {1: 7 * 48 + 3 * 220, 2: 16 * 80 + 3 * 350, 3: 36 * 120 + 3 * 735, 4: 64 * 168 + 3 * 1176}[k]

@@ -28,8 +28,24 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the engine is CUDA-only and cannot be built without it")
 
 
+def _nccl_include() -> list:
+    """-I for <nccl.h> (csrc/hdg_comm.cuh needs the types only; the library itself is bound with dlopen at run time):
+    the system header if there is one, else the copy that ships with torch's nvidia-nccl wheel"""
+    if os.path.exists("/usr/include/nccl.h"):
+        return []
+    try:
+        import nvidia.nccl
+
+        inc = os.path.join(os.path.dirname(nvidia.nccl.__file__ or list(nvidia.nccl.__path__)[0]), "include")
+        if os.path.exists(os.path.join(inc, "nccl.h")):
+            return ["-I", inc]
+    except Exception:
+        pass
+    return []
+
+
 def _command() -> list:
-    cmd = [_nvcc(), *NVCC_FLAGS, *(os.path.join(CSRC, s) for s in SOURCES), "-o", LIB]
+    cmd = [_nvcc(), *NVCC_FLAGS, *_nccl_include(), *(os.path.join(CSRC, s) for s in SOURCES), "-o", LIB]
     # development shortcut: HDG_DEV_DEGREES="2" compiles only k=2 (the shipped build has k=1..4)
     dev = os.environ.get("HDG_DEV_DEGREES")
     if dev:

@@ -181,6 +181,7 @@ def main(argv=None, file=None):
     outdir = None if args.output == "none" else args.output
     if outdir is not None:
         os.makedirs(outdir, exist_ok=True)
+    t_start = time.perf_counter()
     mesh = build_mesh(args)
     callbacks = None
     if args.animation and outdir is not None:
@@ -208,10 +209,21 @@ def main(argv=None, file=None):
     q_0 = None
     if args.tracer_advection:  # `driver.py:340-342`
         q_0 = Expression(lambda x, y: np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y), 0)
+    setup_s = time.perf_counter() - t_start
     Q, p = timestepper.solve(Q_0, p_0, q_0, model_problem.f_rhs(), args.tfinal, warmup=args.warmup)
     result.update(Q=Q, p=p, q_tracer=getattr(timestepper, "q_tracer", None))
 
     log_summary(file=file)
+    # engine resources (no counterpart in the reference's output): host set-up time and device memory of this rank
+    try:
+        import torch
+
+        free_b, total_b = torch.cuda.mem_get_info(device)
+        result.update(setup_seconds=setup_s, device_memory_gb=(total_b - free_b) / 2**30)
+        print(f"engine: {int(os.environ.get('WORLD_SIZE', '1'))} rank(s), {timestepper.engine.nc} local cells on rank 0, "
+              f"set-up {setup_s:.1f} s, device memory in use {(total_b - free_b) / 2**30:.2f} GB", file=file)
+    except Exception:  # reporting only
+        pass
 
     if not args.warmup:
         eng = timestepper.engine

@@ -116,6 +116,12 @@ int kh_bi_p(size_t n, const double* r, const double* v, double* p, const double*
   k_bi_p(n, r, v, p, p_rv, p_ts, p_tt, p_rho, p_rr, &g_bi);
   return 0;
 }
+// continue a converged run with the tolerance tightened by `factor` (k_bi_resume, the acceptance loop of run_tentative_aug)
+int kh_bi_resume(size_t n, const double* r, const double* v, double* p, const double* p_rv, const double* p_ts,
+                 const double* p_tt, double factor) {
+  k_bi_resume(n, r, v, p, p_rv, p_ts, p_tt, &g_bi, factor);
+  return 0;
+}
 int kh_bi_state(int* iters, int* done) {
   *iters = g_bi.iters; *done = g_bi.done;
   return 0;

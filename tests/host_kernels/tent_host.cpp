@@ -30,6 +30,30 @@ int th_fimpl(int k, int upwind, int nc, const double* xy, const int* nbr, const 
           else k_fimpl<K, false>(xy, nbr, nbr_e, nc, alpha, Qstar, X, Z, c0, c1, Y))
 }
 
+// FP32 instantiations of the mixed-precision solver (run_tentative_mixed): operator in FP32 arithmetic, the
+// bandwidth-bound kernels with float storage and FP64 registers
+int th_fimpl32(int k, int upwind, int nc, const double* xy, const int* nbr, const int* nbr_e, double alpha,
+               const float* Qstar, const float* X, const float* Z, float c0, float c1, float* Y) {
+  BY_K(k, if (upwind) k_fimpl<K, true, float>(xy, nbr, nbr_e, nc, alpha, Qstar, X, Z, c0, c1, Y);
+          else k_fimpl<K, false, float>(xy, nbr, nbr_e, nc, alpha, Qstar, X, Z, c0, c1, Y))
+}
+int th_moments32(int k, int nc, const double* xy, const int* flip, const float* Y, float* cm) {
+  BY_K(k, (k_tent_moments<K, float>(xy, flip, nc, Y, cm)))
+}
+int th_trhs32(int k, int nc, int nf, const float* cm, const int* facet_cell, const int* facet_local, const float* ymu,
+              float* t, float* nyx) {
+  BY_K(k, (k_tent_trhs<K, float>(cm, facet_cell, facet_local, nc, nf, ymu, t, nyx)))
+}
+int th_xhat32(int k, int nc, int nf, const double* xy, const int* flip, const int* cell_facet, const float* Y,
+              const float* mu, float* Xh, const double* sK, float* Zout) {
+  BY_K(k, (k_tent_xhat<K, float>(xy, flip, cell_facet, nc, nf, Y, mu, Xh, 0, sK, Zout)))
+}
+int th_sweep_f(int k, int nf, const int* facet_local, const double* tc, const int* tcol, const int* tbits,
+               double inv_aalpha, const float* rhs, const float* x, float* xout, int mode) {
+  BY_K(k, (k_tent_sweep<K, 5, float>(nf, facet_local, tc, tcol, tbits, inv_aalpha, rhs, (const float*)nullptr, x,
+                                     (float*)nullptr, xout, 0.0, 0.0, 0, mode)))
+}
+
 int th_moments(int k, int nc, const double* xy, const int* flip, const double* Y, double* cm) {
   BY_K(k, k_tent_moments<K>(xy, flip, nc, Y, cm))
 }

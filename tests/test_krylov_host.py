@@ -110,7 +110,7 @@ def test_trace_cg_kernels_on_the_host(libs, k, nx):
     assert np.array_equal(s_, a.T) and np.array_equal(back, a)
 
 
-def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit, flex=None):
+def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit, flex=None, resume=()):
     """bicgstab_loop with the engine's BiCGStab kernels; returns the accumulated update y and the iteration count.
     flex = (xh, x, nx) selects the flexible variant ("tent_flex"): `op` leaves [Phat^-1 in]_x in the array xh and
     the solution x (velocity part, nx entries) is accumulated from these directions instead of y."""
@@ -121,8 +121,12 @@ def bicgstab_kernels(lk, op, n, r0, bb, rtol, maxit, flex=None):
     lk.kh_bi_init(sz(n), dp(r), dp(r), dp(rhat), dp(p), dp(p_rr))
     lk.kh_bi_start(dp(p_rr), dp(p_bb), cd(rtol), maxit)
     it, done = ctypes.c_int(0), ctypes.c_int(0)
+    resume = list(resume)  # tolerance factors applied, one after the other, whenever the run reports convergence
     while True:
         lk.kh_bi_state(ctypes.byref(it), ctypes.byref(done))
+        if done.value == 1 and resume and it.value < maxit:
+            lk.kh_bi_resume(sz(n), dp(r), dp(v), dp(p), dp(p_rv), dp(p_ts), dp(p_tt), cd(resume.pop(0)))
+            continue
         if done.value or it.value >= maxit:
             break
         v[:] = op(p)
@@ -189,6 +193,43 @@ def test_bicgstab_kernels_on_the_host(libs, k, nx):
                                       flex=(tent_xh, xf, nq))
     assert done == 1 and abs(its_f - its) <= 2
     assert np.abs(aos(xf, o.nQ1) - x_ref).max() < 1e-9 * np.abs(x_ref).max()
+
+
+def test_bicgstab_resume_continues_the_same_iteration(libs):
+    """k_bi_resume (the acceptance loop of run_tentative_aug: a run that met its tolerance is continued with a tighter
+    one): a solve stopped at 1e-5 and 1e-8 and resumed each time produces bit for bit the solution and the iteration
+    count of the uninterrupted solve to 1e-12 -- the direction update skipped at the converged iteration is rebuilt
+    from the partial sums that are still in place"""
+    k, nx = 2, 4
+    mesh, o, Q0, Qs, adt = _problem(k, nx, "upwind")
+    ht = HostTentative(libs["tent"], mesh, k)
+    lk = libs["krylov"]
+    b = Q0 + 0.01 * np.random.default_rng(5).standard_normal(Q0.shape)
+    nq, nmu = 2 * ht.nq1 * ht.nc, ht.nm * ht.nf
+    inv_aalpha = 1.0 / (adt * ht.alpha)
+    Qstar, bs = soa(Qs), soa(b)
+    tent_xh = np.zeros((2 * ht.nq1, ht.nc))
+
+    def op(vec):
+        vx = np.ascontiguousarray(vec[:nq].reshape(2 * ht.nq1, ht.nc))
+        vmu = np.ascontiguousarray(vec[nq:].reshape(ht.nm, ht.nf))
+        mu, nyx = ht.precond_x(inv_aalpha, vx, vmu)
+        xh = ht.xhat(vx, mu)
+        tent_xh[:] = xh
+        out_x = ht.fimpl(True, Qstar, xh, 1.0, -adt, Z=vx, alpha=0.0)
+        out_mu = ht.sweep(inv_aalpha, nyx, mu, 0.0, 0.0, 0, 1)
+        return np.concatenate([out_x.ravel(), out_mu.ravel()])
+
+    r0 = np.concatenate([bs.ravel(), np.zeros(nmu)])
+    bb = float(bs.ravel() @ bs.ravel())
+    x_one = np.zeros((2 * ht.nq1, ht.nc))
+    _, its_one, done = bicgstab_kernels(lk, op, nq + nmu, r0, bb, 1e-12, 400, flex=(tent_xh, x_one, nq))
+    assert done == 1
+    x_res = np.zeros((2 * ht.nq1, ht.nc))
+    _, its_res, done = bicgstab_kernels(lk, op, nq + nmu, r0, bb, 1e-5, 400, flex=(tent_xh, x_res, nq),
+                                        resume=(1e-3, 1e-4))
+    assert done == 1 and its_res == its_one
+    assert np.array_equal(x_res, x_one)
 
 
 def test_fp32_stored_sweeps_need_and_work_with_the_flexible_update(libs):

@@ -343,3 +343,50 @@ def test_fgmres_fallback_on_the_host(lib, klib, k, nx, cfl):
           f"error {err_b:.1e}")
     assert err < 1e-9, (its, cycles, err)
     assert its <= its_u
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_float_instantiations_of_the_mixed_precision_kernels(lib, k):
+    """the kernels the opt-in mixed-precision solver (run_tentative_mixed) instantiates with float -- k_fimpl in FP32
+    arithmetic, moments / facet right-hand side / back-substitution / residual sweep with float storage -- against
+    their FP64 versions on the same data: FP32 accuracy, nothing more and nothing less"""
+    FP = ctypes.POINTER(ctypes.c_float)
+    fp = lambda a: None if a is None else a.ctypes.data_as(FP)  # noqa: E731
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    mesh = UnitSquareMesh(4, perturb=0.15)
+    ht = HostTentative(lib, mesh, k)
+    rng = np.random.default_rng(k)
+    X, Qs, Z = (rng.standard_normal((2 * ht.nq1, ht.nc)) for _ in range(3))
+    mu = rng.standard_normal((ht.nm, ht.nf))
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())  # noqa: E731
+    # operator
+    Y64 = ht.fimpl(True, Qs, X, 1.0, -0.01, Z=Z, alpha=0.0)
+    Y32 = np.zeros_like(X, dtype=np.float32)
+    assert lib.th_fimpl32(k, 1, ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), ctypes.c_double(0.0), fp(f32(Qs)), fp(f32(X)),
+                          fp(f32(Z)), ctypes.c_float(1.0), ctypes.c_float(-0.01), fp(Y32)) == 0
+    assert rel(Y32, Y64) < 2e-5
+    # moments, facet right-hand side
+    cm64 = np.zeros((3 * ht.nm, ht.nc))
+    assert lib.th_moments(k, ht.nc, dp(ht.xy), ip(ht.cell_flip), dp(X), dp(cm64)) == 0
+    cm32 = np.zeros_like(cm64, dtype=np.float32)
+    assert lib.th_moments32(k, ht.nc, dp(ht.xy), ip(ht.cell_flip), fp(f32(X)), fp(cm32)) == 0
+    assert rel(cm32, cm64) < 2e-6
+    t64, n64 = np.zeros((ht.nm, ht.nf)), np.zeros((ht.nm, ht.nf))
+    assert lib.th_trhs(k, ht.nc, ht.nf, dp(cm64), ip(ht.facet_cell), ip(ht.facet_local), dp(mu), dp(t64), dp(n64)) == 0
+    t32, n32 = np.zeros_like(t64, dtype=np.float32), np.zeros_like(t64, dtype=np.float32)
+    assert lib.th_trhs32(k, ht.nc, ht.nf, fp(f32(cm64)), ip(ht.facet_cell), ip(ht.facet_local), fp(f32(mu)), fp(t32),
+                         fp(n32)) == 0
+    assert rel(t32, t64) < 2e-6 and rel(n32, n64) < 2e-6
+    # back-substitution of the multiplier with the scaled Schur complement, residual row of the operator
+    sK = 0.5 + rng.random(ht.nc)
+    ht.sK = sK
+    Xh64, Z64 = ht.xhat(X, mu, with_z=True)
+    Xh32, Z32 = np.zeros_like(X, dtype=np.float32), np.zeros_like(X, dtype=np.float32)
+    assert lib.th_xhat32(k, ht.nc, ht.nf, dp(ht.xy), ip(ht.cell_flip), ip(ht.cell_facet), fp(f32(X)), fp(f32(mu)),
+                         fp(Xh32), dp(sK), fp(Z32)) == 0
+    assert rel(Xh32, Xh64) < 2e-6 and rel(Z32, Z64) < 2e-6
+    r64 = ht.sweep(3.0, n64, mu, 0.0, 0.0, 0, 1)
+    r32 = np.zeros_like(r64, dtype=np.float32)
+    assert lib.th_sweep_f(k, ht.nf, ip(ht.facet_local), dp(ht.tc), ip(ht.tcol), ip(ht.tbits), ctypes.c_double(3.0),
+                          fp(f32(n64)), fp(f32(mu)), fp(r32), 1) == 0
+    assert rel(r32, r64) < 5e-6

@@ -139,6 +139,9 @@ struct hdg_engine {
                               // launches_r2f_mixed.md) the FP32-stored kernels are latency bound like their FP64
                               // versions (4.3 vs 5.0 ms per iteration) while the refinement restarts cost 20-30 % more
                               // iterations: 8.1-8.7 vs 8.0-9.0 timesteps/s, no gain
+  int tune_fimpl_pre = 1;     // tabulate the Q*-dependent factors of k_fimpl once per tentative solve ("fimpl_pre")
+  double* fimpl_pre = nullptr;  // [2 NQ + 3 NQF][nc]
+  size_t fimpl_pre_len = 0;
   int tune_p2p_fused = 1;     // halo exchange as one kernel (k_p2p_exchange) instead of push + wait/unpack ("p2p_fused")
   double mixed_failed_adt = -1.0;  // a dt for which the refinement stagnated: later solves use the FP64 solver
   int tune_inner_tol = 50;    // inner tolerance 10^-(value/10) of the recurrence residual ("tent_inner_tol")
@@ -1308,6 +1311,20 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   }
   const double* tcx = scaledx ? h->tent_cs : h->tent_c;
   const double* sKx = scaledx ? h->adv_sK : (const double*)nullptr;
+  // everything k_fimpl derives from the fixed Q*, tabulated once per solve (k_fimpl_pre / k_fimpl_q, hdg_flow.cuh)
+  const double* fpre = nullptr;
+  if (h->tune_fimpl_pre) {
+    const size_t npre = (size_t)FimplPre<K>::N * h->nc;
+    if (h->fimpl_pre_len < npre) {
+      if (h->fimpl_pre) cudaFree(h->fimpl_pre);
+      h->fimpl_pre = nullptr;
+      h->fimpl_pre_len = 0;
+      CUDA_TRY(h, dmalloc(&h->fimpl_pre, npre));
+      h->fimpl_pre_len = npre;
+    }
+    LAUNCH(h, k_fimpl_pre<K>, cgrid, 128, h->cell_xy, h->nc, Qstar, h->fimpl_pre);
+    fpre = h->fimpl_pre;
+  }
   // x part of the vector the multiplier preconditioner sees: C in_x (cell-local, so it is applied before the
   // ghost refresh inside precond_x) or in_x itself
   auto scaled_x = [&](const double* in) -> const double* {
@@ -1335,7 +1352,17 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
     {
       ScopedTimer tf(h, T_FIMPL);
       // out_x = (I - a F0) xh + M^-1 N^T mu = z - a F0(xh),  z = xh + M^-1 N^T mu (= in_x without the scaling)
-      launch_fimpl<K>(h, upwind, Qstar, xh, 1.0, -adt, out, scaledx ? (const double*)h->tent_z : in, 0.0);
+      const double* zz = scaledx ? (const double*)h->tent_z : in;
+      if (fpre) {  // Q* is fixed during the solve: its values at the quadrature points come from the table
+        if (upwind)
+          LAUNCH(h, (k_fimpl_q<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, 0.0, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+        else
+          LAUNCH(h, (k_fimpl_q<K, false>), cgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, 0.0, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+      } else {
+        launch_fimpl<K>(h, upwind, Qstar, xh, 1.0, -adt, out, zz, 0.0);
+      }
     }
     // out_mu = N in_x - X mu
     LAUNCH_SWEEP(h, K, h->nf, h->facet_local, tcx, h->tent_col, h->tent_bits,
@@ -1347,7 +1374,7 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
                                key_of(h->adv_blk32), key_of(h->adv_in), (uint64_t)tent_fp32_active(h),
                                key_of(h->tent_f32[0]), key_of(h->tent_f32[1]), key_of(h->tent_f32[2]),
-                               (uint64_t)scaledx, key_of(tcx), key_of(sKx), key_of(h->tent_z)};
+                               (uint64_t)scaledx, key_of(tcx), key_of(sKx), key_of(h->tent_z), key_of(fpre)};
   // true residual of the primal system:  out_r (length nx, may be null) = b - A x ; returns ||.||^2 over the owned cells
   // in *rr (host).  The augmented residual the Krylov loops monitor bounds it only up to the penalty stiffness.
   auto true_residual = [&](double* out_r, double* rr) -> int {
@@ -2035,7 +2062,8 @@ int hdg_destroy(hdg_handle h) {
                   h->tent_xh, h->tent_y, h->adv_blk, h->adv_blk32, h->adv_in, h->tent_f32[0], h->tent_f32[1],
                   h->tent_f32[2], h->adv_sK, h->tent_cs, h->tent_z, h->gm_V, h->gm_Z, h->gm_part, h->gm_red, h->gm_coef,
                   h->mxb[0], h->mxb[1], h->mxb[2], h->mxb[3], h->mxb[4], h->mxb[5], h->mx_adv, h->mx_cm, h->mx_t,
-                  h->mx_nyx, h->mx_mu, h->mx_xh, h->mx_z, h->mx_qstar, h->mx_dx, h->mx_r64, h->mx_w64, h->back_partial};
+                  h->mx_nyx, h->mx_mu, h->mx_xh, h->mx_z, h->mx_qstar, h->mx_dx, h->mx_r64, h->mx_w64, h->back_partial,
+                  h->fimpl_pre};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (GraphCache* gc : {&h->g_bicg, &h->g_pcg, &h->g_cg, &h->g_bicg32})
@@ -2781,6 +2809,10 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     if (value < 1) return HDG_EINVAL;
     h->tune_bicg_cap = value;
     h->bicg_failed_adt = -1.0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "fimpl_pre")) {
+    h->tune_fimpl_pre = value != 0;
     return HDG_OK;
   }
   if (!strcmp(name, "p2p_fused")) {

@@ -54,6 +54,16 @@ int th_sweep_f(int k, int nf, const int* facet_local, const double* tc, const in
                                      (float*)nullptr, xout, 0.0, 0.0, 0, mode)))
 }
 
+// operator with the Q*-dependent factors tabulated once per solve (k_fimpl_pre + k_fimpl_q); npre = FimplPre<K>::N
+int th_fimpl_pre(int k, int nc, const double* xy, const double* Qstar, double* pre, int* npre) {
+  BY_K(k, *npre = FimplPre<K>::N; if (pre) k_fimpl_pre<K>(xy, nc, Qstar, pre))
+}
+int th_fimpl_q(int k, int upwind, int nc, const double* xy, const int* nbr, const int* nbr_e, double alpha,
+               const double* pre, const double* X, const double* Z, double c0, double c1, double* Y) {
+  BY_K(k, if (upwind) k_fimpl_q<K, true>(xy, nbr, nbr_e, nc, alpha, pre, X, Z, c0, c1, Y);
+          else k_fimpl_q<K, false>(xy, nbr, nbr_e, nc, alpha, pre, X, Z, c0, c1, Y))
+}
+
 int th_moments(int k, int nc, const double* xy, const int* flip, const double* Y, double* cm) {
   BY_K(k, k_tent_moments<K>(xy, flip, nc, Y, cm))
 }

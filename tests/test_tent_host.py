@@ -390,3 +390,24 @@ def test_float_instantiations_of_the_mixed_precision_kernels(lib, k):
     assert lib.th_sweep_f(k, ht.nf, ip(ht.facet_local), dp(ht.tc), ip(ht.tcol), ip(ht.tbits), ctypes.c_double(3.0),
                           fp(f32(n64)), fp(f32(mu)), fp(r32), 1) == 0
     assert rel(r32, r64) < 5e-6
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+@pytest.mark.parametrize("upwind", [True, False])
+def test_operator_with_tabulated_advecting_velocity_is_the_same_operator(lib, k, upwind):
+    """k_fimpl_pre + k_fimpl_q (the operator of the Krylov iterations: everything derived from the fixed Q* is
+    tabulated once per solve) against k_fimpl: the same floating-point operations in the same order, hence identical"""
+    mesh = UnitSquareMesh(4, perturb=0.15)
+    ht = HostTentative(lib, mesh, k)
+    rng = np.random.default_rng(10 + k)
+    X, Qs, Z = (rng.standard_normal((2 * ht.nq1, ht.nc)) for _ in range(3))
+    npre = ctypes.c_int(0)
+    assert lib.th_fimpl_pre(k, ht.nc, dp(ht.xy), dp(Qs), None, ctypes.byref(npre)) == 0
+    pre = np.zeros((npre.value, ht.nc))
+    assert lib.th_fimpl_pre(k, ht.nc, dp(ht.xy), dp(Qs), dp(pre), ctypes.byref(npre)) == 0
+    for alpha, Zarg in ((0.0, Z), (1.0, None)):
+        Y = ht.fimpl(upwind, Qs, X, 1.0, -0.37, Z=Zarg, alpha=alpha)
+        Yq = np.zeros_like(X)
+        assert lib.th_fimpl_q(k, int(upwind), ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), ctypes.c_double(alpha), dp(pre),
+                              dp(X), dp(Zarg), ctypes.c_double(1.0), ctypes.c_double(-0.37), dp(Yq)) == 0
+        assert np.abs(Yq - Y).max() <= 1e-13 * np.abs(Y).max()

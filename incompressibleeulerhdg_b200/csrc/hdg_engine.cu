@@ -139,7 +139,9 @@ struct hdg_engine {
                               // launches_r2f_mixed.md) the FP32-stored kernels are latency bound like their FP64
                               // versions (4.3 vs 5.0 ms per iteration) while the refinement restarts cost 20-30 % more
                               // iterations: 8.1-8.7 vs 8.0-9.0 timesteps/s, no gain
-  int tune_fimpl_pre = 1;     // tabulate the Q*-dependent factors of k_fimpl once per tentative solve ("fimpl_pre")
+  int tune_fimpl_pre = 0;     // tabulate the Q*-dependent factors of k_fimpl once per tentative solve ("fimpl_pre"); measured
+                              // on a B200 (gpurun_out/bench_r2o_pre{0,1}.json): 8.79 vs 9.08 timesteps/s -- the kernel is
+                              // latency bound, the extra 216 B per cell cost what the 470 saved FMAs gain; off by default
   double* fimpl_pre = nullptr;  // [2 NQ + 3 NQF][nc]
   size_t fimpl_pre_len = 0;
   int tune_p2p_fused = 1;     // halo exchange as one kernel (k_p2p_exchange) instead of push + wait/unpack ("p2p_fused")

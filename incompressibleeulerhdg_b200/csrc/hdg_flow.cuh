@@ -420,6 +420,123 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 3 : 1)) k_fimpl_q(const double*
 }
 
 // ------------------------------------------------------------------------------------------------
+// The operator of the augmented tentative-velocity iteration is f_impl WITHOUT the normal-jump penalty (alpha = 0: the
+// penalty lives in the multiplier rows, hdg_tent.cuh).  Without it the two velocity components do not couple: the
+// advection form acts on x_0 and x_1 separately with the same scalar weights (Q* at the volume points, n.Q* at the facet
+// points, both in the table of k_fimpl_pre).  k_fimpl_c therefore gives every (cell, component) its own thread:
+//   * per thread 10 + 10 (+ 10 neighbour) doubles of state instead of 20 + 20 + 20 (k = 2): no spills, 4 instead of 3
+//     resident CTAs, twice the threads (k_fimpl: 168 registers + 208 B of spills, 12 % occupancy, FP64 pipe 45 % active
+//     in ncu r1h);
+//   * 2 000 instead of 2 330 FMAs per cell at k = 2 (no Q* evaluation, no penalty).
+// Lanes 0-15 of a warp take component 0 of 16 consecutive cells, lanes 16-31 component 1 of the same cells, so every
+// half-warp reads 128 contiguous bytes of the SoA fields and both halves share the table lines.
+//   Y = c0 Z + c1 M^-1 f_impl(., X; Q*)|_{alpha = 0}        (Z = X if null)
+// ------------------------------------------------------------------------------------------------
+template <int K, int E>
+__device__ __forceinline__ void trace1_at_points(const double (&x)[Dims<K>::NQ1], bool reversed,
+                                                 double (&out)[RefTables<K>::NQF]) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
+  HDG_UNROLL
+  for (int q = 0; q < NQF; ++q) {
+    double v = 0.0;
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) v = fma(T::PHIF(E, q, i), x[i], v);
+    out[reversed ? NQF - 1 - q : q] = v;  // Gauss points are symmetric: s_q -> 1 - s_q is q -> NQF-1-q
+  }
+}
+
+template <int K, bool UPWIND, int E>
+__device__ __forceinline__ void fimpl_c_facet(double scale, int nc, int nbr, int nbr_e, const double* __restrict__ Xc,
+                                              const double* __restrict__ sflux, size_t cell,
+                                              const double (&x)[Dims<K>::NQ1], double (&acc)[Dims<K>::NQ1]) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
+  if (nbr < 0) return;  // boundary facet: only the penalty acts there
+  double xn[NQ1], sf[NQF];
+  HDG_UNROLL
+  for (int i = 0; i < NQ1; ++i) xn[i] = Xc[(size_t)i * nc + nbr];
+  HDG_UNROLL
+  for (int q = 0; q < NQF; ++q) sf[q] = sflux[(size_t)q * nc + cell];
+  double xo[NQF], xnb[NQF];
+  trace1_at_points<K, E>(x, false, xo);
+  switch (nbr_e) {
+    case 0: trace1_at_points<K, 0>(xn, true, xnb); break;
+    case 1: trace1_at_points<K, 1>(xn, true, xnb); break;
+    default: trace1_at_points<K, 2>(xn, true, xnb); break;
+  }
+  HDG_UNROLL
+  for (int q = 0; q < NQF; ++q) {
+    const double s = sf[q];
+    const double coef = 0.5 * s - (UPWIND ? fabs(s) : 0.0);
+    xo[q] = (T::WF(q) * scale) * (coef * (xo[q] - xnb[q]));
+  }
+  HDG_UNROLL
+  for (int q = 0; q < NQF; ++q)
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) acc[i] = fma(T::PHIF(E, q, i), xo[q], acc[i]);
+}
+
+template <int K, bool UPWIND>
+__global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
+    k_fimpl_c(const double* __restrict__ xy, const int* __restrict__ nbr, const int* __restrict__ nbr_e, int nc,
+              const double* __restrict__ pre, const double* __restrict__ X, const double* __restrict__ Z, double c0,
+              double c1, double* __restrict__ Y) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ, NQF = T::NQF;
+  const long long nitems = 32LL * ((nc + 15) / 16);
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
+       item += (long long)gridDim.x * blockDim.x) {
+    const int lane = (int)(item & 31);
+    const int c = lane >> 4;
+    const long long cell_ll = (item >> 5) * 16 + (lane & 15);
+    if (cell_ll >= nc) continue;
+    const size_t cell = (size_t)cell_ll;
+    const double* __restrict__ Xc = X + (size_t)c * NQ1 * nc;
+    double x[NQ1], acc[NQ1];
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) {
+      x[i] = Xc[(size_t)i * nc + cell];
+      acc[i] = 0.0;
+    }
+    // volume term: -sum_q WQ[q] phi_i(q) (Qh . grad^ x_c)(q), Qh(q) from the table
+    HDG_UNROLL
+    for (int q = 0; q < NQ; ++q) {
+      const double a0 = pre[(size_t)(2 * q) * nc + cell], a1 = pre[(size_t)(2 * q + 1) * nc + cell];
+      double g0 = 0.0, g1 = 0.0;
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) {
+        if (T::DPHI(0, q, i) != 0.0) g0 = fma(T::DPHI(0, q, i), x[i], g0);
+        if (T::DPHI(1, q, i) != 0.0) g1 = fma(T::DPHI(1, q, i), x[i], g1);
+      }
+      const double v = -T::WQ(q) * (a0 * g0 + a1 * g1);
+      HDG_UNROLL
+      for (int i = 0; i < NQ1; ++i) acc[i] = fma(T::PHI(q, i), v, acc[i]);
+    }
+    // facet terms: int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr) w,  weight |e| / detJ
+    {
+      const double x0 = xy[cell], y0 = xy[(size_t)nc + cell], x1 = xy[2 * (size_t)nc + cell],
+                   y1 = xy[3 * (size_t)nc + cell], x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];
+      const double idetJ = 1.0 / ((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
+      // facet e runs from vertex (e+1)%3 to (e+2)%3 (make_geo)
+      const double l0 = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+      const double l1 = sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2));
+      const double l2 = sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
+      const double* __restrict__ sfl = pre + (size_t)(2 * NQ) * nc;
+      fimpl_c_facet<K, UPWIND, 0>(l0 * idetJ, nc, nbr[cell], nbr_e[cell], Xc, sfl, cell, x, acc);
+      fimpl_c_facet<K, UPWIND, 1>(l1 * idetJ, nc, nbr[(size_t)nc + cell], nbr_e[(size_t)nc + cell], Xc,
+                                  sfl + (size_t)NQF * nc, cell, x, acc);
+      fimpl_c_facet<K, UPWIND, 2>(l2 * idetJ, nc, nbr[2 * (size_t)nc + cell], nbr_e[2 * (size_t)nc + cell], Xc,
+                                  sfl + (size_t)(2 * NQF) * nc, cell, x, acc);
+    }
+    const double* __restrict__ Zc = Z ? Z + (size_t)c * NQ1 * nc : nullptr;
+    double* __restrict__ Yc = Y + (size_t)c * NQ1 * nc;
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) Yc[(size_t)i * nc + cell] = c0 * (Zc ? Zc[(size_t)i * nc + cell] : x[i]) + c1 * acc[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weak divergence as a dual vector on the pressure space:
 //   mode 0:  Rp = scale * int_K psi div Q                                  (hdg_implicit.py:145)
 //   mode 1:  Rp = scale * _weak_divergence(psi, Q)                          (hdg_imex.py:353-365)

@@ -112,38 +112,53 @@ __global__ void __launch_bounds__(256) k_tent_trhs(const S* __restrict__ cm, con
   }
 }
 
-// contribution of the cell on one side of facet f to (G mu)_f and to the diagonal block.  All global
-// loads (geometric coefficients c[0..2], neighbour values v[0..1][.]) are issued by the caller *before*
-// the switch over the local facet index, so that the divergent part is arithmetic only and the ~22
-// independent loads of a facet are in flight together (the kernel is latency bound: ncu r1h shows 50 %
-// long-scoreboard stalls at 52 % occupancy with DRAM traffic already at the algorithmic minimum).
-template <int K, int E, typename V>  // V: register type of the neighbour values (float in k_tent_sweep32)
+// The reference blocks GG(e, e') = BF_e BF_e'^T are Gram matrices of the facet functionals in an L2-orthonormal basis of
+// the full space P_{k+1}, hence independent of that basis and invariant under the affine maps of the reference triangle
+// onto itself.  The cyclic vertex permutation maps facet e to e + 1 with its parametrisation (from vertex e + 1 to e + 2)
+// and has unit Jacobian determinant, so
+//     GG(e, (e + j) % 3) = GG(0, j)   for every e,   and   GG(e, e) is diagonal (Legendre moments of one facet)
+// (checked on the tables by tests/test_tent_host.py::test_gram_blocks_do_not_depend_on_the_local_facet).  The sweeps use
+// this: no switch over the local facet index.  Facets of one warp carry 2-3 different local indices on every mesh
+// numbering, so the switch executed its body 2-3 times per side (ncu r2l: 820 instructions per facet, issue slots 52 %
+// busy in a kernel that should only wait for memory).
+template <int K>
+__host__ __device__ constexpr bool tent_gram_diagonal() {
+  for (int j = 0; j < TentDims<K>::NM; ++j)
+    for (int l = 0; l < TentDims<K>::NM; ++l)
+      if (j != l && RefTables<K>::GG(0, 0, j, l) != 0.0) return false;
+  return true;
+}
+
+// contribution of the cell on one side of facet f to the off-diagonal part of (G mu)_f.  All global loads (geometric
+// coefficients c[1..2], neighbour values v[0..1][.]) are issued by the caller before the arithmetic so that the
+// independent loads of a facet are in flight together; a missing side has zero coefficients and contributes nothing.
+template <int K, typename V>  // V: register type of the neighbour values (float in k_tent_sweep32)
 __device__ __forceinline__ void tent_side(int fl0, const int (&fl)[2], const double (&c)[3],
-                                          const V (&v)[2][TentDims<K>::NM], bool offdiag,
-                                          double (&acc)[TentDims<K>::NM], double (&D)[TentDims<K>::NMH]) {
+                                          const V (&v)[2][TentDims<K>::NM], double (&acc)[TentDims<K>::NM]) {
   using T = RefTables<K>;
   constexpr int NM = TentDims<K>::NM;
-  // diagonal block (also part of G mu)
-  HDG_UNROLL
-  for (int j = 0; j < NM; ++j) {
-    HDG_UNROLL
-    for (int l = 0; l <= j; ++l) {
-      if (T::GG(E, E, j, l) != 0.0) D[tri(j, l)] += c[0] * T::GG(E, E, j, l) * flip_sign(fl0, j) * flip_sign(fl0, l);
-    }
-  }
-  if (!offdiag) return;
   HDG_UNROLL
   for (int jj = 1; jj < 3; ++jj) {
-    const int E2 = (E + jj) % 3;
+    double w[NM];
+    HDG_UNROLL
+    for (int l = 0; l < NM; ++l) w[l] = flip_sign(fl[jj - 1], l) * (double)v[jj - 1][l];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
       double sum = 0.0;
       HDG_UNROLL
       for (int l = 0; l < NM; ++l)
-        if (T::GG(E, E2, j, l) != 0.0) sum = fma(T::GG(E, E2, j, l), flip_sign(fl[jj - 1], l) * (double)v[jj - 1][l], sum);
+        if (T::GG(0, jj, j, l) != 0.0) sum = fma(T::GG(0, jj, j, l), w[l], sum);
       acc[j] = fma(c[jj] * flip_sign(fl0, j), sum, acc[j]);
     }
   }
+}
+
+// diagonal of X = inv_aalpha I + G on facet f: inv_aalpha + (c_0[0] + c_1[0]) GG(0, 0, j, j)   (sign flips squared)
+template <int K>
+__device__ __forceinline__ void tent_diag(double inv_aalpha, double c00, double c10, double (&D)[TentDims<K>::NM]) {
+  static_assert(tent_gram_diagonal<K>(), "GG(e, e) is expected to be diagonal");
+  HDG_UNROLL
+  for (int j = 0; j < TentDims<K>::NM; ++j) D[j] = fma(c00 + c10, RefTables<K>::GG(0, 0, j, j), inv_aalpha);
 }
 
 // One sweep on X = inv_aalpha I + G, matrix-free.
@@ -166,11 +181,10 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     // ---- all loads first ------------------------------------------------------------------------
     const int bits = tbits[f];
-    int e[2], col[2][2];
+    int col[2][2];
     double c[2][3], v[2][2][NM], own[NM], b[NM], dprev[NM];
     HDG_UNROLL
     for (int s = 0; s < 2; ++s) {
-      e[s] = facet_local[(size_t)s * nf + f];
       HDG_UNROLL
       for (int j = 0; j < 3; ++j) c[s][j] = tc[(size_t)(3 * s + j) * nf + f];  // zero on a missing side
       HDG_UNROLL
@@ -193,33 +207,22 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
         HDG_UNROLL
         for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0 : x[(size_t)l * nf + col[s][jj]];
     // ---- arithmetic -----------------------------------------------------------------------------
-    double acc[NM], D[NMH];
+    double acc[NM], D[NM];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) acc[j] = 0.0;
-    HDG_UNROLL
-    for (int i = 0; i < NMH; ++i) D[i] = 0.0;
-    HDG_UNROLL
-    for (int j = 0; j < NM; ++j) D[tri(j, j)] = inv_aalpha;
-    HDG_UNROLL
-    for (int s = 0; s < 2; ++s) {
-      if (e[s] < 0) continue;
-      const int fl0 = (bits >> (3 * s)) & 1;
-      const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
-      switch (e[s]) {
-        case 0: tent_side<K, 0>(fl0, fl, c[s], v[s], !zero, acc, D); break;
-        case 1: tent_side<K, 1>(fl0, fl, c[s], v[s], !zero, acc, D); break;
-        default: tent_side<K, 2>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+    tent_diag<K>(inv_aalpha, c[0][0], c[1][0], D);
+    if (!zero) {
+      HDG_UNROLL
+      for (int s = 0; s < 2; ++s) {
+        const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
+        tent_side<K>((bits >> (3 * s)) & 1, fl, c[s], v[s], acc);
       }
     }
     // X x = D own + off-diagonal part
     double r[NM];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
-      double w = acc[j];
-      if (!zero) {
-        HDG_UNROLL
-        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], own[l], w);
-      }
+      const double w = zero ? 0.0 : fma(D[j], own[j], acc[j]);
       r[j] = (mode != 2) ? b[j] - w : w;
     }
     if (mode == 1) {
@@ -227,8 +230,8 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep(int nf, const int* __r
       for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = (S)r[j];
       continue;
     }
-    cholesky<NM>(D);
-    chol_solve<NM>(D, r);
+    HDG_UNROLL
+    for (int j = 0; j < NM; ++j) r[j] /= D[j];
     if (mode == 2) {
       HDG_UNROLL
       for (int j = 0; j < NM; ++j) xout[(size_t)j * nf + f] = (S)r[j];
@@ -260,14 +263,13 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
   constexpr int NM = TentDims<K>::NM, NMH = TentDims<K>::NMH;
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += gridDim.x * blockDim.x) {
     const int bits = tbits[f];
-    int e[2], col[2][2];
-    // the FP32-stored values stay float in registers until they are used (the kernel is latency bound at 31 %
-    // occupancy, ncu r2i: every register saved while the ~22 loads are in flight buys resident warps)
+    int col[2][2];
+    // the FP32-stored values stay float in registers until they are used (every register saved while the loads are in
+    // flight buys resident warps)
     double c[2][3], b[NM];
     float v[2][2][NM], own[NM], dprev[NM];
     HDG_UNROLL
     for (int s = 0; s < 2; ++s) {
-      e[s] = facet_local[(size_t)s * nf + f];
       HDG_UNROLL
       for (int j = 0; j < 3; ++j) c[s][j] = tc[(size_t)(3 * s + j) * nf + f];
       HDG_UNROLL
@@ -285,36 +287,20 @@ __global__ void __launch_bounds__(128, MINB) k_tent_sweep32(int nf, const int* _
       for (int jj = 0; jj < 2; ++jj)
         HDG_UNROLL
         for (int l = 0; l < NM; ++l) v[s][jj][l] = zero ? 0.0f : x[(size_t)l * nf + col[s][jj]];
-    double acc[NM], D[NMH];
+    double acc[NM], D[NM], r[NM];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) acc[j] = 0.0;
-    HDG_UNROLL
-    for (int i = 0; i < NMH; ++i) D[i] = 0.0;
-    HDG_UNROLL
-    for (int j = 0; j < NM; ++j) D[tri(j, j)] = inv_aalpha;
-    HDG_UNROLL
-    for (int s = 0; s < 2; ++s) {
-      if (e[s] < 0) continue;
-      const int fl0 = (bits >> (3 * s)) & 1;
-      const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
-      switch (e[s]) {
-        case 0: tent_side<K, 0>(fl0, fl, c[s], v[s], !zero, acc, D); break;
-        case 1: tent_side<K, 1>(fl0, fl, c[s], v[s], !zero, acc, D); break;
-        default: tent_side<K, 2>(fl0, fl, c[s], v[s], !zero, acc, D); break;
+    tent_diag<K>(inv_aalpha, c[0][0], c[1][0], D);
+    if (!zero) {
+      HDG_UNROLL
+      for (int s = 0; s < 2; ++s) {
+        const int fl[2] = {(bits >> (3 * s + 1)) & 1, (bits >> (3 * s + 2)) & 1};
+        tent_side<K>((bits >> (3 * s)) & 1, fl, c[s], v[s], acc);
       }
     }
-    double r[NM];
+    // D^-1 (rhs - X x) = D^-1 (rhs - offdiag x) - x
     HDG_UNROLL
-    for (int j = 0; j < NM; ++j) {
-      double w = acc[j];
-      if (!zero) {
-        HDG_UNROLL
-        for (int l = 0; l < NM; ++l) w = fma(D[l <= j ? tri(j, l) : tri(l, j)], (double)own[l], w);
-      }
-      r[j] = b[j] - w;
-    }
-    cholesky<NM>(D);
-    chol_solve<NM>(D, r);
+    for (int j = 0; j < NM; ++j) r[j] = (b[j] - acc[j]) / D[j] - (double)own[j];
     HDG_UNROLL
     for (int j = 0; j < NM; ++j) {
       const double di = fma(cd, (double)dprev[j], cr * r[j]);

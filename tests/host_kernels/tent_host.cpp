@@ -64,6 +64,18 @@ int th_fimpl_q(int k, int upwind, int nc, const double* xy, const int* nbr, cons
           else k_fimpl_q<K, false>(xy, nbr, nbr_e, nc, alpha, pre, X, Z, c0, c1, Y))
 }
 
+// penalty-free operator with one thread per (cell, component) (k_fimpl_c), reading the table of k_fimpl_pre
+int th_fimpl_c(int k, int upwind, int nc, const double* xy, const int* nbr, const int* nbr_e, const double* pre,
+               const double* X, const double* Z, double c0, double c1, double* Y) {
+  BY_K(k, if (upwind) k_fimpl_c<K, true>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y);
+          else k_fimpl_c<K, false>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y))
+}
+
+// entry (j, l) of the reference Gram block GG(e, f) = BF_e BF_f^T the Schur-complement sweeps are built from
+int th_gram(int k, int e, int f, int j, int l, double* out) {
+  BY_K(k, *out = RefTables<K>::GG(e, f, j, l))
+}
+
 int th_moments(int k, int nc, const double* xy, const int* flip, const double* Y, double* cm) {
   BY_K(k, k_tent_moments<K>(xy, flip, nc, Y, cm))
 }

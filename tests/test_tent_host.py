@@ -411,3 +411,46 @@ def test_operator_with_tabulated_advecting_velocity_is_the_same_operator(lib, k,
         assert lib.th_fimpl_q(k, int(upwind), ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), ctypes.c_double(alpha), dp(pre),
                               dp(X), dp(Zarg), ctypes.c_double(1.0), ctypes.c_double(-0.37), dp(Yq)) == 0
         assert np.abs(Yq - Y).max() <= 1e-13 * np.abs(Y).max()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_gram_blocks_do_not_depend_on_the_local_facet(lib, k):
+    """what k_tent_sweep / k_tent_sweep32 rely on to run without a switch over the local facet index (csrc/hdg_tent.cuh):
+    GG(e, (e + j) % 3) = GG(0, j) for every local facet e, and the facet's own block GG(e, e) is diagonal"""
+    nm = k + 2
+    G = np.zeros((3, 3, nm, nm))
+    out = ctypes.c_double()
+    for e in range(3):
+        for f in range(3):
+            for j in range(nm):
+                for l in range(nm):  # noqa: E741
+                    assert lib.th_gram(k, e, f, j, l, ctypes.byref(out)) == 0
+                    G[e, f, j, l] = out.value
+    for e in range(3):
+        for jj in range(3):
+            assert np.abs(G[e, (e + jj) % 3] - G[0, jj]).max() <= 4e-16 * np.abs(G[0, jj]).max()
+        assert np.abs(G[e, e] - np.diag(np.diag(G[e, e]))).max() == 0.0
+        assert np.all(np.diag(G[e, e]) > 0.0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+@pytest.mark.parametrize("upwind", [True, False])
+def test_component_split_operator_is_the_penalty_free_operator(lib, k, upwind):
+    """k_fimpl_c (one thread per (cell, component), Q* from the table of k_fimpl_pre; the operator of the augmented
+    Krylov iteration, where the penalty lives in the multiplier rows) against k_fimpl with alpha = 0, with and without
+    a separate Z, on a mesh whose cell count is not a multiple of 16"""
+    for nx in (3, 5):
+        mesh = UnitSquareMesh(nx, perturb=0.15)
+        ht = HostTentative(lib, mesh, k)
+        rng = np.random.default_rng(20 + k)
+        X, Qs, Z = (rng.standard_normal((2 * ht.nq1, ht.nc)) for _ in range(3))
+        npre = ctypes.c_int(0)
+        assert lib.th_fimpl_pre(k, ht.nc, dp(ht.xy), dp(Qs), None, ctypes.byref(npre)) == 0
+        pre = np.zeros((npre.value, ht.nc))
+        assert lib.th_fimpl_pre(k, ht.nc, dp(ht.xy), dp(Qs), dp(pre), ctypes.byref(npre)) == 0
+        for Zarg in (Z, None):
+            Y = ht.fimpl(upwind, Qs, X, 1.0, -0.37, Z=Zarg, alpha=0.0)
+            Yc = np.full_like(X, np.nan)
+            assert lib.th_fimpl_c(k, int(upwind), ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), dp(pre), dp(X), dp(Zarg),
+                                  ctypes.c_double(1.0), ctypes.c_double(-0.37), dp(Yc)) == 0
+            assert np.abs(Yc - Y).max() <= 1e-13 * np.abs(Y).max()

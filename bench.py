@@ -206,6 +206,12 @@ def workload_config(args, world=1):
 # ------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_tent_sweep32 launch inside a step (ncu --set full), keyed by
+# (fp32 storage, ranks, nx, k); filled in from the capture of the kernel version that is shipped
+SWEEP_TRAFFIC = {}
+SWEEP_TRAFFIC_SOURCE = None
+
+
 def run_ours(args):
     import torch
 
@@ -347,6 +353,28 @@ def run_ours(args):
     e2e_value = work_units * e2e_steps / e2e_s
     e2e_probe = float(Q_host[(e2e_state["n"] - 1) % 2].abs().max())  # the result was really read on the host
 
+    # ---- in-situ kernel times: the same step once more with an event pair around every kernel launch and the CUDA graphs
+    # off (hdg_kernel_times; diagnostics, never part of `value`): where the device time of a step goes, kernel by kernel,
+    # with the caches and the launch order of the real step.  One untimed step afterwards re-captures the graphs.
+    insitu = None
+    if args.insitu_steps > 0 and world == 1:
+        eng.set_tuning("ktime", 1)
+        eng.kernel_times()
+        # (forcing as in the end-to-end arm just before, so that the time-extrapolated guesses see a continuous history)
+        ims, _, its_insitu, step_no = timed_steps(args.insitu_steps, step_no, lambda kk: ts.step(kk, f_rhs, f_field=f_dev))
+        kt = eng.kernel_times()
+        eng.set_tuning("ktime", 0)
+        ts.step(step_no, f_rhs)
+        step_no += 1
+        tot = sum(v[1] for v in kt.values())
+        insitu = {"steps": args.insitu_steps, "iterations": {kk: v for kk, v in its_insitu.items() if kk != "per_step_tentative_pressure"},
+                  "wall_ms_per_step_without_graphs": ims / args.insitu_steps,
+                  "kernel_ms_per_step": tot / args.insitu_steps,
+                  "graph_mode_ms_per_step": ms / args.steps,
+                  "by_kernel": {name: {"launches_per_step": v[0] / args.insitu_steps, "ms_per_step": v[1] / args.insitu_steps,
+                                       "us_per_launch": 1e3 * v[1] / max(v[0], 1), "share": v[1] / tot}
+                                for name, v in sorted(kt.items(), key=lambda kv: -kv[1][1])[:30]}}
+
     # ---- cold start: the reference's behaviour (zero / Q^n initial guesses), a few steps of the same run ----------
     cold = None
     if args.cold_steps > 0:
@@ -456,29 +484,52 @@ def run_ours(args):
                                    traffic_source="ncu --set full, profiles/ncu_r1b_cg_spmv_raw.csv.gz")
         nm = k + 2
         f32 = bool(getattr(eng, "tuning", {}).get("tent_fp32", 1))
-        # per facet: geometry 6 doubles + 7 ints, rhs (double) and x, d (read), d, xout (written) of NM entries each:
-        # FP32-stored iterate / correction (default on one GPU) or FP64; the 4 neighbour facets' x are L2 re-reads
-        sweep_bytes = (6 * 8 + 7 * 4 + nm * 8 + 4 * nm * (4 if f32 else 8)) * nf_loc
+        # per facet: geometry 6 doubles + 5 ints (4 neighbour facets, orientation bits), rhs (double) and x, d (read), d,
+        # xout (written) of NM entries each: FP32-stored iterate / correction (default) or FP64; the 4 neighbour facets' x
+        # are L2 re-reads
+        sweep_bytes = (6 * 8 + 5 * 4 + nm * 8 + 4 * nm * (4 if f32 else 8)) * nf_loc
         sweep_name = "k_tent_sweep32" if f32 else "k_tent_sweep"
         if sweep_b2b_ms:
             kernels[sweep_name] = hbm(f"{sweep_name}<{k}> (Chebyshev / facet-block-Jacobi sweep on the facet Schur complement "
                                       "of the tentative-velocity preconditioner)", sweep_b2b_ms, sweep_bytes,
-                                      note="latency-limited: 31 % theoretical occupancy (96 registers), 0.7 eligible of 4.4 "
-                                           "active warps per scheduler, DRAM traffic = algorithmic bytes "
-                                           "(profiles/r2/ncu_r2l_tent_sweep32_summary.txt)", launches_timed=n_sweep,
-                                      traffic=(440709120 + 88334592) if (f32 and world == 1 and nx == 1024 and k == 2) else None,
-                                      traffic_source="ncu --set full of one launch inside a step, "
-                                                     "profiles/r2/ncu_r2l_tent_sweep32_raw.csv.gz")
+                                      note="no switch over the local facet index since r2p (GG(e, e+j) = GG(0, j)); the r2l "
+                                           "capture of the divergent version (profiles/r2/ncu_r2l_tent_sweep32_summary.txt) "
+                                           "showed DRAM traffic = algorithmic bytes at 31 % occupancy",
+                                      launches_timed=n_sweep, traffic=SWEEP_TRAFFIC.get((f32, world, nx, k)),
+                                      traffic_source=SWEEP_TRAFFIC_SOURCE)
         else:
             kernels[sweep_name] = {"error": sweep_err}
         dfma_per_cell = {1: 7 * 48 + 3 * 220, 2: 16 * 80 + 3 * 350, 3: 36 * 120 + 3 * 735, 4: 64 * 168 + 3 * 1176}[k]
         tf = 2.0 * dfma_per_cell * nc_loc / fimpl_b2b_ms / 1e9
-        kernels["k_fimpl"] = {"kernel": f"k_fimpl<{k},upwind> (matrix-free advection + flux + penalty operator)",
+        kernels["k_fimpl"] = {"kernel": f"k_fimpl<{k},upwind> (matrix-free advection + flux + penalty operator: residuals, "
+                                        "explicit terms; the Krylov iteration runs k_fimpl_c)",
                               "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                               "peak_source": "self-measured FP64 FMA rate (hdg_measure_fp64_peak; MEASURED_PEAKS.json has no "
                                              "FP64 entry)", "dfma_per_cell": dfma_per_cell, "launch_ms": fimpl_b2b_ms,
                               "launches_timed": 10,
                               "hbm_frac": (4 * 2 * nq1 * 8) * nc_loc / fimpl_b2b_ms / 1e6 / peak}
+        # operator of the Krylov iteration since r2p: k_fimpl_c (penalty-free, one thread per (cell, component), Q* from
+        # the table of k_fimpl_pre).  Timed in situ (event pairs around every launch of a real step); per cell it moves
+        # the table (2 NQ + 3 NQF doubles), x, z (read) and y (written) of 2 NQ1 doubles each, 6 geometry doubles and
+        # 6 neighbour ints -- the neighbours' x are L2 re-reads.  FP64 work next to it: ~2 000 DFMA per cell at k = 2.
+        nqv, nqf = {1: 7, 2: 16, 3: 36, 4: 64}[k], (3 * k + 5) // 2
+        insitu_k = (insitu or {}).get("by_kernel", {})
+        if "k_fimpl_c" in insitu_k:
+            fc_ms = insitu_k["k_fimpl_c"]["us_per_launch"] / 1e3
+            fc_bytes = ((2 * nqv + 3 * nqf + 3 * 2 * nq1 + 6) * 8 + 6 * 4) * nc_loc
+            kernels["k_fimpl_c"] = hbm(f"k_fimpl_c<{k},upwind> (matrix-free advection + upwind flux operator of the "
+                                       "tentative-velocity Krylov iteration, one thread per (cell, component))", fc_ms,
+                                       fc_bytes, launches_timed=int(insitu_k["k_fimpl_c"]["launches_per_step"] * insitu["steps"]),
+                                       timed="in situ: event pair around every launch of a real step (insitu_kernel_times)",
+                                       note="HBM is the tighter of the two bounds (0.30 ms of bytes against 0.25 ms of FP64 "
+                                            "work at k = 2); the kernel is issue / latency limited between them: 1.35 UMOV "
+                                            "per DFMA for the table immediates, 16 warps per SM")
+            if k == 2:
+                kernels["k_fimpl_c"]["dfma_per_cell"] = 2000
+                kernels["k_fimpl_c"]["fp64_frac"] = 2.0 * 2000 * nc_loc / fc_ms / 1e9 / fp64_peak
+        for kname, entry in kernels.items():
+            if kname in insitu_k and "launch_ms" in entry:
+                entry["insitu_launch_ms"] = insitu_k[kname]["us_per_launch"] / 1e3
         # condensation metric of BASELINE.json ("condensation % of roofline"): DESIGN.md 4 / SURVEY.md 8d bytes per cell
         kernels["k_condense"] = hbm(f"k_condense<{k}> (local operator + Schur complement S_K, closed form)", condense_ms,
                                     (6 + nl * nl) * 8 * nc_loc, launches_timed=3,
@@ -492,7 +543,8 @@ def run_ours(args):
         # share of the step: launches per step (counted by the engine) x back-to-back launch time
         counts = {"k_cg_spmv": per_step_launches.get("k_cg_spmv", 0.0),
                   sweep_name: per_step_launches.get("k_tent_sweep32", 0.0) + per_step_launches.get("k_tent_sweep", 0.0),
-                  "k_fimpl": per_step_launches.get("k_fimpl", 0.0), "k_forward": per_step_launches.get("k_forward", 0.0),
+                  "k_fimpl": per_step_launches.get("k_fimpl", 0.0), "k_fimpl_c": per_step_launches.get("k_fimpl_c", 0.0),
+                  "k_forward": per_step_launches.get("k_forward", 0.0),
                   "k_back": per_step_launches.get("k_back", 0.0)}
         for name, cnt in counts.items():
             if "launch_ms" in kernels.get(name, {}):
@@ -533,6 +585,7 @@ def run_ours(args):
             "roofline": roofline,
             "other_kernels": other,
             "cpu_baseline": cpu,
+            "insitu_kernel_times": insitu,
             "cold_start": cold,
             "high_cfl": high,
             "high_cfl_more": high_all[1:],
@@ -570,6 +623,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=1, help="timed steps of the cpu_baseline leg of the own arm")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end arm (0 = the same as --steps)")
     ap.add_argument("--warm-order", type=int, default=3, help="degree of the time extrapolation of the initial guesses")
+    ap.add_argument("--insitu-steps", type=int, default=1,
+                    help="extra steps with an event pair around every kernel (in-situ kernel times; 0 = skip)")
     ap.add_argument("--cold-steps", type=int, default=2, help="extra steps with the reference's cold starts (0 = skip)")
     ap.add_argument("--high-cfl-steps", type=int, default=1,
                     help="extra steps at the reference's default dt (src/driver.py:80-86), reported under high_cfl")

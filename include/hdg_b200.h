@@ -348,6 +348,10 @@ int64_t hdg_launch_count(hdg_handle h);
 /* The same per kernel: "name=launches\n" lines (names without template arguments) written into buf (at most len
  * bytes, NUL-terminated); returns the number of bytes the complete text needs. */
 int64_t hdg_kernel_counts(hdg_handle h, char* buf, int64_t len);
+/* In-situ device time per kernel (diagnostics): after hdg_set_tuning(h, "ktime", 1) every launch is bracketed by an
+ * event pair and the CUDA graphs are off; "name=launches:milliseconds\n" lines since the last read (reading with a
+ * buffer synchronises and clears the record); returns the number of bytes the complete text needs. */
+int64_t hdg_kernel_times(hdg_handle h, char* buf, int64_t len);
 
 #ifdef __cplusplus
 }

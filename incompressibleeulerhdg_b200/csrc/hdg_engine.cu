@@ -103,7 +103,9 @@ struct hdg_engine {
   int tent_sweeps = 4;        // Chebyshev sweeps on the facet Schur complement (4 with the cell blocks: fewest ms per
                               // step at nx=1024, profiles/r2/bench_r2a_knob_ab.jsonl; 8 was the optimum without them)
   double tent_lmax = 0.0;     // lambda_max(D^-1 X) estimate (0 = not yet computed)
-  int tune_sweep = 5;         // register-allocation variant of k_tent_sweep (hdg_set_tuning)
+  int tune_sweep = 6;         // register-allocation variant of k_tent_sweep (hdg_set_tuning); 6 = 80 registers, spill-free
+                              // at k = 2 since the sweeps lost their local-facet switch: 0.1145 vs 0.1253 ms (5) and
+                              // 0.135 ms (8, spills) per launch (profiles/r2/bench_r2p_*.json)
   int tune_tracer = 1;        // 1 = tracer advection from the compile-time tables, 0 = runtime tables
   int tune_condense = 0;      // K >= 3: 0 = fully unrolled thread-per-cell kernel (default, faster),
                               //         1 = row-loop condensation with the Cholesky factor in shared memory
@@ -142,6 +144,9 @@ struct hdg_engine {
   int tune_fimpl_pre = 0;     // tabulate the Q*-dependent factors of k_fimpl once per tentative solve ("fimpl_pre"); measured
                               // on a B200 (gpurun_out/bench_r2o_pre{0,1}.json): 8.79 vs 9.08 timesteps/s -- the kernel is
                               // latency bound, the extra 216 B per cell cost what the 470 saved FMAs gain; off by default
+  int tune_fimpl_split = 1;   // operator of the augmented iteration with one thread per (cell, component) and Q* from the
+                              // table (k_fimpl_c, hdg_flow.cuh; "fimpl_split": 1 = reference tables as immediates, 2 = from
+                              // the constant bank)
   double* fimpl_pre = nullptr;  // [2 NQ + 3 NQF][nc]
   size_t fimpl_pre_len = 0;
   int tune_p2p_fused = 1;     // halo exchange as one kernel (k_p2p_exchange) instead of push + wait/unpack ("p2p_fused")
@@ -190,6 +195,13 @@ struct hdg_engine {
   // bookkeeping
   int64_t launches = 0;
   std::unordered_map<const char*, int64_t> kcount;  // launches per kernel, keyed by the LAUNCH macro's string literal
+  // in-situ kernel timing (hdg_set_tuning "ktime", diagnostics only): one event pair around every launch, graphs off
+  bool ktime = false;
+  struct KTime {
+    const char* name;
+    cudaEvent_t a, b;
+  };
+  std::vector<KTime> ktimes;
   std::string err;
   struct Timer {
     double ms = 0;
@@ -219,7 +231,17 @@ static std::string g_create_err;
 
 #define LAUNCH(h, kernel, grid, block, ...)                      \
   do {                                                           \
+    cudaEvent_t _ka = nullptr, _kb = nullptr;                    \
+    if ((h)->ktime) {                                            \
+      cudaEventCreate(&_ka);                                     \
+      cudaEventCreate(&_kb);                                     \
+      cudaEventRecord(_ka, (h)->stream);                         \
+    }                                                            \
     kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);    \
+    if ((h)->ktime) {                                            \
+      cudaEventRecord(_kb, (h)->stream);                         \
+      (h)->ktimes.push_back({#kernel, _ka, _kb});                \
+    }                                                            \
     (h)->launches++;                                             \
     (h)->kcount[#kernel]++;                                      \
   } while (0)
@@ -485,7 +507,7 @@ static inline uint64_t key_of(double v) {
   return u;
 }
 static inline bool graphs_usable(const hdg_engine* h) {
-  if (!h->use_graphs) return false;
+  if (!h->use_graphs || h->ktime) return false;
   const Comm* c = h->comm;
   return !c || c->nranks == 1 || c->p2p.enabled;
 }
@@ -1315,7 +1337,8 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
   const double* sKx = scaledx ? h->adv_sK : (const double*)nullptr;
   // everything k_fimpl derives from the fixed Q*, tabulated once per solve (k_fimpl_pre / k_fimpl_q, hdg_flow.cuh)
   const double* fpre = nullptr;
-  if (h->tune_fimpl_pre) {
+  const bool split = h->tune_fimpl_split != 0;
+  if (h->tune_fimpl_pre || split) {
     const size_t npre = (size_t)FimplPre<K>::N * h->nc;
     if (h->fimpl_pre_len < npre) {
       if (h->fimpl_pre) cudaFree(h->fimpl_pre);
@@ -1355,7 +1378,22 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
       ScopedTimer tf(h, T_FIMPL);
       // out_x = (I - a F0) xh + M^-1 N^T mu = z - a F0(xh),  z = xh + M^-1 N^T mu (= in_x without the scaling)
       const double* zz = scaledx ? (const double*)h->tent_z : in;
-      if (fpre) {  // Q* is fixed during the solve: its values at the quadrature points come from the table
+      if (split) {  // penalty-free operator, one thread per (cell, component)
+        const int sgrid = cdiv(32 * (int64_t)cdiv(h->nc, 16), 128);
+        const bool ct = h->tune_fimpl_split >= 2;  // table values from the constant bank instead of immediates
+        if (upwind && ct)
+          LAUNCH(h, (k_fimpl_c<K, true, true>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+        else if (upwind)
+          LAUNCH(h, (k_fimpl_c<K, true, false>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+        else if (ct)
+          LAUNCH(h, (k_fimpl_c<K, false, true>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+        else
+          LAUNCH(h, (k_fimpl_c<K, false, false>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+                 (const double*)xh, zz, 1.0, -adt, out);
+      } else if (fpre) {  // Q* is fixed during the solve: its values at the quadrature points come from the table
         if (upwind)
           LAUNCH(h, (k_fimpl_q<K, true>), cgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, 0.0, fpre,
                  (const double*)xh, zz, 1.0, -adt, out);
@@ -1376,7 +1414,8 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
                                key_of(h->tent_f[2]), key_of(h->tent_f[3]), (uint64_t)cellblock,
                                key_of(h->adv_blk32), key_of(h->adv_in), (uint64_t)tent_fp32_active(h),
                                key_of(h->tent_f32[0]), key_of(h->tent_f32[1]), key_of(h->tent_f32[2]),
-                               (uint64_t)scaledx, key_of(tcx), key_of(sKx), key_of(h->tent_z), key_of(fpre)};
+                               (uint64_t)scaledx, key_of(tcx), key_of(sKx), key_of(h->tent_z), key_of(fpre),
+                               (uint64_t)h->tune_fimpl_split};
   // true residual of the primal system:  out_r (length nx, may be null) = b - A x ; returns ||.||^2 over the owned cells
   // in *rr (host).  The augmented residual the Krylov loops monitor bounds it only up to the penalty stiffness.
   auto true_residual = [&](double* out_r, double* rr) -> int {
@@ -2748,6 +2787,43 @@ int64_t hdg_kernel_counts(hdg_handle h, char* buf, int64_t len) {
   return (int64_t)out.size() + 1;
 }
 
+// In-situ device time per kernel since the last call (diagnostics; enabled by hdg_set_tuning("ktime", 1), which also
+// switches the CUDA graphs off): "kernel=launches:milliseconds\n" lines, names without template arguments.  Reading
+// synchronises the stream and clears the record.
+int64_t hdg_kernel_times(hdg_handle h, char* buf, int64_t len) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->stream);
+  std::map<std::string, std::pair<int64_t, double>> merged;
+  for (const auto& kt : h->ktimes) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, kt.a, kt.b);
+    std::string name(kt.name);
+    size_t a = name.find_first_not_of("( ");
+    name = name.substr(a == std::string::npos ? 0 : a);
+    size_t b = name.find_first_of("<) ");
+    auto& e = merged[name.substr(0, b)];
+    e.first++;
+    e.second += ms;
+  }
+  std::string out;
+  char num[64];
+  for (const auto& kv : merged) {
+    snprintf(num, sizeof(num), "%lld:%.6f", (long long)kv.second.first, kv.second.second);
+    out += kv.first + "=" + num + "\n";
+  }
+  if (buf && len > 0) {
+    const size_t ncopy = std::min<size_t>(out.size(), (size_t)len - 1);
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+    for (const auto& kt : h->ktimes) {
+      cudaEventDestroy(kt.a);
+      cudaEventDestroy(kt.b);
+    }
+    h->ktimes.clear();
+  }
+  return (int64_t)out.size() + 1;
+}
+
 // ---- velocity side ------------------------------------------------------------------------------
 int hdg_set_penalty(hdg_handle h, double alpha) {
   if (!h || !(alpha >= 0)) return HDG_EINVAL;
@@ -2813,8 +2889,16 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     h->bicg_failed_adt = -1.0;
     return HDG_OK;
   }
+  if (!strcmp(name, "ktime")) {
+    h->ktime = value != 0;
+    return HDG_OK;
+  }
   if (!strcmp(name, "fimpl_pre")) {
     h->tune_fimpl_pre = value != 0;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "fimpl_split")) {
+    h->tune_fimpl_split = value;  // 0: k_fimpl, 1: k_fimpl_c with immediates, 2: k_fimpl_c with constant-bank tables
     return HDG_OK;
   }
   if (!strcmp(name, "p2p_fused")) {

@@ -432,25 +432,68 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 3 : 1)) k_fimpl_q(const double*
 // half-warp reads 128 contiguous bytes of the SoA fields and both halves share the table lines.
 //   Y = c0 Z + c1 M^-1 f_impl(., X; Q*)|_{alpha = 0}        (Z = X if null)
 // ------------------------------------------------------------------------------------------------
-template <int K, int E>
+// Where the table values come from (CT): sm_100a has no 64-bit immediate operand, so a compile-time table entry costs two
+// UMOVs into a uniform register pair per use (cuobjdump: 1.3-1.4 UMOV per DFMA in these kernels); a copy of the tables in
+// the constant bank is fetched with LDCU.128, two entries per instruction.  The sparsity tests stay compile time.
+template <int K>
+struct FlowCTab {
+  using T = RefTables<K>;
+  double PHI[T::NQ][Dims<K>::NQ1], DPHI[2][T::NQ][Dims<K>::NQ1], PHIF[3][T::NQF][Dims<K>::NQ1], WQ[T::NQ], WF[T::NQF];
+  constexpr FlowCTab() : PHI{}, DPHI{}, PHIF{}, WQ{}, WF{} {
+    for (int q = 0; q < T::NQ; ++q) {
+      WQ[q] = T::WQ(q);
+      for (int i = 0; i < Dims<K>::NQ1; ++i) {
+        PHI[q][i] = T::PHI(q, i);
+        DPHI[0][q][i] = T::DPHI(0, q, i);
+        DPHI[1][q][i] = T::DPHI(1, q, i);
+      }
+    }
+    for (int q = 0; q < T::NQF; ++q) {
+      WF[q] = T::WF(q);
+      for (int e = 0; e < 3; ++e)
+        for (int i = 0; i < Dims<K>::NQ1; ++i) PHIF[e][q][i] = T::PHIF(e, q, i);
+    }
+  }
+};
+template <int K>
+__constant__ FlowCTab<K> g_flow_ctab = FlowCTab<K>();
+
+template <int K, bool CT>
+struct FlowTab {
+  using T = RefTables<K>;
+  static __device__ __forceinline__ double PHI(int q, int i) { return CT ? g_flow_ctab<K>.PHI[q][i] : T::PHI(q, i); }
+  static __device__ __forceinline__ double DPHI(int d, int q, int i) {
+    return CT ? g_flow_ctab<K>.DPHI[d][q][i] : T::DPHI(d, q, i);
+  }
+  static __device__ __forceinline__ double PHIF(int e, int q, int i) {
+    return CT ? g_flow_ctab<K>.PHIF[e][q][i] : T::PHIF(e, q, i);
+  }
+  static __device__ __forceinline__ double WQ(int q) { return CT ? g_flow_ctab<K>.WQ[q] : T::WQ(q); }
+  static __device__ __forceinline__ double WF(int q) { return CT ? g_flow_ctab<K>.WF[q] : T::WF(q); }
+};
+
+template <int K, int E, bool CT>
 __device__ __forceinline__ void trace1_at_points(const double (&x)[Dims<K>::NQ1], bool reversed,
                                                  double (&out)[RefTables<K>::NQF]) {
   using T = RefTables<K>;
+  using V = FlowTab<K, CT>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) {
     double v = 0.0;
     HDG_UNROLL
-    for (int i = 0; i < NQ1; ++i) v = fma(T::PHIF(E, q, i), x[i], v);
+    for (int i = 0; i < NQ1; ++i)
+      if (T::PHIF(E, q, i) != 0.0) v = fma(V::PHIF(E, q, i), x[i], v);
     out[reversed ? NQF - 1 - q : q] = v;  // Gauss points are symmetric: s_q -> 1 - s_q is q -> NQF-1-q
   }
 }
 
-template <int K, bool UPWIND, int E>
+template <int K, bool UPWIND, int E, bool CT>
 __device__ __forceinline__ void fimpl_c_facet(double scale, int nc, int nbr, int nbr_e, const double* __restrict__ Xc,
                                               const double* __restrict__ sflux, size_t cell,
                                               const double (&x)[Dims<K>::NQ1], double (&acc)[Dims<K>::NQ1]) {
   using T = RefTables<K>;
+  using V = FlowTab<K, CT>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
   if (nbr < 0) return;  // boundary facet: only the penalty acts there
   double xn[NQ1], sf[NQF];
@@ -459,30 +502,32 @@ __device__ __forceinline__ void fimpl_c_facet(double scale, int nc, int nbr, int
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) sf[q] = sflux[(size_t)q * nc + cell];
   double xo[NQF], xnb[NQF];
-  trace1_at_points<K, E>(x, false, xo);
+  trace1_at_points<K, E, CT>(x, false, xo);
   switch (nbr_e) {
-    case 0: trace1_at_points<K, 0>(xn, true, xnb); break;
-    case 1: trace1_at_points<K, 1>(xn, true, xnb); break;
-    default: trace1_at_points<K, 2>(xn, true, xnb); break;
+    case 0: trace1_at_points<K, 0, CT>(xn, true, xnb); break;
+    case 1: trace1_at_points<K, 1, CT>(xn, true, xnb); break;
+    default: trace1_at_points<K, 2, CT>(xn, true, xnb); break;
   }
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) {
     const double s = sf[q];
     const double coef = 0.5 * s - (UPWIND ? fabs(s) : 0.0);
-    xo[q] = (T::WF(q) * scale) * (coef * (xo[q] - xnb[q]));
+    xo[q] = (V::WF(q) * scale) * (coef * (xo[q] - xnb[q]));
   }
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q)
     HDG_UNROLL
-    for (int i = 0; i < NQ1; ++i) acc[i] = fma(T::PHIF(E, q, i), xo[q], acc[i]);
+    for (int i = 0; i < NQ1; ++i)
+      if (T::PHIF(E, q, i) != 0.0) acc[i] = fma(V::PHIF(E, q, i), xo[q], acc[i]);
 }
 
-template <int K, bool UPWIND>
+template <int K, bool UPWIND, bool CT>
 __global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
     k_fimpl_c(const double* __restrict__ xy, const int* __restrict__ nbr, const int* __restrict__ nbr_e, int nc,
               const double* __restrict__ pre, const double* __restrict__ X, const double* __restrict__ Z, double c0,
               double c1, double* __restrict__ Y) {
   using T = RefTables<K>;
+  using V = FlowTab<K, CT>;
   constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ, NQF = T::NQF;
   const long long nitems = 32LL * ((nc + 15) / 16);
   for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
@@ -506,12 +551,13 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
       double g0 = 0.0, g1 = 0.0;
       HDG_UNROLL
       for (int i = 0; i < NQ1; ++i) {
-        if (T::DPHI(0, q, i) != 0.0) g0 = fma(T::DPHI(0, q, i), x[i], g0);
-        if (T::DPHI(1, q, i) != 0.0) g1 = fma(T::DPHI(1, q, i), x[i], g1);
+        if (T::DPHI(0, q, i) != 0.0) g0 = fma(V::DPHI(0, q, i), x[i], g0);
+        if (T::DPHI(1, q, i) != 0.0) g1 = fma(V::DPHI(1, q, i), x[i], g1);
       }
-      const double v = -T::WQ(q) * (a0 * g0 + a1 * g1);
+      const double v = -V::WQ(q) * (a0 * g0 + a1 * g1);
       HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i) acc[i] = fma(T::PHI(q, i), v, acc[i]);
+      for (int i = 0; i < NQ1; ++i)
+        if (T::PHI(q, i) != 0.0) acc[i] = fma(V::PHI(q, i), v, acc[i]);
     }
     // facet terms: int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr) w,  weight |e| / detJ
     {
@@ -523,11 +569,11 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
       const double l1 = sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2));
       const double l2 = sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
       const double* __restrict__ sfl = pre + (size_t)(2 * NQ) * nc;
-      fimpl_c_facet<K, UPWIND, 0>(l0 * idetJ, nc, nbr[cell], nbr_e[cell], Xc, sfl, cell, x, acc);
-      fimpl_c_facet<K, UPWIND, 1>(l1 * idetJ, nc, nbr[(size_t)nc + cell], nbr_e[(size_t)nc + cell], Xc,
-                                  sfl + (size_t)NQF * nc, cell, x, acc);
-      fimpl_c_facet<K, UPWIND, 2>(l2 * idetJ, nc, nbr[2 * (size_t)nc + cell], nbr_e[2 * (size_t)nc + cell], Xc,
-                                  sfl + (size_t)(2 * NQF) * nc, cell, x, acc);
+      fimpl_c_facet<K, UPWIND, 0, CT>(l0 * idetJ, nc, nbr[cell], nbr_e[cell], Xc, sfl, cell, x, acc);
+      fimpl_c_facet<K, UPWIND, 1, CT>(l1 * idetJ, nc, nbr[(size_t)nc + cell], nbr_e[(size_t)nc + cell], Xc,
+                                      sfl + (size_t)NQF * nc, cell, x, acc);
+      fimpl_c_facet<K, UPWIND, 2, CT>(l2 * idetJ, nc, nbr[2 * (size_t)nc + cell], nbr_e[2 * (size_t)nc + cell], Xc,
+                                      sfl + (size_t)(2 * NQF) * nc, cell, x, acc);
     }
     const double* __restrict__ Zc = Z ? Z + (size_t)c * NQ1 * nc : nullptr;
     double* __restrict__ Yc = Y + (size_t)c * NQ1 * nc;

@@ -109,6 +109,7 @@ SIGNATURES = {
     "hdg_guess_restarts": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "hdg_launch_count": (C.c_int64, [_vp]),
     "hdg_kernel_counts": (C.c_int64, [_vp, C.c_char_p, C.c_int64]),
+    "hdg_kernel_times": (C.c_int64, [_vp, C.c_char_p, C.c_int64]),
     "hdg_upload_begin": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
     "hdg_upload_end": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "hdg_download_begin": (C.c_int, [_vp, C.c_int, _vp, _dp, C.c_int]),
@@ -445,6 +446,20 @@ class HDGEngine:
             name, _, cnt = line.partition("=")
             if name:
                 out[name] = int(cnt)
+        return out
+
+    def kernel_times(self) -> dict:
+        """in-situ device time per kernel since the last call: {name: (launches, milliseconds)}; needs
+        set_tuning("ktime", 1) (diagnostics: event pairs around every launch, CUDA graphs off)"""
+        need = self.lib.hdg_kernel_times(self._h, None, 0)
+        buf = C.create_string_buffer(int(need) + 256)
+        self.lib.hdg_kernel_times(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, _, rest = line.partition("=")
+            cnt, _, ms = rest.partition(":")
+            if name:
+                out[name] = (int(cnt), float(ms))
         return out
 
     # -- condensed mixed-Poisson path ----------------------------------------------------------------

@@ -209,7 +209,8 @@ def workload_config(args, world=1):
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_tent_sweep32 launch inside a step (ncu --set full), keyed by
 # (fp32 storage, ranks, nx, k); filled in from the capture of the kernel version that is shipped
 SWEEP_TRAFFIC = {}
-SWEEP_TRAFFIC_SOURCE = None
+SWEEP_TRAFFIC_SOURCE = ("no capture of a later sweep of the shipped kernel; profiles/r2/ncu_r2s_tent_sweep32_raw.csv.gz is a "
+                        "first (zero-iterate) sweep: 395 MB in 64 us")
 
 
 def run_ours(args):
@@ -521,9 +522,13 @@ def run_ours(args):
                                        "tentative-velocity Krylov iteration, one thread per (cell, component))", fc_ms,
                                        fc_bytes, launches_timed=int(insitu_k["k_fimpl_c"]["launches_per_step"] * insitu["steps"]),
                                        timed="in situ: event pair around every launch of a real step (insitu_kernel_times)",
+                                       traffic=(1611003000 + 322940416) if (world == 1 and nx == 1024 and k == 2) else None,
+                                       traffic_source="ncu --set full of one launch inside a step, "
+                                                      "profiles/r2/ncu_r2s_fimpl_c_raw.csv.gz",
                                        note="HBM is the tighter of the two bounds (0.30 ms of bytes against 0.25 ms of FP64 "
-                                            "work at k = 2); the kernel is issue / latency limited between them: 1.35 UMOV "
-                                            "per DFMA for the table immediates, 16 warps per SM")
+                                            "work at k = 2); ncu r2s: DRAM 42 %, FP64 pipe 44 %, issue slots 59 % busy (1.35 "
+                                            "UMOV per DFMA for the table immediates), 16 warps per SM, power-capped; "
+                                            "constant-bank tables, L1 prefetch and TMA staging measured slower (DESIGN.md 4)")
             if k == 2:
                 kernels["k_fimpl_c"]["dfma_per_cell"] = 2000
                 kernels["k_fimpl_c"]["fp64_frac"] = 2.0 * 2000 * nc_loc / fc_ms / 1e9 / fp64_peak

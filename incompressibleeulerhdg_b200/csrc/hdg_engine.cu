@@ -145,8 +145,9 @@ struct hdg_engine {
                               // on a B200 (gpurun_out/bench_r2o_pre{0,1}.json): 8.79 vs 9.08 timesteps/s -- the kernel is
                               // latency bound, the extra 216 B per cell cost what the 470 saved FMAs gain; off by default
   int tune_fimpl_split = 1;   // operator of the augmented iteration with one thread per (cell, component) and Q* from the
-                              // table (k_fimpl_c, hdg_flow.cuh; "fimpl_split": 1 = reference tables as immediates, 2 = from
-                              // the constant bank)
+                              // table (k_fimpl_c, hdg_flow.cuh; "fimpl_split": 0 = k_fimpl, 1 = k_fimpl_c (default: 94.8
+                              // vs 103.3 ms per solve, profiles/r2/bench_r2p_*.json), 3 = k_fimpl_t, the cell's own rows
+                              // staged in shared memory by TMA bulk copies: parity-green, 9 % slower, opt-in)
   double* fimpl_pre = nullptr;  // [2 NQ + 3 NQF][nc]
   size_t fimpl_pre_len = 0;
   int tune_p2p_fused = 1;     // halo exchange as one kernel (k_p2p_exchange) instead of push + wait/unpack ("p2p_fused")
@@ -229,7 +230,8 @@ static std::string g_create_err;
     return (code);         \
   } while (0)
 
-#define LAUNCH(h, kernel, grid, block, ...)                      \
+#define LAUNCH(h, kernel, grid, block, ...) LAUNCH_SMEM(h, kernel, grid, block, 0, __VA_ARGS__)
+#define LAUNCH_SMEM(h, kernel, grid, block, smem, ...)           \
   do {                                                           \
     cudaEvent_t _ka = nullptr, _kb = nullptr;                    \
     if ((h)->ktime) {                                            \
@@ -237,7 +239,7 @@ static std::string g_create_err;
       cudaEventCreate(&_kb);                                     \
       cudaEventRecord(_ka, (h)->stream);                         \
     }                                                            \
-    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);    \
+    kernel<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__); \
     if ((h)->ktime) {                                            \
       cudaEventRecord(_kb, (h)->stream);                         \
       (h)->ktimes.push_back({#kernel, _ka, _kb});                \
@@ -807,6 +809,28 @@ static void launch_fimpl(hdg_engine* h, bool upwind, const double* Qstar, const 
 struct NoAccept {
   double operator()() const { return 0.0; }
 };
+// k_fimpl_t (hdg_flow.cuh): one CTA per 64 cells, its rows of the table / x / z staged in shared memory by bulk copies
+template <int K>
+static void launch_fimpl_t(hdg_engine* h, bool upwind, const double* pre, const double* X, const double* Z, double c0,
+                           double c1, double* out) {
+  if constexpr (K <= 2) {
+    static bool configured = false;
+    if (!configured) {  // 4 CTAs of 44.5 KB per SM need the large shared-memory carve-out
+      cudaFuncSetAttribute(k_fimpl_t<K, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 80);
+      cudaFuncSetAttribute(k_fimpl_t<K, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 80);
+      configured = true;
+    }
+    const int grid = cdiv(h->nc, 64);
+    const size_t smem = FimplTile<K>::SMEM;
+    if (upwind)
+      LAUNCH_SMEM(h, (k_fimpl_t<K, true>), grid, 128, smem, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, pre, X, Z, c0,
+                  c1, out);
+    else
+      LAUNCH_SMEM(h, (k_fimpl_t<K, false>), grid, 128, smem, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, pre, X, Z, c0,
+                  c1, out);
+  }
+}
+
 template <class Op, class Accept = NoAccept>
 static int bicgstab_loop(hdg_engine* h, size_t n, OwnMask own, Op op, std::vector<uint64_t> key, double* y,
                          const double* part_ref, double rtol, int maxit, int* iters,
@@ -1380,18 +1404,16 @@ static int run_tentative_aug(hdg_engine* h, const double* Qstar, double adt, boo
       const double* zz = scaledx ? (const double*)h->tent_z : in;
       if (split) {  // penalty-free operator, one thread per (cell, component)
         const int sgrid = cdiv(32 * (int64_t)cdiv(h->nc, 16), 128);
-        const bool ct = h->tune_fimpl_split >= 2;  // table values from the constant bank instead of immediates
-        if (upwind && ct)
-          LAUNCH(h, (k_fimpl_c<K, true, true>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
-                 (const double*)xh, zz, 1.0, -adt, out);
+        // rows staged by the TMA (k_fimpl_t, opt-in): k <= 2 (tile <= 48 KB), 16-byte aligned rows
+        const bool tma = h->tune_fimpl_split == 3 && K <= 2 && h->nc % 2 == 0 &&
+                         ((uintptr_t)fpre | (uintptr_t)xh | (uintptr_t)zz) % 16 == 0;
+        if (tma)
+          launch_fimpl_t<K>(h, upwind, fpre, xh, zz, 1.0, -adt, out);
         else if (upwind)
-          LAUNCH(h, (k_fimpl_c<K, true, false>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
-                 (const double*)xh, zz, 1.0, -adt, out);
-        else if (ct)
-          LAUNCH(h, (k_fimpl_c<K, false, true>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+          LAUNCH(h, (k_fimpl_c<K, true>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
                  (const double*)xh, zz, 1.0, -adt, out);
         else
-          LAUNCH(h, (k_fimpl_c<K, false, false>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
+          LAUNCH(h, (k_fimpl_c<K, false>), sgrid, 128, h->cell_xy, h->cell_nbr, h->cell_nbr_e, h->nc, fpre,
                  (const double*)xh, zz, 1.0, -adt, out);
       } else if (fpre) {  // Q* is fixed during the solve: its values at the quadrature points come from the table
         if (upwind)
@@ -2898,7 +2920,7 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     return HDG_OK;
   }
   if (!strcmp(name, "fimpl_split")) {
-    h->tune_fimpl_split = value;  // 0: k_fimpl, 1: k_fimpl_c with immediates, 2: k_fimpl_c with constant-bank tables
+    h->tune_fimpl_split = value;  // 0: k_fimpl, 1: k_fimpl_c, 3: k_fimpl_t (TMA-staged rows)
     return HDG_OK;
   }
   if (!strcmp(name, "p2p_fused")) {

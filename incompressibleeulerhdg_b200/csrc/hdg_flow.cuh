@@ -431,104 +431,132 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 3 : 1)) k_fimpl_q(const double*
 // Lanes 0-15 of a warp take component 0 of 16 consecutive cells, lanes 16-31 component 1 of the same cells, so every
 // half-warp reads 128 contiguous bytes of the SoA fields and both halves share the table lines.
 //   Y = c0 Z + c1 M^-1 f_impl(., X; Q*)|_{alpha = 0}        (Z = X if null)
+// Measured on a B200 at nx = 1024, k = 2 (in situ, profiles/r2/bench_r2t_*.json, bench_r2u_*.json): 547 us per launch
+// against 627 us of k_fimpl in the same loop; ncu (profiles/r2/ncu_r2s_fimpl_c_*): DRAM traffic 1.93 GB = the algorithmic
+// bytes, DRAM at 42 %, FP64 pipe at 44 %, issue slots 59 % busy, the chip at its power cap.  Three attempts to hide the
+// load latency the stall sampling points at were all SLOWER and are not kept, except the last as an opt-in:
+//   * reference tables from the constant bank (LDCU.128, 24 % fewer instructions than the UMOV pairs sm_100a needs for
+//     every 64-bit immediate): 98.6 vs 94.8 ms per solve;
+//   * prefetch.global.L1 of the neighbour coefficients (and of the facet rows of the table) as soon as the indices are
+//     known: 604 vs 546 us per launch;
+//   * the cell's own rows staged in shared memory by TMA bulk copies (k_fimpl_t below): 598 vs 547 us.
 // ------------------------------------------------------------------------------------------------
-// Where the table values come from (CT): sm_100a has no 64-bit immediate operand, so a compile-time table entry costs two
-// UMOVs into a uniform register pair per use (cuobjdump: 1.3-1.4 UMOV per DFMA in these kernels); a copy of the tables in
-// the constant bank is fetched with LDCU.128, two entries per instruction.  The sparsity tests stay compile time.
-template <int K>
-struct FlowCTab {
-  using T = RefTables<K>;
-  double PHI[T::NQ][Dims<K>::NQ1], DPHI[2][T::NQ][Dims<K>::NQ1], PHIF[3][T::NQF][Dims<K>::NQ1], WQ[T::NQ], WF[T::NQF];
-  constexpr FlowCTab() : PHI{}, DPHI{}, PHIF{}, WQ{}, WF{} {
-    for (int q = 0; q < T::NQ; ++q) {
-      WQ[q] = T::WQ(q);
-      for (int i = 0; i < Dims<K>::NQ1; ++i) {
-        PHI[q][i] = T::PHI(q, i);
-        DPHI[0][q][i] = T::DPHI(0, q, i);
-        DPHI[1][q][i] = T::DPHI(1, q, i);
-      }
-    }
-    for (int q = 0; q < T::NQF; ++q) {
-      WF[q] = T::WF(q);
-      for (int e = 0; e < 3; ++e)
-        for (int i = 0; i < Dims<K>::NQ1; ++i) PHIF[e][q][i] = T::PHIF(e, q, i);
-    }
-  }
-};
-template <int K>
-__constant__ FlowCTab<K> g_flow_ctab = FlowCTab<K>();
-
-template <int K, bool CT>
-struct FlowTab {
-  using T = RefTables<K>;
-  static __device__ __forceinline__ double PHI(int q, int i) { return CT ? g_flow_ctab<K>.PHI[q][i] : T::PHI(q, i); }
-  static __device__ __forceinline__ double DPHI(int d, int q, int i) {
-    return CT ? g_flow_ctab<K>.DPHI[d][q][i] : T::DPHI(d, q, i);
-  }
-  static __device__ __forceinline__ double PHIF(int e, int q, int i) {
-    return CT ? g_flow_ctab<K>.PHIF[e][q][i] : T::PHIF(e, q, i);
-  }
-  static __device__ __forceinline__ double WQ(int q) { return CT ? g_flow_ctab<K>.WQ[q] : T::WQ(q); }
-  static __device__ __forceinline__ double WF(int q) { return CT ? g_flow_ctab<K>.WF[q] : T::WF(q); }
-};
-
-template <int K, int E, bool CT>
+template <int K, int E>
 __device__ __forceinline__ void trace1_at_points(const double (&x)[Dims<K>::NQ1], bool reversed,
                                                  double (&out)[RefTables<K>::NQF]) {
   using T = RefTables<K>;
-  using V = FlowTab<K, CT>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) {
     double v = 0.0;
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i)
-      if (T::PHIF(E, q, i) != 0.0) v = fma(V::PHIF(E, q, i), x[i], v);
+      if (T::PHIF(E, q, i) != 0.0) v = fma(T::PHIF(E, q, i), x[i], v);
     out[reversed ? NQF - 1 - q : q] = v;  // Gauss points are symmetric: s_q -> 1 - s_q is q -> NQF-1-q
   }
 }
 
-template <int K, bool UPWIND, int E, bool CT>
+// Src: where the cell's own rows come from -- global memory (FimplSrcGlobal) or the shared-memory tile that the bulk
+// copies of k_fimpl_t filled (FimplSrcTile); pre(r) = table row r, x(i) / z(i) = coefficient i of this thread's component
+struct FimplSrcGlobal {
+  const double* __restrict__ pre;
+  const double* __restrict__ Xc;
+  const double* __restrict__ Zc;  // may be null: z = x
+  size_t nc, cell;
+  __device__ __forceinline__ double P(int r) const { return pre[(size_t)r * nc + cell]; }
+  __device__ __forceinline__ double X(int i) const { return Xc[(size_t)i * nc + cell]; }
+  __device__ __forceinline__ bool has_z() const { return Zc != nullptr; }
+  __device__ __forceinline__ double Zv(int i) const { return Zc[(size_t)i * nc + cell]; }
+};
+
+template <int K, bool UPWIND, int E, class Src>
 __device__ __forceinline__ void fimpl_c_facet(double scale, int nc, int nbr, int nbr_e, const double* __restrict__ Xc,
-                                              const double* __restrict__ sflux, size_t cell,
-                                              const double (&x)[Dims<K>::NQ1], double (&acc)[Dims<K>::NQ1]) {
+                                              const Src& src, int sfrow, const double (&x)[Dims<K>::NQ1],
+                                              double (&acc)[Dims<K>::NQ1]) {
   using T = RefTables<K>;
-  using V = FlowTab<K, CT>;
   constexpr int NQ1 = Dims<K>::NQ1, NQF = T::NQF;
   if (nbr < 0) return;  // boundary facet: only the penalty acts there
   double xn[NQ1], sf[NQF];
   HDG_UNROLL
   for (int i = 0; i < NQ1; ++i) xn[i] = Xc[(size_t)i * nc + nbr];
   HDG_UNROLL
-  for (int q = 0; q < NQF; ++q) sf[q] = sflux[(size_t)q * nc + cell];
+  for (int q = 0; q < NQF; ++q) sf[q] = src.P(sfrow + q);
   double xo[NQF], xnb[NQF];
-  trace1_at_points<K, E, CT>(x, false, xo);
+  trace1_at_points<K, E>(x, false, xo);
   switch (nbr_e) {
-    case 0: trace1_at_points<K, 0, CT>(xn, true, xnb); break;
-    case 1: trace1_at_points<K, 1, CT>(xn, true, xnb); break;
-    default: trace1_at_points<K, 2, CT>(xn, true, xnb); break;
+    case 0: trace1_at_points<K, 0>(xn, true, xnb); break;
+    case 1: trace1_at_points<K, 1>(xn, true, xnb); break;
+    default: trace1_at_points<K, 2>(xn, true, xnb); break;
   }
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q) {
     const double s = sf[q];
     const double coef = 0.5 * s - (UPWIND ? fabs(s) : 0.0);
-    xo[q] = (V::WF(q) * scale) * (coef * (xo[q] - xnb[q]));
+    xo[q] = (T::WF(q) * scale) * (coef * (xo[q] - xnb[q]));
   }
   HDG_UNROLL
   for (int q = 0; q < NQF; ++q)
     HDG_UNROLL
     for (int i = 0; i < NQ1; ++i)
-      if (T::PHIF(E, q, i) != 0.0) acc[i] = fma(V::PHIF(E, q, i), xo[q], acc[i]);
+      if (T::PHIF(E, q, i) != 0.0) acc[i] = fma(T::PHIF(E, q, i), xo[q], acc[i]);
 }
 
-template <int K, bool UPWIND, bool CT>
+// one (cell, component): Yc[i] = c0 z_i + c1 [M^-1 f_impl(., x; Q*)]_i  for the NQ1 coefficients of the component
+template <int K, bool UPWIND, class Src>
+__device__ __forceinline__ void fimpl_c_item(const double* __restrict__ xy, const int* __restrict__ nbr,
+                                             const int* __restrict__ nbr_e, int nc, size_t cell,
+                                             const double* __restrict__ Xc, const Src& src, double c0, double c1,
+                                             double* __restrict__ Yc) {
+  using T = RefTables<K>;
+  constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ, NQF = T::NQF;
+  // everything the facet terms need from global memory is requested first (indices, geometry)
+  const int n0 = nbr[cell], n1 = nbr[(size_t)nc + cell], n2 = nbr[2 * (size_t)nc + cell];
+  const int e0 = nbr_e[cell], e1 = nbr_e[(size_t)nc + cell], e2 = nbr_e[2 * (size_t)nc + cell];
+  const double x0 = xy[cell], y0 = xy[(size_t)nc + cell], x1 = xy[2 * (size_t)nc + cell], y1 = xy[3 * (size_t)nc + cell],
+               x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];
+  double x[NQ1], acc[NQ1];
+  HDG_UNROLL
+  for (int i = 0; i < NQ1; ++i) {
+    x[i] = src.X(i);
+    acc[i] = 0.0;
+  }
+  // volume term: -sum_q WQ[q] phi_i(q) (Qh . grad^ x_c)(q), Qh(q) from the table
+  HDG_UNROLL
+  for (int q = 0; q < NQ; ++q) {
+    const double a0 = src.P(2 * q), a1 = src.P(2 * q + 1);
+    double g0 = 0.0, g1 = 0.0;
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i) {
+      if (T::DPHI(0, q, i) != 0.0) g0 = fma(T::DPHI(0, q, i), x[i], g0);
+      if (T::DPHI(1, q, i) != 0.0) g1 = fma(T::DPHI(1, q, i), x[i], g1);
+    }
+    const double v = -T::WQ(q) * (a0 * g0 + a1 * g1);
+    HDG_UNROLL
+    for (int i = 0; i < NQ1; ++i)
+      if (T::PHI(q, i) != 0.0) acc[i] = fma(T::PHI(q, i), v, acc[i]);
+  }
+  // facet terms: int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr) w,  weight |e| / detJ
+  {
+    const double idetJ = 1.0 / ((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
+    // facet e runs from vertex (e+1)%3 to (e+2)%3 (make_geo)
+    const double l0 = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    const double l1 = sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2));
+    const double l2 = sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
+    fimpl_c_facet<K, UPWIND, 0>(l0 * idetJ, nc, n0, e0, Xc, src, 2 * NQ, x, acc);
+    fimpl_c_facet<K, UPWIND, 1>(l1 * idetJ, nc, n1, e1, Xc, src, 2 * NQ + NQF, x, acc);
+    fimpl_c_facet<K, UPWIND, 2>(l2 * idetJ, nc, n2, e2, Xc, src, 2 * NQ + 2 * NQF, x, acc);
+  }
+  const bool hz = src.has_z();
+  HDG_UNROLL
+  for (int i = 0; i < NQ1; ++i) Yc[(size_t)i * nc + cell] = c0 * (hz ? src.Zv(i) : x[i]) + c1 * acc[i];
+}
+
+template <int K, bool UPWIND>
 __global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
     k_fimpl_c(const double* __restrict__ xy, const int* __restrict__ nbr, const int* __restrict__ nbr_e, int nc,
               const double* __restrict__ pre, const double* __restrict__ X, const double* __restrict__ Z, double c0,
               double c1, double* __restrict__ Y) {
-  using T = RefTables<K>;
-  using V = FlowTab<K, CT>;
-  constexpr int NQ1 = Dims<K>::NQ1, NQ = T::NQ, NQF = T::NQF;
+  constexpr int NQ1 = Dims<K>::NQ1;
   const long long nitems = 32LL * ((nc + 15) / 16);
   for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < nitems;
        item += (long long)gridDim.x * blockDim.x) {
@@ -538,49 +566,101 @@ __global__ void __launch_bounds__(128, (K <= 2 ? 4 : (K == 3 ? 2 : 1)))
     if (cell_ll >= nc) continue;
     const size_t cell = (size_t)cell_ll;
     const double* __restrict__ Xc = X + (size_t)c * NQ1 * nc;
-    double x[NQ1], acc[NQ1];
-    HDG_UNROLL
-    for (int i = 0; i < NQ1; ++i) {
-      x[i] = Xc[(size_t)i * nc + cell];
-      acc[i] = 0.0;
-    }
-    // volume term: -sum_q WQ[q] phi_i(q) (Qh . grad^ x_c)(q), Qh(q) from the table
-    HDG_UNROLL
-    for (int q = 0; q < NQ; ++q) {
-      const double a0 = pre[(size_t)(2 * q) * nc + cell], a1 = pre[(size_t)(2 * q + 1) * nc + cell];
-      double g0 = 0.0, g1 = 0.0;
-      HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i) {
-        if (T::DPHI(0, q, i) != 0.0) g0 = fma(V::DPHI(0, q, i), x[i], g0);
-        if (T::DPHI(1, q, i) != 0.0) g1 = fma(V::DPHI(1, q, i), x[i], g1);
-      }
-      const double v = -V::WQ(q) * (a0 * g0 + a1 * g1);
-      HDG_UNROLL
-      for (int i = 0; i < NQ1; ++i)
-        if (T::PHI(q, i) != 0.0) acc[i] = fma(V::PHI(q, i), v, acc[i]);
-    }
-    // facet terms: int_{dK int} (s/2 - [upwind]|s|) (x_K - x_nbr) w,  weight |e| / detJ
-    {
-      const double x0 = xy[cell], y0 = xy[(size_t)nc + cell], x1 = xy[2 * (size_t)nc + cell],
-                   y1 = xy[3 * (size_t)nc + cell], x2 = xy[4 * (size_t)nc + cell], y2 = xy[5 * (size_t)nc + cell];
-      const double idetJ = 1.0 / ((x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0));
-      // facet e runs from vertex (e+1)%3 to (e+2)%3 (make_geo)
-      const double l0 = sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
-      const double l1 = sqrt((x0 - x2) * (x0 - x2) + (y0 - y2) * (y0 - y2));
-      const double l2 = sqrt((x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0));
-      const double* __restrict__ sfl = pre + (size_t)(2 * NQ) * nc;
-      fimpl_c_facet<K, UPWIND, 0, CT>(l0 * idetJ, nc, nbr[cell], nbr_e[cell], Xc, sfl, cell, x, acc);
-      fimpl_c_facet<K, UPWIND, 1, CT>(l1 * idetJ, nc, nbr[(size_t)nc + cell], nbr_e[(size_t)nc + cell], Xc,
-                                      sfl + (size_t)NQF * nc, cell, x, acc);
-      fimpl_c_facet<K, UPWIND, 2, CT>(l2 * idetJ, nc, nbr[2 * (size_t)nc + cell], nbr_e[2 * (size_t)nc + cell], Xc,
-                                      sfl + (size_t)(2 * NQF) * nc, cell, x, acc);
-    }
-    const double* __restrict__ Zc = Z ? Z + (size_t)c * NQ1 * nc : nullptr;
-    double* __restrict__ Yc = Y + (size_t)c * NQ1 * nc;
-    HDG_UNROLL
-    for (int i = 0; i < NQ1; ++i) Yc[(size_t)i * nc + cell] = c0 * (Zc ? Zc[(size_t)i * nc + cell] : x[i]) + c1 * acc[i];
+    const FimplSrcGlobal src{pre, Xc, Z ? Z + (size_t)c * NQ1 * nc : nullptr, (size_t)nc, cell};
+    fimpl_c_item<K, UPWIND>(xy, nbr, nbr_e, nc, cell, Xc, src, c0, c1, Y + (size_t)c * NQ1 * nc);
   }
 }
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// k_fimpl_t (opt-in, hdg_set_tuning("fimpl_split", 3); k <= 2): k_fimpl_c with the cell's own rows staged by the TMA.
+// One CTA = 64 consecutive cells x 2 components; its rows of the table, of x and of z are 512 contiguous bytes each in
+// the SoA layout, so warp 0 hands all of them to the copy engine at once (cp.async.bulk global -> shared, completion
+// counted in bytes on an mbarrier) and the threads read them from shared memory: every byte of the tile is in flight
+// from the first cycle and none of it occupies a register.  Only the neighbour cells' coefficients (gathers) remain
+// ordinary loads.  Needs nc even (16-byte aligned rows) and full tiles; the last, partial tile takes the global path.
+// Parity-green on the GPU (profiles/r2/pytest_tma_r2t.log) but 9 % slower than k_fimpl_c (598 vs 547 us in situ): all
+// threads of a CTA wait for the whole tile before the first FMA, whereas the row-by-row loads of k_fimpl_c let the warps
+// of a CTA drift apart and overlap their load and FMA phases; hence not the default.
+// ------------------------------------------------------------------------------------------------
+struct FimplSrcTile {
+  const double* tile;  // [rows][64] in shared memory: table rows, then x (2 NQ1 rows), then z (2 NQ1 rows, optional)
+  int j;               // cell within the tile
+  int xrow, zrow;      // first row of this thread's component of x / z (zrow < 0: z = x)
+  __device__ __forceinline__ double P(int r) const { return tile[r * 64 + j]; }
+  __device__ __forceinline__ double X(int i) const { return tile[(xrow + i) * 64 + j]; }
+  __device__ __forceinline__ bool has_z() const { return zrow >= 0; }
+  __device__ __forceinline__ double Zv(int i) const { return tile[(zrow + i) * 64 + j]; }
+};
+
+template <int K>
+struct FimplTile {
+  static constexpr int NPRE = 2 * RefTables<K>::NQ + 3 * RefTables<K>::NQF, NX = 2 * Dims<K>::NQ1;
+  static constexpr int ROWS = NPRE + 2 * NX;
+  static constexpr size_t SMEM = (size_t)ROWS * 64 * sizeof(double) + 16;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int K, bool UPWIND>
+__global__ void __launch_bounds__(128, (K <= 2 ? 4 : 1))
+    k_fimpl_t(const double* __restrict__ xy, const int* __restrict__ nbr, const int* __restrict__ nbr_e, int nc,
+              const double* __restrict__ pre, const double* __restrict__ X, const double* __restrict__ Z, double c0,
+              double c1, double* __restrict__ Y) {
+  constexpr int NQ1 = Dims<K>::NQ1, NPRE = FimplTile<K>::NPRE, NX = FimplTile<K>::NX;
+  extern __shared__ __align__(128) unsigned char fimpl_smem[];
+  double* tile = reinterpret_cast<double*>(fimpl_smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fimpl_smem + (size_t)FimplTile<K>::ROWS * 64 * sizeof(double));
+  const int cell0 = blockIdx.x * 64;
+  const bool staged = cell0 + 64 <= nc;  // block-uniform
+  const int nrows = NPRE + NX + (Z ? NX : 0);
+  if (staged) {
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(nrows * 512) : "memory");
+      __syncwarp();
+      for (int r = threadIdx.x; r < nrows; r += 32) {
+        const double* src = r < NPRE        ? pre + (size_t)r * nc + cell0
+                            : r < NPRE + NX ? X + (size_t)(r - NPRE) * nc + cell0
+                                            : Z + (size_t)(r - NPRE - NX) * nc + cell0;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(tile + (size_t)r * 64)),
+                     "l"(src), "r"(512), "r"(bar_a)
+                     : "memory");
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, c = lane >> 4, j = (threadIdx.x >> 5) * 16 + (lane & 15);
+  const long long cell_ll = (long long)cell0 + j;
+  const double* __restrict__ Xc = X + (size_t)c * NQ1 * nc;
+  double* __restrict__ Yc = Y + (size_t)c * NQ1 * nc;
+  if (staged) {
+    // wait for the bytes (phase 0 of the barrier); a copy that never completes traps instead of hanging the device
+    const uint32_t bar_a = smem_u32(bar);
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar_a), "r"(0)
+          : "memory");
+      if (!done && clock64() - t0 > 4000000000LL) __trap();
+    }
+    const FimplSrcTile src{tile, j, NPRE + c * NQ1, Z ? NPRE + NX + c * NQ1 : -1};
+    fimpl_c_item<K, UPWIND>(xy, nbr, nbr_e, nc, (size_t)cell_ll, Xc, src, c0, c1, Yc);
+  } else if (cell_ll < nc) {
+    const FimplSrcGlobal src{pre, Xc, Z ? Z + (size_t)c * NQ1 * nc : nullptr, (size_t)nc, (size_t)cell_ll};
+    fimpl_c_item<K, UPWIND>(xy, nbr, nbr_e, nc, (size_t)cell_ll, Xc, src, c0, c1, Yc);
+  }
+}
+#endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------------
 // weak divergence as a dual vector on the pressure space:

@@ -19,7 +19,6 @@ struct HostDim3 {
 static const HostDim3 gridDim = {1, 1, 1}, blockDim = {1, 1, 1}, blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
 // stand-ins that only have to compile (kernels that reduce across a block are not run on the host)
 #define __shared__ static
-#define __constant__ static const
 static inline void __syncthreads() {}
 static inline double __shfl_down_sync(unsigned, double v, int) { return 0.0 * v; }
 template <class T>

@@ -65,13 +65,10 @@ int th_fimpl_q(int k, int upwind, int nc, const double* xy, const int* nbr, cons
 }
 
 // penalty-free operator with one thread per (cell, component) (k_fimpl_c), reading the table of k_fimpl_pre
-// ct: table values from the constant-bank copy (FlowCTab) instead of compile-time immediates
-int th_fimpl_c(int k, int upwind, int ct, int nc, const double* xy, const int* nbr, const int* nbr_e, const double* pre,
+int th_fimpl_c(int k, int upwind, int nc, const double* xy, const int* nbr, const int* nbr_e, const double* pre,
                const double* X, const double* Z, double c0, double c1, double* Y) {
-  BY_K(k, if (upwind && ct) k_fimpl_c<K, true, true>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y);
-          else if (upwind) k_fimpl_c<K, true, false>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y);
-          else if (ct) k_fimpl_c<K, false, true>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y);
-          else k_fimpl_c<K, false, false>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y))
+  BY_K(k, if (upwind) k_fimpl_c<K, true>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y);
+          else k_fimpl_c<K, false>(xy, nbr, nbr_e, nc, pre, X, Z, c0, c1, Y))
 }
 
 // entry (j, l) of the reference Gram block GG(e, f) = BF_e BF_f^T the Schur-complement sweeps are built from

@@ -450,8 +450,7 @@ def test_component_split_operator_is_the_penalty_free_operator(lib, k, upwind):
         assert lib.th_fimpl_pre(k, ht.nc, dp(ht.xy), dp(Qs), dp(pre), ctypes.byref(npre)) == 0
         for Zarg in (Z, None):
             Y = ht.fimpl(upwind, Qs, X, 1.0, -0.37, Z=Zarg, alpha=0.0)
-            for ct in (0, 1):  # table values as immediates / from the constant-bank copy
-                Yc = np.full_like(X, np.nan)
-                assert lib.th_fimpl_c(k, int(upwind), ct, ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), dp(pre), dp(X),
-                                      dp(Zarg), ctypes.c_double(1.0), ctypes.c_double(-0.37), dp(Yc)) == 0
-                assert np.abs(Yc - Y).max() <= 1e-13 * np.abs(Y).max()
+            Yc = np.full_like(X, np.nan)
+            assert lib.th_fimpl_c(k, int(upwind), ht.nc, dp(ht.xy), ip(ht.nbr), ip(ht.nbr_e), dp(pre), dp(X), dp(Zarg),
+                                  ctypes.c_double(1.0), ctypes.c_double(-0.37), dp(Yc)) == 0
+            assert np.abs(Yc - Y).max() <= 1e-13 * np.abs(Y).max()

@@ -555,6 +555,16 @@ def run_ours(args):
             if "launch_ms" in kernels.get(name, {}):
                 kernels[name]["launches_per_step"] = cnt
                 kernels[name]["share_of_step"] = cnt * kernels[name]["launch_ms"] / ms_step
+        # where the in-situ step timed a kernel, its share is the measured one: device time of its launches / device time
+        # of all launches of that step (the probes run on warm buffers; k_tent_sweep32 and the FP64 residual sweep
+        # k_tent_sweep are separate kernels there)
+        if insitu_k:
+            for name in counts:
+                if name in insitu_k and name in kernels and "launch_ms" in kernels[name]:
+                    kernels[name]["launches_per_step_counted"] = kernels[name].get("launches_per_step")
+                    kernels[name]["launches_per_step"] = insitu_k[name]["launches_per_step"]
+                    kernels[name]["share_of_step"] = insitu_k[name]["share"]
+                    kernels[name]["share_source"] = "in situ (insitu_kernel_times)"
         dominant = max((n_ for n_ in counts if "share_of_step" in kernels.get(n_, {})),
                        key=lambda n_: kernels[n_]["share_of_step"])
         roofline = dict(kernels[dominant])

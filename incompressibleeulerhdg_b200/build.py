@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhdg_b200.so")
 SOURCES = ["hdg_engine.cu"]
-HEADERS = ["hdg_local.cuh", "hdg_krylov.cuh", "hdg_poisson.cuh", "hdg_flow.cuh", "hdg_mg.cuh", "hdg_tent.cuh", "hdg_advblock.cuh", "hdg_comm.cuh", "hdg_tracer.cuh",
+HEADERS = ["hdg_local.cuh", "hdg_krylov.cuh", "hdg_poisson.cuh", "hdg_poisson_s.cuh", "hdg_flow.cuh", "hdg_mg.cuh", "hdg_tent.cuh", "hdg_advblock.cuh", "hdg_comm.cuh", "hdg_tracer.cuh",
            "hdg_tables.inc",
            os.path.join("..", "..", "include", "hdg_b200.h")]
 STAMP = LIB + ".flags"

@@ -32,6 +32,7 @@
 #include "hdg_local.cuh"
 #include "hdg_krylov.cuh"
 #include "hdg_poisson.cuh"
+#include "hdg_poisson_s.cuh"
 #include "hdg_flow.cuh"
 #include "hdg_tent.cuh"
 #include "hdg_advblock.cuh"
@@ -110,6 +111,10 @@ struct hdg_engine {
   int tune_condense = 0;      // K >= 3: 0 = fully unrolled thread-per-cell kernel (default, faster),
                               //         1 = row-loop condensation with the Cholesky factor in shared memory
                               //             (hdg_set_tuning "condense_rows")
+  int tune_lsmem = 0;         // K >= 3: bit mask of the per-cell Poisson kernels that keep the Cholesky factor in shared
+                              // memory (hdg_poisson_s.cuh; hdg_set_tuning "poisson_lsmem"): 1 = condensation
+                              // (k_condense_b), 2 = forward elimination (k_forward_s), 4 = back-substitution
+                              // (k_back_s / k_back_update_s)
   bool tent_local_sweeps = false;  // multi-GPU: skip the halo exchanges between the Chebyshev sweeps
                                    // (hdg_set_tentative_comm; costs ~+40 % BiCGStab iterations, profiles/summary_r1.md)
   double *tent_c = nullptr;   // [6][nf]
@@ -720,6 +725,10 @@ static cudaError_t launch_condense(hdg_engine* h) {
     }
     k_condense_rows<K><<<cdiv(h->nc, CONDENSE_ROWS_BLOCK), CONDENSE_ROWS_BLOCK, smem, h->stream>>>(
         h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
+  } else if (K >= 3 && (h->tune_lsmem & 1)) {
+    if constexpr (K >= 3)
+      k_condense_b<K><<<cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, 0, h->stream>>>(h->cell_xy, h->cell_flip, h->nc,
+                                                                                    h->tau, h->SK);
   } else {
     k_condense<K><<<cdiv(h->nc, 128), 128, 0, h->stream>>>(h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
   }
@@ -2408,7 +2417,16 @@ int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* r
     halo_exchange(h, PLAN_CELLS, np, rhs_p);
   }
   DISPATCH_K(h, {
-    LAUNCH(h, k_forward<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, rhs_Q, rhs_p, h->gK);
+    bool done = false;
+    if constexpr (K >= 3) {
+      if (h->tune_lsmem & 2) {
+        LAUNCH(h, k_forward_s<K>, cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->nc, h->tau,
+               rhs_Q, rhs_p, h->gK);
+        done = true;
+      }
+    }
+    if (!done)
+      LAUNCH(h, k_forward<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->nc, h->tau, rhs_Q, rhs_p, h->gK);
     LAUNCH(h, k_trace_rhs<K>, h->grid, BLOCK, h->gK, rhs_l, h->facet_cell, h->facet_local, h->nc, h->nf, h->nf_own,
            r_l, h->partial);
   });
@@ -2423,8 +2441,17 @@ int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs
   ScopedTimer t(h, T_BACK);
   halo_exchange(h, PLAN_FACETS, h->k + 1, l);
   DISPATCH_K(h, {
-    LAUNCH(h, k_back<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
-           rhs_p, l, Q, p);
+    bool done = false;
+    if constexpr (K >= 3) {
+      if (h->tune_lsmem & 4) {
+        LAUNCH(h, k_back_s<K>, cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->cell_facet,
+               h->nc, h->nf, h->tau, rhs_Q, rhs_p, l, Q, p);
+        done = true;
+      }
+    }
+    if (!done)
+      LAUNCH(h, k_back<K>, cdiv(h->nc, 128), 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
+             rhs_p, l, Q, p);
   });
   CUDA_TRY(h, cudaGetLastError());
   return HDG_OK;
@@ -2564,8 +2591,19 @@ static int poisson_apply_impl(hdg_handle h, const double* rhs_Q, const double* r
     upd->nc_own = h->nc_own;
     const BackUpdate U = *upd;
     DISPATCH_K(h, {
-      LAUNCH(h, k_back_update<K>, nblk, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
-             rhs_p, (const double*)l, U);
+      bool done = false;
+      if constexpr (K >= 3) {
+        if (h->tune_lsmem & 4) {
+          // nblk blocks of BD < 128 threads: the grid-stride loop of the kernel visits 128 / BD cells per thread, and
+          // the partial sums keep their nblk slots
+          LAUNCH(h, k_back_update_s<K>, nblk, LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf,
+                 h->tau, rhs_Q, rhs_p, (const double*)l, U);
+          done = true;
+        }
+      }
+      if (!done)
+        LAUNCH(h, k_back_update<K>, nblk, 128, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf, h->tau, rhs_Q,
+               rhs_p, (const double*)l, U);
     });
     if (!h->gm_red) {
       CUDA_TRY(h, dmalloc(&h->gm_red, 8));
@@ -2956,6 +2994,11 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
   }
   if (!strcmp(name, "condense_rows")) {
     h->tune_condense = value;
+    return HDG_OK;
+  }
+  if (!strcmp(name, "poisson_lsmem")) {
+    if (value < 0 || value > 7) FAIL(h, HDG_EINVAL, "hdg_set_tuning: poisson_lsmem is a bit mask 0..7");
+    h->tune_lsmem = value;
     return HDG_OK;
   }
   FAIL(h, HDG_EINVAL, std::string("hdg_set_tuning: unknown knob ") + name);

@@ -49,20 +49,30 @@ class HostMesh:
         self.facet_cell, self.facet_local = t32(mesh.facet_cell), t32(mesh.facet_local)
 
 
-def condense(lib, hm, k):
+def condense(lib, hm, k, suffix=""):
     nl = 3 * (k + 1)
-    SK = np.zeros((nl * nl, hm.nc))
-    assert lib.ph_condense(k, hm.nc, dp(hm.xy), ip(hm.cell_flip), ctypes.c_double(TAU), dp(SK)) == 0
+    SK = np.full((nl * nl, hm.nc), np.nan)
+    fn = getattr(lib, "ph_condense" + suffix)
+    assert fn(k, hm.nc, dp(hm.xy), ip(hm.cell_flip), ctypes.c_double(TAU), dp(SK)) == 0
     return SK
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4])
-def test_condense_kernel_matches_the_oracle(lib, k):
+# suffix "_s": the variants of csrc/hdg_poisson_s.cuh (Cholesky factor in shared memory, facet-blocked condensation;
+# hdg_set_tuning "poisson_lsmem"), instantiated for k >= 3
+VARIANTS = [(1, ""), (2, ""), (3, ""), (4, ""), (3, "_s"), (4, "_s")]
+
+
+@pytest.mark.parametrize("k,suffix", VARIANTS)
+def test_condense_kernel_matches_the_oracle(lib, k, suffix):
     mesh = RandomAffineCells(37)
     hm, o = HostMesh(mesh), HDGOracle(mesh, k)
     nl = 3 * (k + 1)
-    SK = condense(lib, hm, k).T.reshape(mesh.nc, nl, nl)
+    SK = condense(lib, hm, k, suffix).T.reshape(mesh.nc, nl, nl)
     assert rel(SK, o.condensed_local()) < 1e-11
+    if suffix:  # same operation order per entry as the register kernel: agreement to the last bits, symmetric by construction
+        ref = condense(lib, hm, k).T.reshape(mesh.nc, nl, nl)
+        assert rel(SK, ref) < 1e-14
+        assert np.array_equal(SK, SK.transpose(0, 2, 1))
 
 
 @pytest.mark.parametrize("k", [1, 2, 3])
@@ -87,8 +97,10 @@ def test_assemble_kernel_matches_the_oracle(lib, k, mesh_fn):
     assert np.abs(np.einsum("fij,fjk->fik", D, blocks[:, 0]) - np.eye(b)).max() < 1e-11  # facet-block-Jacobi
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4])
-def test_forward_and_back_kernels_match_the_oracle(lib, k):
+@pytest.mark.parametrize("k,suffix", VARIANTS)
+def test_forward_and_back_kernels_match_the_oracle(lib, k, suffix):
+    ph_forward, ph_back = getattr(lib, "ph_forward" + suffix), getattr(lib, "ph_back" + suffix)
+    ph_back_update = getattr(lib, "ph_back_update" + suffix)
     mesh = UnitSquareMesh(3, perturb=0.2)
     hm, o = HostMesh(mesh), HDGOracle(mesh, k)
     nc, nf, nl1 = mesh.nc, mesh.nf, k + 1
@@ -101,12 +113,12 @@ def test_forward_and_back_kernels_match_the_oracle(lib, k):
     Rloc = np.concatenate([Ru.reshape(nc, o.nQ), Rp], axis=1)
     # forward elimination: gK = C_K A_K^-1 (Ru, Rp), in the global facet orientation
     gK = np.zeros((3 * nl1, nc))
-    assert lib.ph_forward(k, nc, dp(hm.xy), ip(hm.cell_flip), ctypes.c_double(TAU), dp(Ru_s), dp(Rp_s), dp(gK)) == 0
+    assert ph_forward(k, nc, dp(hm.xy), ip(hm.cell_flip), ctypes.c_double(TAU), dp(Ru_s), dp(Rp_s), dp(gK)) == 0
     x0 = np.linalg.solve(A, Rloc[:, :, None])[:, :, 0]
     assert rel(gK.T, np.einsum("nla,na->nl", Ck, x0)) < 1e-11
     # back-substitution: (u, phi) = A_K^-1 ((Ru, Rp) - B_K lam_K)
     uo, po = np.zeros((2 * o.nQ1, nc)), np.zeros((o.np_, nc))
-    assert lib.ph_back(k, nc, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ctypes.c_double(TAU), dp(Ru_s),
+    assert ph_back(k, nc, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ctypes.c_double(TAU), dp(Ru_s),
                        dp(Rp_s), dp(lam_s), dp(uo), dp(po)) == 0
     xl = np.linalg.solve(A, (Rloc - np.einsum("nal,nl->na", Bk, lam.ravel()[o.trace_dofs()]))[:, :, None])[:, :, 0]
     assert rel(uo.reshape(2, o.nQ1, nc).transpose(2, 0, 1), xl[:, :o.nQ].reshape(nc, 2, o.nQ1)) < 1e-11
@@ -117,9 +129,9 @@ def test_forward_and_back_kernels_match_the_oracle(lib, k):
     for cq, cb, cu, cp in ((0.0, 1.0, 0.37, 0.0), (1.0, 1.0, 0.05, 1.0), (0.0, 0.0, 1.0, 0.0)):
         Qacc, pacc, part = Qa.copy(), pa.copy(), np.zeros(1)
         nc_own = nc - 2
-        assert lib.ph_back_update(k, nc, nc_own, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ctypes.c_double(TAU),
-                                  dp(Ru_s), dp(Rp_s), dp(lam_s), ctypes.c_double(cq), ctypes.c_double(cb),
-                                  ctypes.c_double(cu), ctypes.c_double(cp), dp(Qb), dp(Qacc), dp(pacc), dp(part)) == 0
+        assert ph_back_update(k, nc, nc_own, nf, dp(hm.xy), ip(hm.cell_flip), ip(hm.cell_facet), ctypes.c_double(TAU),
+                              dp(Ru_s), dp(Rp_s), dp(lam_s), ctypes.c_double(cq), ctypes.c_double(cb),
+                              ctypes.c_double(cu), ctypes.c_double(cp), dp(Qb), dp(Qacc), dp(pacc), dp(part)) == 0
         assert rel(Qacc, cq * Qa + cb * Qb + cu * uo) < 1e-12
         assert rel(pacc, cp * pa + po) < 1e-12
         assert abs(part[0] - np.sum(o.detJ[:nc_own] * po[0, :nc_own])) < 1e-12 * np.abs(po).max()

@@ -111,10 +111,13 @@ struct hdg_engine {
   int tune_condense = 0;      // K >= 3: 0 = fully unrolled thread-per-cell kernel (default, faster),
                               //         1 = row-loop condensation with the Cholesky factor in shared memory
                               //             (hdg_set_tuning "condense_rows")
-  int tune_lsmem = 0;         // K >= 3: bit mask of the per-cell Poisson kernels that keep the Cholesky factor in shared
+  int tune_lsmem = -1;        // K >= 3: bit mask of the per-cell Poisson kernels that keep the Cholesky factor in shared
                               // memory (hdg_poisson_s.cuh; hdg_set_tuning "poisson_lsmem"): 1 = condensation
                               // (k_condense_b), 2 = forward elimination (k_forward_s), 4 = back-substitution
-                              // (k_back_s / k_back_update_s)
+                              // (k_back_s / k_back_update_s); -1 = what measured faster on a B200 at 10^6 cells
+                              // (profiles/r2/condense_bench_r2x.jsonl): k = 3: 1 | 4 (condense 0.515 -> 0.424 ms, back
+                              // 0.220 -> 0.209 ms, forward would be 0.210 -> 0.236 ms), k = 4: all three (5.49 -> 2.53,
+                              // 0.577 -> 0.555, 0.693 -> 0.566 ms)
   bool tent_local_sweeps = false;  // multi-GPU: skip the halo exchanges between the Chebyshev sweeps
                                    // (hdg_set_tentative_comm; costs ~+40 % BiCGStab iterations, profiles/summary_r1.md)
   double *tent_c = nullptr;   // [6][nf]
@@ -619,6 +622,12 @@ __device__ __forceinline__ double W_entry_dyn(const Geo& g, const double (&nu)[3
 
 constexpr int CONDENSE_ROWS_BLOCK = 64;
 
+// which per-cell Poisson kernels use the shared-memory factor (hdg_poisson_s.cuh): the knob, or the measured default
+static inline int lsmem_mask(const hdg_engine* h) {
+  if (h->tune_lsmem >= 0) return h->k >= 3 ? h->tune_lsmem : 0;
+  return h->k >= 4 ? 7 : h->k == 3 ? 5 : 0;
+}
+
 template <int K>
 __global__ void __launch_bounds__(CONDENSE_ROWS_BLOCK) k_condense_rows(const double* __restrict__ xy,
                                                                        const int* __restrict__ flip, int nc, double tau,
@@ -725,7 +734,7 @@ static cudaError_t launch_condense(hdg_engine* h) {
     }
     k_condense_rows<K><<<cdiv(h->nc, CONDENSE_ROWS_BLOCK), CONDENSE_ROWS_BLOCK, smem, h->stream>>>(
         h->cell_xy, h->cell_flip, h->nc, h->tau, h->SK);
-  } else if (K >= 3 && (h->tune_lsmem & 1)) {
+  } else if (K >= 3 && (lsmem_mask(h) & 1)) {
     if constexpr (K >= 3)
       k_condense_b<K><<<cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, 0, h->stream>>>(h->cell_xy, h->cell_flip, h->nc,
                                                                                     h->tau, h->SK);
@@ -2419,7 +2428,7 @@ int hdg_forward_eliminate_dev(hdg_handle h, const double* rhs_Q, const double* r
   DISPATCH_K(h, {
     bool done = false;
     if constexpr (K >= 3) {
-      if (h->tune_lsmem & 2) {
+      if (lsmem_mask(h) & 2) {
         LAUNCH(h, k_forward_s<K>, cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->nc, h->tau,
                rhs_Q, rhs_p, h->gK);
         done = true;
@@ -2443,7 +2452,7 @@ int hdg_back_substitute_dev(hdg_handle h, const double* rhs_Q, const double* rhs
   DISPATCH_K(h, {
     bool done = false;
     if constexpr (K >= 3) {
-      if (h->tune_lsmem & 4) {
+      if (lsmem_mask(h) & 4) {
         LAUNCH(h, k_back_s<K>, cdiv(h->nc, LsBlock<K>::BD), LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->cell_facet,
                h->nc, h->nf, h->tau, rhs_Q, rhs_p, l, Q, p);
         done = true;
@@ -2593,7 +2602,7 @@ static int poisson_apply_impl(hdg_handle h, const double* rhs_Q, const double* r
     DISPATCH_K(h, {
       bool done = false;
       if constexpr (K >= 3) {
-        if (h->tune_lsmem & 4) {
+        if (lsmem_mask(h) & 4) {
           // nblk blocks of BD < 128 threads: the grid-stride loop of the kernel visits 128 / BD cells per thread, and
           // the partial sums keep their nblk slots
           LAUNCH(h, k_back_update_s<K>, nblk, LsBlock<K>::BD, h->cell_xy, h->cell_flip, h->cell_facet, h->nc, h->nf,
@@ -2997,7 +3006,7 @@ int hdg_set_tuning(hdg_handle h, const char* name, int value) {
     return HDG_OK;
   }
   if (!strcmp(name, "poisson_lsmem")) {
-    if (value < 0 || value > 7) FAIL(h, HDG_EINVAL, "hdg_set_tuning: poisson_lsmem is a bit mask 0..7");
+    if (value < -1 || value > 7) FAIL(h, HDG_EINVAL, "hdg_set_tuning: poisson_lsmem is a bit mask 0..7 (-1 = default)");
     h->tune_lsmem = value;
     return HDG_OK;
   }

@@ -38,21 +38,22 @@ def test_local_schur_matches_oracle(k):
     SK = eng.get_local_schur()
     ref = o.condensed_local()
     assert rel(SK, ref) < 1e-11
-    if k <= 3:  # computed on and above the diagonal and mirrored on store (k = 4 keeps the full loop nest)
-        assert np.array_equal(SK, SK.transpose(0, 2, 1))
-    else:
-        assert rel(SK, SK.transpose(0, 2, 1)) < 1e-12
+    # every default kernel computes an entry and its mirror image once: k <= 2 on and above the diagonal (k_condense),
+    # k >= 3 facet block by facet block (k_condense_b, csrc/hdg_poisson_s.cuh)
+    assert np.array_equal(SK, SK.transpose(0, 2, 1))
 
 
 @pytest.mark.parametrize("k", [3, 4])
 def test_condensation_kernel_variants_agree(k):
-    """K >= 3 ships two condensation kernels (fully unrolled thread-per-cell = default; row loop with the
-    Cholesky factor in shared memory, hdg_set_tuning "condense_rows"); both must reproduce the oracle.
-    257 cells leave the last block of either launch partially filled."""
+    """K >= 3 ships three condensation kernels: facet-blocked with the Cholesky factor in shared memory (k_condense_b,
+    the default, tests/test_zz_lsmem_gpu.py), fully unrolled thread-per-cell with the factor in registers (k_condense,
+    "poisson_lsmem" = 0) and a row loop with warp-uniform table loads ("condense_rows" = 1); the latter two are compared
+    here and must both reproduce the oracle.  257 cells leave the last block of either launch partially filled."""
     require_degree(k)
     m = RandomAffineCells(257)
     ref = HDGOracle(m, k).condensed_local()
     eng = HDGEngine(m, k)
+    eng.set_tuning("poisson_lsmem", 0)
     out = {}
     for variant in (0, 1):
         eng.set_tuning("condense_rows", variant)

@@ -32,7 +32,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--lsmem", action="store_true",
                     help="k >= 3: also time the kernels with the Cholesky factor in shared memory "
-                         "(csrc/hdg_poisson_s.cuh, hdg_set_tuning poisson_lsmem=7) and report them beside the defaults")
+                         "(csrc/hdg_poisson_s.cuh, hdg_set_tuning poisson_lsmem=7) and with it in registers "
+                         "(poisson_lsmem=0) and report both beside the engine's defaults")
     args = ap.parse_args()
     peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))) \
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
@@ -80,21 +81,23 @@ def main():
             t_back = tm["back_substitution"][0] / tm["back_substitution"][1]
             lsmem = None
             if k >= 3 and args.lsmem:
-                eng.set_tuning("poisson_lsmem", 7)
-                eng.setup_poisson(keep_local=True)
-                eng.forward_eliminate_dev(Ru, Rp, None, out_l)
-                eng.back_substitute_dev(Ru, Rp, lam, Q, p)
-                eng.reset_timers()
-                for _ in range(args.reps):
+                lsmem = {}
+                for label, mask in (("register_kernels", 0), ("shared_factor_kernels", 7)):
+                    eng.set_tuning("poisson_lsmem", mask)
                     eng.setup_poisson(keep_local=True)
                     eng.forward_eliminate_dev(Ru, Rp, None, out_l)
                     eng.back_substitute_dev(Ru, Rp, lam, Q, p)
-                eng.synchronize()
-                tl = eng.timers()
-                lsmem = {name: tl[key][0] / tl[key][1] for name, key in
-                         (("condense_ms", "condense"), ("forward_ms", "forward_elimination"),
-                          ("back_ms", "back_substitution"))}
-                eng.set_tuning("poisson_lsmem", 0)
+                    eng.reset_timers()
+                    for _ in range(args.reps):
+                        eng.setup_poisson(keep_local=True)
+                        eng.forward_eliminate_dev(Ru, Rp, None, out_l)
+                        eng.back_substitute_dev(Ru, Rp, lam, Q, p)
+                    eng.synchronize()
+                    tl = eng.timers()
+                    lsmem[label] = {name: tl[key][0] / tl[key][1] for name, key in
+                                    (("condense_ms", "condense"), ("forward_ms", "forward_elimination"),
+                                     ("back_ms", "back_substitution"))}
+                eng.set_tuning("poisson_lsmem", -1)
             flops = (2.0 / 3.0) * nA ** 3 + 2.0 * nA * nA * nl + 2.0 * nl * nl * nA
             by_cond = (6 + 3 + nl * nl) * 8
             by_fwd = (6 + 3 + nA + nl) * 8 + 2 * 3 * b * 8  # + the facet gather/write of k_trace_rhs
@@ -110,10 +113,12 @@ def main():
                 "cells_per_s_condense": nc / t_cond * 1e3,
                 "condense_rows_variant_ms": unrolled_ms,
             }
-            if lsmem:
-                res["lsmem"] = dict(lsmem, condense_hbm_frac=gbs(by_cond, lsmem["condense_ms"]) / hbm,
-                                    forward_hbm_frac=gbs(by_fwd, lsmem["forward_ms"]) / hbm,
-                                    back_hbm_frac=gbs(by_back, lsmem["back_ms"]) / hbm)
+            if lsmem:  # A/B of hdg_set_tuning("poisson_lsmem", 0 / 7); the line above is the engine's default (k = 3: 5, k = 4: 7)
+                for v in lsmem.values():
+                    v.update(condense_hbm_frac=gbs(by_cond, v["condense_ms"]) / hbm,
+                             forward_hbm_frac=gbs(by_fwd, v["forward_ms"]) / hbm,
+                             back_hbm_frac=gbs(by_back, v["back_ms"]) / hbm)
+                res["poisson_lsmem_ab"] = lsmem
             print(json.dumps(res), flush=True)
             del eng, Ru, Rp, lam, out_l, Q, p
             torch.cuda.empty_cache()

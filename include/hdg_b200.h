@@ -339,8 +339,22 @@ int hdg_tent_sweep_probe(hdg_handle h, double adt, int nrep, double* ms_per_laun
  * iterations, done) and of the last BiCGStab (out[5..9]: ||b||^2, ||r||^2, rtol^2, iterations, done) */
 int hdg_debug_scalars(hdg_handle h, double* out10);
 int hdg_set_graphs(hdg_handle h, int on);
-/* tuning knobs that do not change results: "sweep_minblocks" in {5, 6, 8} selects the register-allocation
- * variant of k_tent_sweep (96 / 80 / 64 registers per thread at k = 2; default 5) */
+/* Engine knobs by name (no reference counterpart; also settable at start-up with HDG_TUNING="name=value,...").  They
+ * select between implementations of the same operation and never change what is computed beyond the solver tolerance:
+ *   "sweep_minblocks" 5 | 6 | 8   register-allocation variant of k_tent_sweep (96 / 80 / 64 registers at k = 2; default 6)
+ *   "tent_cellblock", "tent_scaledx", "tent_flex", "tent_fp32", "tent_verify"   0 | 1, parts of the default
+ *                                  tentative-velocity preconditioner / BiCGStab (all default 1)
+ *   "tent_mixed" 0 | 1             FP64 refinement around an FP32 BiCGStab (default 0), with "tent_inner_tol", "tent_inner_cap"
+ *   "tent_krylov" 0 | 1 | 2        BiCGStab with FGMRES fallback | BiCGStab only | FGMRES only; "tent_gmres_m", "tent_bicg_cap"
+ *   "fimpl_split" 0 | 1 | 3        operator of the tentative iteration: k_fimpl | k_fimpl_c (default) | k_fimpl_t; "fimpl_pre" 0 | 1
+ *   "condense_rows" 0 | 1          k >= 3: row-loop condensation kernel (default 0)
+ *   "poisson_lsmem" -1 | 0..7      k >= 3: bit mask of the per-cell Poisson kernels that keep the Cholesky factor in shared
+ *                                  memory (1 condensation, 2 forward elimination, 4 back-substitution); -1 = measured default
+ *   "tracer_tables" 0 | 1          tracer advection from runtime | compile-time tables (default 1)
+ *   "p2p_fused" 0 | 1              halo exchange as one kernel (default 1)
+ *   "ktime" 0 | 1                  event pair around every launch (hdg_kernel_times), CUDA graphs off
+ *   "tent_trace" 0 | 1             residual norms of the tentative solves on stderr
+ * Unknown names return HDG_EINVAL. */
 int hdg_set_tuning(hdg_handle h, const char* name, int value);
 int hdg_graph_replays(hdg_handle h, int64_t* replays);
 /* Number of engine kernels launched since creation (bench.py "gpu_launches"). */

@@ -15,8 +15,11 @@
 // The arithmetic per entry is the one of hdg_poisson.cuh (same operation order per right-hand side), so the results
 // agree to round-off; tests/test_poisson_host.py executes both on the CPU and compares, the GPU parity tests run both.
 //
-// Selected with hdg_set_tuning(h, "poisson_lsmem", 1) for K >= 3 (hdg_engine.cu).  K <= 2 has no instantiation: there
-// the register versions are spill-free.
+// Defaults for K >= 3 where they measured faster on a B200 (lsmem_mask in hdg_engine.cu; hdg_set_tuning "poisson_lsmem" is
+// the bit mask 1 condensation | 2 forward | 4 back; profiles/r2/condense_bench_r2x/r2A-C.jsonl): k = 4 condensation
+// 5.49 -> 2.53 ms per 10^6 cells, back 0.69 -> 0.57 ms; k = 3 condensation 0.515 -> 0.424 ms.  What limits k_condense_b<4>
+// now is instruction fetch (ncu profiles/r2/ncu_r2y_condense_b4_*: 64 % "no instruction" stalls on a 192 KB straight-line
+// body), see DESIGN.md 9.  K <= 2 has no instantiation: there the register versions are spill-free.
 //
 // Reference: the firedrake.SCPC static condensation of a_mixed_poisson, hdg_imex.py:123-135 (as hdg_poisson.cuh).
 #pragma once
